@@ -1,0 +1,245 @@
+"""gaussian-splatting-cuda_b200: B200-native (sm_100a) 3DGUT rasterizer hot path.
+
+Python host-side mirror used by the tests and bench.py.  The product is the C-ABI CUDA library
+(lib/libgsb200.so, include/gsb200.h) and the libtorch shim exporting the reference's
+`gsplat::` operator API (lib/libgsplat_b200.so, include/gsplat/Ops.h); this module only loads the
+shim and re-states, in Python, the thin L3 caller the reference keeps in
+src/training/rasterization/{rasterizer,rasterizer_autograd}.cpp so the whole path can be driven
+and differentiated from Python.  There is no CPU / eager fallback: if the native library is
+missing or cannot be loaded every entry point raises.
+
+The directory name contains '-' (it is the reference's name + "_b200"), so import it with
+`__graft_entry__.load_package()` or tests/conftest.py, which register it as `gsplat_b200`.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_DIR = os.path.join(_HERE, "lib")
+SHIM_PATH = os.path.join(LIB_DIR, "libgsplat_b200.so")
+CABI_PATH = os.path.join(LIB_DIR, "libgsb200.so")
+
+PINHOLE, ORTHO, FISHEYE = 0, 1, 2  # gsplat::CameraModelType
+SHUTTER_GLOBAL = 4                 # ShutterType::GLOBAL
+
+_loaded = False
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+def build(verbose: bool = False, force: bool = False) -> dict:
+    """Compile libgsb200.so and libgsplat_b200.so in-tree (nvcc cross-compiles; no GPU needed)."""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("_gsb_build", os.path.join(_HERE, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build_all(verbose=verbose, force=force)
+
+
+def load() -> None:
+    """Load the native shim (registers torch.ops.gsplat_b200.*).  Raises if it is not built."""
+    global _loaded
+    if _loaded:
+        return
+    for p in (CABI_PATH, SHIM_PATH):
+        if not os.path.exists(p):
+            raise NativeLibraryError(
+                f"{p} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no CPU fallback for the B200 backend)")
+    torch.ops.load_library(SHIM_PATH)
+    _loaded = True
+
+
+def ops():
+    load()
+    return torch.ops.gsplat_b200
+
+
+@dataclass
+class UTParams:
+    """UnscentedTransformParameters defaults (gsplat/Cameras.h:27-44)."""
+    alpha: float = 0.1
+    beta: float = 2.0
+    kappa: float = 0.0
+    in_image_margin_factor: float = 0.1
+    require_all_sigma_points_valid: bool = True
+
+
+# ---------------------------------------------------------------------------------------------
+# Thin wrappers with the reference's argument names (gsplat/Ops.h)
+# ---------------------------------------------------------------------------------------------
+
+def projection_ut_3dgs_fused(means, quats, scales, opacities, viewmats0, Ks, image_width, image_height,
+                             eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
+                             calc_compensations=False, camera_model=PINHOLE, ut_params: UTParams | None = None,
+                             viewmats1=None, rs_type=SHUTTER_GLOBAL, radial_coeffs=None, tangential_coeffs=None,
+                             thin_prism_coeffs=None):
+    ut = ut_params or UTParams()
+    r = ops().projection_ut_3dgs_fused(
+        means, quats, scales, opacities, viewmats0, viewmats1, Ks, image_width, image_height, eps2d, near_plane,
+        far_plane, radius_clip, calc_compensations, camera_model, ut.alpha, ut.beta, ut.kappa,
+        ut.in_image_margin_factor, ut.require_all_sigma_points_valid, rs_type, radial_coeffs, tangential_coeffs,
+        thin_prism_coeffs)
+    comp = r[4] if r[4].numel() else None
+    return r[0], r[1], r[2], r[3], comp
+
+
+def spherical_harmonics_fwd(degrees_to_use, dirs, coeffs, masks=None):
+    return ops().spherical_harmonics_fwd(degrees_to_use, dirs, coeffs, masks)
+
+
+def spherical_harmonics_bwd(K, degrees_to_use, dirs, coeffs, masks, v_colors, compute_v_dirs=True):
+    v_coeffs, v_dirs = ops().spherical_harmonics_bwd(K, degrees_to_use, dirs, coeffs, masks, v_colors, compute_v_dirs)
+    return v_coeffs, (v_dirs if compute_v_dirs else None)
+
+
+def intersect_tile(means2d, radii, depths, C, tile_size, tile_width, tile_height, sort=True):
+    return ops().intersect_tile(means2d, radii, depths, C, tile_size, tile_width, tile_height, sort)
+
+
+def intersect_offset(isect_ids, C, tile_width, tile_height):
+    return ops().intersect_offset(isect_ids, C, tile_width, tile_height)
+
+
+def rasterize_to_pixels_from_world_3dgs_fwd(means, quats, scales, colors, opacities, backgrounds, masks,
+                                            image_width, image_height, tile_size, viewmats0, Ks, tile_offsets,
+                                            flatten_ids, camera_model=PINHOLE, viewmats1=None,
+                                            rs_type=SHUTTER_GLOBAL, radial_coeffs=None, tangential_coeffs=None,
+                                            thin_prism_coeffs=None):
+    return ops().rasterize_to_pixels_from_world_3dgs_fwd(
+        means, quats, scales, colors, opacities, backgrounds, masks, image_width, image_height, tile_size,
+        viewmats0, viewmats1, Ks, camera_model, rs_type, radial_coeffs, tangential_coeffs, thin_prism_coeffs,
+        tile_offsets, flatten_ids)
+
+
+def rasterize_to_pixels_from_world_3dgs_bwd(means, quats, scales, colors, opacities, backgrounds, masks,
+                                            image_width, image_height, tile_size, viewmats0, Ks, tile_offsets,
+                                            flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas,
+                                            camera_model=PINHOLE, viewmats1=None, rs_type=SHUTTER_GLOBAL,
+                                            radial_coeffs=None, tangential_coeffs=None, thin_prism_coeffs=None):
+    return ops().rasterize_to_pixels_from_world_3dgs_bwd(
+        means, quats, scales, colors, opacities, backgrounds, masks, image_width, image_height, tile_size,
+        viewmats0, viewmats1, Ks, camera_model, rs_type, radial_coeffs, tangential_coeffs, thin_prism_coeffs,
+        tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas)
+
+
+def quats_to_rotmats(quats):
+    return ops().quats_to_rotmats(quats)
+
+
+def relocation(opacities, scales, ratios, binoms, n_max):
+    return ops().relocation(opacities, scales, ratios, binoms, n_max)
+
+
+def add_noise(raw_opacities, raw_scales, raw_quats, noise, means, current_lr):
+    ops().add_noise(raw_opacities, raw_scales, raw_quats, noise, means, current_lr)
+
+
+# ---------------------------------------------------------------------------------------------
+# L3 mirror: what gs::training::rasterize does around the ops (rasterizer.cpp:46-437,
+# rasterizer_autograd.cpp:12-391).  Activated parameters in, image + explicit gradients out.
+# ---------------------------------------------------------------------------------------------
+
+class SphericalHarmonicsFunction(torch.autograd.Function):
+    """rasterizer_autograd.cpp:12-132."""
+
+    @staticmethod
+    def forward(ctx, sh_degree: int, dirs, coeffs, masks):
+        dirs = dirs.contiguous()
+        coeffs = coeffs.contiguous()
+        colors = spherical_harmonics_fwd(sh_degree, dirs.reshape(-1, 3), coeffs.reshape(-1, coeffs.shape[-2], 3),
+                                         masks.reshape(-1).contiguous())
+        ctx.save_for_backward(dirs, coeffs, masks)
+        ctx.sh_degree = sh_degree
+        return colors.reshape(dirs.shape)
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        dirs, coeffs, masks = ctx.saved_tensors
+        K = coeffs.shape[-2]
+        v_coeffs, v_dirs = spherical_harmonics_bwd(
+            K, ctx.sh_degree, dirs.reshape(-1, 3), coeffs.reshape(-1, K, 3), masks.reshape(-1).contiguous(),
+            v_colors.contiguous().reshape(-1, 3), ctx.needs_input_grad[1])
+        return (None, v_dirs.reshape(dirs.shape) if v_dirs is not None else None,
+                v_coeffs.reshape(coeffs.shape) if ctx.needs_input_grad[2] else None, None)
+
+
+class GUTRasterizationFunction(torch.autograd.Function):
+    """rasterizer_autograd.cpp:267-391."""
+
+    @staticmethod
+    def forward(ctx, means, quats, scales, colors, opacities, bg, viewmat, K, isect_offsets, flatten_ids, width,
+                height, tile_size):
+        renders, alphas, last_ids = rasterize_to_pixels_from_world_3dgs_fwd(
+            means.contiguous(), quats.contiguous(), scales.contiguous(), colors.contiguous(),
+            opacities.contiguous(), bg, None, width, height, tile_size, viewmat.contiguous(), K.contiguous(),
+            isect_offsets.contiguous(), flatten_ids.contiguous())
+        ctx.save_for_backward(means, quats, scales, colors, opacities, bg if bg is not None else torch.empty(0),
+                              viewmat, K, isect_offsets, flatten_ids, alphas, last_ids)
+        ctx.dims = (width, height, tile_size, bg is not None)
+        return renders, alphas
+
+    @staticmethod
+    def backward(ctx, v_render_colors, v_render_alphas):
+        (means, quats, scales, colors, opacities, bg, viewmat, K, isect_offsets, flatten_ids, alphas,
+         last_ids) = ctx.saved_tensors
+        width, height, tile_size, has_bg = ctx.dims
+        g = rasterize_to_pixels_from_world_3dgs_bwd(
+            means, quats, scales, colors, opacities, bg if has_bg else None, None, width, height, tile_size, viewmat,
+            K, isect_offsets, flatten_ids, alphas, last_ids, v_render_colors.contiguous(),
+            v_render_alphas.contiguous())
+        v_bg = None
+        if has_bg and ctx.needs_input_grad[5]:
+            v_bg = (v_render_colors * (1.0 - alphas)).sum(dim=(-3, -2))
+        return g[0], g[1], g[2], g[3], g[4], v_bg, None, None, None, None, None, None, None
+
+
+@dataclass
+class RenderOutput:
+    image: torch.Tensor          # [3, H, W], clamped to [0, 1] (rasterizer.cpp:401)
+    alpha: torch.Tensor          # [1, H, W]
+    render_colors: torch.Tensor  # [1, H, W, 3] unclamped (what the loss gradient flows through)
+    radii: torch.Tensor          # [N]
+    depths: torch.Tensor         # [N]
+    means2d: torch.Tensor        # [1, N, 2]
+    n_isects: int
+    n_visible: int
+
+
+def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K, width, height, bg_color=None,
+              scaling_modifier=1.0, tile_size=16, eps2d=0.3, near_plane=0.01, far_plane=10000.0,
+              radius_clip=0.0) -> RenderOutput:
+    """gs::training::rasterize for RenderMode::RGB, perfect pinhole, C == 1 (rasterizer.cpp:46-437).
+
+    Inputs are the ACTIVATED parameters (get_means/get_rotation/get_scaling/get_opacity/get_shs of
+    SplatData): means [N,3], unit quats [N,4] (w,x,y,z), scales [N,3] > 0, opacities [N] in (0,1),
+    sh_coeffs [N,K,3]; viewmat [1,4,4], K [1,3,3]; bg_color [1,3] or None.
+    """
+    scaled = scales * scaling_modifier if scaling_modifier != 1.0 else scales
+    with torch.no_grad():  # "none differentiable" (Ops.h:67)
+        radii, means2d, depths, _conics, _ = projection_ut_3dgs_fused(
+            means.detach().contiguous(), quats.detach().contiguous(), scaled.detach().contiguous(),
+            opacities.detach().contiguous(), viewmat, K, width, height, eps2d, near_plane, far_plane, radius_clip)
+        campos = torch.linalg.inv(viewmat)[:, :3, 3]                     # rasterizer.cpp:250-251
+        masks = (radii > 0).all(-1)                                      # :257
+    dirs = means.unsqueeze(0) - campos.unsqueeze(1)                      # :254
+    colors = SphericalHarmonicsFunction.apply(sh_degree, dirs, sh_coeffs.unsqueeze(0), masks)
+    colors = torch.clamp_min(colors + 0.5, 0.0)                          # :266
+    tile_w = (width + tile_size - 1) // tile_size
+    tile_h = (height + tile_size - 1) // tile_size
+    with torch.no_grad():
+        _tpg, isect_ids, flatten_ids = intersect_tile(means2d, radii, depths, 1, tile_size, tile_w, tile_h, True)
+        offsets = intersect_offset(isect_ids, 1, tile_w, tile_h)
+    renders, alphas = GUTRasterizationFunction.apply(means, quats, scaled, colors, opacities.unsqueeze(0), bg_color,
+                                                     viewmat, K, offsets, flatten_ids, width, height, tile_size)
+    return RenderOutput(
+        image=torch.clamp(renders[0].permute(2, 0, 1), 0.0, 1.0), alpha=alphas[0].permute(2, 0, 1),
+        render_colors=renders, radii=radii[0].max(-1).values, depths=depths[0], means2d=means2d,
+        n_isects=int(flatten_ids.shape[0]), n_visible=int(masks.sum().item()))

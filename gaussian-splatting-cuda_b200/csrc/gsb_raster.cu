@@ -1,0 +1,652 @@
+// gsb_raster.cu -- a7/a8: front-to-back alpha compositing from world-space rays, and its gradient.
+//
+// Implements gsplat::rasterize_to_pixels_from_world_3dgs_fwd / _bwd (reference:
+// gsplat/RasterizeToPixelsFromWorld3DGSFwd.cu:20-279, ...Bwd.cu:17-373, gsplat/Utils.cuh:80-194)
+// for the perfect-pinhole / global-shutter camera.  See gsb_raster.cuh for the math.
+//
+// Kernel structure (B200):
+//   prep      one thread per Gaussian, float64: 64-byte GaussRec (quadratic-form coefficients,
+//             log2 opacity, colour).  N x 64 B stays L2-resident (64 MB at 1 M Gaussians, 126 MB L2).
+//   fwd       one CTA (4 warps, 128 threads) per 16x16 tile; each thread owns two pixels of an
+//             8x8 sub-block so a warp covers 64 pixels.  The tile's depth-sorted records are
+//             gathered by 64-byte TMA bulk copies (cp.async.bulk -> mbarrier complete_tx) into a
+//             two-stage shared-memory ring; ids are prefetched one batch ahead so the gather of
+//             batch b+1 overlaps the blending of batch b.  Per pair: MUFU-free rejection test,
+//             then warp-vote: only warps with a surviving lane pay for rcp/ex2 and the colour row.
+//             A warp whose 64 pixels are saturated stops blending; the CTA leaves when all are.
+//   bwd       same tiling, back-to-front from the CTA-wide max(last_ids); 15 moments per pair are
+//             summed over the thread's two pixels, reduced across the warp with a 16-value
+//             butterfly (16 shuffles instead of 15 x 5) and added to a per-Gaussian 64-byte row
+//             with one 16-lane red.global.add.f32.
+//   finalize  one thread per Gaussian, float64 chain rule from the moments to
+//             (v_means, v_quats, v_scales, v_opacities, v_colors); writes every output element.
+#include "gsb_raster.cuh"
+
+namespace gsb {
+
+constexpr int kPrepThreads = 128;
+constexpr int kTileThreads = 128; // 4 warps x 64 pixels
+constexpr int kBatch = 128;       // records per pipeline stage (one per thread)
+constexpr int kStages = 2;
+
+// ------------------------------------------------------------------------------------------
+// prep
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPrepThreads) prep_records_kernel(uint32_t N, const float *__restrict__ means,
+                                                                     const float *__restrict__ quats,
+                                                                     const float *__restrict__ scales,
+                                                                     const float *__restrict__ colors,
+                                                                     const float *__restrict__ opacities,
+                                                                     const float *__restrict__ viewmat,
+                                                                     const float *__restrict__ K,
+                                                                     GaussRec *__restrict__ recs) {
+    __shared__ CamConst cam;
+    if (threadIdx.x == 0) cam_const_from(viewmat, K, cam);
+    __syncthreads();
+    const uint32_t g = blockIdx.x * kPrepThreads + threadIdx.x;
+    if (g >= N) return;
+    const float mean[3] = {means[(size_t)g * 3], means[(size_t)g * 3 + 1], means[(size_t)g * 3 + 2]};
+    const float quat[4] = {quats[(size_t)g * 4], quats[(size_t)g * 4 + 1], quats[(size_t)g * 4 + 2],
+                           quats[(size_t)g * 4 + 3]};
+    const float scale[3] = {scales[(size_t)g * 3], scales[(size_t)g * 3 + 1], scales[(size_t)g * 3 + 2]};
+    const float opac = opacities[g];
+    GaussGeom gg;
+    gauss_geom(cam, mean, quat, scale, gg);
+    float4 v0, v1, v2, v3;
+    v3 = make_float4(colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2], __int_as_float((int)g));
+    const bool dead = gg.degenerate || !(opac > 0.f);
+    if (dead) {
+        // never passes the rejection test: Ns (== 0) >= +inf * Ds is false
+        v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        v2 = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+    } else {
+        const double ax = 1.0 / cam.fx, ay = 1.0 / cam.fy;
+        const double id0 = 1.0 / gg.d0;
+        const double kk = -0.5 * 1.4426950408889634 * id0;
+        const float lop = (float)log2((double)opac);
+        v0 = make_float4((float)(cam.fx * gg.uc + cam.cx), (float)(cam.fy * gg.vc + cam.cy),
+                         (float)(kk * gg.n[0] * ax * ax), (float)(kk * gg.n[1] * ax * ay));
+        v1 = make_float4((float)(kk * gg.n[2] * ay * ay), (float)(gg.d[0] * id0 * ax), (float)(gg.d[1] * id0 * ay),
+                         (float)(gg.d[2] * id0 * ax * ax));
+        v2 = make_float4((float)(gg.d[3] * id0 * ax * ay), (float)(gg.d[4] * id0 * ay * ay), lop,
+                         kLog2AlphaThr - kTauMargin - lop);
+    }
+    float4 *dst = reinterpret_cast<float4 *>(recs + g);
+    dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3;
+}
+
+// ------------------------------------------------------------------------------------------
+// tile geometry shared by fwd and bwd
+// ------------------------------------------------------------------------------------------
+struct TileParams {
+    uint32_t n_isects;
+    uint32_t W, H, tile_w, tile_h;
+    const GaussRec *recs;
+    const float *backgrounds; // [3] or null
+    const uint8_t *masks;     // [tile_h*tile_w] or null
+    const int32_t *tile_offsets;
+    const int32_t *flatten_ids;
+};
+
+struct PixelMap {
+    uint32_t x, y0, y1; // pixel coordinates (two rows, same column)
+    bool in0, in1;
+};
+__device__ __forceinline__ PixelMap pixel_map(uint32_t tile_x, uint32_t tile_y, uint32_t W, uint32_t H) {
+    const uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    PixelMap m;
+    m.x = tile_x * 16 + (w & 1) * 8 + (l & 7);
+    m.y0 = tile_y * 16 + (w >> 1) * 8 + (l >> 3);
+    m.y1 = m.y0 + 4;
+    m.in0 = (m.x < W) && (m.y0 < H);
+    m.in1 = (m.x < W) && (m.y1 < H);
+    return m;
+}
+
+// Thread i gathers the record of Gaussian `gid` into slot i of the stage with one 64-byte bulk
+// copy (TMA unit); thread 0 arms the stage's mbarrier with the byte count of the whole batch.
+__device__ __forceinline__ void issue_batch(GaussRec *stage, uint64_t *bar, const GaussRec *recs, int32_t gid,
+                                            uint32_t cnt) {
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) mbar_arrive_expect_tx(bar, cnt * (uint32_t)sizeof(GaussRec));
+    if (tid < cnt) bulk_g2s(stage + tid, recs + gid, (uint32_t)sizeof(GaussRec), bar);
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TileParams p, float *__restrict__ renders,
+                                                                   float *__restrict__ alphas,
+                                                                   int32_t *__restrict__ last_ids) {
+    __shared__ __align__(128) GaussRec s_rec[kStages][kBatch];
+    __shared__ __align__(8) uint64_t s_full[kStages];
+
+    const uint32_t tile_id = blockIdx.x;
+    const uint32_t tile_y = tile_id / p.tile_w, tile_x = tile_id % p.tile_w;
+    const PixelMap pm = pixel_map(tile_x, tile_y, p.W, p.H);
+    const uint32_t tid = threadIdx.x;
+    const bool has_bg = p.backgrounds != nullptr;
+    const float bg0 = has_bg ? p.backgrounds[0] : 0.f;
+    const float bg1 = has_bg ? p.backgrounds[1] : 0.f;
+    const float bg2 = has_bg ? p.backgrounds[2] : 0.f;
+
+    const size_t pix0 = (size_t)pm.y0 * p.W + pm.x, pix1 = (size_t)pm.y1 * p.W + pm.x;
+    if (p.masks != nullptr && !p.masks[tile_id]) { // Fwd.cu:143-150: background only, alpha/last_ids untouched
+        if (pm.in0) { renders[pix0 * 3] = bg0; renders[pix0 * 3 + 1] = bg1; renders[pix0 * 3 + 2] = bg2; }
+        if (pm.in1) { renders[pix1 * 3] = bg0; renders[pix1 * 3 + 1] = bg1; renders[pix1 * 3 + 2] = bg2; }
+        return;
+    }
+
+    const int32_t range_start = p.tile_offsets[tile_id];
+    const int32_t range_end = (tile_id == p.tile_w * p.tile_h - 1) ? (int32_t)p.n_isects : p.tile_offsets[tile_id + 1];
+    const int32_t total = max(range_end - range_start, 0);
+    const int32_t n_batches = (total + kBatch - 1) / kBatch;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const float px = (float)pm.x + 0.5f;
+    const float py0 = (float)pm.y0 + 0.5f, py1 = (float)pm.y1 + 0.5f;
+    float T0 = 1.f, T1 = 1.f;
+    float c0r = 0.f, c0g = 0.f, c0b = 0.f, c1r = 0.f, c1g = 0.f, c1b = 0.f;
+    int32_t last0 = 0, last1 = 0;
+    bool done0 = !pm.in0, done1 = !pm.in1;
+
+    // prologue: batch 0 in flight, ids of batch 1 prefetched into a register
+    int32_t gid_next = 0;
+    if (n_batches > 0) {
+        const int32_t idx = range_start + (int32_t)tid;
+        const int32_t gid = (idx < range_end) ? p.flatten_ids[idx] : 0;
+        issue_batch(s_rec[0], &s_full[0], p.recs, gid, (uint32_t)min(total, kBatch));
+        const int32_t idx1 = idx + kBatch;
+        gid_next = (idx1 < range_end) ? p.flatten_ids[idx1] : 0;
+    }
+
+    int32_t b = 0;
+    bool saturated = false;
+    for (; b < n_batches; ++b) {
+        const int st = b & 1;
+        if (b + 1 < n_batches) { // gather batch b+1 while blending batch b
+            const int32_t cnt1 = min(total - (b + 1) * kBatch, kBatch);
+            issue_batch(s_rec[st ^ 1], &s_full[st ^ 1], p.recs, gid_next, (uint32_t)cnt1);
+            const int32_t idx2 = range_start + (b + 2) * kBatch + (int32_t)tid;
+            gid_next = (idx2 < range_end) ? p.flatten_ids[idx2] : 0;
+        }
+        mbar_wait(&s_full[st], (uint32_t)((b >> 1) & 1));
+
+        const int32_t cnt = min(total - b * kBatch, kBatch);
+        const int32_t batch_start = range_start + b * kBatch;
+        if (!__all_sync(0xffffffffu, done0 && done1)) { // this warp's 64 pixels are not all saturated
+            const float4 *rec4 = reinterpret_cast<const float4 *>(s_rec[st]);
+#pragma unroll 2
+            for (int32_t t = 0; t < cnt; ++t) {
+                const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
+                const float x = px - q0.x;
+                const PairEval e0 = pair_eval(q0, q1, q2, x, py0 - q0.y);
+                const PairEval e1 = pair_eval(q0, q1, q2, x, py1 - q0.y);
+                const bool p0 = e0.pass && !done0, p1 = e1.pass && !done1;
+                if (!__any_sync(0xffffffffu, p0 || p1)) continue;
+                const float4 q3 = rec4[t * 4 + 3];
+                if (p0) {
+                    float ex;
+                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw(e0, q2.z, ex));
+                    if (alpha >= kAlphaThreshold) {
+                        const float nT = T0 * (1.0f - alpha);
+                        if (nT <= kMinTransmittance) {
+                            done0 = true; // this Gaussian is NOT composited (Fwd.cu:244-248)
+                        } else {
+                            const float vis = alpha * T0;
+                            c0r += q3.x * vis; c0g += q3.y * vis; c0b += q3.z * vis;
+                            last0 = batch_start + t;
+                            T0 = nT;
+                        }
+                    }
+                }
+                if (p1) {
+                    float ex;
+                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw(e1, q2.z, ex));
+                    if (alpha >= kAlphaThreshold) {
+                        const float nT = T1 * (1.0f - alpha);
+                        if (nT <= kMinTransmittance) {
+                            done1 = true;
+                        } else {
+                            const float vis = alpha * T1;
+                            c1r += q3.x * vis; c1g += q3.y * vis; c1b += q3.z * vis;
+                            last1 = batch_start + t;
+                            T1 = nT;
+                        }
+                    }
+                }
+            }
+        }
+        // releases stage `st` for batch b+2 and tells every warp whether the tile is saturated
+        if (__syncthreads_and(done0 && done1)) { saturated = true; break; }
+    }
+    // never retire the CTA with a bulk copy still landing in its shared memory
+    if (saturated && b + 1 < n_batches) mbar_wait(&s_full[(b + 1) & 1], (uint32_t)(((b + 1) >> 1) & 1));
+
+    if (pm.in0) {
+        alphas[pix0] = 1.0f - T0;
+        renders[pix0 * 3] = has_bg ? c0r + T0 * bg0 : c0r;
+        renders[pix0 * 3 + 1] = has_bg ? c0g + T0 * bg1 : c0g;
+        renders[pix0 * 3 + 2] = has_bg ? c0b + T0 * bg2 : c0b;
+        last_ids[pix0] = last0;
+    }
+    if (pm.in1) {
+        alphas[pix1] = 1.0f - T1;
+        renders[pix1 * 3] = has_bg ? c1r + T1 * bg0 : c1r;
+        renders[pix1 * 3 + 1] = has_bg ? c1g + T1 * bg1 : c1g;
+        renders[pix1 * 3 + 2] = has_bg ? c1b + T1 * bg2 : c1b;
+        last_ids[pix1] = last1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+
+// Sum 16 per-lane values across the warp: after the call lane L holds in v[0] the warp-wide
+// total of slot (L >> 1).  16 shuffles (8+4+2+1+1) instead of 16 x 5.
+__device__ __forceinline__ void butterfly16(float (&v)[16]) {
+    const uint32_t lane = threadIdx.x & 31;
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const float send = hi ? v[i] : v[i + 8];
+            const float keep = hi ? v[i + 8] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = hi ? v[i] : v[i + 4];
+            const float keep = hi ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = hi ? v[i] : v[i + 2];
+            const float keep = hi ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool hi = lane & 2;
+        const float send = hi ? v[0] : v[1];
+        const float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+struct BwdPixel {
+    float T, br, bgc, bb; // running transmittance and colour accumulated behind
+    float vr, vg, vb;     // dL/d(render colour)
+    float tfva;           // T_final * (dL/d(alpha) - bg . dL/d(colour))
+    int32_t last;
+    bool in;
+};
+
+// Moment layout (row of 16 floats per Gaussian), x/y in pixels relative to (pcx, pcy):
+//  0: w1 x   1: w1 y   2: w1 xx  3: w1 xy  4: w1 yy
+//  5: w2     6: w2 x   7: w2 y   8: w2 xx  9: w2 xy  10: w2 yy
+//  11: g (= dL/dpower summed)    12..14: dL/d(colour)      15: unused
+__device__ __forceinline__ void bwd_pair(BwdPixel &s, const PairEval &e, float lop, float x, float y, float cr,
+                                         float cg, float cb, float (&acc)[16]) {
+    float ex;
+    const float rD = fast_rcp(e.Ds);
+    ex = __fmaf_rn(e.Ns, rD, lop);
+    const float a_raw = fast_ex2(ex);
+    const float alpha = fminf(kMaxAlpha, a_raw);
+    if (alpha < kAlphaThreshold) return;
+    const float ra = 1.0f / (1.0f - alpha);
+    s.T *= ra;
+    const float fac = alpha * s.T;
+    float v_alpha = (cr * s.T - s.br * ra) * s.vr + (cg * s.T - s.bgc * ra) * s.vg + (cb * s.T - s.bb * ra) * s.vb;
+    v_alpha += s.tfva * ra;
+    acc[12] += fac * s.vr; acc[13] += fac * s.vg; acc[14] += fac * s.vb;
+    if (a_raw <= kMaxAlpha) { // Bwd.cu:318: gradient through opacity*vis only when not clamped
+        const float g = a_raw * v_alpha;
+        const float w1 = g * kLn2 * rD;
+        const float w2 = -w1 * (e.Ns * rD);
+        const float xx = x * x, xy = x * y, yy = y * y;
+        acc[0] += w1 * x; acc[1] += w1 * y; acc[2] += w1 * xx; acc[3] += w1 * xy; acc[4] += w1 * yy;
+        acc[5] += w2; acc[6] += w2 * x; acc[7] += w2 * y; acc[8] += w2 * xx; acc[9] += w2 * xy; acc[10] += w2 * yy;
+        acc[11] += g;
+    }
+    s.br += cr * fac; s.bgc += cg * fac; s.bb += cb * fac;
+}
+
+__global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TileParams p,
+                                                                   const float *__restrict__ render_alphas,
+                                                                   const int32_t *__restrict__ last_ids,
+                                                                   const float *__restrict__ v_render_colors,
+                                                                   const float *__restrict__ v_render_alphas,
+                                                                   float *__restrict__ moments) {
+    __shared__ __align__(128) GaussRec s_rec[kStages][kBatch];
+    __shared__ __align__(8) uint64_t s_full[kStages];
+    __shared__ int32_t s_warp_max[kTileThreads / 32];
+
+    const uint32_t tile_id = blockIdx.x;
+    if (p.masks != nullptr && !p.masks[tile_id]) return; // Bwd.cu:84-86
+    const uint32_t tile_y = tile_id / p.tile_w, tile_x = tile_id % p.tile_w;
+    const PixelMap pm = pixel_map(tile_x, tile_y, p.W, p.H);
+    const uint32_t tid = threadIdx.x;
+
+    const int32_t range_start = p.tile_offsets[tile_id];
+    const int32_t range_end = (tile_id == p.tile_w * p.tile_h - 1) ? (int32_t)p.n_isects : p.tile_offsets[tile_id + 1];
+
+    float bgdot_scale[3] = {0.f, 0.f, 0.f};
+    if (p.backgrounds) { bgdot_scale[0] = p.backgrounds[0]; bgdot_scale[1] = p.backgrounds[1]; bgdot_scale[2] = p.backgrounds[2]; }
+
+    BwdPixel s0, s1;
+    auto load_pixel = [&](BwdPixel &s, bool in, uint32_t y) {
+        s.in = in; s.br = s.bgc = s.bb = 0.f;
+        if (in) {
+            const size_t pix = (size_t)y * p.W + pm.x;
+            const float Tf = 1.0f - render_alphas[pix];
+            s.T = Tf;
+            s.last = last_ids[pix];
+            s.vr = v_render_colors[pix * 3]; s.vg = v_render_colors[pix * 3 + 1]; s.vb = v_render_colors[pix * 3 + 2];
+            const float va = v_render_alphas[pix];
+            const float bgd = bgdot_scale[0] * s.vr + bgdot_scale[1] * s.vg + bgdot_scale[2] * s.vb;
+            s.tfva = Tf * va - Tf * bgd; // Bwd.cu:307-316
+        } else {
+            s.T = 1.f; s.last = -1; s.vr = s.vg = s.vb = 0.f; s.tfva = 0.f;
+        }
+    };
+    load_pixel(s0, pm.in0, pm.y0);
+    load_pixel(s1, pm.in1, pm.y1);
+
+    // CTA-wide newest contributor: nothing behind it can receive gradient
+    int32_t wmax = __reduce_max_sync(0xffffffffu, max(s0.last, s1.last));
+    if ((tid & 31) == 0) s_warp_max[tid >> 5] = wmax;
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    int32_t hi = s_warp_max[0];
+#pragma unroll
+    for (int w = 1; w < kTileThreads / 32; ++w) hi = max(hi, s_warp_max[w]);
+    hi = min(hi, range_end - 1);
+    const int32_t total = hi - range_start + 1;
+    if (total <= 0) return;
+    const int32_t n_batches = (total + kBatch - 1) / kBatch;
+    // this warp only needs records at or before its own newest contributor
+    wmax = min(wmax, hi);
+
+    const float px = (float)pm.x + 0.5f;
+    const float py0 = (float)pm.y0 + 0.5f, py1 = (float)pm.y1 + 0.5f;
+
+    int32_t gid_next = 0;
+    {
+        const int32_t idx = hi - (int32_t)tid;
+        const int32_t gid = (idx >= range_start) ? p.flatten_ids[idx] : 0;
+        issue_batch(s_rec[0], &s_full[0], p.recs, gid, (uint32_t)min(total, kBatch));
+        const int32_t idx1 = idx - kBatch;
+        gid_next = (idx1 >= range_start) ? p.flatten_ids[idx1] : 0;
+    }
+
+    for (int32_t b = 0; b < n_batches; ++b) {
+        const int st = b & 1;
+        if (b + 1 < n_batches) {
+            const int32_t cnt1 = min(total - (b + 1) * kBatch, kBatch);
+            issue_batch(s_rec[st ^ 1], &s_full[st ^ 1], p.recs, gid_next, (uint32_t)cnt1);
+            const int32_t idx2 = hi - (b + 2) * kBatch - (int32_t)tid;
+            gid_next = (idx2 >= range_start) ? p.flatten_ids[idx2] : 0;
+        }
+        mbar_wait(&s_full[st], (uint32_t)((b >> 1) & 1));
+
+        const int32_t cnt = min(total - b * kBatch, kBatch);
+        const int32_t top = hi - b * kBatch; // sorted index of slot 0
+        const float4 *rec4 = reinterpret_cast<const float4 *>(s_rec[st]);
+        for (int32_t t = max(0, top - wmax); t < cnt; ++t) {
+            const int32_t idx = top - t;
+            const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
+            const float x = px - q0.x;
+            const float y0 = py0 - q0.y, y1 = py1 - q0.y;
+            const PairEval e0 = pair_eval(q0, q1, q2, x, y0);
+            const PairEval e1 = pair_eval(q0, q1, q2, x, y1);
+            const bool p0 = e0.pass && s0.in && idx <= s0.last;
+            const bool p1 = e1.pass && s1.in && idx <= s1.last;
+            if (!__any_sync(0xffffffffu, p0 || p1)) continue;
+            const float4 q3 = rec4[t * 4 + 3];
+            float acc[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
+            if (p0) bwd_pair(s0, e0, q2.z, x, y0, q3.x, q3.y, q3.z, acc);
+            if (p1) bwd_pair(s1, e1, q2.z, x, y1, q3.x, q3.y, q3.z, acc);
+            butterfly16(acc);
+            if ((tid & 1) == 0) {
+                const uint32_t slot = (tid & 31) >> 1;
+                if (slot < 15) red_add_f32(moments + (size_t)__float_as_int(q3.w) * kMomFloats + slot, acc[0]);
+            }
+        }
+        __syncthreads(); // stage `st` may be refilled by batch b+2
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// finalize: moments -> gradients (float64 chain rule, once per Gaussian)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kPrepThreads) finalize_grads_kernel(
+    uint32_t N, const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
+    const float *__restrict__ opacities, const float *__restrict__ viewmat, const float *__restrict__ K,
+    const GaussRec *__restrict__ recs, const float *__restrict__ moments, float *__restrict__ v_means,
+    float *__restrict__ v_quats, float *__restrict__ v_scales, float *__restrict__ v_colors,
+    float *__restrict__ v_opacities) {
+    __shared__ CamConst cam;
+    if (threadIdx.x == 0) cam_const_from(viewmat, K, cam);
+    __syncthreads();
+    const uint32_t g = blockIdx.x * kPrepThreads + threadIdx.x;
+    if (g >= N) return;
+
+    float m[16];
+    {
+        const float4 *m4 = reinterpret_cast<const float4 *>(moments + (size_t)g * kMomFloats);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 v = m4[i];
+            m[i * 4] = v.x; m[i * 4 + 1] = v.y; m[i * 4 + 2] = v.z; m[i * 4 + 3] = v.w;
+        }
+    }
+    v_colors[(size_t)g * 3] = m[12]; v_colors[(size_t)g * 3 + 1] = m[13]; v_colors[(size_t)g * 3 + 2] = m[14];
+    const float opac = opacities[g];
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) any = any || (m[i] != 0.f);
+    float om[3] = {0.f, 0.f, 0.f}, oq[4] = {0.f, 0.f, 0.f, 0.f}, os[3] = {0.f, 0.f, 0.f}, oo = 0.f;
+    if (any) {
+        const float mean[3] = {means[(size_t)g * 3], means[(size_t)g * 3 + 1], means[(size_t)g * 3 + 2]};
+        const float quat[4] = {quats[(size_t)g * 4], quats[(size_t)g * 4 + 1], quats[(size_t)g * 4 + 2],
+                               quats[(size_t)g * 4 + 3]};
+        const float scale[3] = {scales[(size_t)g * 3], scales[(size_t)g * 3 + 1], scales[(size_t)g * 3 + 2]};
+        GaussGeom gg;
+        gauss_geom(cam, mean, quat, scale, gg);
+        if (!gg.degenerate) {
+            const float4 *r4 = reinterpret_cast<const float4 *>(recs + g);
+            const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
+            const double cn0 = q0.z, cn1 = q0.w, cn2 = q1.x;
+            const double cd1 = q1.y, cd2 = q1.z, cd3 = q1.w, cd4 = q2.x, cd5 = q2.y;
+            const double M0 = m[0], M1 = m[1], M2 = m[2], M3_ = m[3], M4 = m[4], M5 = m[5], M6 = m[6], M7 = m[7],
+                         M8 = m[8], M9 = m[9], M10 = m[10];
+            const double ax = 1.0 / cam.fx, ay = 1.0 / cam.fy;
+            const double id0 = 1.0 / gg.d0;
+            const double kk = -0.5 * 1.4426950408889634;
+            // gradients w.r.t. the projected centre (pixels -> normalised image coordinates)
+            const double vpcx = -(2.0 * cn0 * M0 + cn1 * M1 + cd1 * M5 + 2.0 * cd3 * M6 + cd4 * M7);
+            const double vpcy = -(cn1 * M0 + 2.0 * cn2 * M1 + cd2 * M5 + cd4 * M6 + 2.0 * cd5 * M7);
+            double vuc = cam.fx * vpcx, vvc = cam.fy * vpcy;
+            // gradients w.r.t. the un-normalised quadratic-form coefficients
+            const double vn0 = M2 * kk * ax * ax * id0, vn1 = M3_ * kk * ax * ay * id0, vn2 = M4 * kk * ay * ay * id0;
+            const double vd1 = M6 * ax * id0, vd2 = M7 * ay * id0, vd3 = M8 * ax * ax * id0, vd4 = M9 * ax * ay * id0,
+                         vd5 = M10 * ay * ay * id0;
+            const double vd0 = -(cn0 * M2 + cn1 * M3_ + cn2 * M4 + cd1 * M6 + cd2 * M7 + cd3 * M8 + cd4 * M9 + cd5 * M10) * id0;
+            // n = (E0.E0, 2 E0.E1, E1.E1), d = (G.G, 2 G.A0, 2 G.A1, A0.A0, 2 A0.A1, A1.A1)
+            const V3<double> vE0 = gg.E0 * (2.0 * vn0) + gg.E1 * (2.0 * vn1);
+            const V3<double> vE1 = gg.E1 * (2.0 * vn2) + gg.E0 * (2.0 * vn1);
+            V3<double> vG = gg.G * (2.0 * vd0) + gg.A0 * (2.0 * vd1) + gg.A1 * (2.0 * vd2);
+            V3<double> vA0 = gg.G * (2.0 * vd1) + gg.A0 * (2.0 * vd3) + gg.A1 * (2.0 * vd4) + cross(gg.gro, vE0);
+            V3<double> vA1 = gg.G * (2.0 * vd2) + gg.A1 * (2.0 * vd5) + gg.A0 * (2.0 * vd4) + cross(gg.gro, vE1);
+            const V3<double> vgro = cross(vE0, gg.A0) + cross(vE1, gg.A1);
+            vG = vG - vgro * gg.zc;
+            double vzc = -dot(gg.G, vgro);
+            vA0 = vA0 + vG * gg.uc;
+            vA1 = vA1 + vG * gg.vc;
+            const V3<double> vA2 = vG;
+            vuc += dot(gg.A0, vG);
+            vvc += dot(gg.A1, vG);
+            const double iz = 1.0 / gg.zc;
+            const double vxc = vuc * iz, vyc = vvc * iz;
+            vzc += -(gg.uc * vuc + gg.vc * vvc) * iz;
+            // mu_c = Binv mu + t
+            om[0] = (float)(cam.Binv[0][0] * vxc + cam.Binv[1][0] * vyc + cam.Binv[2][0] * vzc);
+            om[1] = (float)(cam.Binv[0][1] * vxc + cam.Binv[1][1] * vyc + cam.Binv[2][1] * vzc);
+            om[2] = (float)(cam.Binv[0][2] * vxc + cam.Binv[1][2] * vyc + cam.Binv[2][2] * vzc);
+            // A = M B  ->  vM = vA B^T ;  M[i][k] = Rg[k][i] / s_i
+            const double vA[3][3] = {{vA0.x, vA1.x, vA2.x}, {vA0.y, vA1.y, vA2.y}, {vA0.z, vA1.z, vA2.z}};
+            double vRg[3][3];
+            for (int i = 0; i < 3; ++i) {
+                double vsi = 0.0;
+                for (int k = 0; k < 3; ++k) {
+                    const double vM = vA[i][0] * cam.B[k][0] + vA[i][1] * cam.B[k][1] + vA[i][2] * cam.B[k][2];
+                    vsi += vM * gg.Rg.m[k][i];
+                    vRg[k][i] = vM * gg.inv_s[i];
+                }
+                os[i] = (float)(-vsi * gg.inv_s[i] * gg.inv_s[i]);
+            }
+            // quaternion VJP including the normalisation (Utils.cuh:104-126)
+            const double w = gg.qn[0], x = gg.qn[1], y = gg.qn[2], z = gg.qn[3];
+            double vq[4];
+            vq[0] = 2.0 * (x * (vRg[2][1] - vRg[1][2]) + y * (vRg[0][2] - vRg[2][0]) + z * (vRg[1][0] - vRg[0][1]));
+            vq[1] = 2.0 * (-2.0 * x * (vRg[1][1] + vRg[2][2]) + y * (vRg[1][0] + vRg[0][1]) + z * (vRg[2][0] + vRg[0][2]) +
+                           w * (vRg[2][1] - vRg[1][2]));
+            vq[2] = 2.0 * (x * (vRg[1][0] + vRg[0][1]) - 2.0 * y * (vRg[0][0] + vRg[2][2]) + z * (vRg[2][1] + vRg[1][2]) +
+                           w * (vRg[0][2] - vRg[2][0]));
+            vq[3] = 2.0 * (x * (vRg[2][0] + vRg[0][2]) + y * (vRg[2][1] + vRg[1][2]) - 2.0 * z * (vRg[0][0] + vRg[1][1]) +
+                           w * (vRg[1][0] - vRg[0][1]));
+            const double dq = vq[0] * w + vq[1] * x + vq[2] * y + vq[3] * z;
+            for (int k = 0; k < 4; ++k) oq[k] = (float)((vq[k] - dq * gg.qn[k]) * gg.inv_qnorm);
+            oo = (opac > 0.f) ? (float)((double)m[11] / (double)opac) : 0.f; // sum vis * v_alpha
+        }
+    }
+    v_means[(size_t)g * 3] = om[0]; v_means[(size_t)g * 3 + 1] = om[1]; v_means[(size_t)g * 3 + 2] = om[2];
+    v_scales[(size_t)g * 3] = os[0]; v_scales[(size_t)g * 3 + 1] = os[1]; v_scales[(size_t)g * 3 + 2] = os[2];
+    reinterpret_cast<float4 *>(v_quats)[g] = make_float4(oq[0], oq[1], oq[2], oq[3]);
+    v_opacities[g] = oo;
+}
+
+static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static int check_camera(const GsbCamera *cam) {
+    if (!cam || !cam->viewmats0 || !cam->Ks) return GSB_E_INVALID;
+    const bool distorted = cam->radial_coeffs || cam->tangential_coeffs || cam->thin_prism_coeffs;
+    if (cam->camera_model != GSB_CAMERA_PINHOLE || distorted || cam->viewmats1 ||
+        cam->shutter_type != GSB_SHUTTER_GLOBAL)
+        return GSB_E_UNSUPPORTED;
+    return GSB_OK;
+}
+
+} // namespace gsb
+
+extern "C" size_t gsb_raster_fwd_workspace(uint32_t N) { return gsb::align256((size_t)N * sizeof(gsb::GaussRec)) + 256; }
+
+extern "C" size_t gsb_raster_bwd_workspace(uint32_t N) {
+    return gsb::align256((size_t)N * sizeof(gsb::GaussRec)) + gsb::align256((size_t)N * gsb::kMomFloats * 4) + 256;
+}
+
+extern "C" int gsb_raster_fwd(uint32_t C, uint32_t N, uint64_t n_isects, const float *means, const float *quats,
+                              const float *scales, const float *colors, const float *opacities,
+                              const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                              uint32_t image_height, uint32_t tile_size, const GsbCamera *cam,
+                              const int32_t *tile_offsets, const int32_t *flatten_ids, float *renders, float *alphas,
+                              int32_t *last_ids, void *workspace, size_t workspace_bytes, gsb_stream_t stream) {
+    using namespace gsb;
+    if (int rc = check_camera(cam)) return rc;
+    if (image_width == 0 || image_height == 0) return GSB_OK;
+    if (C != 1) return GSB_E_UNSUPPORTED;       // the reference's kernels are single-camera too (Fwd.cu:197-200)
+    if (tile_size != 16) return GSB_E_UNSUPPORTED; // the reference's callers hard-code 16 (rasterizer.cpp:180)
+    if (!renders || !alphas || !last_ids || !tile_offsets) return GSB_E_INVALID;
+    if (n_isects > 0 && (!means || !quats || !scales || !colors || !opacities || !flatten_ids)) return GSB_E_INVALID;
+    if (n_isects > 0x7fffffffull) return GSB_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < gsb_raster_fwd_workspace(N))
+        return GSB_E_WORKSPACE;
+    cudaStream_t s = as_stream(stream);
+    GaussRec *recs = reinterpret_cast<GaussRec *>(workspace);
+    if (N > 0 && n_isects > 0) {
+        prep_records_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
+            N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs);
+        GSB_LAUNCH_CHECK();
+    }
+    TileParams p;
+    p.n_isects = (uint32_t)n_isects;
+    p.W = image_width; p.H = image_height;
+    p.tile_w = (image_width + 15) / 16; p.tile_h = (image_height + 15) / 16;
+    p.recs = recs; p.backgrounds = backgrounds; p.masks = masks;
+    p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
+    raster_fwd_kernel<<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const float *means, const float *quats,
+                              const float *scales, const float *colors, const float *opacities,
+                              const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                              uint32_t image_height, uint32_t tile_size, const GsbCamera *cam,
+                              const int32_t *tile_offsets, const int32_t *flatten_ids, const float *render_alphas,
+                              const int32_t *last_ids, const float *v_render_colors, const float *v_render_alphas,
+                              float *v_means, float *v_quats, float *v_scales, float *v_colors, float *v_opacities,
+                              void *workspace, size_t workspace_bytes, gsb_stream_t stream) {
+    using namespace gsb;
+    if (int rc = check_camera(cam)) return rc;
+    if (N == 0) return GSB_OK;
+    if (C != 1) return GSB_E_UNSUPPORTED;
+    if (tile_size != 16) return GSB_E_UNSUPPORTED;
+    if (!v_means || !v_quats || !v_scales || !v_colors || !v_opacities) return GSB_E_INVALID;
+    cudaStream_t s = as_stream(stream);
+    if (n_isects == 0 || image_width == 0 || image_height == 0) { // Bwd.cu:434-437: gradients stay zero
+        GSB_CUDA_TRY(cudaMemsetAsync(v_means, 0, (size_t)N * 12, s));
+        GSB_CUDA_TRY(cudaMemsetAsync(v_quats, 0, (size_t)N * 16, s));
+        GSB_CUDA_TRY(cudaMemsetAsync(v_scales, 0, (size_t)N * 12, s));
+        GSB_CUDA_TRY(cudaMemsetAsync(v_colors, 0, (size_t)N * 12, s));
+        GSB_CUDA_TRY(cudaMemsetAsync(v_opacities, 0, (size_t)N * 4, s));
+        return GSB_OK;
+    }
+    if (!means || !quats || !scales || !colors || !opacities || !flatten_ids || !tile_offsets || !render_alphas ||
+        !last_ids || !v_render_colors || !v_render_alphas)
+        return GSB_E_INVALID;
+    if (n_isects > 0x7fffffffull) return GSB_E_INVALID;
+    if ((reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < gsb_raster_bwd_workspace(N))
+        return GSB_E_WORKSPACE;
+    GaussRec *recs = reinterpret_cast<GaussRec *>(workspace);
+    float *moments = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align256((size_t)N * sizeof(GaussRec)));
+    GSB_CUDA_TRY(cudaMemsetAsync(moments, 0, (size_t)N * kMomFloats * 4, s));
+    prep_records_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
+        N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs);
+    GSB_LAUNCH_CHECK();
+    TileParams p;
+    p.n_isects = (uint32_t)n_isects;
+    p.W = image_width; p.H = image_height;
+    p.tile_w = (image_width + 15) / 16; p.tile_h = (image_height + 15) / 16;
+    p.recs = recs; p.backgrounds = backgrounds; p.masks = masks;
+    p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
+    raster_bwd_kernel<<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids, v_render_colors,
+                                                                  v_render_alphas, moments);
+    GSB_LAUNCH_CHECK();
+    finalize_grads_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
+        N, means, quats, scales, opacities, cam->viewmats0, cam->Ks, recs, moments, v_means, v_quats, v_scales,
+        v_colors, v_opacities);
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}

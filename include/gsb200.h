@@ -1,0 +1,202 @@
+/*
+ * gsb200.h -- C ABI of the B200-native (sm_100a) 3DGUT rasterizer hot path.
+ *
+ * This is the drop-in boundary underneath the reference's C++ operator API
+ * (namespace gsplat, /root/reference/gsplat/Ops.h:12-165).  Every entry point
+ * below states which reference operator it implements; the thin libtorch shim
+ * in gaussian-splatting-cuda_b200/shim/Ops.cpp exports the identical gsplat::
+ * signatures on top of it, so the reference's src/training and src/rendering
+ * link against it unchanged.
+ *
+ * Conventions
+ *  - plain C: raw DEVICE pointers, sizes, POD structs, a cudaStream_t.  No torch
+ *    types, no exceptions.  All tensors are contiguous row-major float32 unless
+ *    stated; layouts are exactly the reference's (Ops.h comments).
+ *  - nothing here allocates device memory: outputs and workspaces are provided
+ *    by the caller (the shim allocates them through the torch caching allocator,
+ *    like gsplat/Common.h:23-30 does for CUB).  Workspace sizes come from the
+ *    *_workspace() queries; workspaces need 256-byte alignment.
+ *  - every call is asynchronous on `stream` and re-entrant (no static mutable
+ *    state) -- the reference calls these ops from the training thread and the
+ *    viewer thread.
+ *  - return value: GSB_OK (0), a negative GSB_E_* code, or a positive
+ *    cudaError_t from a failed launch.  gsb_error_string() names them.
+ *  - there is NO CPU fallback: on a machine without an sm_100 device every
+ *    compute entry point returns a CUDA error.
+ */
+#ifndef GSB200_H_
+#define GSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#ifndef GSB_API
+#define GSB_API __attribute__((visibility("default")))
+#endif
+
+/* Opaque to C callers that do not include cuda_runtime.h. */
+typedef struct CUstream_st *gsb_stream_t;
+
+enum {
+    GSB_OK = 0,
+    GSB_E_INVALID = -1,     /* bad argument (null pointer, zero size where not allowed) */
+    GSB_E_UNSUPPORTED = -2, /* valid in the reference but not implemented here */
+    GSB_E_WORKSPACE = -3    /* workspace too small / misaligned */
+};
+
+/* gsplat::CameraModelType, gsplat/Common.h:46-50 */
+enum { GSB_CAMERA_PINHOLE = 0, GSB_CAMERA_ORTHO = 1, GSB_CAMERA_FISHEYE = 2 };
+
+/* ShutterType, gsplat/Cameras.h:16-22 */
+enum {
+    GSB_SHUTTER_ROLLING_TOP_TO_BOTTOM = 0,
+    GSB_SHUTTER_ROLLING_LEFT_TO_RIGHT = 1,
+    GSB_SHUTTER_ROLLING_BOTTOM_TO_TOP = 2,
+    GSB_SHUTTER_ROLLING_RIGHT_TO_LEFT = 3,
+    GSB_SHUTTER_GLOBAL = 4
+};
+
+/* UnscentedTransformParameters, gsplat/Cameras.h:27-44 */
+typedef struct GsbUTParams {
+    float alpha;
+    float beta;
+    float kappa;
+    float in_image_margin_factor;
+    int32_t require_all_sigma_points_valid;
+} GsbUTParams;
+
+/* Camera block shared by projection and the from-world rasterizer.
+ * viewmats1 / distortion pointers are nullable; *_count gives the number of
+ * floats per camera behind each distortion pointer (the reference reads a fixed
+ * 6/2/4 regardless of what the caller allocated; here the
+ * count is explicit and missing coefficients are zero-filled). */
+typedef struct GsbCamera {
+    const float *viewmats0; /* [C,4,4] world->camera, row-major */
+    const float *viewmats1; /* [C,4,4] end-of-frame pose for rolling shutter, or NULL */
+    const float *Ks;        /* [C,3,3] */
+    int32_t camera_model;   /* GSB_CAMERA_* */
+    int32_t shutter_type;   /* GSB_SHUTTER_* */
+    const float *radial_coeffs;
+    int32_t radial_count;
+    const float *tangential_coeffs;
+    int32_t tangential_count;
+    const float *thin_prism_coeffs;
+    int32_t thin_prism_count;
+    GsbUTParams ut;
+} GsbCamera;
+
+GSB_API const char *gsb_error_string(int code);
+GSB_API int gsb_version(void);
+
+/* ---- a1: gsplat::projection_ut_3dgs_fused (Ops.h:69-98, Projection.cpp:16-110,
+ *      ProjectionUT3DGSFused.cu:17-203) ------------------------------------------
+ * radii [C,N,2] int32 (0,0 = culled), means2d [C,N,2], depths [C,N], conics [C,N,3],
+ * compensations [C,N] or NULL.  Culled rows of means2d/depths/conics are left
+ * untouched, like the reference (Projection.cpp:70-73). */
+GSB_API int gsb_projection_ut(
+    uint32_t C, uint32_t N,
+    const float *means, const float *quats, const float *scales, const float *opacities /*nullable*/,
+    const GsbCamera *cam, uint32_t image_width, uint32_t image_height,
+    float eps2d, float near_plane, float far_plane, float radius_clip,
+    int32_t *radii, float *means2d, float *depths, float *conics, float *compensations /*nullable*/,
+    gsb_stream_t stream);
+
+/* ---- a3/a4: gsplat::spherical_harmonics_fwd / _bwd (Ops.h:12-25,
+ *      SphericalHarmonics.cpp:15-75, SphericalHarmonicsCUDA.cu:374-481) -----------
+ * M = number of (camera, Gaussian) elements, K = coefficients per element.
+ * masks: [M] bytes (bool) or NULL.  fwd leaves masked-out rows of `colors`
+ * untouched.  bwd writes EVERY element of v_coeffs (zeros for masked rows and for
+ * k >= (degree+1)^2) and of v_dirs -- the caller need not zero-fill them
+ * (the reference memsets 192 B/Gaussian first, SphericalHarmonics.cpp:58). */
+GSB_API int gsb_sh_fwd(uint32_t M, uint32_t K, uint32_t degrees_to_use, const float *dirs,
+                       const float *coeffs, const uint8_t *masks, float *colors, gsb_stream_t stream);
+GSB_API int gsb_sh_bwd(uint32_t M, uint32_t K, uint32_t degrees_to_use, const float *dirs,
+                       const float *coeffs, const uint8_t *masks, const float *v_colors,
+                       float *v_coeffs, float *v_dirs /*nullable*/, gsb_stream_t stream);
+
+/* ---- a5: gsplat::intersect_tile (Ops.h:28-38, Intersect.cpp:15-122,
+ *      IntersectTile.cu:24-114,290-328) ----------------------------------------------
+ * Three device steps around the one host read-back the API forces (the op
+ * returns exactly-sized tensors):
+ *   gsb_isect_count      tiles_per_gauss [C*N] int32 and its inclusive int64 scan
+ *                        cum_tiles [C*N]; n_isects = cum_tiles[C*N-1].
+ *   gsb_isect_emit       unsorted isect_ids [I] int64 / flatten_ids [I] int32.
+ *   gsb_isect_sort       stable sort by the low 32+tile_bits+cam_bits key bits
+ *                        (equal keys keep emission order, like CUB).
+ * Non-packed ([C,N,...]) layout only; packed mode is rejected by the reference's
+ * caller too (rasterizer.cpp:56). */
+GSB_API size_t gsb_isect_count_workspace(uint64_t n_elements);
+GSB_API int gsb_isect_count(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
+                            uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                            int32_t *tiles_per_gauss, int64_t *cum_tiles,
+                            void *workspace, size_t workspace_bytes, gsb_stream_t stream);
+GSB_API int gsb_isect_emit(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
+                           const float *depths, const int64_t *cum_tiles,
+                           uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                           int64_t *isect_ids, int32_t *flatten_ids, gsb_stream_t stream);
+GSB_API size_t gsb_isect_sort_workspace(uint64_t n_isects);
+GSB_API int gsb_isect_sort(uint64_t n_isects, uint32_t C, uint32_t tile_width, uint32_t tile_height,
+                           const int64_t *isect_ids_in, const int32_t *flatten_ids_in,
+                           int64_t *isect_ids_out, int32_t *flatten_ids_out,
+                           void *workspace, size_t workspace_bytes, gsb_stream_t stream);
+
+/* ---- a6: gsplat::intersect_offset (Ops.h:39-43, IntersectTile.cu:206-288) --------
+ * offsets [C,tile_height,tile_width] int32; all zero when n_isects == 0. */
+GSB_API int gsb_isect_offsets(uint64_t n_isects, const int64_t *isect_ids_sorted, uint32_t C,
+                              uint32_t tile_width, uint32_t tile_height, int32_t *offsets,
+                              gsb_stream_t stream);
+
+/* ---- a7: gsplat::rasterize_to_pixels_from_world_3dgs_fwd (Ops.h:100-129,
+ *      Rasterization.cpp:20-132, RasterizeToPixelsFromWorld3DGSFwd.cu:20-279) ---------
+ * colors [C,N,3] (3 channels only, as the reference asserts), opacities [C,N],
+ * backgrounds [C,3] or NULL, masks [C,th,tw] bytes or NULL, tile_offsets [C,th,tw],
+ * flatten_ids [I].  C must be 1 (the reference's kernels index means[] with the
+ * flattened id, Fwd.cu:197-200).  Outputs: renders [C,H,W,3], alphas [C,H,W,1],
+ * last_ids [C,H,W] int32. */
+GSB_API size_t gsb_raster_fwd_workspace(uint32_t N);
+GSB_API int gsb_raster_fwd(
+    uint32_t C, uint32_t N, uint64_t n_isects,
+    const float *means, const float *quats, const float *scales, const float *colors,
+    const float *opacities, const float *backgrounds, const uint8_t *masks,
+    uint32_t image_width, uint32_t image_height, uint32_t tile_size, const GsbCamera *cam,
+    const int32_t *tile_offsets, const int32_t *flatten_ids,
+    float *renders, float *alphas, int32_t *last_ids,
+    void *workspace, size_t workspace_bytes, gsb_stream_t stream);
+
+/* ---- a8: gsplat::rasterize_to_pixels_from_world_3dgs_bwd (Ops.h:131-165,
+ *      Rasterization.cpp:134-261, RasterizeToPixelsFromWorld3DGSBwd.cu:17-373) --------
+ * Writes every element of v_means [N,3], v_quats [N,4], v_scales [N,3],
+ * v_colors [C,N,3], v_opacities [C,N] (zeros for untouched Gaussians): the caller
+ * need not zero-fill (the reference does, Rasterization.cpp:190-194). */
+GSB_API size_t gsb_raster_bwd_workspace(uint32_t N);
+GSB_API int gsb_raster_bwd(
+    uint32_t C, uint32_t N, uint64_t n_isects,
+    const float *means, const float *quats, const float *scales, const float *colors,
+    const float *opacities, const float *backgrounds, const uint8_t *masks,
+    uint32_t image_width, uint32_t image_height, uint32_t tile_size, const GsbCamera *cam,
+    const int32_t *tile_offsets, const int32_t *flatten_ids,
+    const float *render_alphas, const int32_t *last_ids,
+    const float *v_render_colors, const float *v_render_alphas,
+    float *v_means, float *v_quats, float *v_scales, float *v_colors, float *v_opacities,
+    void *workspace, size_t workspace_bytes, gsb_stream_t stream);
+
+/* ---- link-surface ops used by the densification strategies -------------------------
+ * gsplat::quats_to_rotmats (Ops.h:46-48, QuatToRotmatCUDA.cu:14-39): [N,4] -> [N,3,3] */
+GSB_API int gsb_quat_to_rotmat(uint32_t N, const float *quats, float *rotmats, gsb_stream_t stream);
+/* gsplat::relocation (Ops.h:52-57, RelocationCUDA.cu:12-43) */
+GSB_API int gsb_relocation(uint32_t N, const float *opacities, const float *scales, const int32_t *ratios,
+                           const float *binoms, int32_t n_max, float *new_opacities, float *new_scales,
+                           gsb_stream_t stream);
+/* gsplat::add_noise (Ops.h:59-65, RelocationCUDA.cu:113-144): means updated in place */
+GSB_API int gsb_add_noise(uint32_t N, const float *raw_opacities, const float *raw_scales,
+                          const float *raw_quats, const float *noise, float *means, float current_lr,
+                          gsb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSB200_H_ */
