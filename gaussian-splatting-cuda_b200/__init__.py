@@ -210,7 +210,11 @@ class RenderOutput:
     depths: torch.Tensor         # [N]
     means2d: torch.Tensor        # [1, N, 2]
     n_isects: int
-    n_visible: int
+    visibility: torch.Tensor     # [N] bool (radii > 0), rasterizer.cpp:419
+
+    @property
+    def n_visible(self) -> int:  # host sync; kept out of the render path
+        return int(self.visibility.sum().item())
 
 
 def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K, width, height, bg_color=None,
@@ -242,4 +246,4 @@ def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K,
     return RenderOutput(
         image=torch.clamp(renders[0].permute(2, 0, 1), 0.0, 1.0), alpha=alphas[0].permute(2, 0, 1),
         render_colors=renders, radii=radii[0].max(-1).values, depths=depths[0], means2d=means2d,
-        n_isects=int(flatten_ids.shape[0]), n_visible=int(masks.sum().item()))
+        n_isects=int(flatten_ids.shape[0]), visibility=masks[0])

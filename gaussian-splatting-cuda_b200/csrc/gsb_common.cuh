@@ -12,6 +12,7 @@
     do {                                           \
         cudaError_t e__ = cudaPeekAtLastError();   \
         if (e__ != cudaSuccess) return (int)e__;   \
+        gsb::count_launch();                       \
     } while (0)
 
 #define GSB_CUDA_TRY(expr)                         \
@@ -21,6 +22,16 @@
     } while (0)
 
 namespace gsb {
+
+// launch counter + opt-in per-kernel event timing (gsb_misc.cu); both are diagnostics only
+void count_launch();
+struct ProfScope {
+    const char *name;
+    cudaStream_t stream;
+    void *slot;
+    ProfScope(const char *name, cudaStream_t stream);
+    ~ProfScope();
+};
 
 constexpr float kAlphaThreshold = 1.0f / 255.0f; // gsplat/Common.h:53
 constexpr float kMaxAlpha = 0.999f;              // RasterizeToPixelsFromWorld3DGSFwd.cu:239

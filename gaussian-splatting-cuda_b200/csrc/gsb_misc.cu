@@ -2,9 +2,44 @@
 // housekeeping.  References: gsplat/QuatToRotmatCUDA.cu:14-39 (gsplat::quats_to_rotmats, caller
 // default_strategy.cpp:96), gsplat/RelocationCUDA.cu:12-43 (gsplat::relocation, mcmc.cpp:153,231),
 // gsplat/RelocationCUDA.cu:86-144 (gsplat::add_noise, mcmc.cpp:360).
+#include <atomic>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "gsb_common.cuh"
 
 namespace gsb {
+
+// ---- diagnostics: launch counter and opt-in event timing --------------------------------------
+// Off by default; the compute path holds no mutable state.  bench.py enables it to time the
+// dominant kernel with CUDA events on the launching stream (roofline.achieved).
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<int> g_prof_on{0};
+struct ProfRec { std::string name; cudaEvent_t e0, e1; };
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+ProfScope::ProfScope(const char *n, cudaStream_t s) : name(n), stream(s), slot(nullptr) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec *r = new ProfRec();
+    r->name = n;
+    cudaEventCreate(&r->e0);
+    cudaEventCreate(&r->e1);
+    cudaEventRecord(r->e0, s);
+    slot = r;
+}
+ProfScope::~ProfScope() {
+    if (!slot) return;
+    ProfRec *r = static_cast<ProfRec *>(slot);
+    cudaEventRecord(r->e1, stream);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(*r);
+    delete r;
+}
 
 constexpr int kMiscThreads = 256;
 
@@ -125,3 +160,28 @@ extern "C" const char *gsb_error_string(int code) {
 }
 
 extern "C" int gsb_version(void) { return 100; }
+
+extern "C" uint64_t gsb_launch_count(void) { return gsb::g_launches.load(); }
+
+extern "C" void gsb_profile_enable(int on) {
+    std::lock_guard<std::mutex> lk(gsb::g_prof_mu);
+    for (auto &r : gsb::g_prof) { cudaEventDestroy(r.e0); cudaEventDestroy(r.e1); }
+    gsb::g_prof.clear();
+    gsb::g_prof_on.store(on ? 1 : 0);
+}
+
+// Sum of the recorded durations of kernel `name` since gsb_profile_enable(1); synchronises on the
+// recorded events.  Returns the number of launches found.
+extern "C" int gsb_profile_read(const char *name, double *total_ms) {
+    std::lock_guard<std::mutex> lk(gsb::g_prof_mu);
+    int n = 0;
+    double tot = 0.0;
+    for (auto &r : gsb::g_prof) {
+        if (r.name != name) continue;
+        if (cudaEventSynchronize(r.e1) != cudaSuccess) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.e0, r.e1) == cudaSuccess) { tot += ms; ++n; }
+    }
+    if (total_ms) *total_ms = tot;
+    return n;
+}

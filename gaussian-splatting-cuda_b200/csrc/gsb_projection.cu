@@ -256,7 +256,10 @@ extern "C" int gsb_projection_ut(
     p.ut = cam->ut;
     p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.compensations = compensations;
     dim3 grid((N + gsb::kProjThreads - 1) / gsb::kProjThreads, C);
-    gsb::projection_ut_kernel<<<grid, gsb::kProjThreads, 0, gsb::as_stream(stream)>>>(p);
+    {
+        gsb::ProfScope ps("projection_ut", gsb::as_stream(stream));
+        gsb::projection_ut_kernel<<<grid, gsb::kProjThreads, 0, gsb::as_stream(stream)>>>(p);
+    }
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }

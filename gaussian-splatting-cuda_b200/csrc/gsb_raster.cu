@@ -151,6 +151,9 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
 
     const float px = (float)pm.x + 0.5f;
     const float py0 = (float)pm.y0 + 0.5f, py1 = (float)pm.y1 + 0.5f;
+    // first pixel centre of this warp's 8x8 block (for block_may_pass)
+    const float bx0 = (float)(tile_x * 16 + ((tid >> 5) & 1) * 8) + 0.5f;
+    const float by0 = (float)(tile_y * 16 + (tid >> 6) * 8) + 0.5f;
     float T0 = 1.f, T1 = 1.f;
     float c0r = 0.f, c0g = 0.f, c0b = 0.f, c1r = 0.f, c1g = 0.f, c1b = 0.f;
     int32_t last0 = 0, last1 = 0;
@@ -182,8 +185,15 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
         const int32_t batch_start = range_start + b * kBatch;
         if (!__all_sync(0xffffffffu, done0 && done1)) { // this warp's 64 pixels are not all saturated
             const float4 *rec4 = reinterpret_cast<const float4 *>(s_rec[st]);
-#pragma unroll 2
-            for (int32_t t = 0; t < cnt; ++t) {
+            for (int32_t c0 = 0; c0 < cnt; c0 += 32) {
+              // lane-parallel culling of 32 records against this warp's 8x8 pixel block
+              const int32_t rl = c0 + (int32_t)(tid & 31);
+              bool cand = false;
+              if (rl < cnt) cand = block_may_pass(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], bx0, by0);
+              uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+              while (cmask) {
+                const int32_t t = c0 + __ffs(cmask) - 1;
+                cmask &= cmask - 1;
                 const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
                 const float x = px - q0.x;
                 const PairEval e0 = pair_eval(q0, q1, q2, x, py0 - q0.y);
@@ -221,6 +231,8 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
                         }
                     }
                 }
+              }
+              if (__all_sync(0xffffffffu, done0 && done1)) break;
             }
         }
         // releases stage `st` for batch b+2 and tells every warp whether the tile is saturated
@@ -388,6 +400,8 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
 
     const float px = (float)pm.x + 0.5f;
     const float py0 = (float)pm.y0 + 0.5f, py1 = (float)pm.y1 + 0.5f;
+    const float bx0 = (float)(tile_x * 16 + ((tid >> 5) & 1) * 8) + 0.5f;
+    const float by0 = (float)(tile_y * 16 + (tid >> 6) * 8) + 0.5f;
 
     int32_t gid_next = 0;
     {
@@ -411,7 +425,16 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
         const int32_t cnt = min(total - b * kBatch, kBatch);
         const int32_t top = hi - b * kBatch; // sorted index of slot 0
         const float4 *rec4 = reinterpret_cast<const float4 *>(s_rec[st]);
-        for (int32_t t = max(0, top - wmax); t < cnt; ++t) {
+        const int32_t t_first = max(0, top - wmax);
+        for (int32_t c0 = t_first & ~31; c0 < cnt; c0 += 32) {
+          const int32_t rl = c0 + (int32_t)(tid & 31);
+          bool cand = false;
+          if (rl >= t_first && rl < cnt)
+              cand = block_may_pass(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], bx0, by0);
+          uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+          while (cmask) {
+            const int32_t t = c0 + __ffs(cmask) - 1;
+            cmask &= cmask - 1;
             const int32_t idx = top - t;
             const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
             const float x = px - q0.x;
@@ -432,6 +455,7 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
                 const uint32_t slot = (tid & 31) >> 1;
                 if (slot < 15) red_add_f32(moments + (size_t)__float_as_int(q3.w) * kMomFloats + slot, acc[0]);
             }
+          }
         }
         __syncthreads(); // stage `st` may be refilled by batch b+2
     }
@@ -585,8 +609,11 @@ extern "C" int gsb_raster_fwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     cudaStream_t s = as_stream(stream);
     GaussRec *recs = reinterpret_cast<GaussRec *>(workspace);
     if (N > 0 && n_isects > 0) {
-        prep_records_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
-            N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs);
+        {
+            ProfScope ps("raster_prep", s);
+            prep_records_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
+                N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs);
+        }
         GSB_LAUNCH_CHECK();
     }
     TileParams p;
@@ -595,7 +622,10 @@ extern "C" int gsb_raster_fwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     p.tile_w = (image_width + 15) / 16; p.tile_h = (image_height + 15) / 16;
     p.recs = recs; p.backgrounds = backgrounds; p.masks = masks;
     p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
-    raster_fwd_kernel<<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
+    {
+        ProfScope ps("raster_fwd", s);
+        raster_fwd_kernel<<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
+    }
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }
@@ -632,8 +662,11 @@ extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     GaussRec *recs = reinterpret_cast<GaussRec *>(workspace);
     float *moments = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align256((size_t)N * sizeof(GaussRec)));
     GSB_CUDA_TRY(cudaMemsetAsync(moments, 0, (size_t)N * kMomFloats * 4, s));
-    prep_records_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
-        N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs);
+    {
+        ProfScope ps("raster_prep", s);
+        prep_records_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
+            N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs);
+    }
     GSB_LAUNCH_CHECK();
     TileParams p;
     p.n_isects = (uint32_t)n_isects;
@@ -641,12 +674,18 @@ extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     p.tile_w = (image_width + 15) / 16; p.tile_h = (image_height + 15) / 16;
     p.recs = recs; p.backgrounds = backgrounds; p.masks = masks;
     p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
-    raster_bwd_kernel<<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids, v_render_colors,
-                                                                  v_render_alphas, moments);
+    {
+        ProfScope ps("raster_bwd", s);
+        raster_bwd_kernel<<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids, v_render_colors,
+                                                                      v_render_alphas, moments);
+    }
     GSB_LAUNCH_CHECK();
-    finalize_grads_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
-        N, means, quats, scales, opacities, cam->viewmats0, cam->Ks, recs, moments, v_means, v_quats, v_scales,
-        v_colors, v_opacities);
+    {
+        ProfScope ps("raster_finalize", s);
+        finalize_grads_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
+            N, means, quats, scales, opacities, cam->viewmats0, cam->Ks, recs, moments, v_means, v_quats, v_scales,
+            v_colors, v_opacities);
+    }
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }

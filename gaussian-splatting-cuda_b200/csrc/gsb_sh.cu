@@ -252,6 +252,7 @@ extern "C" int gsb_sh_fwd(uint32_t M, uint32_t K, uint32_t degree, const float *
     if (degree > 4 || (degree + 1) * (degree + 1) > K) return GSB_E_INVALID;
     const dim3 grid((M + gsb::kShThreads - 1) / gsb::kShThreads);
     cudaStream_t s = gsb::as_stream(stream);
+    gsb::ProfScope ps("sh_fwd", s);
     switch (degree) {
     case 0: gsb::sh_fwd_kernel<0><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, colors); break;
     case 1: gsb::sh_fwd_kernel<1><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, colors); break;
@@ -271,6 +272,7 @@ extern "C" int gsb_sh_bwd(uint32_t M, uint32_t K, uint32_t degree, const float *
     if (degree > 4 || (degree + 1) * (degree + 1) > K) return GSB_E_INVALID;
     const dim3 grid((M + gsb::kShThreads - 1) / gsb::kShThreads);
     cudaStream_t s = gsb::as_stream(stream);
+    gsb::ProfScope ps("sh_bwd", s);
     switch (degree) {
     case 0: gsb::sh_bwd_kernel<0><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
     case 1: gsb::sh_bwd_kernel<1><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
