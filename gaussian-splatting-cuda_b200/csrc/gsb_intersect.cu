@@ -6,11 +6,24 @@
 // reference: same float tile-bbox arithmetic (division by the tile size, floor/ceil, CUDA's
 // saturating float->uint32 conversion), same 64-bit key layout
 //      cam_id << (32 + tile_bits) | tile_id << 32 | float_bits(depth)
-// and a stable LSD radix sort over the same low 32+tile_bits+cam_bits bits, so ties keep the
-// emission order exactly like cub::DeviceRadixSort does in the reference.
+// and the same final order: ascending (camera, tile, depth bits), ties in emission order
+// (ascending flattened Gaussian index), which is what the reference's stable
+// cub::DeviceRadixSort::SortPairs over 32+tile_bits+cam_bits key bits produces.
+//
+// How the sorted lists are built (gsb_isect_emit_sorted): the reference radix-sorts all I
+// intersections on 46 bits (six 8-bit passes over 12-byte pairs, ~150 B of HBM traffic per
+// intersection).  Here the depth order is established ONCE per Gaussian instead of once per
+// intersection:
+//   1. stable radix sort of the C*N Gaussians by (camera, depth bits)      [N elements, not I]
+//   2. scan of tiles_per_gauss in that order, emit the intersections in that order
+//   3. stable radix sort of the I intersections on the (camera, tile) bits ONLY (13-14 bits:
+//      two passes instead of six).
+// A stable sort by tile of a sequence already ordered by (depth, index) is ordered by
+// (tile, depth, index): the same permutation as the reference's single 46-bit sort.
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
-#include <cub/iterator/transform_input_iterator.cuh>
+#include <thrust/iterator/permutation_iterator.h>
+#include <thrust/iterator/transform_iterator.h>
 
 #include "gsb_common.cuh"
 
@@ -57,30 +70,49 @@ __global__ void __launch_bounds__(kIsectThreads) isect_count_kernel(uint64_t n, 
     tiles_per_gauss[idx] = b.active ? (int32_t)((b.y1 - b.y0) * (b.x1 - b.x0)) : 0;
 }
 
+// Emits the intersections of Gaussian perm[i] (or i when perm == nullptr) at cum[i-1].
 __global__ void __launch_bounds__(kIsectThreads) isect_emit_kernel(uint64_t n, uint32_t N,
                                                                     const float *__restrict__ means2d,
                                                                     const int32_t *__restrict__ radii,
                                                                     const float *__restrict__ depths,
+                                                                    const uint32_t *__restrict__ perm,
                                                                     const int64_t *__restrict__ cum_tiles,
                                                                     uint32_t tile_size, uint32_t tile_width,
                                                                     uint32_t tile_height, uint32_t tile_n_bits,
                                                                     int64_t *__restrict__ isect_ids,
                                                                     int32_t *__restrict__ flatten_ids) {
-    const uint64_t idx = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
-    if (idx >= n) return;
+    const uint64_t i = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t idx = perm ? (uint64_t)perm[i] : i;
     const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
     if (!b.active) return;
     const int64_t cid = (int64_t)(idx / N);
     const int64_t cid_enc = cid << (32 + tile_n_bits);
     const int64_t depth_enc = (int64_t)__float_as_uint(depths[idx]); // zero-extended bit pattern (:98-99)
-    int64_t cur = (idx == 0) ? 0 : cum_tiles[idx - 1];
-    for (uint32_t i = b.y0; i < b.y1; ++i)
-        for (uint32_t j = b.x0; j < b.x1; ++j) {
-            const int64_t tile_id = (int64_t)i * tile_width + j;
+    int64_t cur = (i == 0) ? 0 : cum_tiles[i - 1];
+    for (uint32_t y = b.y0; y < b.y1; ++y)
+        for (uint32_t x = b.x0; x < b.x1; ++x) {
+            const int64_t tile_id = (int64_t)y * tile_width + x;
             isect_ids[cur] = cid_enc | (tile_id << 32) | depth_enc;
             flatten_ids[cur] = (int32_t)idx;
             ++cur;
         }
+}
+
+// (camera, depth bits) key and identity value for every Gaussian
+__global__ void __launch_bounds__(kIsectThreads) depth_keys_kernel(uint64_t n, uint32_t N,
+                                                                    const float *__restrict__ depths,
+                                                                    const int32_t *__restrict__ tiles_per_gauss,
+                                                                    uint64_t *__restrict__ keys64,
+                                                                    uint32_t *__restrict__ keys32,
+                                                                    uint32_t *__restrict__ vals) {
+    const uint64_t idx = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
+    if (idx >= n) return;
+    // Gaussians without intersections never emit; park them at the end (any order is fine)
+    const uint32_t d = tiles_per_gauss[idx] > 0 ? __float_as_uint(depths[idx]) : 0xffffffffu;
+    if (keys64) keys64[idx] = ((uint64_t)(idx / N) << 32) | d;
+    else keys32[idx] = d;
+    vals[idx] = (uint32_t)idx;
 }
 
 // IntersectTile.cu:206-252, restated as "first sorted position whose (cam, tile) >= id".
@@ -108,228 +140,45 @@ __global__ void __launch_bounds__(kIsectThreads) isect_offsets_kernel(uint64_t n
 struct CastI64 {
     __host__ __device__ __forceinline__ int64_t operator()(const int32_t &v) const { return (int64_t)v; }
 };
-using CountIter = cub::TransformInputIterator<int64_t, CastI64, const int32_t *>;
+using CountIter = thrust::transform_iterator<CastI64, const int32_t *, int64_t>;
+using PermCountIter =
+    thrust::transform_iterator<CastI64, thrust::permutation_iterator<const int32_t *, const uint32_t *>, int64_t>;
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
-// ------------------------------------------------------------------------------------------
-// Binned path (sort == true): instead of a 46-bit global radix sort over 12-byte pairs
-// (6 CUB passes, ~150 B of HBM traffic per intersection) the intersections are
-//   1. counted per Gaussian AND per (camera, tile) bucket   (isect_count_hist_kernel)
-//   2. bucket starts = exclusive scan of the per-tile counts (tile_scan_kernel, one CTA)
-//   3. scattered into their tile's segment as (depth_bits << 32 | flat_index) keys
-//   4. sorted inside each tile by that 64-bit key in shared memory (tile_sort_kernel), which
-//      writes the final isect_ids / flatten_ids.
-// Because the key orders by depth first and by the flattened Gaussian index second, the result is
-// exactly the stable sort of the emission sequence by (camera, tile, depth) that the reference's
-// cub::DeviceRadixSort produces -- including ties -- but with ~36 B of traffic per intersection
-// and no dependence on the scatter order (atomics only hand out slots).
-// ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kIsectThreads) isect_count_hist_kernel(
-    uint64_t n, uint32_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii, uint32_t tile_size,
-    uint32_t tile_width, uint32_t tile_height, int32_t *__restrict__ tiles_per_gauss,
-    uint32_t *__restrict__ tile_counts) {
-    const uint64_t idx = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
-    if (idx >= n) return;
-    const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
-    tiles_per_gauss[idx] = b.active ? (int32_t)((b.y1 - b.y0) * (b.x1 - b.x0)) : 0;
-    if (!b.active) return;
-    uint32_t *tc = tile_counts + (size_t)(idx / N) * tile_width * tile_height;
-    for (uint32_t i = b.y0; i < b.y1; ++i)
-        for (uint32_t j = b.x0; j < b.x1; ++j) atomicAdd(tc + i * tile_width + j, 1u);
+// Workspace carve-up of gsb_isect_emit_sorted
+struct SortedWs {
+    size_t keys_a, keys_b, vals_a, vals_b, cum, tmp_keys, tmp_vals, cub, cub_bytes, total;
+};
+static SortedWs sorted_ws(uint64_t n, uint64_t n_isects, bool multi_cam) {
+    SortedWs w;
+    const size_t kb = multi_cam ? 8 : 4;
+    size_t off = 0;
+    w.keys_a = off; off += align256(n * kb);
+    w.keys_b = off; off += align256(n * kb);
+    w.vals_a = off; off += align256(n * 4);
+    w.vals_b = off; off += align256(n * 4);
+    w.cum = off; off += align256(n * 8);
+    w.tmp_keys = off; off += align256(n_isects * 8);
+    w.tmp_vals = off; off += align256(n_isects * 4);
+    size_t b1 = 0, b2 = 0, b3 = 0;
+    if (multi_cam)
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n, 0, 64);
+    else
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n, 0, 32);
+    PermCountIter it(thrust::permutation_iterator<const int32_t *, const uint32_t *>(nullptr, nullptr), CastI64());
+    cub::DeviceScan::InclusiveSum(nullptr, b2, it, (int64_t *)nullptr, (int64_t)n);
+    cub::DeviceRadixSort::SortPairs(nullptr, b3, (const int64_t *)nullptr, (int64_t *)nullptr, (const int32_t *)nullptr,
+                                    (int32_t *)nullptr, (int64_t)n_isects, 32, 64);
+    w.cub_bytes = align256(b1 > b2 ? (b1 > b3 ? b1 : b3) : (b2 > b3 ? b2 : b3)) + 256;
+    w.cub = off; off += w.cub_bytes;
+    w.total = off + 256;
+    return w;
 }
-
-// One CTA: exclusive scan of the per-tile counts, total and maximum.  totals = {n_isects, max count}.
-constexpr int kScanThreads = 1024;
-__global__ void __launch_bounds__(kScanThreads) tile_scan_kernel(uint32_t total_tiles,
-                                                                 const uint32_t *__restrict__ tile_counts,
-                                                                 uint32_t *__restrict__ tile_starts,
-                                                                 uint64_t *__restrict__ totals) {
-    __shared__ uint32_t s_warp[kScanThreads / 32];
-    __shared__ uint32_t s_carry, s_max;
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) { s_carry = 0; s_max = 0; }
-    __syncthreads();
-    uint32_t lmax = 0;
-    for (uint32_t base = 0; base < total_tiles; base += kScanThreads) {
-        const uint32_t i = base + tid;
-        const uint32_t v = (i < total_tiles) ? tile_counts[i] : 0;
-        lmax = max(lmax, v);
-        uint32_t x = v;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= (uint32_t)o) x += y;
-        }
-        if (lane == 31) s_warp[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = s_warp[lane];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t y = __shfl_up_sync(0xffffffffu, w, o);
-                if (lane >= (uint32_t)o) w += y;
-            }
-            s_warp[lane] = w; // inclusive scan of warp totals
-        }
-        __syncthreads();
-        const uint32_t carry = s_carry;
-        const uint32_t excl = carry + (wid ? s_warp[wid - 1] : 0) + (x - v);
-        if (i < total_tiles) tile_starts[i] = excl;
-        __syncthreads();
-        if (tid == kScanThreads - 1) s_carry = excl + v;
-        __syncthreads();
-    }
-    lmax = __reduce_max_sync(0xffffffffu, lmax);
-    if (lane == 0) atomicMax(&s_max, lmax);
-    __syncthreads();
-    if (tid == 0) { totals[0] = s_carry; totals[1] = s_max; }
-}
-
-__global__ void __launch_bounds__(kIsectThreads) isect_scatter_kernel(
-    uint64_t n, uint32_t N, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
-    const float *__restrict__ depths, uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-    const uint32_t *__restrict__ tile_starts, uint32_t *__restrict__ tile_cursor, uint64_t *__restrict__ bucket) {
-    const uint64_t idx = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
-    if (idx >= n) return;
-    const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
-    if (!b.active) return;
-    const size_t cam_off = (size_t)(idx / N) * tile_width * tile_height;
-    const uint64_t key = ((uint64_t)__float_as_uint(depths[idx]) << 32) | (uint64_t)(uint32_t)idx;
-    for (uint32_t i = b.y0; i < b.y1; ++i)
-        for (uint32_t j = b.x0; j < b.x1; ++j) {
-            const size_t t = cam_off + (size_t)i * tile_width + j;
-            const uint32_t pos = tile_starts[t] + atomicAdd(tile_cursor + t, 1u);
-            bucket[pos] = key;
-        }
-}
-
-// One CTA per (camera, tile): bitonic sort of the tile's 64-bit keys in shared memory.
-constexpr int kTileSortThreads = 256;
-__global__ void __launch_bounds__(kTileSortThreads) tile_sort_kernel(
-    uint32_t n_tiles, uint32_t tile_n_bits, const uint32_t *__restrict__ tile_starts,
-    const uint32_t *__restrict__ tile_counts, const uint64_t *__restrict__ bucket, int64_t *__restrict__ isect_ids,
-    int32_t *__restrict__ flatten_ids) {
-    extern __shared__ __align__(16) uint64_t s_keys[];
-    const uint32_t t = blockIdx.x;
-    const uint32_t n = tile_counts[t];
-    if (n == 0) return;
-    const uint32_t start = tile_starts[t];
-    const uint32_t tid = threadIdx.x;
-    uint32_t m = 1;
-    while (m < n) m <<= 1;
-    for (uint32_t i = tid; i < m; i += kTileSortThreads) s_keys[i] = (i < n) ? bucket[start + i] : ~0ull;
-    __syncthreads();
-    for (uint32_t k = 2; k <= m; k <<= 1) {
-        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            for (uint32_t p = tid; p < (m >> 1); p += kTileSortThreads) {
-                // p-th compare-exchange of this stage: i has bit j clear
-                const uint32_t i = ((p & ~(j - 1)) << 1) | (p & (j - 1));
-                const uint32_t l = i | j;
-                const uint64_t a = s_keys[i], b = s_keys[l];
-                const bool up = (i & k) == 0;
-                if ((a > b) == up) { s_keys[i] = b; s_keys[l] = a; }
-            }
-            __syncthreads();
-        }
-    }
-    const int64_t hi = ((int64_t)(t / n_tiles) << (32 + tile_n_bits)) | ((int64_t)(t % n_tiles) << 32);
-    for (uint32_t i = tid; i < n; i += kTileSortThreads) {
-        const uint64_t key = s_keys[i];
-        isect_ids[start + i] = hi | (int64_t)(key >> 32);
-        flatten_ids[start + i] = (int32_t)(uint32_t)key;
-    }
-}
-
-constexpr uint32_t kMaxTileSortElems = 16 * 1024; // power of two: 128 KB of shared memory
 
 } // namespace gsb
-
-// tile workspace: [tile_counts | tile_starts | tile_cursor], each total_tiles x uint32
-extern "C" size_t gsb_isect_binned_tile_workspace(uint64_t total_tiles) {
-    return 3 * gsb::align256(total_tiles * 4) + 256;
-}
-// bucket workspace: n_isects x uint64 keys
-extern "C" size_t gsb_isect_binned_bucket_workspace(uint64_t n_isects) { return gsb::align256(n_isects * 8) + 256; }
-
-// Step 1+2: tiles_per_gauss, per-tile counts and starts; totals_out (DEVICE, 2 x uint64) receives
-// {n_isects, largest per-tile count}.  `workspace` must be the buffer later handed to
-// gsb_isect_binned_sort (sized with n_isects = 0 for this call is fine: only the header is used).
-extern "C" int gsb_isect_binned_count(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
-                                      uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-                                      int32_t *tiles_per_gauss, uint64_t *totals_out, void *tile_workspace,
-                                      size_t tile_workspace_bytes, gsb_stream_t stream) {
-    const uint64_t n = (uint64_t)C * N;
-    const uint64_t total_tiles = (uint64_t)C * tile_width * tile_height;
-    if (!totals_out || !tile_workspace) return GSB_E_INVALID;
-    if (tile_workspace_bytes < 3 * gsb::align256(total_tiles * 4)) return GSB_E_WORKSPACE;
-    cudaStream_t s = gsb::as_stream(stream);
-    char *w = reinterpret_cast<char *>(tile_workspace);
-    uint32_t *tile_counts = reinterpret_cast<uint32_t *>(w);
-    uint32_t *tile_starts = reinterpret_cast<uint32_t *>(w + gsb::align256(total_tiles * 4));
-    uint32_t *tile_cursor = reinterpret_cast<uint32_t *>(w + 2 * gsb::align256(total_tiles * 4));
-    GSB_CUDA_TRY(cudaMemsetAsync(tile_counts, 0, total_tiles * 4, s));
-    GSB_CUDA_TRY(cudaMemsetAsync(tile_cursor, 0, total_tiles * 4, s));
-    if (n > 0) {
-        if (!means2d || !radii || !tiles_per_gauss || tile_size == 0) return GSB_E_INVALID;
-        gsb::ProfScope ps("isect_count", s);
-        const uint32_t grid = (uint32_t)((n + gsb::kIsectThreads - 1) / gsb::kIsectThreads);
-        gsb::isect_count_hist_kernel<<<grid, gsb::kIsectThreads, 0, s>>>(n, N, means2d, radii, tile_size, tile_width,
-                                                                        tile_height, tiles_per_gauss, tile_counts);
-        GSB_LAUNCH_CHECK();
-    }
-    {
-        gsb::ProfScope ps("isect_scan", s);
-        gsb::tile_scan_kernel<<<1, gsb::kScanThreads, 0, s>>>((uint32_t)total_tiles, tile_counts, tile_starts, totals_out);
-    }
-    GSB_LAUNCH_CHECK();
-    return GSB_OK;
-}
-
-// Step 3+4.  Returns GSB_E_UNSUPPORTED when a tile holds more keys than fit in shared memory
-// (the caller then falls back to gsb_isect_emit + gsb_isect_sort).
-extern "C" int gsb_isect_binned_sort(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
-                                     const float *depths, uint32_t tile_size, uint32_t tile_width,
-                                     uint32_t tile_height, uint64_t n_isects, uint64_t max_tile_count,
-                                     void *tile_workspace, void *bucket_workspace, size_t bucket_workspace_bytes,
-                                     int64_t *isect_ids, int32_t *flatten_ids, gsb_stream_t stream) {
-    const uint64_t n = (uint64_t)C * N;
-    if (n == 0 || n_isects == 0) return GSB_OK;
-    if (max_tile_count > gsb::kMaxTileSortElems) return GSB_E_UNSUPPORTED;
-    if (!means2d || !radii || !depths || !tile_workspace || !bucket_workspace || !isect_ids || !flatten_ids)
-        return GSB_E_INVALID;
-    if (bucket_workspace_bytes < n_isects * 8) return GSB_E_WORKSPACE;
-    const uint32_t n_tiles = tile_width * tile_height;
-    const uint64_t total_tiles = (uint64_t)C * n_tiles;
-    const uint32_t tile_n_bits = gsb::bit_width_u32(n_tiles);
-    if (tile_n_bits + gsb::bit_width_u32(C) > 32) return GSB_E_INVALID;
-    cudaStream_t s = gsb::as_stream(stream);
-    char *w = reinterpret_cast<char *>(tile_workspace);
-    uint32_t *tile_counts = reinterpret_cast<uint32_t *>(w);
-    uint32_t *tile_starts = reinterpret_cast<uint32_t *>(w + gsb::align256(total_tiles * 4));
-    uint32_t *tile_cursor = reinterpret_cast<uint32_t *>(w + 2 * gsb::align256(total_tiles * 4));
-    uint64_t *bucket = reinterpret_cast<uint64_t *>(bucket_workspace);
-    {
-        gsb::ProfScope ps("isect_emit", s);
-        const uint32_t grid = (uint32_t)((n + gsb::kIsectThreads - 1) / gsb::kIsectThreads);
-        gsb::isect_scatter_kernel<<<grid, gsb::kIsectThreads, 0, s>>>(n, N, means2d, radii, depths, tile_size, tile_width,
-                                                                     tile_height, tile_starts, tile_cursor, bucket);
-    }
-    GSB_LAUNCH_CHECK();
-    uint32_t m = 1;
-    while (m < max_tile_count) m <<= 1;
-    const size_t smem = (size_t)m * 8;
-    // always the same value, so concurrent callers cannot lower each other's limit
-    GSB_CUDA_TRY(cudaFuncSetAttribute(gsb::tile_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(gsb::kMaxTileSortElems * 8)));
-    {
-        gsb::ProfScope ps("isect_sort", s);
-        gsb::tile_sort_kernel<<<(uint32_t)total_tiles, gsb::kTileSortThreads, smem, s>>>(
-            n_tiles, tile_n_bits, tile_starts, tile_counts, bucket, isect_ids, flatten_ids);
-    }
-    GSB_LAUNCH_CHECK();
-    return GSB_OK;
-}
 
 extern "C" size_t gsb_isect_count_workspace(uint64_t n_elements) {
     size_t bytes = 0;
@@ -371,7 +220,7 @@ extern "C" int gsb_isect_emit(uint32_t C, uint32_t N, const float *means2d, cons
     const uint32_t grid = (uint32_t)((n + gsb::kIsectThreads - 1) / gsb::kIsectThreads);
     gsb::ProfScope ps("isect_emit", gsb::as_stream(stream));
     gsb::isect_emit_kernel<<<grid, gsb::kIsectThreads, 0, gsb::as_stream(stream)>>>(
-        n, N, means2d, radii, depths, cum_tiles, tile_size, tile_width, tile_height, tile_n_bits, isect_ids,
+        n, N, means2d, radii, depths, nullptr, cum_tiles, tile_size, tile_width, tile_height, tile_n_bits, isect_ids,
         flatten_ids);
     GSB_LAUNCH_CHECK();
     return GSB_OK;
@@ -398,6 +247,72 @@ extern "C" int gsb_isect_sort(uint64_t n_isects, uint32_t C, uint32_t tile_width
     GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(workspace, bytes, isect_ids_in, isect_ids_out, flatten_ids_in,
                                                  flatten_ids_out, (int64_t)n_isects, 0,
                                                  (int)(32 + tile_n_bits + cam_n_bits), gsb::as_stream(stream)));
+    return GSB_OK;
+}
+
+extern "C" size_t gsb_isect_emit_sorted_workspace(uint32_t C, uint32_t N, uint64_t n_isects) {
+    return gsb::sorted_ws((uint64_t)C * N, n_isects, C > 1).total;
+}
+
+extern "C" int gsb_isect_emit_sorted(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
+                                     const float *depths, const int32_t *tiles_per_gauss, uint32_t tile_size,
+                                     uint32_t tile_width, uint32_t tile_height, uint64_t n_isects,
+                                     int64_t *isect_ids, int32_t *flatten_ids, void *workspace,
+                                     size_t workspace_bytes, gsb_stream_t stream) {
+    using namespace gsb;
+    const uint64_t n = (uint64_t)C * N;
+    if (n == 0 || n_isects == 0) return GSB_OK;
+    if (!means2d || !radii || !depths || !tiles_per_gauss || !isect_ids || !flatten_ids) return GSB_E_INVALID;
+    const uint32_t tile_n_bits = bit_width_u32(tile_width * tile_height);
+    const uint32_t cam_n_bits = bit_width_u32(C);
+    if (tile_n_bits + cam_n_bits > 32) return GSB_E_INVALID;
+    const bool multi = C > 1;
+    const SortedWs w = sorted_ws(n, n_isects, multi);
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < w.total)
+        return GSB_E_WORKSPACE;
+    cudaStream_t s = as_stream(stream);
+    char *base = reinterpret_cast<char *>(workspace);
+    uint32_t *vals_a = reinterpret_cast<uint32_t *>(base + w.vals_a);
+    uint32_t *perm = reinterpret_cast<uint32_t *>(base + w.vals_b);
+    int64_t *cum = reinterpret_cast<int64_t *>(base + w.cum);
+    int64_t *tmp_keys = reinterpret_cast<int64_t *>(base + w.tmp_keys);
+    int32_t *tmp_vals = reinterpret_cast<int32_t *>(base + w.tmp_vals);
+    void *cub_tmp = base + w.cub;
+    const uint32_t grid = (uint32_t)((n + kIsectThreads - 1) / kIsectThreads);
+    {
+        // 1. stable sort of the Gaussians by (camera, depth bits); input order = flattened index
+        ProfScope ps("isect_depth_sort", s);
+        size_t bytes = w.cub_bytes;
+        if (multi) {
+            uint64_t *ka = reinterpret_cast<uint64_t *>(base + w.keys_a), *kb = reinterpret_cast<uint64_t *>(base + w.keys_b);
+            depth_keys_kernel<<<grid, kIsectThreads, 0, s>>>(n, N, depths, tiles_per_gauss, ka, nullptr, vals_a);
+            GSB_LAUNCH_CHECK();
+            GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, ka, kb, vals_a, perm, (int64_t)n, 0,
+                                                         (int)(32 + cam_n_bits), s));
+        } else {
+            uint32_t *ka = reinterpret_cast<uint32_t *>(base + w.keys_a), *kb = reinterpret_cast<uint32_t *>(base + w.keys_b);
+            depth_keys_kernel<<<grid, kIsectThreads, 0, s>>>(n, N, depths, tiles_per_gauss, nullptr, ka, vals_a);
+            GSB_LAUNCH_CHECK();
+            GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, ka, kb, vals_a, perm, (int64_t)n, 0, 32, s));
+        }
+    }
+    {
+        // 2. offsets of every Gaussian's run in depth order, then emit in that order
+        ProfScope ps("isect_emit", s);
+        size_t bytes = w.cub_bytes;
+        PermCountIter it(thrust::permutation_iterator<const int32_t *, const uint32_t *>(tiles_per_gauss, perm), CastI64());
+        GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_tmp, bytes, it, cum, (int64_t)n, s));
+        isect_emit_kernel<<<grid, kIsectThreads, 0, s>>>(n, N, means2d, radii, depths, perm, cum, tile_size, tile_width,
+                                                        tile_height, tile_n_bits, tmp_keys, tmp_vals);
+        GSB_LAUNCH_CHECK();
+    }
+    {
+        // 3. stable partition by (camera, tile): key bits [32, 32 + tile_bits + cam_bits)
+        ProfScope ps("isect_sort", s);
+        size_t bytes = w.cub_bytes;
+        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, tmp_keys, isect_ids, tmp_vals, flatten_ids,
+                                                     (int64_t)n_isects, 32, (int)(32 + tile_n_bits + cam_n_bits), s));
+    }
     return GSB_OK;
 }
 

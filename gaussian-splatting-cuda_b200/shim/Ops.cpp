@@ -148,37 +148,6 @@ GSB_EXPORT std::tuple<at::Tensor, at::Tensor, at::Tensor> intersect_tile(
     at::Tensor tiles_per_gauss = at::empty_like(depths, depths.options().dtype(at::kInt));
     int64_t n_isects = 0;
     at::Tensor cum_tiles;
-    if (n_elements && sort) {
-        // binned path: per-tile histogram + scan, one read-back of {n_isects, max per-tile count},
-        // scatter into tile segments, shared-memory sort per tile.  Same result as the global sort.
-        const uint64_t total_tiles = (uint64_t)C * tile_width * tile_height;
-        const size_t tws_bytes = gsb_isect_binned_tile_workspace(total_tiles);
-        at::Tensor tws = byte_workspace(tws_bytes, depths);
-        at::Tensor totals = at::empty({2}, depths.options().dtype(at::kLong));
-        gsb_check(gsb_isect_binned_count(C, N, means2d.data_ptr<float>(), radii.data_ptr<int32_t>(), tile_size,
-                                         tile_width, tile_height, tiles_per_gauss.data_ptr<int32_t>(),
-                                         reinterpret_cast<uint64_t *>(totals.data_ptr<int64_t>()), tws.data_ptr(),
-                                         tws_bytes, cur_stream()),
-                  "intersect_tile/binned_count");
-        const at::Tensor totals_host = totals.cpu(); // the one host sync the API forces (Intersect.cpp:76)
-        n_isects = totals_host.data_ptr<int64_t>()[0];
-        const int64_t max_tile = totals_host.data_ptr<int64_t>()[1];
-        TORCH_CHECK(n_isects <= INT32_MAX, "too many intersections for int32 tile offsets: ", n_isects);
-        at::Tensor isect_ids = at::empty({n_isects}, depths.options().dtype(at::kLong));
-        at::Tensor flatten_ids = at::empty({n_isects}, depths.options().dtype(at::kInt));
-        if (n_isects == 0) return std::make_tuple(tiles_per_gauss, isect_ids, flatten_ids);
-        const size_t bws_bytes = gsb_isect_binned_bucket_workspace((uint64_t)n_isects);
-        at::Tensor bws = byte_workspace(bws_bytes, depths);
-        const int rc = gsb_isect_binned_sort(C, N, means2d.data_ptr<float>(), radii.data_ptr<int32_t>(),
-                                             depths.data_ptr<float>(), tile_size, tile_width, tile_height,
-                                             (uint64_t)n_isects, (uint64_t)max_tile, tws.data_ptr(), bws.data_ptr(),
-                                             bws_bytes, isect_ids.data_ptr<int64_t>(),
-                                             flatten_ids.data_ptr<int32_t>(), cur_stream());
-        if (rc == GSB_OK) return std::make_tuple(tiles_per_gauss, isect_ids, flatten_ids);
-        if (rc != GSB_E_UNSUPPORTED) gsb_check(rc, "intersect_tile/binned_sort");
-        // a tile too large for shared memory: fall through to the global radix sort below
-        n_isects = 0;
-    }
     if (n_elements) {
         cum_tiles = at::empty({(int64_t)n_elements}, depths.options().dtype(at::kLong));
         const size_t ws_bytes = gsb_isect_count_workspace(n_elements);
@@ -189,6 +158,20 @@ GSB_EXPORT std::tuple<at::Tensor, at::Tensor, at::Tensor> intersect_tile(
                   "intersect_tile/count");
         n_isects = cum_tiles[-1].item<int64_t>(); // the one host sync the API forces (Intersect.cpp:76)
     }
+    if (n_isects && sort) {
+        // depth order per Gaussian first, then a stable sort on the tile bits only (gsb_intersect.cu)
+        at::Tensor isect_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kLong));
+        at::Tensor flatten_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kInt));
+        const size_t ws_bytes = gsb_isect_emit_sorted_workspace(C, N, (uint64_t)n_isects);
+        at::Tensor ws = byte_workspace(ws_bytes, depths);
+        gsb_check(gsb_isect_emit_sorted(C, N, means2d.data_ptr<float>(), radii.data_ptr<int32_t>(),
+                                        depths.data_ptr<float>(), tiles_per_gauss.data_ptr<int32_t>(), tile_size,
+                                        tile_width, tile_height, (uint64_t)n_isects,
+                                        isect_ids_sorted.data_ptr<int64_t>(), flatten_ids_sorted.data_ptr<int32_t>(),
+                                        ws.data_ptr(), ws_bytes, cur_stream()),
+                  "intersect_tile/emit_sorted");
+        return std::make_tuple(tiles_per_gauss, isect_ids_sorted, flatten_ids_sorted);
+    }
     at::Tensor isect_ids = at::empty({n_isects}, depths.options().dtype(at::kLong));
     at::Tensor flatten_ids = at::empty({n_isects}, depths.options().dtype(at::kInt));
     if (n_isects) {
@@ -196,17 +179,6 @@ GSB_EXPORT std::tuple<at::Tensor, at::Tensor, at::Tensor> intersect_tile(
                                  cum_tiles.data_ptr<int64_t>(), tile_size, tile_width, tile_height,
                                  isect_ids.data_ptr<int64_t>(), flatten_ids.data_ptr<int32_t>(), cur_stream()),
                   "intersect_tile/emit");
-    }
-    if (n_isects && sort) {
-        at::Tensor isect_ids_sorted = at::empty_like(isect_ids);
-        at::Tensor flatten_ids_sorted = at::empty_like(flatten_ids);
-        const size_t ws_bytes = gsb_isect_sort_workspace((uint64_t)n_isects);
-        at::Tensor ws = byte_workspace(ws_bytes, depths);
-        gsb_check(gsb_isect_sort((uint64_t)n_isects, C, tile_width, tile_height, isect_ids.data_ptr<int64_t>(),
-                                 flatten_ids.data_ptr<int32_t>(), isect_ids_sorted.data_ptr<int64_t>(),
-                                 flatten_ids_sorted.data_ptr<int32_t>(), ws.data_ptr(), ws_bytes, cur_stream()),
-                  "intersect_tile/sort");
-        return std::make_tuple(tiles_per_gauss, isect_ids_sorted, flatten_ids_sorted);
     }
     return std::make_tuple(tiles_per_gauss, isect_ids, flatten_ids);
 }

@@ -154,27 +154,17 @@ GSB_API int gsb_isect_sort(uint64_t n_isects, uint32_t C, uint32_t tile_width, u
                            int64_t *isect_ids_out, int32_t *flatten_ids_out,
                            void *workspace, size_t workspace_bytes, gsb_stream_t stream);
 
-/* Binned alternative for sort == true (same outputs, bit for bit, ~4x less HBM traffic than the
- * global radix sort): intersections are bucketed per (camera, tile) with a histogram + scan, then
- * each tile's (depth, flat index) keys are sorted in shared memory.  Call order:
- *   gsb_isect_binned_count  -> tiles_per_gauss, and totals_out (DEVICE, 2 x uint64) =
- *                              {n_isects, largest per-tile count}; the caller reads them back
- *                              (the one host sync the reference API forces anyway);
- *   gsb_isect_binned_sort   -> isect_ids / flatten_ids, final sorted order.  Returns
- *                              GSB_E_UNSUPPORTED when a tile has more keys than fit in shared
- *                              memory (16384): fall back to gsb_isect_count/emit/sort.
- * tile_workspace must be the same buffer in both calls. */
-GSB_API size_t gsb_isect_binned_tile_workspace(uint64_t total_tiles);
-GSB_API size_t gsb_isect_binned_bucket_workspace(uint64_t n_isects);
-GSB_API int gsb_isect_binned_count(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
-                                   uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-                                   int32_t *tiles_per_gauss, uint64_t *totals_out, void *tile_workspace,
-                                   size_t tile_workspace_bytes, gsb_stream_t stream);
-GSB_API int gsb_isect_binned_sort(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
-                                  const float *depths, uint32_t tile_size, uint32_t tile_width,
-                                  uint32_t tile_height, uint64_t n_isects, uint64_t max_tile_count,
-                                  void *tile_workspace, void *bucket_workspace, size_t bucket_workspace_bytes,
-                                  int64_t *isect_ids, int32_t *flatten_ids, gsb_stream_t stream);
+/* Fused emit + sort for sort == true (same outputs as gsb_isect_emit + gsb_isect_sort, bit for
+ * bit, with a third of the sort traffic): the Gaussians are first ordered by (camera, depth bits)
+ * -- N elements instead of I -- the intersections are emitted in that order, and a stable radix
+ * sort on the (camera, tile) key bits only finishes the job.  tiles_per_gauss is the output of
+ * gsb_isect_count; n_isects the value read back from cum_tiles. */
+GSB_API size_t gsb_isect_emit_sorted_workspace(uint32_t C, uint32_t N, uint64_t n_isects);
+GSB_API int gsb_isect_emit_sorted(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
+                                  const float *depths, const int32_t *tiles_per_gauss, uint32_t tile_size,
+                                  uint32_t tile_width, uint32_t tile_height, uint64_t n_isects,
+                                  int64_t *isect_ids, int32_t *flatten_ids, void *workspace,
+                                  size_t workspace_bytes, gsb_stream_t stream);
 
 /* ---- a6: gsplat::intersect_offset (Ops.h:39-43, IntersectTile.cu:206-288) --------
  * offsets [C,tile_height,tile_width] int32; all zero when n_isects == 0. */
