@@ -57,11 +57,6 @@ def load() -> None:
     _loaded = True
 
 
-def ops():
-    load()
-    return torch.ops.gsplat_b200
-
-
 @dataclass
 class UTParams:
     """UnscentedTransformParameters defaults (gsplat/Cameras.h:27-44)."""
@@ -72,118 +67,153 @@ class UTParams:
     require_all_sigma_points_valid: bool = True
 
 
-# ---------------------------------------------------------------------------------------------
-# Thin wrappers with the reference's argument names (gsplat/Ops.h)
-# ---------------------------------------------------------------------------------------------
+class OpsBackend:
+    """The eleven gsplat:: operators (gsplat/Ops.h) of one native library, by the reference's
+    names and argument order.  `namespace` is a torch.ops namespace registered by a TORCH_LIBRARY
+    binding with the flattened signatures of shim/torch_binding.cpp.  The product backend is
+    `default_backend()`; tests build a second one over the reference's own kernels
+    (oracle/ref_ops.py) to compare the two through identical call sites."""
 
-def projection_ut_3dgs_fused(means, quats, scales, opacities, viewmats0, Ks, image_width, image_height,
-                             eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
-                             calc_compensations=False, camera_model=PINHOLE, ut_params: UTParams | None = None,
-                             viewmats1=None, rs_type=SHUTTER_GLOBAL, radial_coeffs=None, tangential_coeffs=None,
-                             thin_prism_coeffs=None):
-    ut = ut_params or UTParams()
-    r = ops().projection_ut_3dgs_fused(
-        means, quats, scales, opacities, viewmats0, viewmats1, Ks, image_width, image_height, eps2d, near_plane,
-        far_plane, radius_clip, calc_compensations, camera_model, ut.alpha, ut.beta, ut.kappa,
-        ut.in_image_margin_factor, ut.require_all_sigma_points_valid, rs_type, radial_coeffs, tangential_coeffs,
-        thin_prism_coeffs)
-    comp = r[4] if r[4].numel() else None
-    return r[0], r[1], r[2], r[3], comp
+    def __init__(self, namespace_getter):
+        self._get = namespace_getter
+
+    @property
+    def ns(self):
+        return self._get()
+
+    def projection_ut_3dgs_fused(self, means, quats, scales, opacities, viewmats0, Ks, image_width, image_height,
+                                 eps2d=0.3, near_plane=0.01, far_plane=1e10, radius_clip=0.0,
+                                 calc_compensations=False, camera_model=PINHOLE, ut_params: UTParams | None = None,
+                                 viewmats1=None, rs_type=SHUTTER_GLOBAL, radial_coeffs=None, tangential_coeffs=None,
+                                 thin_prism_coeffs=None):
+        ut = ut_params or UTParams()
+        r = self.ns.projection_ut_3dgs_fused(
+            means, quats, scales, opacities, viewmats0, viewmats1, Ks, image_width, image_height, eps2d, near_plane,
+            far_plane, radius_clip, calc_compensations, camera_model, ut.alpha, ut.beta, ut.kappa,
+            ut.in_image_margin_factor, ut.require_all_sigma_points_valid, rs_type, radial_coeffs, tangential_coeffs,
+            thin_prism_coeffs)
+        comp = r[4] if r[4].numel() else None
+        return r[0], r[1], r[2], r[3], comp
+
+    def spherical_harmonics_fwd(self, degrees_to_use, dirs, coeffs, masks=None):
+        return self.ns.spherical_harmonics_fwd(degrees_to_use, dirs, coeffs, masks)
+
+    def spherical_harmonics_bwd(self, K, degrees_to_use, dirs, coeffs, masks, v_colors, compute_v_dirs=True):
+        v_coeffs, v_dirs = self.ns.spherical_harmonics_bwd(K, degrees_to_use, dirs, coeffs, masks, v_colors,
+                                                           compute_v_dirs)
+        return v_coeffs, (v_dirs if compute_v_dirs else None)
+
+    def intersect_tile(self, means2d, radii, depths, C, tile_size, tile_width, tile_height, sort=True):
+        return self.ns.intersect_tile(means2d, radii, depths, C, tile_size, tile_width, tile_height, sort)
+
+    def intersect_offset(self, isect_ids, C, tile_width, tile_height):
+        return self.ns.intersect_offset(isect_ids, C, tile_width, tile_height)
+
+    def rasterize_to_pixels_from_world_3dgs_fwd(self, means, quats, scales, colors, opacities, backgrounds, masks,
+                                                image_width, image_height, tile_size, viewmats0, Ks, tile_offsets,
+                                                flatten_ids, camera_model=PINHOLE, viewmats1=None,
+                                                rs_type=SHUTTER_GLOBAL, radial_coeffs=None, tangential_coeffs=None,
+                                                thin_prism_coeffs=None):
+        return self.ns.rasterize_to_pixels_from_world_3dgs_fwd(
+            means, quats, scales, colors, opacities, backgrounds, masks, image_width, image_height, tile_size,
+            viewmats0, viewmats1, Ks, camera_model, rs_type, radial_coeffs, tangential_coeffs, thin_prism_coeffs,
+            tile_offsets, flatten_ids)
+
+    def rasterize_to_pixels_from_world_3dgs_bwd(self, means, quats, scales, colors, opacities, backgrounds, masks,
+                                                image_width, image_height, tile_size, viewmats0, Ks, tile_offsets,
+                                                flatten_ids, render_alphas, last_ids, v_render_colors,
+                                                v_render_alphas, camera_model=PINHOLE, viewmats1=None,
+                                                rs_type=SHUTTER_GLOBAL, radial_coeffs=None, tangential_coeffs=None,
+                                                thin_prism_coeffs=None):
+        return self.ns.rasterize_to_pixels_from_world_3dgs_bwd(
+            means, quats, scales, colors, opacities, backgrounds, masks, image_width, image_height, tile_size,
+            viewmats0, viewmats1, Ks, camera_model, rs_type, radial_coeffs, tangential_coeffs, thin_prism_coeffs,
+            tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas)
+
+    def quats_to_rotmats(self, quats):
+        return self.ns.quats_to_rotmats(quats)
+
+    def relocation(self, opacities, scales, ratios, binoms, n_max):
+        return self.ns.relocation(opacities, scales, ratios, binoms, n_max)
+
+    def add_noise(self, raw_opacities, raw_scales, raw_quats, noise, means, current_lr):
+        self.ns.add_noise(raw_opacities, raw_scales, raw_quats, noise, means, current_lr)
 
 
-def spherical_harmonics_fwd(degrees_to_use, dirs, coeffs, masks=None):
-    return ops().spherical_harmonics_fwd(degrees_to_use, dirs, coeffs, masks)
+def _product_ns():
+    load()
+    return torch.ops.gsplat_b200
 
 
-def spherical_harmonics_bwd(K, degrees_to_use, dirs, coeffs, masks, v_colors, compute_v_dirs=True):
-    v_coeffs, v_dirs = ops().spherical_harmonics_bwd(K, degrees_to_use, dirs, coeffs, masks, v_colors, compute_v_dirs)
-    return v_coeffs, (v_dirs if compute_v_dirs else None)
+_DEFAULT = OpsBackend(_product_ns)
 
 
-def intersect_tile(means2d, radii, depths, C, tile_size, tile_width, tile_height, sort=True):
-    return ops().intersect_tile(means2d, radii, depths, C, tile_size, tile_width, tile_height, sort)
+def default_backend() -> OpsBackend:
+    return _DEFAULT
 
 
-def intersect_offset(isect_ids, C, tile_width, tile_height):
-    return ops().intersect_offset(isect_ids, C, tile_width, tile_height)
+def ops():
+    return _product_ns()
 
 
-def rasterize_to_pixels_from_world_3dgs_fwd(means, quats, scales, colors, opacities, backgrounds, masks,
-                                            image_width, image_height, tile_size, viewmats0, Ks, tile_offsets,
-                                            flatten_ids, camera_model=PINHOLE, viewmats1=None,
-                                            rs_type=SHUTTER_GLOBAL, radial_coeffs=None, tangential_coeffs=None,
-                                            thin_prism_coeffs=None):
-    return ops().rasterize_to_pixels_from_world_3dgs_fwd(
-        means, quats, scales, colors, opacities, backgrounds, masks, image_width, image_height, tile_size,
-        viewmats0, viewmats1, Ks, camera_model, rs_type, radial_coeffs, tangential_coeffs, thin_prism_coeffs,
-        tile_offsets, flatten_ids)
-
-
-def rasterize_to_pixels_from_world_3dgs_bwd(means, quats, scales, colors, opacities, backgrounds, masks,
-                                            image_width, image_height, tile_size, viewmats0, Ks, tile_offsets,
-                                            flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas,
-                                            camera_model=PINHOLE, viewmats1=None, rs_type=SHUTTER_GLOBAL,
-                                            radial_coeffs=None, tangential_coeffs=None, thin_prism_coeffs=None):
-    return ops().rasterize_to_pixels_from_world_3dgs_bwd(
-        means, quats, scales, colors, opacities, backgrounds, masks, image_width, image_height, tile_size,
-        viewmats0, viewmats1, Ks, camera_model, rs_type, radial_coeffs, tangential_coeffs, thin_prism_coeffs,
-        tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas)
-
-
-def quats_to_rotmats(quats):
-    return ops().quats_to_rotmats(quats)
-
-
-def relocation(opacities, scales, ratios, binoms, n_max):
-    return ops().relocation(opacities, scales, ratios, binoms, n_max)
-
-
-def add_noise(raw_opacities, raw_scales, raw_quats, noise, means, current_lr):
-    ops().add_noise(raw_opacities, raw_scales, raw_quats, noise, means, current_lr)
+# module-level aliases of the product backend (same names as gsplat/Ops.h)
+projection_ut_3dgs_fused = _DEFAULT.projection_ut_3dgs_fused
+spherical_harmonics_fwd = _DEFAULT.spherical_harmonics_fwd
+spherical_harmonics_bwd = _DEFAULT.spherical_harmonics_bwd
+intersect_tile = _DEFAULT.intersect_tile
+intersect_offset = _DEFAULT.intersect_offset
+rasterize_to_pixels_from_world_3dgs_fwd = _DEFAULT.rasterize_to_pixels_from_world_3dgs_fwd
+rasterize_to_pixels_from_world_3dgs_bwd = _DEFAULT.rasterize_to_pixels_from_world_3dgs_bwd
+quats_to_rotmats = _DEFAULT.quats_to_rotmats
+relocation = _DEFAULT.relocation
+add_noise = _DEFAULT.add_noise
 
 
 # ---------------------------------------------------------------------------------------------
 # L3 mirror: what gs::training::rasterize does around the ops (rasterizer.cpp:46-437,
-# rasterizer_autograd.cpp:12-391).  Activated parameters in, image + explicit gradients out.
+# rasterizer_autograd.cpp:12-391).  Activated parameters in, image + gradients out.
 # ---------------------------------------------------------------------------------------------
 
 class SphericalHarmonicsFunction(torch.autograd.Function):
     """rasterizer_autograd.cpp:12-132."""
 
     @staticmethod
-    def forward(ctx, sh_degree: int, dirs, coeffs, masks):
+    def forward(ctx, backend: OpsBackend, sh_degree: int, dirs, coeffs, masks):
         dirs = dirs.contiguous()
         coeffs = coeffs.contiguous()
-        colors = spherical_harmonics_fwd(sh_degree, dirs.reshape(-1, 3), coeffs.reshape(-1, coeffs.shape[-2], 3),
-                                         masks.reshape(-1).contiguous())
+        colors = backend.spherical_harmonics_fwd(sh_degree, dirs.reshape(-1, 3),
+                                                 coeffs.reshape(-1, coeffs.shape[-2], 3),
+                                                 masks.reshape(-1).contiguous())
         ctx.save_for_backward(dirs, coeffs, masks)
         ctx.sh_degree = sh_degree
+        ctx.backend = backend
         return colors.reshape(dirs.shape)
 
     @staticmethod
     def backward(ctx, v_colors):
         dirs, coeffs, masks = ctx.saved_tensors
         K = coeffs.shape[-2]
-        v_coeffs, v_dirs = spherical_harmonics_bwd(
+        v_coeffs, v_dirs = ctx.backend.spherical_harmonics_bwd(
             K, ctx.sh_degree, dirs.reshape(-1, 3), coeffs.reshape(-1, K, 3), masks.reshape(-1).contiguous(),
-            v_colors.contiguous().reshape(-1, 3), ctx.needs_input_grad[1])
-        return (None, v_dirs.reshape(dirs.shape) if v_dirs is not None else None,
-                v_coeffs.reshape(coeffs.shape) if ctx.needs_input_grad[2] else None, None)
+            v_colors.contiguous().reshape(-1, 3), ctx.needs_input_grad[2])
+        return (None, None, v_dirs.reshape(dirs.shape) if v_dirs is not None else None,
+                v_coeffs.reshape(coeffs.shape) if ctx.needs_input_grad[3] else None, None)
 
 
 class GUTRasterizationFunction(torch.autograd.Function):
     """rasterizer_autograd.cpp:267-391."""
 
     @staticmethod
-    def forward(ctx, means, quats, scales, colors, opacities, bg, viewmat, K, isect_offsets, flatten_ids, width,
-                height, tile_size):
-        renders, alphas, last_ids = rasterize_to_pixels_from_world_3dgs_fwd(
+    def forward(ctx, backend: OpsBackend, means, quats, scales, colors, opacities, bg, viewmat, K, isect_offsets,
+                flatten_ids, width, height, tile_size):
+        renders, alphas, last_ids = backend.rasterize_to_pixels_from_world_3dgs_fwd(
             means.contiguous(), quats.contiguous(), scales.contiguous(), colors.contiguous(),
             opacities.contiguous(), bg, None, width, height, tile_size, viewmat.contiguous(), K.contiguous(),
             isect_offsets.contiguous(), flatten_ids.contiguous())
         ctx.save_for_backward(means, quats, scales, colors, opacities, bg if bg is not None else torch.empty(0),
                               viewmat, K, isect_offsets, flatten_ids, alphas, last_ids)
         ctx.dims = (width, height, tile_size, bg is not None)
+        ctx.backend = backend
         return renders, alphas
 
     @staticmethod
@@ -191,14 +221,14 @@ class GUTRasterizationFunction(torch.autograd.Function):
         (means, quats, scales, colors, opacities, bg, viewmat, K, isect_offsets, flatten_ids, alphas,
          last_ids) = ctx.saved_tensors
         width, height, tile_size, has_bg = ctx.dims
-        g = rasterize_to_pixels_from_world_3dgs_bwd(
+        g = ctx.backend.rasterize_to_pixels_from_world_3dgs_bwd(
             means, quats, scales, colors, opacities, bg if has_bg else None, None, width, height, tile_size, viewmat,
             K, isect_offsets, flatten_ids, alphas, last_ids, v_render_colors.contiguous(),
             v_render_alphas.contiguous())
         v_bg = None
-        if has_bg and ctx.needs_input_grad[5]:
+        if has_bg and ctx.needs_input_grad[6]:
             v_bg = (v_render_colors * (1.0 - alphas)).sum(dim=(-3, -2))
-        return g[0], g[1], g[2], g[3], g[4], v_bg, None, None, None, None, None, None, None
+        return None, g[0], g[1], g[2], g[3], g[4], v_bg, None, None, None, None, None, None, None
 
 
 @dataclass
@@ -219,30 +249,32 @@ class RenderOutput:
 
 def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K, width, height, bg_color=None,
               scaling_modifier=1.0, tile_size=16, eps2d=0.3, near_plane=0.01, far_plane=10000.0,
-              radius_clip=0.0) -> RenderOutput:
+              radius_clip=0.0, backend: OpsBackend | None = None) -> RenderOutput:
     """gs::training::rasterize for RenderMode::RGB, perfect pinhole, C == 1 (rasterizer.cpp:46-437).
 
     Inputs are the ACTIVATED parameters (get_means/get_rotation/get_scaling/get_opacity/get_shs of
     SplatData): means [N,3], unit quats [N,4] (w,x,y,z), scales [N,3] > 0, opacities [N] in (0,1),
     sh_coeffs [N,K,3]; viewmat [1,4,4], K [1,3,3]; bg_color [1,3] or None.
     """
+    be = backend or _DEFAULT
     scaled = scales * scaling_modifier if scaling_modifier != 1.0 else scales
     with torch.no_grad():  # "none differentiable" (Ops.h:67)
-        radii, means2d, depths, _conics, _ = projection_ut_3dgs_fused(
+        radii, means2d, depths, _conics, _ = be.projection_ut_3dgs_fused(
             means.detach().contiguous(), quats.detach().contiguous(), scaled.detach().contiguous(),
             opacities.detach().contiguous(), viewmat, K, width, height, eps2d, near_plane, far_plane, radius_clip)
         campos = torch.linalg.inv(viewmat)[:, :3, 3]                     # rasterizer.cpp:250-251
         masks = (radii > 0).all(-1)                                      # :257
     dirs = means.unsqueeze(0) - campos.unsqueeze(1)                      # :254
-    colors = SphericalHarmonicsFunction.apply(sh_degree, dirs, sh_coeffs.unsqueeze(0), masks)
+    colors = SphericalHarmonicsFunction.apply(be, sh_degree, dirs, sh_coeffs.unsqueeze(0), masks)
     colors = torch.clamp_min(colors + 0.5, 0.0)                          # :266
     tile_w = (width + tile_size - 1) // tile_size
     tile_h = (height + tile_size - 1) // tile_size
     with torch.no_grad():
-        _tpg, isect_ids, flatten_ids = intersect_tile(means2d, radii, depths, 1, tile_size, tile_w, tile_h, True)
-        offsets = intersect_offset(isect_ids, 1, tile_w, tile_h)
-    renders, alphas = GUTRasterizationFunction.apply(means, quats, scaled, colors, opacities.unsqueeze(0), bg_color,
-                                                     viewmat, K, offsets, flatten_ids, width, height, tile_size)
+        _tpg, isect_ids, flatten_ids = be.intersect_tile(means2d, radii, depths, 1, tile_size, tile_w, tile_h, True)
+        offsets = be.intersect_offset(isect_ids, 1, tile_w, tile_h)
+    renders, alphas = GUTRasterizationFunction.apply(be, means, quats, scaled, colors, opacities.unsqueeze(0),
+                                                     bg_color, viewmat, K, offsets, flatten_ids, width, height,
+                                                     tile_size)
     return RenderOutput(
         image=torch.clamp(renders[0].permute(2, 0, 1), 0.0, 1.0), alpha=alphas[0].permute(2, 0, 1),
         render_colors=renders, radii=radii[0].max(-1).values, depths=depths[0], means2d=means2d,

@@ -1,0 +1,99 @@
+"""Build the REFERENCE's own gsplat CUDA library for the GPU box (checker + same-box baseline).
+
+Compiles the reference's sources WHERE THEY LIE under /root/reference/gsplat (nothing is copied into
+this repo), with the reference's own flags (-O3 --use_fast_math --expt-relaxed-constexpr,
+gsplat/CMakeLists.txt:76) for plain sm_100, plus oracle/ref_binding.cpp, into
+oracle/_ref/libgsplat_ref.so (git-ignored, shipped to the GPU box by gpurun).
+
+The reference's device math depends on GLM, which is not vendored in the reference tree and not
+installed here; oracle/glm_shim/ provides the subset it uses (see glm_shim/glm/glm.hpp).
+
+This does NOT run the reference's build system; it is a short explicit recipe (DESIGN.md "Oracle").
+Runs only in the build container (needs /root/reference).
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = "/root/reference/gsplat"
+OUT = os.path.join(HERE, "_ref")
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+CXX = "/usr/bin/g++"
+
+CU = ["ProjectionUT3DGSFused.cu", "IntersectTile.cu", "SphericalHarmonicsCUDA.cu", "QuatToRotmatCUDA.cu",
+      "RelocationCUDA.cu", "RasterizeToPixelsFromWorld3DGSFwd.cu", "RasterizeToPixelsFromWorld3DGSBwd.cu"]
+CPP = ["Projection.cpp", "Intersect.cpp", "SphericalHarmonics.cpp", "QuatToRotmat.cpp", "Relocation.cpp",
+       "Rasterization.cpp"]
+
+
+def available() -> bool:
+    return os.path.exists(os.path.join(OUT, "libgsplat_ref.so"))
+
+
+def _stamp() -> str:
+    h = hashlib.sha256()
+    for f in CU + CPP:
+        h.update(open(os.path.join(REF, f), "rb").read())
+    for root, _, files in os.walk(os.path.join(HERE, "glm_shim")):
+        for f in sorted(files):
+            h.update(open(os.path.join(root, f), "rb").read())
+    h.update(open(os.path.join(HERE, "ref_binding.cpp"), "rb").read())
+    return h.hexdigest()
+
+
+def build(verbose: bool = True, jobs: int = 7) -> str | None:
+    if not os.path.isdir(REF):
+        return None
+    from torch.utils import cpp_extension as ce
+
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, "libgsplat_ref.so")
+    stamp_file = so + ".stamp"
+    st = _stamp()
+    if os.path.exists(so) and os.path.exists(stamp_file) and open(stamp_file).read() == st:
+        return so
+    inc = []
+    for i in [os.path.join(HERE, "glm_shim"), REF] + ce.include_paths():
+        inc += ["-I", i]
+    common = ["-O3", "-std=c++20", "-Xcompiler", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=1", "-ccbin", CXX,
+              "-gencode", "arch=compute_100,code=sm_100", "--use_fast_math", "--expt-relaxed-constexpr",
+              "-diag-suppress", "20012,20011,20014,177,550"]
+
+    def compile_one(src: str):
+        sp = os.path.join(REF, src) if not src.endswith("ref_binding.cpp") else src
+        obj = os.path.join(OUT, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        cmd = [NVCC, "-c", sp, "-o", obj, "-x", "cu"] + common + inc
+        if verbose:
+            print("[build_ref]", os.path.basename(src), flush=True)
+        p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout[-6000:])
+            raise RuntimeError(f"reference source failed to compile: {src}")
+        return obj
+
+    srcs = CU + CPP + [os.path.join(HERE, "ref_binding.cpp")]
+    with ThreadPoolExecutor(max_workers=jobs) as ex:
+        objs = list(ex.map(compile_one, srcs))
+    tl = ce.library_paths()[0]
+    cmd = [NVCC, "-shared", "-o", so] + objs + ["-gencode", "arch=compute_100,code=sm_100", "-ccbin", CXX, "-L", tl,
+                                                 "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_cuda", "-lc10_cuda",
+                                                 "-Xlinker", "-rpath," + tl, "-Xlinker", "-Bsymbolic"]
+    p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout[-6000:])
+        raise RuntimeError("linking oracle/_ref/libgsplat_ref.so failed")
+    for o in objs:
+        os.remove(o)
+    with open(stamp_file, "w") as f:
+        f.write(st)
+    return so
+
+
+if __name__ == "__main__":
+    print(build())

@@ -1,0 +1,35 @@
+"""Backend over the REFERENCE's own gsplat CUDA kernels (oracle/_ref/libgsplat_ref.so, built by
+oracle/build_ref.py from /root/reference/gsplat with the GLM shim).
+
+TEST INFRASTRUCTURE ONLY: lets tests and bench.py drive the reference's kernels through the very
+same Python call sites as the product backend (OpsBackend of the package), to pin parity on the
+rows the reference's tests do not cover and to time the reference's CUDA build on the same box.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "_ref", "libgsplat_ref.so")
+_loaded = False
+
+
+def available() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def _ns():
+    global _loaded
+    if not _loaded:
+        if not available():
+            raise RuntimeError(f"{REF_SO} not built (python oracle/build_ref.py in the build container)")
+        torch.ops.load_library(REF_SO)
+        _loaded = True
+    return torch.ops.gsplat_ref
+
+
+def backend(pkg):
+    """An OpsBackend (class from the product package) bound to the reference library."""
+    return pkg.OpsBackend(_ns)

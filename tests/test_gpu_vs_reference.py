@@ -1,0 +1,183 @@
+"""GPU: the sm_100a path and the CPU oracle against the REFERENCE's own CUDA kernels
+(oracle/_ref/libgsplat_ref.so = /root/reference/gsplat/*.cu compiled unmodified with the reference's
+flags; GLM provided by oracle/glm_shim).  This is the pin for the rows the reference's own tests
+do not cover: UT projection and from-world blend forward / backward.
+
+Skipped when the reference library was not built (it needs /root/reference at build time)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def ref(native):
+    from oracle import ref_ops
+    if not ref_ops.available():
+        pytest.skip("oracle/_ref/libgsplat_ref.so not built")
+    return ref_ops.backend(native)
+
+
+def to_dev(sc, dev):
+    return {k: torch.from_numpy(v).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
+
+
+def _scene(name):
+    return {"a": lambda: scenes.scene_a(background=False),
+            "small_rot": lambda: scenes.scene_small(N=3000, width=200, height=120, view=1),
+            "b30k": lambda: scenes.scene_b(N=30000, width=640, height=360, view=3, scale_mul=2.0),
+            "b200k": lambda: scenes.scene_b(N=200000, view=5)}[name]()
+
+
+@pytest.mark.parametrize("name", ["a", "small_rot", "b30k", "b200k"])
+def test_projection_reference_vs_b200_and_oracle(native, ref, orc, cuda_device, name):
+    sc = _scene(name)
+    t = to_dev(sc, cuda_device)
+    args = (t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"], sc["width"], sc["height"],
+            0.3, 0.01, 1e4, 0.0)
+    r_ref, m_ref, d_ref, c_ref, _ = ref.projection_ut_3dgs_fused(*args)
+    r_new, m_new, d_new, c_new, _ = native.projection_ut_3dgs_fused(*args)
+    r_ref, r_new = r_ref.cpu().numpy(), r_new.cpu().numpy()
+    N = r_ref.shape[1]
+    mism = int((r_ref != r_new).any(-1).sum())
+    r_orc = orc.projection_ut(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["viewmats"], sc["Ks"],
+                              sc["width"], sc["height"], 0.3, 0.01, 1e4, 0.0)[0]
+    mism_orc = int((r_ref != r_orc).any(-1).sum())
+    print(f"[{name}] radii: reference vs b200 {mism}/{N} differ, reference vs oracle {mism_orc}/{N}")
+    # ceil()/cull borderline flips only (fast-math vs IEEE arithmetic): a few per 10^4
+    assert mism <= max(3, N // 1000) and mism_orc <= max(3, N // 1000)
+    # every flipped radius is a +-1 step or a cull decision at the boundary
+    d = np.abs(r_ref.astype(np.int64) - r_new.astype(np.int64))
+    bad = (d > 1) & (r_ref > 0) & (r_new > 0)
+    assert not bad.any()
+    both = (r_ref > 0).all(-1) & (r_new > 0).all(-1)
+    assert rel(m_new.cpu().numpy()[both], m_ref.cpu().numpy()[both]) < 1e-5
+    assert rel(d_new.cpu().numpy()[both], d_ref.cpu().numpy()[both]) < 1e-6
+    assert rel(c_new.cpu().numpy()[both], c_ref.cpu().numpy()[both]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["small_rot", "b30k"])
+def test_intersect_bit_exact_vs_reference(native, ref, cuda_device, name):
+    sc = _scene(name)
+    t = to_dev(sc, cuda_device)
+    W, H = sc["width"], sc["height"]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    radii, means2d, depths, _, _ = ref.projection_ut_3dgs_fused(t["means"], t["quats"], t["scales"], t["opacities"],
+                                                                t["viewmats"], t["Ks"], W, H, 0.3, 0.01, 1e4, 0.0)
+    # culled rows of means2d / depths are uninitialised in the reference: both libraries see the same bytes
+    a = ref.intersect_tile(means2d, radii, depths, 1, 16, tw, th, True)
+    b = native.intersect_tile(means2d, radii, depths, 1, 16, tw, th, True)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    assert torch.equal(ref.intersect_offset(a[1], 1, tw, th), native.intersect_offset(b[1], 1, tw, th))
+
+
+@pytest.mark.parametrize("name", ["a", "small_rot", "b30k"])
+def test_blend_reference_vs_b200_and_oracle(native, ref, orc, cuda_device, name):
+    sc = _scene(name)
+    W, H = sc["width"], sc["height"]
+    rng = np.random.default_rng(2)
+    vrc = rng.standard_normal((1, H, W, 3)).astype(np.float32)
+    vra = rng.standard_normal((1, H, W, 1)).astype(np.float32)
+    o32 = orc.render_pipeline(sc, "f32", True, vrc, vra)
+    o64 = orc.render_pipeline(sc, "f64", True, vrc, vra)
+    t = to_dev(sc, cuda_device)
+    colors = torch.from_numpy(o32["colors"]).to(cuda_device)
+    off = torch.from_numpy(o32["tile_offsets"]).to(cuda_device)
+    flat = torch.from_numpy(o32["flatten_ids"]).to(cuda_device)
+    bg = t.get("background")
+    fa = (t["means"], t["quats"], t["scales"], colors, t["opacities"][None], bg, None, W, H, 16, t["viewmats"], t["Ks"],
+          off, flat)
+    r_ref, a_ref, l_ref = ref.rasterize_to_pixels_from_world_3dgs_fwd(*fa)
+    r_new, a_new, l_new = native.rasterize_to_pixels_from_world_3dgs_fwd(*fa)
+    e_new = rel(r_new.cpu().numpy(), r_ref.cpu().numpy())
+    e_orc = rel(o32["renders"], r_ref.cpu().numpy())
+    e_ref64 = rel(r_ref.cpu().numpy(), o64["renders"])
+    e_new64 = rel(r_new.cpu().numpy(), o64["renders"])
+    lm = float((l_new != l_ref).float().mean())
+    print(f"[{name}] image rel_l2: b200 vs reference {e_new:.2e}; oracle(f32) vs reference {e_orc:.2e}; "
+          f"reference vs f64 truth {e_ref64:.2e}; b200 vs f64 truth {e_new64:.2e}; last_ids differ {lm:.2e}")
+    assert e_new < 1e-4 and e_orc < 1e-4
+    assert rel(a_new.cpu().numpy(), a_ref.cpu().numpy()) < 1e-4
+    assert lm < 2e-3
+    # backward, both fed with the REFERENCE's forward outputs
+    vr, va = torch.from_numpy(vrc).to(cuda_device), torch.from_numpy(vra).to(cuda_device)
+    g_ref = ref.rasterize_to_pixels_from_world_3dgs_bwd(*fa, a_ref, l_ref, vr, va)
+    g_new = native.rasterize_to_pixels_from_world_3dgs_bwd(*fa, a_ref, l_ref, vr, va)
+    g_orc = orc.raster_bwd(sc["means"], sc["quats"], sc["scales"], o32["colors"], sc["opacities"][None],
+                           sc.get("background"), None, W, H, 16, sc["viewmats"], sc["Ks"], o32["tile_offsets"],
+                           o32["flatten_ids"], a_ref.cpu().numpy(), l_ref.cpu().numpy(), vrc, vra, precision="f64")
+    for nm, gr, gn, go in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), g_ref, g_new, g_orc):
+        gr, gn = gr.cpu().numpy(), gn.cpu().numpy()
+        e1, e2, e3 = rel(gn, gr), rel(go.reshape(gr.shape), gr), rel(gn, go.reshape(gr.shape))
+        print(f"[{name}] {nm}: b200 vs reference {e1:.2e}; oracle(f64) vs reference {e2:.2e}; b200 vs oracle(f64) {e3:.2e}")
+        assert e1 < 1e-3 and e2 < 1e-3, (nm, e1, e2)
+
+
+def test_whole_path_autograd_reference_vs_b200(native, ref, cuda_device):
+    """Same L3 call sequence, two backends: image and parameter gradients."""
+    sc = _scene("b30k")
+    W, H = sc["width"], sc["height"]
+    t = to_dev(sc, cuda_device)
+    rng = np.random.default_rng(9)
+    target = torch.from_numpy(rng.random((1, H, W, 3), dtype=np.float32)).to(cuda_device)
+    res = {}
+    for tag, be in (("ref", ref), ("new", None)):
+        P = {k: t[k].clone().requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "sh_coeffs")}
+        out = native.rasterize(P["means"], P["quats"], P["scales"], P["opacities"], P["sh_coeffs"], sc["sh_degree"],
+                               t["viewmats"], t["Ks"], W, H, bg_color=t["background"], backend=be)
+        ((out.render_colors - target) ** 2).mean().backward()
+        res[tag] = (out, {k: v.grad.detach().cpu().numpy() for k, v in P.items()})
+    if res["ref"][0].n_isects != res["new"][0].n_isects:
+        pytest.skip("a radius flipped at a ceil() boundary between the two projections")
+    assert rel(res["new"][0].render_colors.detach().cpu().numpy(), res["ref"][0].render_colors.detach().cpu().numpy()) < 1e-4
+    for k in res["ref"][1]:
+        e = rel(res["new"][1][k], res["ref"][1][k])
+        print(f"[whole path] grad {k}: rel_l2 {e:.2e}")
+        assert e < 1e-3, (k, e)
+
+
+def test_dump_reference_golden(ref, cuda_device):
+    """Writes gpurun_out/ref_cuda_small.npz: outputs of the reference's own kernels on a small scene.
+    The file is committed as tests/golden/ref_cuda_small.npz and pins the CPU oracle in the
+    no-GPU suite (tests/test_oracle_vs_reference_golden.py)."""
+    sc = scenes.scene_small(N=1200, width=160, height=96, sh_degree=3, view=2)
+    t = to_dev(sc, cuda_device)
+    W, H = sc["width"], sc["height"]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    radii, means2d, depths, conics, comp = ref.projection_ut_3dgs_fused(
+        t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"], W, H, 0.3, 0.01, 1e4, 0.0,
+        calc_compensations=True)
+    vis = (radii > 0).all(-1)
+    means2d = torch.where(vis[..., None], means2d, torch.zeros_like(means2d))
+    depths = torch.where(vis, depths, torch.zeros_like(depths))
+    conics = torch.where(vis[..., None], conics, torch.zeros_like(conics))
+    rng = np.random.default_rng(11)
+    colors = torch.from_numpy(rng.random((1, sc["means"].shape[0], 3), dtype=np.float32)).to(cuda_device)
+    tpg, ids, flat = ref.intersect_tile(means2d, radii, depths, 1, 16, tw, th, True)
+    off = ref.intersect_offset(ids, 1, tw, th)
+    fa = (t["means"], t["quats"], t["scales"], colors, t["opacities"][None], t["background"], None, W, H, 16,
+          t["viewmats"], t["Ks"], off, flat)
+    r, a, li = ref.rasterize_to_pixels_from_world_3dgs_fwd(*fa)
+    vrc = torch.from_numpy(rng.standard_normal((1, H, W, 3)).astype(np.float32)).to(cuda_device)
+    vra = torch.from_numpy(rng.standard_normal((1, H, W, 1)).astype(np.float32)).to(cuda_device)
+    g = ref.rasterize_to_pixels_from_world_3dgs_bwd(*fa, a, li, vrc, vra)
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.savez_compressed(
+        "gpurun_out/ref_cuda_small.npz", radii=radii.cpu().numpy(), means2d=means2d.cpu().numpy(),
+        depths=depths.cpu().numpy(), conics=conics.cpu().numpy(), compensations=comp.cpu().numpy(),
+        colors=colors.cpu().numpy(), tiles_per_gauss=tpg.cpu().numpy(), isect_ids=ids.cpu().numpy(),
+        flatten_ids=flat.cpu().numpy(), tile_offsets=off.cpu().numpy(), renders=r.cpu().numpy(), alphas=a.cpu().numpy(),
+        last_ids=li.cpu().numpy(), v_render_colors=vrc.cpu().numpy(), v_render_alphas=vra.cpu().numpy(),
+        v_means=g[0].cpu().numpy(), v_quats=g[1].cpu().numpy(), v_scales=g[2].cpu().numpy(),
+        v_colors=g[3].cpu().numpy(), v_opacities=g[4].cpu().numpy())
