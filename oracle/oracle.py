@@ -76,7 +76,19 @@ def set_threads(n: int) -> None:
 
 
 def max_threads() -> int:
-    return int(lib("f32").orc_max_threads())
+    """Host threads this process may actually use: min(online CPUs, affinity, cgroup CPU quota)."""
+    n = int(lib("f32").orc_max_threads())
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(np.ceil(int(quota) / int(period)))))
+    except (OSError, ValueError):
+        pass
+    return max(1, n)
 
 
 def _f32(a):
@@ -290,13 +302,23 @@ def render_pipeline(scene: dict, precision="f32", with_bwd=False, v_render_color
                                            ts, viewmats, Ks, off, flat, precision=precision)
     out.update(renders=renders, alphas=alphas, last_ids=last_ids)
     if with_bwd:
-        g = raster_bwd(means, quats, scales, colors_act, opac[None], bg, None, W, H, ts, viewmats, Ks,
-                       off, flat, alphas, last_ids, v_render_colors, v_render_alphas,
-                       precision=precision)
-        out.update(v_means=g[0], v_quats=g[1], v_scales=g[2], v_colors=g[3], v_opacities=g[4])
-        # clamp_min(+0.5) backward, then SH backward (rasterizer_autograd.cpp:84-132)
-        v_sh_colors = (g[3] * ((colors + 0.5) > 0)).astype(np.float32)
-        v_coeffs, v_dirs = sh_bwd(deg, dirs, np.broadcast_to(sh[None], (1,) + sh.shape), masks,
-                                  v_sh_colors, True, precision=precision)
-        out.update(v_sh_coeffs=v_coeffs[0], v_dirs=v_dirs)
+        backward_pipeline(scene, out, v_render_colors, v_render_alphas, precision)
+    return out
+
+
+def backward_pipeline(scene: dict, out: dict, v_render_colors, v_render_alphas, precision="f32"):
+    """Backward chain of render_pipeline's forward `out` (blend bwd -> clamp -> SH bwd); adds the
+    gradients to `out` in place and returns it."""
+    W, H, ts = scene["width"], scene["height"], scene.get("tile_size", 16)
+    means, quats, scales, opac = scene["means"], scene["quats"], scene["scales"], scene["opacities"]
+    sh, deg = scene["sh_coeffs"], scene["sh_degree"]
+    g = raster_bwd(means, quats, scales, out["colors"], opac[None], scene.get("background"), None, W, H, ts,
+                   scene["viewmats"], scene["Ks"], out["tile_offsets"], out["flatten_ids"], out["alphas"],
+                   out["last_ids"], v_render_colors, v_render_alphas, precision=precision)
+    out.update(v_means=g[0], v_quats=g[1], v_scales=g[2], v_colors=g[3], v_opacities=g[4])
+    # clamp_min(+0.5) backward, then SH backward (rasterizer_autograd.cpp:84-132)
+    v_sh_colors = (g[3] * ((out["sh_colors"] + 0.5) > 0)).astype(np.float32)
+    v_coeffs, v_dirs = sh_bwd(deg, out["dirs"], np.broadcast_to(sh[None], (1,) + sh.shape), out["masks"],
+                              v_sh_colors, True, precision=precision)
+    out.update(v_sh_coeffs=v_coeffs[0], v_dirs=v_dirs)
     return out
