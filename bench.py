@@ -203,6 +203,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     pkg = ge.load_package()
     pkg.load()
+    from gsplat_b200 import multiview
     cabi = ctypes.CDLL(pkg.CABI_PATH)
     cabi.gsb_launch_count.restype = ctypes.c_uint64
     cabi.gsb_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
@@ -231,9 +232,7 @@ def run_b200(args):
         loss.backward()
         if world > 1:
             # one fused NCCL launch for the five gradient tensors (236 B/Gaussian)
-            with dist._coalescing_manager(device=dev, async_ops=False):
-                for k in names:
-                    dist.all_reduce(Pd[k].grad)
+            multiview.allreduce_gradients([Pd[k].grad for k in names])
         stats["n_isects"], stats["vis"] = out.n_isects, out.visibility
         return loss, out
 
@@ -250,12 +249,7 @@ def run_b200(args):
             fn()
         e1.record()
         sync_all()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return multiview.max_over_ranks(e0.elapsed_time(e1), dev)
 
     # ---- warm-up + device-resident timing -------------------------------------------------------
     for _ in range(max(args.warmup, 3)):
