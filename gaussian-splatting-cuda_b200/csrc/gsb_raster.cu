@@ -321,21 +321,20 @@ __device__ __forceinline__ void bwd_pair(BwdPixel &s, const PairEval &e, float l
     const float a_raw = fast_ex2(ex);
     const float alpha = fminf(kMaxAlpha, a_raw);
     if (alpha < kAlphaThreshold) return;
-    const float ra = 1.0f / (1.0f - alpha);
+    // the reference evaluates 1/(1-alpha) with the fast-math reciprocal too (Bwd.cu:291 under --use_fast_math)
+    const float ra = fast_rcp(1.0f - alpha);
     s.T *= ra;
     const float fac = alpha * s.T;
     float v_alpha = (cr * s.T - s.br * ra) * s.vr + (cg * s.T - s.bgc * ra) * s.vg + (cb * s.T - s.bb * ra) * s.vb;
     v_alpha += s.tfva * ra;
     acc[12] += fac * s.vr; acc[13] += fac * s.vg; acc[14] += fac * s.vb;
-    if (a_raw <= kMaxAlpha) { // Bwd.cu:318: gradient through opacity*vis only when not clamped
-        const float g = a_raw * v_alpha;
-        const float w1 = g * kLn2 * rD;
-        const float w2 = -w1 * (e.Ns * rD);
-        const float xx = x * x, xy = x * y, yy = y * y;
-        acc[0] += w1 * x; acc[1] += w1 * y; acc[2] += w1 * xx; acc[3] += w1 * xy; acc[4] += w1 * yy;
-        acc[5] += w2; acc[6] += w2 * x; acc[7] += w2 * y; acc[8] += w2 * xx; acc[9] += w2 * xy; acc[10] += w2 * yy;
-        acc[11] += g;
-    }
+    // Bwd.cu:318: gradient through opacity*vis only when alpha was not clamped (branch-free select)
+    const float g = (a_raw <= kMaxAlpha) ? a_raw * v_alpha : 0.0f;
+    const float w1 = g * kLn2 * rD;
+    const float w2 = -w1 * (e.Ns * rD);
+    acc[0] += w1 * x; acc[1] += w1 * y; acc[2] += w1 * e.xx; acc[3] += w1 * e.xy; acc[4] += w1 * e.yy;
+    acc[5] += w2; acc[6] += w2 * x; acc[7] += w2 * y; acc[8] += w2 * e.xx; acc[9] += w2 * e.xy; acc[10] += w2 * e.yy;
+    acc[11] += g;
     s.br += cr * fac; s.bgc += cg * fac; s.bb += cb * fac;
 }
 

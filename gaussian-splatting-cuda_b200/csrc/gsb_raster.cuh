@@ -125,11 +125,13 @@ __device__ inline void gauss_geom(const CamConst &c, const float *mean, const fl
 // intrinsics: the two kernels must agree bit-for-bit on which pairs pass the alpha test).
 struct PairEval {
     float Ns, Ds;
+    float xx, xy, yy; // monomials, reused by the backward's moment accumulation
     bool pass;
 };
 __device__ __forceinline__ PairEval pair_eval(const float4 q0, const float4 q1, const float4 q2, float x, float y) {
     PairEval r;
     const float xx = __fmul_rn(x, x), xy = __fmul_rn(x, y), yy = __fmul_rn(y, y);
+    r.xx = xx; r.xy = xy; r.yy = yy;
     r.Ns = __fmaf_rn(q1.x, yy, __fmaf_rn(q0.w, xy, __fmul_rn(q0.z, xx)));
     float D = __fmaf_rn(q1.y, x, 1.0f);
     D = __fmaf_rn(q1.z, y, D);

@@ -309,14 +309,219 @@ static int in_bounds_margin(real px, real py, uint32_t W, uint32_t H, real margi
     return valid;
 }
 
-/* Cameras.cuh:431-455 PerfectPinholeCameraModel::camera_ray_to_image_point */
-static int pinhole_project(v3 cam, real fx, real fy, real cx, real cy, uint32_t W, uint32_t H,
-                           real margin, real *ox, real *oy) {
+/* ---- camera models (Cameras.cuh:416-1001), global shutter ------------------------------- */
+enum { CM_PERFECT_PINHOLE = 0, CM_OPENCV_PINHOLE = 1, CM_OPENCV_FISHEYE = 2 };
+typedef struct {
+    int kind;
+    uint32_t W, H;
+    real fx, fy, cx, cy;
+    real k[6], p[2], s[4];    /* OpenCV pinhole: radial, tangential, thin prism (Cameras.cuh:481-487) */
+    real fk[4];               /* fisheye radial (Cameras.cuh:824-828) */
+    real fwd[5], dfwd[5];     /* fisheye forward polynomial (odd) and its derivative (even) */
+    real bwd0, bwd1;          /* fisheye linear approximation of the inverse */
+    real max_angle, min_2d_norm;
+} CamModel;
+
+/* Cameras.cuh:759-815 */
+static real fisheye_max_angle_cubic(real a, real b, real c) {
+    const real INF = (real)3.402823466e+38;
+    if (c == (real)0) {
+        if (b == (real)0) return a >= (real)0 ? INF : (real)-1 / a;
+        real delta = a * a - (real)4 * b;
+        if (delta >= (real)0) {
+            delta = R_SQRT(delta) - a;
+            if (delta > (real)0) return (real)2 / delta;
+        }
+    } else {
+        real boc = b / c, boc2 = boc * boc;
+        real t1 = ((real)9 * a * boc - (real)2 * b * boc2 - (real)27) / c;
+        real t2 = (real)3 * a / c - boc2;
+        real delta = t1 * t1 + (real)4 * t2 * t2 * t2;
+        if (delta >= (real)0) {
+            real d2 = R_SQRT(delta);
+            real cube_root = (real)cbrt((double)((d2 + t1) / (real)2));
+            if (cube_root != (real)0) {
+                real soln = (cube_root - (t2 / cube_root) - boc) / (real)3;
+                if (soln > (real)0) return soln;
+            }
+        } else {
+            real theta = (real)atan2((double)R_SQRT(-delta), (double)t1) / (real)3;
+            const real two_third_pi = (real)2 * (real)3.14159265358979323846 / (real)3;
+            real t3 = (real)2 * R_SQRT(-t2);
+            real soln = INF;
+            for (int i = -1; i <= 1; ++i) {
+                real angle = theta + (real)i * two_third_pi;
+                real sv = (t3 * (real)cos((double)angle) - boc) / (real)3;
+                if (sv > (real)0 && sv < soln) soln = sv;
+            }
+            return soln;
+        }
+    }
+    return INF;
+}
+
+static real poly_horner(const real *c, int n, real x) { /* c0 + c1 x + ... (Cameras.cuh:91-107) */
+    real y = 0;
+    for (int i = n - 1; i >= 0; --i) y = x * y + c[i];
+    return y;
+}
+
+/* nr / nt / ns = number of floats behind each pointer (missing coefficients are zero) */
+static CamModel cam_model_make(int camera_model, uint32_t W, uint32_t H, const float *K, const float *radial, int nr,
+                               const float *tangential, int nt, const float *thin_prism, int ns) {
+    CamModel m;
+    memset(&m, 0, sizeof(m));
+    m.W = W; m.H = H;
+    m.fx = K[0]; m.fy = K[4]; m.cx = K[2]; m.cy = K[5];
+    if (camera_model == ORC_FISHEYE) { /* Cameras.cuh:830-885 */
+        m.kind = CM_OPENCV_FISHEYE;
+        for (int i = 0; i < 4 && radial && i < nr; ++i) m.fk[i] = radial[i];
+        const real k1 = m.fk[0], k2 = m.fk[1], k3 = m.fk[2], k4 = m.fk[3];
+        m.fwd[0] = 1; m.fwd[1] = k1; m.fwd[2] = k2; m.fwd[3] = k3; m.fwd[4] = k4;
+        m.dfwd[0] = 1; m.dfwd[1] = 3 * k1; m.dfwd[2] = 5 * k2; m.dfwd[3] = 7 * k3; m.dfwd[4] = 9 * k4;
+        m.min_2d_norm = (real)1e-6;
+        real mdx = ((real)W - m.cx) > m.cx ? ((real)W - m.cx) : m.cx;
+        real mdy = ((real)H - m.cy) > m.cy ? ((real)H - m.cy) : m.cy;
+        real max_radius_pixels = R_SQRT(mdx * mdx + mdy * mdy);
+        if (k4 == (real)0) {
+            m.max_angle = R_SQRT(fisheye_max_angle_cubic((real)3 * k1, (real)5 * k2, (real)7 * k3));
+        } else { /* Newton on the derivative polynomial from 1.57 (Cameras.cuh:857-870, 174-206) */
+            const real dd[4] = {6 * k1, 20 * k2, 42 * k3, 72 * k4};
+            real x = (real)1.57;
+            int converged = 0;
+            for (int j = 0; j < 20; ++j) {
+                real dfdx = x * poly_horner(dd, 4, x * x);
+                real residual = poly_horner(m.dfwd, 5, x * x) - (real)0;
+                real dx = residual / dfdx;
+                x -= dx;
+                if (R_FABS(dx) < (real)1e-6) { converged = 1; break; }
+            }
+            m.max_angle = (!converged || x <= (real)0) ? (real)3.402823466e+38 : x;
+        }
+        real a = max_radius_pixels / m.fx, b = max_radius_pixels / m.fy;
+        real lim = a > b ? a : b;
+        if (lim < m.max_angle) m.max_angle = lim;
+        real nx = (real)W / (real)2 / m.fx, ny = (real)H / (real)2 / m.fy;
+        real max_normalized_dist = nx > ny ? nx : ny;
+        m.bwd0 = 0; m.bwd1 = m.max_angle / max_normalized_dist;
+    } else if (radial || tangential || thin_prism) { /* ProjectionUT3DGSFused.cu:98-115 */
+        m.kind = CM_OPENCV_PINHOLE;
+        for (int i = 0; i < 6 && radial && i < nr; ++i) m.k[i] = radial[i];
+        for (int i = 0; i < 2 && tangential && i < nt; ++i) m.p[i] = tangential[i];
+        for (int i = 0; i < 4 && thin_prism && i < ns; ++i) m.s[i] = thin_prism[i];
+    } else {
+        m.kind = CM_PERFECT_PINHOLE;
+    }
+    return m;
+}
+
+/* Cameras.cuh:504-533 */
+static void opencv_distortion(const CamModel *m, real u, real v, real *icD, real *dx, real *dy) {
+    const real u2 = u * u, v2 = v * v, r2 = u2 + v2;
+    const real a1 = (real)2 * u * v, a2 = r2 + (real)2 * u2, a3 = r2 + (real)2 * v2;
+    const real num = (real)1 + r2 * (m->k[0] + r2 * (m->k[1] + r2 * m->k[2]));
+    const real den = (real)1 + r2 * (m->k[3] + r2 * (m->k[4] + r2 * m->k[5]));
+    *icD = num / den;
+    *dx = m->p[0] * a1 + m->p[1] * a2 + r2 * (m->s[0] + r2 * m->s[1]);
+    *dy = m->p[0] * a3 + m->p[1] * a1 + r2 * (m->s[2] + r2 * m->s[3]);
+}
+
+/* camera_ray_to_image_point of the three models (Cameras.cuh:431-455, 535-597, 894-959) */
+static int cam_project(const CamModel *m, v3 cam, real margin, real *ox, real *oy) {
     *ox = 0; *oy = 0;
     if (cam.z <= (real)0) return 0;
-    *ox = (cam.x / cam.z) * fx + cx;
-    *oy = (cam.y / cam.z) * fy + cy;
-    return in_bounds_margin(*ox, *oy, W, H, margin);
+    if (m->kind == CM_PERFECT_PINHOLE) {
+        *ox = (cam.x / cam.z) * m->fx + m->cx;
+        *oy = (cam.y / cam.z) * m->fy + m->cy;
+        return in_bounds_margin(*ox, *oy, m->W, m->H, margin);
+    }
+    if (m->kind == CM_OPENCV_PINHOLE) {
+        const real u = cam.x / cam.z, v = cam.y / cam.z;
+        real icD, dx, dy;
+        opencv_distortion(m, u, v, &icD, &dx, &dy);
+        const int valid_radial = icD > (real)0.8;
+        *ox = (icD * u + dx) * m->fx + m->cx;
+        *oy = (icD * v + dy) * m->fy + m->cy;
+        return valid_radial && in_bounds_margin(*ox, *oy, m->W, m->H, margin);
+    }
+    /* fisheye; numerically_stable_norm2 (Cameras.cuh:77-89) */
+    real ax = R_FABS(cam.x), ay = R_FABS(cam.y);
+    real mn = ax < ay ? ax : ay, mx = ax < ay ? ay : ax;
+    real xy_norm = 0;
+    if (mx > (real)0) { real r = mn / mx; xy_norm = mx * R_SQRT((real)1 + r * r); }
+    if (xy_norm <= (real)0) xy_norm = (real)R_EPS;
+    const real theta_full = (real)atan2((double)xy_norm, (double)cam.z);
+    const real theta = theta_full < m->max_angle ? theta_full : m->max_angle;
+    const real delta = theta * poly_horner(m->fwd, 5, theta * theta) / xy_norm;
+    if (delta <= (real)0) return 0;
+    *ox = m->fx * delta * cam.x + m->cx;
+    *oy = m->fy * delta * cam.y + m->cy;
+    return in_bounds_margin(*ox, *oy, m->W, m->H, margin) && (theta <= m->max_angle);
+}
+
+/* image_point_to_camera_ray (Cameras.cuh:457-470, 698-754, 961-1000): unit camera-space ray */
+static int cam_unproject(const CamModel *m, real px, real py, v3 *ray) {
+    const real u0 = (px - m->cx) / m->fx, v0 = (py - m->cy) / m->fy;
+    if (m->kind == CM_PERFECT_PINHOLE) {
+        real len = R_SQRT(u0 * u0 + v0 * v0 + (real)1);
+        *ray = v3_make(u0 / len, v0 / len, (real)1 / len);
+        return 1;
+    }
+    if (m->kind == CM_OPENCV_PINHOLE) { /* Newton, at most 5 iterations (:698-740) */
+        real x = u0, y = v0;
+        int converged = 0;
+        for (int iter = 0; iter < 5; ++iter) {
+            const real k1 = m->k[0], k2 = m->k[1], k3 = m->k[2], k4 = m->k[3], k5 = m->k[4], k6 = m->k[5];
+            const real p1 = m->p[0], p2 = m->p[1], s1 = m->s[0], s2 = m->s[1], s3 = m->s[2], s4 = m->s[3];
+            const real r = x * x + y * y, r2 = r * r;
+            const real alpha = (real)1 + r * (k1 + r * (k2 + r * k3));
+            const real beta = (real)1 + r * (k4 + r * (k5 + r * k6));
+            const real d = alpha / beta;
+            if (d <= (real)0) break;
+            real fx_ = d * x + 2 * p1 * x * y + p2 * (r + 2 * x * x) + s1 * r + s2 * r2 - u0;
+            real fy_ = d * y + 2 * p2 * x * y + p1 * (r + 2 * y * y) + s3 * r + s4 * r2 - v0;
+            const real alpha_r = k1 + r * ((real)2 * k2 + r * ((real)3 * k3));
+            const real beta_r = k4 + r * ((real)2 * k5 + r * ((real)3 * k6));
+            const real d_r = (alpha_r * beta - alpha * beta_r) / (beta * beta);
+            const real d_x = (real)2 * x * d_r, d_y = (real)2 * y * d_r;
+            real fx_x = d + d_x * x + (real)2 * p1 * y + (real)6 * p2 * x;
+            fx_x += (real)2 * x * (s1 + (real)2 * s2 * r);
+            real fx_y = d_y * x + (real)2 * p1 * x + (real)2 * p2 * y;
+            fx_y += (real)2 * y * (s1 + (real)2 * s2 * r);
+            real fy_x = d_x * y + (real)2 * p2 * y + (real)2 * p1 * x;
+            fy_x += (real)2 * x * (s3 + (real)2 * s4 * r);
+            real fy_y = d + d_y * y + (real)2 * p2 * x + (real)6 * p1 * y;
+            fy_y += (real)2 * y * (s3 + (real)2 * s4 * r);
+            const real det = fx_y * fy_x - fx_x * fy_y;
+            if (R_FABS(det) < (real)1e-6) break;
+            const real dx = (fx_ * fy_y - fy_ * fx_y) / det;
+            const real dy = (fy_ * fx_x - fx_ * fy_x) / det;
+            x += dx; y += dy;
+            if (R_FABS(dx) < (real)1e-6 && R_FABS(dy) < (real)1e-6) { converged = 1; break; }
+        }
+        real len = R_SQRT(x * x + y * y + (real)1);
+        *ray = v3_make(x / len, y / len, (real)1 / len);
+        return converged;
+    }
+    /* fisheye: invert theta * P(theta^2) = delta by Newton from the linear guess (:961-1000, 174-206) */
+    const real delta = R_SQRT(u0 * u0 + v0 * v0);
+    real th = m->bwd0 + m->bwd1 * delta;
+    int converged = 0;
+    for (int j = 0; j < 20; ++j) {
+        const real dfdx = poly_horner(m->dfwd, 5, th * th);
+        const real residual = th * poly_horner(m->fwd, 5, th * th) - delta;
+        const real dx = residual / dfdx;
+        th -= dx;
+        if (R_FABS(dx) < (real)1e-6) { converged = 1; break; }
+    }
+    if (th < (real)0 || th >= m->max_angle || !converged) { *ray = v3_make(0, 0, 1); return 0; }
+    if (delta >= m->min_2d_norm) {
+        const real sf = R_SIN(th) / delta;
+        *ray = v3_make(sf * u0, sf * v0, (real)cos((double)th));
+    } else {
+        *ray = v3_make(0, 0, 1);
+    }
+    return 1;
 }
 
 /*
