@@ -37,7 +37,7 @@ CUDA_SOURCES = [
     ("gsb_raster.cu", []),
     ("gsb_misc.cu", []),
 ]
-CUDA_HEADERS = ["gsb_common.cuh", "gsb_raster.cuh"]
+CUDA_HEADERS = ["gsb_common.cuh", "gsb_raster.cuh", "gsb_camera.cuh"]
 SHIM_SOURCES = ["Ops.cpp", "torch_binding.cpp"]
 
 

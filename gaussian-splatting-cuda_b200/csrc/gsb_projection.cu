@@ -13,7 +13,7 @@
 // This file is compiled with -fmad=false: radii come out of ceilf() and feed the bit-exact tile
 // intersection, so the arithmetic deliberately follows the reference's operation order without
 // FMA contraction (the CPU oracle is built with -ffp-contract=off for the same reason).
-#include "gsb_common.cuh"
+#include "gsb_camera.cuh"
 
 namespace gsb {
 
@@ -26,6 +26,9 @@ struct ProjParams {
     uint32_t W, H;
     float eps2d, near_plane, far_plane, radius_clip;
     GsbUTParams ut;
+    int32_t camera_model;
+    const float *radial, *tangential, *thin_prism; // per-camera coefficient rows, nullable
+    int32_t n_radial, n_tangential, n_thin_prism;
     int32_t *radii;
     float *means2d, *depths, *conics, *compensations;
 };
@@ -80,8 +83,13 @@ __global__ void __launch_bounds__(kProjThreads) projection_ut_kernel(const ProjP
     }
 
     // ---- camera (Cameras.cuh:33-71, 268-280) -----------------------------------------------
-    const float *K = p.Ks + cid * 9;
-    const float fx = K[0], fy = K[4], cx = K[2], cy = K[5];
+    __shared__ CamModel s_cm;
+    if (tid == 0)
+        cam_model_build(s_cm, p.camera_model, p.W, p.H, p.Ks + cid * 9,
+                        p.radial ? p.radial + (size_t)cid * p.n_radial : nullptr, p.n_radial,
+                        p.tangential ? p.tangential + (size_t)cid * p.n_tangential : nullptr, p.n_tangential,
+                        p.thin_prism ? p.thin_prism + (size_t)cid * p.n_thin_prism : nullptr, p.n_thin_prism);
+    __syncthreads();
     const CamPose pose = cam_pose_from_viewmat(p.viewmats0 + cid * 16);
     // centre-of-shutter pose = slerp(q, q, 0.5), 0.5 t + 0.5 t (global shutter: start == end)
     float mw, mx, my, mz;
@@ -132,8 +140,6 @@ __global__ void __launch_bounds__(kProjThreads) projection_ut_kernel(const ProjP
             float mx2 = 0.f, my2 = 0.f;
             bool valid = p.ut.require_all_sigma_points_valid != 0;
             bool early = false;
-            const float MX = (float)p.W * p.ut.in_image_margin_factor;
-            const float MY = (float)p.H * p.ut.in_image_margin_factor;
 #pragma unroll
             for (int i = 0; i < 7; ++i) {
                 V3<float> pt = mean;
@@ -143,13 +149,8 @@ __global__ void __launch_bounds__(kProjThreads) projection_ut_kernel(const ProjP
                     pt = (i <= 3) ? (mean + delta) : (mean - delta);
                 }
                 const V3<float> cam = quat_rotate(pose.qw, pose.qx, pose.qy, pose.qz, pt) + t0;
-                float px = 0.f, py = 0.f;
-                bool pv = false;
-                if (cam.z > 0.f) { // Cameras.cuh:431-455
-                    px = (cam.x / cam.z) * fx + cx;
-                    py = (cam.y / cam.z) * fy + cy;
-                    pv = (-MX <= px) && (px < (float)p.W + MX) && (-MY <= py) && (py < (float)p.H + MY);
-                }
+                float px, py;
+                const bool pv = cam_project(s_cm, cam, p.ut.in_image_margin_factor, px, py);
                 if (p.ut.require_all_sigma_points_valid) {
                     valid = valid && pv;
                     if (!pv) { early = true; break; }
@@ -243,10 +244,9 @@ extern "C" int gsb_projection_ut(
     if (!cam || !cam->viewmats0 || !cam->Ks) return GSB_E_INVALID;
     if (C == 0 || N == 0) return GSB_OK; // ProjectionUT3DGSFused.cu:242-245
     if (!means || !quats || !scales || !radii || !means2d || !depths || !conics) return GSB_E_INVALID;
-    const bool distorted = cam->radial_coeffs || cam->tangential_coeffs || cam->thin_prism_coeffs;
-    if (cam->camera_model != GSB_CAMERA_PINHOLE || distorted || cam->viewmats1 ||
+    if ((cam->camera_model != GSB_CAMERA_PINHOLE && cam->camera_model != GSB_CAMERA_FISHEYE) || cam->viewmats1 ||
         cam->shutter_type != GSB_SHUTTER_GLOBAL)
-        return GSB_E_UNSUPPORTED; // distortion / fisheye / rolling shutter: SURVEY.md 8(f) "next"
+        return GSB_E_UNSUPPORTED; // orthographic / rolling shutter: no caller of the reference uses them
     gsb::ProjParams p;
     p.C = C; p.N = N;
     p.means = means; p.quats = quats; p.scales = scales; p.opacities = opacities;
@@ -254,6 +254,9 @@ extern "C" int gsb_projection_ut(
     p.W = image_width; p.H = image_height;
     p.eps2d = eps2d; p.near_plane = near_plane; p.far_plane = far_plane; p.radius_clip = radius_clip;
     p.ut = cam->ut;
+    p.camera_model = cam->camera_model;
+    p.radial = cam->radial_coeffs; p.tangential = cam->tangential_coeffs; p.thin_prism = cam->thin_prism_coeffs;
+    p.n_radial = cam->radial_count; p.n_tangential = cam->tangential_count; p.n_thin_prism = cam->thin_prism_count;
     p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.compensations = compensations;
     dim3 grid((N + gsb::kProjThreads - 1) / gsb::kProjThreads, C);
     {

@@ -2,7 +2,7 @@
 //
 // Implements gsplat::rasterize_to_pixels_from_world_3dgs_fwd / _bwd (reference:
 // gsplat/RasterizeToPixelsFromWorld3DGSFwd.cu:20-279, ...Bwd.cu:17-373, gsplat/Utils.cuh:80-194)
-// for the perfect-pinhole / global-shutter camera.  See gsb_raster.cuh for the math.
+// for the global-shutter camera models of gsb_camera.cuh.  See gsb_raster.cuh for the math.
 //
 // Kernel structure (B200):
 //   prep      one thread per Gaussian, float64: 64-byte GaussRec (quadratic-form coefficients,
@@ -87,6 +87,10 @@ struct TileParams {
     const uint8_t *masks;     // [tile_h*tile_w] or null
     const int32_t *tile_offsets;
     const int32_t *flatten_ids;
+    // camera (only read by the general-camera instantiation)
+    int32_t camera_model;
+    const float *Ks, *radial, *tangential, *thin_prism;
+    int32_t n_radial, n_tangential, n_thin_prism;
 };
 
 struct PixelMap {
@@ -104,6 +108,57 @@ __device__ __forceinline__ PixelMap pixel_map(uint32_t tile_x, uint32_t tile_y, 
     return m;
 }
 
+// Per-thread pixel coordinates in the units of GaussRec (x = px - pcx).  Perfect pinhole: the pixel
+// centres themselves.  General camera: the pixel's ray is unprojected through the camera model
+// (Newton undistortion / fisheye polynomial inverse) once per pixel and mapped back through the ideal
+// pinhole, px = fx * x_n + cx; the warp's cull box is the bounding box of its valid pixels.
+struct PixelCoords {
+    float px0, py0, px1, py1;
+    bool ok0, ok1;            // ray valid (Fwd.cu:139, Bwd.cu:151)
+    float bx0, bx1, by0, by1; // cull box of the warp
+};
+template <bool kGeneral>
+__device__ __forceinline__ PixelCoords pixel_coords(const TileParams &p, const PixelMap &pm, uint32_t tile_x,
+                                                    uint32_t tile_y, const CamModel *cm) {
+    PixelCoords c;
+    const uint32_t tid = threadIdx.x;
+    c.px0 = c.px1 = (float)pm.x + 0.5f;
+    c.py0 = (float)pm.y0 + 0.5f;
+    c.py1 = (float)pm.y1 + 0.5f;
+    c.ok0 = c.ok1 = true;
+    c.bx0 = (float)(tile_x * 16 + ((tid >> 5) & 1) * 8) + 0.5f;
+    c.by0 = (float)(tile_y * 16 + (tid >> 6) * 8) + 0.5f;
+    c.bx1 = c.bx0 + 7.0f;
+    c.by1 = c.by0 + 7.0f;
+    if constexpr (kGeneral) {
+        float xn, yn;
+        c.ok0 = cam_unproject_normalized(*cm, c.px0, c.py0, xn, yn);
+        c.px0 = fmaf(cm->fx, xn, cm->cx); c.py0 = fmaf(cm->fy, yn, cm->cy);
+        c.ok1 = cam_unproject_normalized(*cm, c.px1, c.py1, xn, yn);
+        c.px1 = fmaf(cm->fx, xn, cm->cx); c.py1 = fmaf(cm->fy, yn, cm->cy);
+        const float BIG = 3.0e38f;
+        float lox = fminf(c.ok0 && pm.in0 ? c.px0 : BIG, c.ok1 && pm.in1 ? c.px1 : BIG);
+        float hix = fmaxf(c.ok0 && pm.in0 ? c.px0 : -BIG, c.ok1 && pm.in1 ? c.px1 : -BIG);
+        float loy = fminf(c.ok0 && pm.in0 ? c.py0 : BIG, c.ok1 && pm.in1 ? c.py1 : BIG);
+        float hiy = fmaxf(c.ok0 && pm.in0 ? c.py0 : -BIG, c.ok1 && pm.in1 ? c.py1 : -BIG);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o));
+            hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+            loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o));
+            hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+        }
+        c.bx0 = lox; c.bx1 = hix; c.by0 = loy; c.by1 = hiy;
+    }
+    return c;
+}
+
+__device__ __forceinline__ void tile_cam_build(const TileParams &p, CamModel &cm) {
+    cam_model_build(cm, p.camera_model, p.W, p.H, p.Ks, p.radial, p.n_radial, p.tangential, p.n_tangential, p.thin_prism,
+                    p.n_thin_prism);
+}
+
+
 // Thread i gathers the record of Gaussian `gid` into slot i of the stage with one 64-byte bulk
 // copy (TMA unit); thread 0 arms the stage's mbarrier with the byte count of the whole batch.
 __device__ __forceinline__ void issue_batch(GaussRec *stage, uint64_t *bar, const GaussRec *recs, int32_t gid,
@@ -116,11 +171,13 @@ __device__ __forceinline__ void issue_batch(GaussRec *stage, uint64_t *bar, cons
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
+template <bool kGeneral>
 __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TileParams p, float *__restrict__ renders,
                                                                    float *__restrict__ alphas,
                                                                    int32_t *__restrict__ last_ids) {
     __shared__ __align__(128) GaussRec s_rec[kStages][kBatch];
     __shared__ __align__(8) uint64_t s_full[kStages];
+    __shared__ CamModel s_cm;
 
     const uint32_t tile_id = blockIdx.x;
     const uint32_t tile_y = tile_id / p.tile_w, tile_x = tile_id % p.tile_w;
@@ -146,18 +203,15 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
         mbar_fence_init();
+        if constexpr (kGeneral) tile_cam_build(p, s_cm);
     }
     __syncthreads();
 
-    const float px = (float)pm.x + 0.5f;
-    const float py0 = (float)pm.y0 + 0.5f, py1 = (float)pm.y1 + 0.5f;
-    // first pixel centre of this warp's 8x8 block (for block_may_pass)
-    const float bx0 = (float)(tile_x * 16 + ((tid >> 5) & 1) * 8) + 0.5f;
-    const float by0 = (float)(tile_y * 16 + (tid >> 6) * 8) + 0.5f;
+    const PixelCoords pc = pixel_coords<kGeneral>(p, pm, tile_x, tile_y, &s_cm);
     float T0 = 1.f, T1 = 1.f;
     float c0r = 0.f, c0g = 0.f, c0b = 0.f, c1r = 0.f, c1g = 0.f, c1b = 0.f;
     int32_t last0 = 0, last1 = 0;
-    bool done0 = !pm.in0, done1 = !pm.in1;
+    bool done0 = !pm.in0 || !pc.ok0, done1 = !pm.in1 || !pc.ok1;
 
     // prologue: batch 0 in flight, ids of batch 1 prefetched into a register
     int32_t gid_next = 0;
@@ -189,15 +243,15 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
               // lane-parallel culling of 32 records against this warp's 8x8 pixel block
               const int32_t rl = c0 + (int32_t)(tid & 31);
               bool cand = false;
-              if (rl < cnt) cand = block_may_pass(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], bx0, by0);
+              if (rl < cnt)
+                  cand = block_may_pass(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], pc.bx0, pc.bx1, pc.by0, pc.by1);
               uint32_t cmask = __ballot_sync(0xffffffffu, cand);
               while (cmask) {
                 const int32_t t = c0 + __ffs(cmask) - 1;
                 cmask &= cmask - 1;
                 const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
-                const float x = px - q0.x;
-                const PairEval e0 = pair_eval(q0, q1, q2, x, py0 - q0.y);
-                const PairEval e1 = pair_eval(q0, q1, q2, x, py1 - q0.y);
+                const PairEval e0 = pair_eval(q0, q1, q2, pc.px0 - q0.x, pc.py0 - q0.y);
+                const PairEval e1 = pair_eval(q0, q1, q2, pc.px1 - q0.x, pc.py1 - q0.y);
                 const bool p0 = e0.pass && !done0, p1 = e1.pass && !done1;
                 if (!__any_sync(0xffffffffu, p0 || p1)) continue;
                 const float4 q3 = rec4[t * 4 + 3];
@@ -338,6 +392,7 @@ __device__ __forceinline__ void bwd_pair(BwdPixel &s, const PairEval &e, float l
     s.br += cr * fac; s.bgc += cg * fac; s.bb += cb * fac;
 }
 
+template <bool kGeneral>
 __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TileParams p,
                                                                    const float *__restrict__ render_alphas,
                                                                    const int32_t *__restrict__ last_ids,
@@ -347,6 +402,7 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
     __shared__ __align__(128) GaussRec s_rec[kStages][kBatch];
     __shared__ __align__(8) uint64_t s_full[kStages];
     __shared__ int32_t s_warp_max[kTileThreads / 32];
+    __shared__ CamModel s_cm;
 
     const uint32_t tile_id = blockIdx.x;
     if (p.masks != nullptr && !p.masks[tile_id]) return; // Bwd.cu:84-86
@@ -376,8 +432,13 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
             s.T = 1.f; s.last = -1; s.vr = s.vg = s.vb = 0.f; s.tfva = 0.f;
         }
     };
-    load_pixel(s0, pm.in0, pm.y0);
-    load_pixel(s1, pm.in1, pm.y1);
+    if constexpr (kGeneral) {
+        if (tid == 0) tile_cam_build(p, s_cm);
+        __syncthreads();
+    }
+    const PixelCoords pc = pixel_coords<kGeneral>(p, pm, tile_x, tile_y, &s_cm);
+    load_pixel(s0, pm.in0 && pc.ok0, pm.y0);
+    load_pixel(s1, pm.in1 && pc.ok1, pm.y1);
 
     // CTA-wide newest contributor: nothing behind it can receive gradient
     int32_t wmax = __reduce_max_sync(0xffffffffu, max(s0.last, s1.last));
@@ -396,11 +457,6 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
     const int32_t n_batches = (total + kBatch - 1) / kBatch;
     // this warp only needs records at or before its own newest contributor
     wmax = min(wmax, hi);
-
-    const float px = (float)pm.x + 0.5f;
-    const float py0 = (float)pm.y0 + 0.5f, py1 = (float)pm.y1 + 0.5f;
-    const float bx0 = (float)(tile_x * 16 + ((tid >> 5) & 1) * 8) + 0.5f;
-    const float by0 = (float)(tile_y * 16 + (tid >> 6) * 8) + 0.5f;
 
     int32_t gid_next = 0;
     {
@@ -429,17 +485,17 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
           const int32_t rl = c0 + (int32_t)(tid & 31);
           bool cand = false;
           if (rl >= t_first && rl < cnt)
-              cand = block_may_pass(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], bx0, by0);
+              cand = block_may_pass(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], pc.bx0, pc.bx1, pc.by0, pc.by1);
           uint32_t cmask = __ballot_sync(0xffffffffu, cand);
           while (cmask) {
             const int32_t t = c0 + __ffs(cmask) - 1;
             cmask &= cmask - 1;
             const int32_t idx = top - t;
             const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
-            const float x = px - q0.x;
-            const float y0 = py0 - q0.y, y1 = py1 - q0.y;
-            const PairEval e0 = pair_eval(q0, q1, q2, x, y0);
-            const PairEval e1 = pair_eval(q0, q1, q2, x, y1);
+            const float x0 = pc.px0 - q0.x, x1 = pc.px1 - q0.x;
+            const float y0 = pc.py0 - q0.y, y1 = pc.py1 - q0.y;
+            const PairEval e0 = pair_eval(q0, q1, q2, x0, y0);
+            const PairEval e1 = pair_eval(q0, q1, q2, x1, y1);
             const bool p0 = e0.pass && s0.in && idx <= s0.last;
             const bool p1 = e1.pass && s1.in && idx <= s1.last;
             if (!__any_sync(0xffffffffu, p0 || p1)) continue;
@@ -447,8 +503,8 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
             float acc[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-            if (p0) bwd_pair(s0, e0, q2.z, x, y0, q3.x, q3.y, q3.z, acc);
-            if (p1) bwd_pair(s1, e1, q2.z, x, y1, q3.x, q3.y, q3.z, acc);
+            if (p0) bwd_pair(s0, e0, q2.z, x0, y0, q3.x, q3.y, q3.z, acc);
+            if (p1) bwd_pair(s1, e1, q2.z, x1, y1, q3.x, q3.y, q3.z, acc);
             butterfly16(acc);
             if ((tid & 1) == 0) {
                 const uint32_t slot = (tid & 31) >> 1;
@@ -574,11 +630,22 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static int check_camera(const GsbCamera *cam) {
     if (!cam || !cam->viewmats0 || !cam->Ks) return GSB_E_INVALID;
-    const bool distorted = cam->radial_coeffs || cam->tangential_coeffs || cam->thin_prism_coeffs;
-    if (cam->camera_model != GSB_CAMERA_PINHOLE || distorted || cam->viewmats1 ||
+    if ((cam->camera_model != GSB_CAMERA_PINHOLE && cam->camera_model != GSB_CAMERA_FISHEYE) || cam->viewmats1 ||
         cam->shutter_type != GSB_SHUTTER_GLOBAL)
-        return GSB_E_UNSUPPORTED;
+        return GSB_E_UNSUPPORTED; // orthographic / rolling shutter
     return GSB_OK;
+}
+
+static bool general_camera(const GsbCamera *cam) {
+    return cam->camera_model == GSB_CAMERA_FISHEYE || cam->radial_coeffs || cam->tangential_coeffs ||
+           cam->thin_prism_coeffs;
+}
+
+static void fill_camera(TileParams &p, const GsbCamera *cam) {
+    p.camera_model = cam->camera_model;
+    p.Ks = cam->Ks;
+    p.radial = cam->radial_coeffs; p.tangential = cam->tangential_coeffs; p.thin_prism = cam->thin_prism_coeffs;
+    p.n_radial = cam->radial_count; p.n_tangential = cam->tangential_count; p.n_thin_prism = cam->thin_prism_count;
 }
 
 } // namespace gsb
@@ -623,7 +690,11 @@ extern "C" int gsb_raster_fwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
     {
         ProfScope ps("raster_fwd", s);
-        raster_fwd_kernel<<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
+        fill_camera(p, cam);
+        if (general_camera(cam))
+            raster_fwd_kernel<true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
+        else
+            raster_fwd_kernel<false><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
     }
     GSB_LAUNCH_CHECK();
     return GSB_OK;
@@ -675,8 +746,13 @@ extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
     {
         ProfScope ps("raster_bwd", s);
-        raster_bwd_kernel<<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids, v_render_colors,
-                                                                      v_render_alphas, moments);
+        fill_camera(p, cam);
+        if (general_camera(cam))
+            raster_bwd_kernel<true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids,
+                                                                                v_render_colors, v_render_alphas, moments);
+        else
+            raster_bwd_kernel<false><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids,
+                                                                                 v_render_colors, v_render_alphas, moments);
     }
     GSB_LAUNCH_CHECK();
     {

@@ -24,7 +24,7 @@
 // DESIGN.md "Blend kernels".
 #pragma once
 
-#include "gsb_common.cuh"
+#include "gsb_camera.cuh"
 
 namespace gsb {
 
@@ -141,20 +141,20 @@ __device__ __forceinline__ PairEval pair_eval(const float4 q0, const float4 q1, 
     r.pass = __fmaf_rn(-q2.w, r.Ds, r.Ns) >= 0.0f; // Ns >= tau * Ds
     return r;
 }
-// Warp-level culling: can ANY pixel centre of the 8x8 block whose first centre is (bx0, by0) pass
-// the rejection test of this record?  The pass region {Ns - tau Ds >= 0} is the interior of an
+// Warp-level culling: can ANY pixel of the warp's block, whose (undistorted) pixel coordinates lie
+// in the box [bx0, bx1] x [by0, by1], pass the rejection test of this record?  The pass region {Ns - tau Ds >= 0} is the interior of an
 // ellipse (the form F = A x^2 + B xy + C y^2 + D x + E y + F0 is concave for every realistic
 // Gaussian), so the exact answer is max_box F >= 0: the unconstrained maximiser if it lies in the
 // box, else the best point on the (at most two) box edges facing it.  One lane tests one record,
 // so a warp classifies 32 records per pass; `slack` absorbs the float rounding of both this test
 // and pair_eval's, keeping the cull strictly conservative.  Non-concave forms are never culled.
 __device__ __forceinline__ bool block_may_pass(const float4 q0, const float4 q1, const float4 q2, float bx0,
-                                               float by0) {
+                                               float bx1, float by0, float by1) {
     const float tau = q2.w;
     if (!(tau < 3.0e38f)) return false; // dead record (tau = +inf)
     const float A = __fmaf_rn(-tau, q1.w, q0.z), B = __fmaf_rn(-tau, q2.x, q0.w), C = __fmaf_rn(-tau, q2.y, q1.x);
     const float D = -tau * q1.y, E = -tau * q1.z, F0 = -tau;
-    const float x0 = bx0 - q0.x, x1 = x0 + 7.0f, y0 = by0 - q0.y, y1 = y0 + 7.0f;
+    const float x0 = bx0 - q0.x, x1 = bx1 - q0.x, y0 = by0 - q0.y, y1 = by1 - q0.y;
     const float det = 4.0f * A * C - B * B;
     if (!(A < 0.0f && C < 0.0f && det > 0.0f)) return true;
     const float idet = 1.0f / det;

@@ -536,16 +536,21 @@ ORC_API int orc_projection_ut(
     uint32_t image_width, uint32_t image_height,
     float eps2d_f, float near_plane, float far_plane, float radius_clip,
     int camera_model, OrcUTParams ut, int global_shutter,
-    const float *radial, const float *tangential, const float *thin_prism,
+    const float *radial, int n_radial, const float *tangential, int n_tangential, const float *thin_prism,
+    int n_thin_prism,
     int32_t *radii, float *means2d, float *depths, float *conics, float *compensations /*nullable*/) {
-    if (camera_model != ORC_PINHOLE || radial || tangential || thin_prism || viewmats1 || !global_shutter)
-        return ORC_E_UNSUPPORTED;
+    if ((camera_model != ORC_PINHOLE && camera_model != ORC_FISHEYE) || viewmats1 || !global_shutter)
+        return ORC_E_UNSUPPORTED; /* rolling shutter / ortho: not restated */
     const real eps2d = eps2d_f;
     for (uint32_t cid = 0; cid < C; ++cid) {
         const real fx = Ks[cid * 9 + 0], fy = Ks[cid * 9 + 4];
         const real cx = Ks[cid * 9 + 2], cy = Ks[cid * 9 + 5];
         const Pose start = pose_from_viewmat(viewmats0 + cid * 16);
         const Pose mid = interpolate_pose_global(start, (real)0.5);
+        const CamModel cm = cam_model_make(camera_model, image_width, image_height, Ks + cid * 9,
+                                           radial ? radial + cid * n_radial : NULL, n_radial,
+                                           tangential ? tangential + cid * n_tangential : NULL, n_tangential,
+                                           thin_prism ? thin_prism + cid * n_thin_prism : NULL, n_thin_prism);
 #pragma omp parallel for num_threads(g_threads) schedule(static)
         for (uint32_t gid = 0; gid < N; ++gid) {
             const uint64_t idx = (uint64_t)cid * N + gid;
@@ -589,8 +594,7 @@ ORC_API int orc_projection_ut(
             for (int i = 0; i < 7; ++i) {
                 v3 cam = v3_add(quat_rotate(start.q, pts[i]), start.t);
                 real px, py;
-                int pv = pinhole_project(cam, fx, fy, cx, cy, image_width, image_height,
-                                         (real)ut.in_image_margin_factor, &px, &py);
+                int pv = cam_project(&cm, cam, (real)ut.in_image_margin_factor, &px, &py);
                 if (ut.require_all_sigma_points_valid) {
                     valid &= pv;
                     if (!pv) { early = 1; break; }
@@ -985,18 +989,16 @@ ORC_API int orc_isect_offsets(int64_t n_isects, const int64_t *isect_ids, uint32
 
 typedef struct { v3 o, d; int valid; } Ray;
 
-/* Cameras.cuh:322-339,457-470,261-265 (perfect pinhole, global shutter:
- * shutter_relative_frame_time == 0, :297-317) */
-static Ray pixel_ray(real px, real py, real fx, real fy, real cx, real cy, Pose start) {
-    real u = (px - cx) / fx, v = (py - cy) / fy;
-    real len = R_SQRT(u * u + v * v + (real)1);
-    v3 cam = v3_make(u / len, v / len, (real)1 / len);
+/* Cameras.cuh:322-339,261-265 (global shutter: shutter_relative_frame_time == 0, :297-317) */
+static Ray pixel_ray(real px, real py, const CamModel *cm, Pose start) {
+    v3 cam;
+    Ray r;
+    r.valid = cam_unproject(cm, px, py, &cam);
+    if (!r.valid) { r.o = v3_make(0, 0, 0); r.d = v3_make(0, 0, 0); return r; }
     Pose p = interpolate_pose_global(start, (real)0);
     m3 R_inv = mat3_cast(quat_inverse(p.q));
-    Ray r;
     r.o = m3_mulv(&R_inv, v3_scale(p.t, (real)-1));
     r.d = m3_mulv(&R_inv, cam);
-    r.valid = 1;
     return r;
 }
 
@@ -1042,9 +1044,11 @@ ORC_API int orc_raster_fwd(
     const float *opacities, const float *backgrounds, const uint8_t *masks,
     uint32_t image_width, uint32_t image_height, uint32_t tile_size,
     const float *viewmats0, const float *Ks, int camera_model,
+    const float *radial, int n_radial, const float *tangential, int n_tangential, const float *thin_prism,
+    int n_thin_prism,
     const int32_t *tile_offsets, const int32_t *flatten_ids,
     float *render_colors, float *render_alphas, int32_t *last_ids) {
-    if (camera_model != ORC_PINHOLE) return ORC_E_UNSUPPORTED;
+    if (camera_model != ORC_PINHOLE && camera_model != ORC_FISHEYE) return ORC_E_UNSUPPORTED;
     (void)N;
     const uint32_t tile_width = (image_width + tile_size - 1) / tile_size;
     const uint32_t tile_height = (image_height + tile_size - 1) / tile_size;
@@ -1052,6 +1056,10 @@ ORC_API int orc_raster_fwd(
         const real fx = Ks[cid * 9 + 0], fy = Ks[cid * 9 + 4];
         const real cx = Ks[cid * 9 + 2], cy = Ks[cid * 9 + 5];
         const Pose start = pose_from_viewmat(viewmats0 + cid * 16);
+        const CamModel cm = cam_model_make(camera_model, image_width, image_height, Ks + cid * 9,
+                                           radial ? radial + cid * n_radial : NULL, n_radial,
+                                           tangential ? tangential + cid * n_tangential : NULL, n_tangential,
+                                           thin_prism ? thin_prism + cid * n_thin_prism : NULL, n_thin_prism);
         const int32_t *toff = tile_offsets + (uint64_t)cid * tile_height * tile_width;
         float *rc = render_colors + (uint64_t)cid * image_height * image_width * 3;
         float *ra = render_alphas + (uint64_t)cid * image_height * image_width;
@@ -1081,11 +1089,11 @@ ORC_API int orc_raster_fwd(
                             for (int k = 0; k < 3; ++k) rc[pix * 3 + k] = bg ? bg[k] : 0.0f;
                             continue;
                         }
-                        const Ray ray = pixel_ray((real)j + (real)0.5, (real)i + (real)0.5, fx, fy, cx, cy, start);
+                        const Ray ray = pixel_ray((real)j + (real)0.5, (real)i + (real)0.5, &cm, start);
                         real T = 1;
                         uint32_t cur_idx = 0;
                         real pix_out[3] = {0, 0, 0};
-                        for (int32_t k = 0; k < cnt; ++k) {
+                        for (int32_t k = 0; k < cnt && ray.valid; ++k) { /* done = !inside || !ray.valid (:139) */
                             const int32_t g = flatten_ids[range_start + k];
                             const real opac = opacities[g];
                             const v3 xyz = v3_make(means[g * 3], means[g * 3 + 1], means[g * 3 + 2]);
@@ -1163,11 +1171,13 @@ ORC_API int orc_raster_bwd(
     const float *opacities, const float *backgrounds, const uint8_t *masks,
     uint32_t image_width, uint32_t image_height, uint32_t tile_size,
     const float *viewmats0, const float *Ks, int camera_model,
+    const float *radial, int n_radial, const float *tangential, int n_tangential, const float *thin_prism,
+    int n_thin_prism,
     const int32_t *tile_offsets, const int32_t *flatten_ids,
     const float *render_alphas, const int32_t *last_ids,
     const float *v_render_colors, const float *v_render_alphas,
     double *v_means, double *v_quats, double *v_scales, double *v_colors, double *v_opacities) {
-    if (camera_model != ORC_PINHOLE) return ORC_E_UNSUPPORTED;
+    if (camera_model != ORC_PINHOLE && camera_model != ORC_FISHEYE) return ORC_E_UNSUPPORTED;
     (void)N;
     if (n_isects == 0) return ORC_OK;
     const uint32_t tile_width = (image_width + tile_size - 1) / tile_size;
@@ -1176,6 +1186,10 @@ ORC_API int orc_raster_bwd(
         const real fx = Ks[cid * 9 + 0], fy = Ks[cid * 9 + 4];
         const real cx = Ks[cid * 9 + 2], cy = Ks[cid * 9 + 5];
         const Pose start = pose_from_viewmat(viewmats0 + cid * 16);
+        const CamModel cm = cam_model_make(camera_model, image_width, image_height, Ks + cid * 9,
+                                           radial ? radial + cid * n_radial : NULL, n_radial,
+                                           tangential ? tangential + cid * n_tangential : NULL, n_tangential,
+                                           thin_prism ? thin_prism + cid * n_thin_prism : NULL, n_thin_prism);
         const int32_t *toff = tile_offsets + (uint64_t)cid * tile_height * tile_width;
         const float *ra_ = render_alphas + (uint64_t)cid * image_height * image_width;
         const int32_t *li = last_ids + (uint64_t)cid * image_height * image_width;
@@ -1196,7 +1210,8 @@ ORC_API int orc_raster_bwd(
                         const uint32_t i = ty * tile_size + iy, j = tx * tile_size + ix;
                         if (!(i < image_height && j < image_width)) continue;
                         const uint64_t pix = (uint64_t)i * image_width + j;
-                        const Ray ray = pixel_ray((real)j + (real)0.5, (real)i + (real)0.5, fx, fy, cx, cy, start);
+                        const Ray ray = pixel_ray((real)j + (real)0.5, (real)i + (real)0.5, &cm, start);
+                        if (!ray.valid) continue; /* Bwd.cu:151: such pixels are never valid */
                         const real T_final = (real)1 - (real)ra_[pix];
                         real T = T_final;
                         real buffer[3] = {0, 0, 0};

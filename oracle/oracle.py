@@ -104,9 +104,23 @@ def _check(rc: int, what: str) -> None:
         raise RuntimeError(f"oracle {what} failed with code {rc} (1 = unsupported configuration)")
 
 
+def _dist(radial, tangential, thin_prism, Cn):
+    """(pointer, floats-per-camera) triples for the optional distortion coefficient arrays."""
+    out, keep = [], []
+    for a in (radial, tangential, thin_prism):
+        if a is None:
+            out += [None, C.c_int(0)]
+        else:
+            a = np.ascontiguousarray(a, dtype=np.float32).reshape(Cn, -1)
+            keep.append(a)
+            out += [_ptr(a), C.c_int(a.shape[1])]
+    return out, keep
+
+
 def projection_ut(means, quats, scales, opacities, viewmats, Ks, width, height, eps2d=0.3,
                   near_plane=0.01, far_plane=1e10, radius_clip=0.0, calc_compensations=False,
-                  camera_model=PINHOLE, ut: UTParams | None = None, precision="f32"):
+                  camera_model=PINHOLE, ut: UTParams | None = None, precision="f32", radial=None, tangential=None,
+                  thin_prism=None):
     """gsplat::projection_ut_3dgs_fused (Ops.h:69-98). Returns radii, means2d, depths, conics,
     compensations (or None). Rows with radii == 0 hold zeros here (garbage in the reference)."""
     means, quats, scales = _f32(means), _f32(quats), _f32(scales)
@@ -119,11 +133,12 @@ def projection_ut(means, quats, scales, opacities, viewmats, Ks, width, height, 
     conics = np.zeros((Cn, N, 3), np.float32)
     comp = np.zeros((Cn, N), np.float32) if calc_compensations else None
     ut = ut or UTParams()
+    dist, _keep = _dist(radial, tangential, thin_prism, Cn)
     rc = lib(precision).orc_projection_ut(
         C.c_uint32(Cn), C.c_uint32(N), _ptr(means), _ptr(quats), _ptr(scales), _ptr(opacities),
         _ptr(viewmats), None, _ptr(Ks), C.c_uint32(width), C.c_uint32(height),
         C.c_float(eps2d), C.c_float(near_plane), C.c_float(far_plane), C.c_float(radius_clip),
-        C.c_int(camera_model), ut.c(), C.c_int(1), None, None, None,
+        C.c_int(camera_model), ut.c(), C.c_int(1), *dist,
         _ptr(radii, C.c_int32), _ptr(means2d), _ptr(depths), _ptr(conics), _ptr(comp))
     _check(rc, "projection_ut")
     return radii, means2d, depths, conics, comp
@@ -188,7 +203,7 @@ def isect_offsets(isect_ids, Cn, tile_width, tile_height):
 
 def raster_fwd(means, quats, scales, colors, opacities, backgrounds, masks, width, height,
                tile_size, viewmats, Ks, tile_offsets, flatten_ids, camera_model=PINHOLE,
-               precision="f32"):
+               precision="f32", radial=None, tangential=None, thin_prism=None):
     """gsplat::rasterize_to_pixels_from_world_3dgs_fwd (Ops.h:100-129)."""
     means, quats, scales = _f32(means), _f32(quats), _f32(scales)
     colors, opacities = _f32(colors), _f32(opacities)
@@ -205,15 +220,16 @@ def raster_fwd(means, quats, scales, colors, opacities, backgrounds, masks, widt
         C.c_uint32(Cn), C.c_uint32(N), C.c_int64(flat.shape[0]), _ptr(means), _ptr(quats),
         _ptr(scales), _ptr(colors), _ptr(opacities), _ptr(bg), _ptr(m, C.c_uint8),
         C.c_uint32(width), C.c_uint32(height), C.c_uint32(tile_size), _ptr(viewmats), _ptr(Ks),
-        C.c_int(camera_model), _ptr(toff, C.c_int32), _ptr(flat, C.c_int32), _ptr(renders),
-        _ptr(alphas), _ptr(last_ids, C.c_int32))
+        C.c_int(camera_model), *_dist(radial, tangential, thin_prism, Cn)[0], _ptr(toff, C.c_int32),
+        _ptr(flat, C.c_int32), _ptr(renders), _ptr(alphas), _ptr(last_ids, C.c_int32))
     _check(rc, "raster_fwd")
     return renders, alphas, last_ids
 
 
 def raster_bwd(means, quats, scales, colors, opacities, backgrounds, masks, width, height,
                tile_size, viewmats, Ks, tile_offsets, flatten_ids, render_alphas, last_ids,
-               v_render_colors, v_render_alphas, camera_model=PINHOLE, precision="f32"):
+               v_render_colors, v_render_alphas, camera_model=PINHOLE, precision="f32", radial=None, tangential=None,
+               thin_prism=None):
     """gsplat::rasterize_to_pixels_from_world_3dgs_bwd (Ops.h:131-165); float64 gradients."""
     means, quats, scales = _f32(means), _f32(quats), _f32(scales)
     colors, opacities = _f32(colors), _f32(opacities)
@@ -235,7 +251,8 @@ def raster_bwd(means, quats, scales, colors, opacities, backgrounds, masks, widt
         C.c_uint32(Cn), C.c_uint32(N), C.c_int64(flat.shape[0]), _ptr(means), _ptr(quats),
         _ptr(scales), _ptr(colors), _ptr(opacities), _ptr(bg), _ptr(m, C.c_uint8),
         C.c_uint32(width), C.c_uint32(height), C.c_uint32(tile_size), _ptr(viewmats), _ptr(Ks),
-        C.c_int(camera_model), _ptr(toff, C.c_int32), _ptr(flat, C.c_int32), _ptr(ra),
+        C.c_int(camera_model), *_dist(radial, tangential, thin_prism, Cn)[0], _ptr(toff, C.c_int32),
+        _ptr(flat, C.c_int32), _ptr(ra),
         _ptr(li, C.c_int32), _ptr(vrc), _ptr(vra), _ptr(v_means, D), _ptr(v_quats, D),
         _ptr(v_scales, D), _ptr(v_colors, D), _ptr(v_opac, D))
     _check(rc, "raster_bwd")

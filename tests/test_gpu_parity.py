@@ -319,8 +319,74 @@ def test_strategy_helpers_vs_oracle(native, orc, cuda_device):
 def test_unsupported_configurations_fail_loudly(native, cuda_device):
     sc = scenes.scene_small(N=64)
     t = to_dev(sc, cuda_device)
-    with pytest.raises(RuntimeError, match="not supported"):
+    with pytest.raises(RuntimeError, match="not supported"):  # orthographic: rejected by the reference too
         native.projection_ut_3dgs_fused(t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"],
-                                        sc["width"], sc["height"], camera_model=native.FISHEYE)
+                                        sc["width"], sc["height"], camera_model=native.ORTHO)
+    with pytest.raises(RuntimeError, match="not supported"):  # rolling shutter (second pose given)
+        native.projection_ut_3dgs_fused(t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"],
+                                        sc["width"], sc["height"], viewmats1=t["viewmats"], rs_type=0)
     with pytest.raises(RuntimeError, match="CUDA"):
         native.quats_to_rotmats(torch.randn(4, 4))
+
+
+# ------------------------------------------------------------------------------------------
+# a2: distorted camera models (OpenCV pinhole with radial/tangential/thin-prism, OpenCV fisheye)
+# ------------------------------------------------------------------------------------------
+DISTORTED = {
+    "opencv": dict(camera_model=0, radial=np.array([[-0.12, 0.05, 0.002, 0.01, -0.003, 0.0005]], np.float32),
+                   tangential=np.array([[0.002, -0.001]], np.float32),
+                   thin_prism=np.array([[0.001, 0.0002, -0.0005, 0.0001]], np.float32)),
+    "fisheye": dict(camera_model=2, radial=np.array([[0.03, -0.004, 0.0007, -0.0001]], np.float32), tangential=None,
+                    thin_prism=None),
+}
+
+
+@pytest.mark.parametrize("model", ["opencv", "fisheye"])
+def test_distorted_camera_whole_path_vs_oracle(native, orc, cuda_device, model):
+    cfg = DISTORTED[model]
+    sc = scenes.scene_small(N=2500, width=208, height=128, view=2)
+    W, H = sc["width"], sc["height"]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    okw = dict(camera_model=cfg["camera_model"], radial=cfg["radial"], tangential=cfg["tangential"],
+               thin_prism=cfg["thin_prism"])
+    dev = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
+    nkw = dict(camera_model=cfg["camera_model"], radial_coeffs=dev(cfg["radial"]), tangential_coeffs=dev(cfg["tangential"]),
+               thin_prism_coeffs=dev(cfg["thin_prism"]))
+    t = to_dev(sc, cuda_device)
+    # projection
+    r_ref, m_ref, d_ref, c_ref, _ = orc.projection_ut(sc["means"], sc["quats"], sc["scales"], sc["opacities"],
+                                                      sc["viewmats"], sc["Ks"], W, H, 0.3, 0.01, 1e4, 0.0, **okw)
+    radii, means2d, depths, conics, _ = native.projection_ut_3dgs_fused(
+        t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"], W, H, 0.3, 0.01, 1e4, 0.0, **nkw)
+    mism = int((radii.cpu().numpy() != r_ref).any(-1).sum())
+    assert mism <= 3, mism
+    both = (radii.cpu().numpy() > 0).all(-1) & (r_ref > 0).all(-1)
+    assert both.sum() > 1000
+    assert rel(means2d.cpu().numpy()[both], m_ref[both]) < 1e-4
+    # blend forward / backward on the oracle's lists
+    tpg, ids, flat = orc.isect_tiles(m_ref, r_ref, d_ref, 1, 16, tw, th)
+    off = orc.isect_offsets(ids, 1, tw, th)
+    rng = np.random.default_rng(21)
+    colors = rng.random((1, sc["means"].shape[0], 3), dtype=np.float32)
+    vrc = rng.standard_normal((1, H, W, 3)).astype(np.float32)
+    vra = rng.standard_normal((1, H, W, 1)).astype(np.float32)
+    img, alp, li = orc.raster_fwd(sc["means"], sc["quats"], sc["scales"], colors, sc["opacities"][None],
+                                  sc["background"], None, W, H, 16, sc["viewmats"], sc["Ks"], off, flat, **okw)
+    fa = (t["means"], t["quats"], t["scales"], torch.from_numpy(colors).to(cuda_device), t["opacities"][None],
+          t["background"], None, W, H, 16, t["viewmats"], t["Ks"], torch.from_numpy(off).to(cuda_device),
+          torch.from_numpy(flat).to(cuda_device))
+    r, a, l = native.rasterize_to_pixels_from_world_3dgs_fwd(*fa, **nkw)
+    e = rel(r.cpu().numpy(), img)
+    print(f"[{model}] image rel_l2 {e:.2e}, last_ids differ {(l.cpu().numpy() != li).mean():.2e}")
+    assert e < 1e-4 and rel(a.cpu().numpy(), alp) < 1e-4
+    assert (l.cpu().numpy() != li).mean() < 3e-3
+    g_ref = orc.raster_bwd(sc["means"], sc["quats"], sc["scales"], colors, sc["opacities"][None], sc["background"], None,
+                           W, H, 16, sc["viewmats"], sc["Ks"], off, flat, alp, li, vrc, vra, precision="f64", **okw)
+    g = native.rasterize_to_pixels_from_world_3dgs_bwd(*fa, torch.from_numpy(alp).to(cuda_device),
+                                                       torch.from_numpy(li).to(cuda_device),
+                                                       torch.from_numpy(vrc).to(cuda_device),
+                                                       torch.from_numpy(vra).to(cuda_device), **nkw)
+    for nm, got, want in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), g, g_ref):
+        eg = rel(got.cpu().numpy().reshape(want.shape), want)
+        print(f"[{model}] {nm}: rel_l2 vs f64 oracle {eg:.2e}")
+        assert eg < 1e-3, (nm, eg)

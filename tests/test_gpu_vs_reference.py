@@ -186,3 +186,56 @@ def test_dump_reference_golden(ref, cuda_device):
         last_ids=li.cpu().numpy(), v_render_colors=vrc.cpu().numpy(), v_render_alphas=vra.cpu().numpy(),
         v_means=g[0].cpu().numpy(), v_quats=g[1].cpu().numpy(), v_scales=g[2].cpu().numpy(),
         v_colors=g[3].cpu().numpy(), v_opacities=g[4].cpu().numpy())
+
+
+DISTORTED = {
+    "opencv": dict(camera_model=0, radial=np.array([[-0.12, 0.05, 0.002, 0.01, -0.003, 0.0005]], np.float32),
+                   tangential=np.array([[0.002, -0.001]], np.float32),
+                   thin_prism=np.array([[0.001, 0.0002, -0.0005, 0.0001]], np.float32)),
+    "fisheye": dict(camera_model=2, radial=np.array([[0.03, -0.004, 0.0007, -0.0001]], np.float32), tangential=None,
+                    thin_prism=None),
+}
+
+
+@pytest.mark.parametrize("model", ["opencv", "fisheye"])
+def test_distorted_cameras_reference_vs_b200(native, ref, cuda_device, model):
+    """OpenCV pinhole with all 6+2+4 distortion coefficients (the only distorted pinhole layout whose reads
+    are in bounds in the reference) and the 4-coefficient fisheye."""
+    cfg = DISTORTED[model]
+    sc = scenes.scene_small(N=3000, width=208, height=128, view=2)
+    W, H = sc["width"], sc["height"]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    dev = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
+    kw = dict(camera_model=cfg["camera_model"], radial_coeffs=dev(cfg["radial"]), tangential_coeffs=dev(cfg["tangential"]),
+              thin_prism_coeffs=dev(cfg["thin_prism"]))
+    t = to_dev(sc, cuda_device)
+    pa = (t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"], W, H, 0.3, 0.01, 1e4, 0.0)
+    r_ref, m_ref, d_ref, c_ref, _ = ref.projection_ut_3dgs_fused(*pa, **kw)
+    r_new, m_new, d_new, c_new, _ = native.projection_ut_3dgs_fused(*pa, **kw)
+    mism = int((r_ref != r_new).any(-1).sum())
+    both = ((r_ref > 0).all(-1) & (r_new > 0).all(-1)).cpu().numpy()
+    em = rel(m_new.cpu().numpy()[both], m_ref.cpu().numpy()[both])
+    print(f"[{model}] radii differ {mism}/{r_ref.shape[1]}, means2d rel {em:.2e}, visible {both.sum()}")
+    assert mism <= 4 and em < 1e-4 and both.sum() > 1000
+    vis = (r_ref > 0).all(-1)
+    m2 = torch.where(vis[..., None], m_ref, torch.zeros_like(m_ref))
+    dp = torch.where(vis, d_ref, torch.zeros_like(d_ref))
+    _, ids, flat = ref.intersect_tile(m2, r_ref, dp, 1, 16, tw, th, True)
+    off = ref.intersect_offset(ids, 1, tw, th)
+    rng = np.random.default_rng(5)
+    colors = torch.from_numpy(rng.random((1, sc["means"].shape[0], 3), dtype=np.float32)).to(cuda_device)
+    fa = (t["means"], t["quats"], t["scales"], colors, t["opacities"][None], t["background"], None, W, H, 16,
+          t["viewmats"], t["Ks"], off, flat)
+    rr, ar, lr = ref.rasterize_to_pixels_from_world_3dgs_fwd(*fa, **kw)
+    rn, an, ln = native.rasterize_to_pixels_from_world_3dgs_fwd(*fa, **kw)
+    e = rel(rn.cpu().numpy(), rr.cpu().numpy())
+    print(f"[{model}] image rel_l2 b200 vs reference {e:.2e}; last_ids differ {float((ln != lr).float().mean()):.2e}")
+    assert e < 1e-4 and rel(an.cpu().numpy(), ar.cpu().numpy()) < 1e-4
+    vr = torch.from_numpy(rng.standard_normal((1, H, W, 3)).astype(np.float32)).to(cuda_device)
+    va = torch.from_numpy(rng.standard_normal((1, H, W, 1)).astype(np.float32)).to(cuda_device)
+    g_ref = ref.rasterize_to_pixels_from_world_3dgs_bwd(*fa, ar, lr, vr, va, **kw)
+    g_new = native.rasterize_to_pixels_from_world_3dgs_bwd(*fa, ar, lr, vr, va, **kw)
+    for nm, a, b in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), g_new, g_ref):
+        eg = rel(a.cpu().numpy(), b.cpu().numpy())
+        print(f"[{model}] {nm}: b200 vs reference {eg:.2e}")
+        assert eg < 1e-3, (nm, eg)
