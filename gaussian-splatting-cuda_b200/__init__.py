@@ -205,11 +205,13 @@ class GUTRasterizationFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, backend: OpsBackend, means, quats, scales, colors, opacities, bg, viewmat, K, isect_offsets,
-                flatten_ids, width, height, tile_size):
+                flatten_ids, width, height, tile_size, camera=None):
+        camera = camera or {}
         renders, alphas, last_ids = backend.rasterize_to_pixels_from_world_3dgs_fwd(
             means.contiguous(), quats.contiguous(), scales.contiguous(), colors.contiguous(),
             opacities.contiguous(), bg, None, width, height, tile_size, viewmat.contiguous(), K.contiguous(),
-            isect_offsets.contiguous(), flatten_ids.contiguous())
+            isect_offsets.contiguous(), flatten_ids.contiguous(), **camera)
+        ctx.camera = camera
         ctx.save_for_backward(means, quats, scales, colors, opacities, bg if bg is not None else torch.empty(0),
                               viewmat, K, isect_offsets, flatten_ids, alphas, last_ids)
         ctx.dims = (width, height, tile_size, bg is not None)
@@ -224,11 +226,11 @@ class GUTRasterizationFunction(torch.autograd.Function):
         g = ctx.backend.rasterize_to_pixels_from_world_3dgs_bwd(
             means, quats, scales, colors, opacities, bg if has_bg else None, None, width, height, tile_size, viewmat,
             K, isect_offsets, flatten_ids, alphas, last_ids, v_render_colors.contiguous(),
-            v_render_alphas.contiguous())
+            v_render_alphas.contiguous(), **ctx.camera)
         v_bg = None
         if has_bg and ctx.needs_input_grad[6]:
             v_bg = (v_render_colors * (1.0 - alphas)).sum(dim=(-3, -2))
-        return None, g[0], g[1], g[2], g[3], g[4], v_bg, None, None, None, None, None, None, None
+        return None, g[0], g[1], g[2], g[3], g[4], v_bg, None, None, None, None, None, None, None, None
 
 
 @dataclass
@@ -249,19 +251,24 @@ class RenderOutput:
 
 def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K, width, height, bg_color=None,
               scaling_modifier=1.0, tile_size=16, eps2d=0.3, near_plane=0.01, far_plane=10000.0,
-              radius_clip=0.0, backend: OpsBackend | None = None) -> RenderOutput:
+              radius_clip=0.0, backend: OpsBackend | None = None, camera_model=PINHOLE, radial_coeffs=None,
+              tangential_coeffs=None, thin_prism_coeffs=None) -> RenderOutput:
     """gs::training::rasterize for RenderMode::RGB, perfect pinhole, C == 1 (rasterizer.cpp:46-437).
 
     Inputs are the ACTIVATED parameters (get_means/get_rotation/get_scaling/get_opacity/get_shs of
     SplatData): means [N,3], unit quats [N,4] (w,x,y,z), scales [N,3] > 0, opacities [N] in (0,1),
-    sh_coeffs [N,K,3]; viewmat [1,4,4], K [1,3,3]; bg_color [1,3] or None.
+    sh_coeffs [N,K,3]; viewmat [1,4,4], K [1,3,3]; bg_color [1,3] or None.  Distortion coefficients as the
+    reference's Camera supplies them (rasterizer.cpp:183-206); camera_model PINHOLE or FISHEYE.
     """
     be = backend or _DEFAULT
+    camera = dict(camera_model=camera_model, radial_coeffs=radial_coeffs, tangential_coeffs=tangential_coeffs,
+                  thin_prism_coeffs=thin_prism_coeffs)
     scaled = scales * scaling_modifier if scaling_modifier != 1.0 else scales
     with torch.no_grad():  # "none differentiable" (Ops.h:67)
         radii, means2d, depths, _conics, _ = be.projection_ut_3dgs_fused(
             means.detach().contiguous(), quats.detach().contiguous(), scaled.detach().contiguous(),
-            opacities.detach().contiguous(), viewmat, K, width, height, eps2d, near_plane, far_plane, radius_clip)
+            opacities.detach().contiguous(), viewmat, K, width, height, eps2d, near_plane, far_plane, radius_clip,
+            **camera)
         campos = torch.linalg.inv(viewmat)[:, :3, 3]                     # rasterizer.cpp:250-251
         masks = (radii > 0).all(-1)                                      # :257
     dirs = means.unsqueeze(0) - campos.unsqueeze(1)                      # :254
@@ -274,7 +281,7 @@ def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K,
         offsets = be.intersect_offset(isect_ids, 1, tile_w, tile_h)
     renders, alphas = GUTRasterizationFunction.apply(be, means, quats, scaled, colors, opacities.unsqueeze(0),
                                                      bg_color, viewmat, K, offsets, flatten_ids, width, height,
-                                                     tile_size)
+                                                     tile_size, camera)
     return RenderOutput(
         image=torch.clamp(renders[0].permute(2, 0, 1), 0.0, 1.0), alpha=alphas[0].permute(2, 0, 1),
         render_colors=renders, radii=radii[0].max(-1).values, depths=depths[0], means2d=means2d,
