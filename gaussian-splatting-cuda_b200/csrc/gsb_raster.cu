@@ -50,8 +50,8 @@ __global__ void __launch_bounds__(kPrepThreads) prep_records_kernel(uint32_t N, 
                            quats[(size_t)g * 4 + 3]};
     const float scale[3] = {scales[(size_t)g * 3], scales[(size_t)g * 3 + 1], scales[(size_t)g * 3 + 2]};
     const float opac = opacities[g];
-    GaussGeom gg;
-    gauss_geom(cam, mean, quat, scale, gg);
+    GaussGeom<double> gg;
+    gauss_geom<double>(cam, mean, quat, scale, gg);
     float4 v0, v1, v2, v3;
     v3 = make_float4(colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2], __int_as_float((int)g));
     const bool dead = gg.degenerate || !(opac > 0.f);
@@ -519,6 +519,9 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
 // ------------------------------------------------------------------------------------------
 // finalize: moments -> gradients (float64 chain rule, once per Gaussian)
 // ------------------------------------------------------------------------------------------
+// chain-rule arithmetic type of finalize (float: validated against the f64 oracle, profiles/r1_parity.md)
+typedef float FT;
+
 __global__ void __launch_bounds__(kPrepThreads) finalize_grads_kernel(
     uint32_t N, const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
     const float *__restrict__ opacities, const float *__restrict__ viewmat, const float *__restrict__ K,
@@ -551,73 +554,73 @@ __global__ void __launch_bounds__(kPrepThreads) finalize_grads_kernel(
         const float quat[4] = {quats[(size_t)g * 4], quats[(size_t)g * 4 + 1], quats[(size_t)g * 4 + 2],
                                quats[(size_t)g * 4 + 3]};
         const float scale[3] = {scales[(size_t)g * 3], scales[(size_t)g * 3 + 1], scales[(size_t)g * 3 + 2]};
-        GaussGeom gg;
-        gauss_geom(cam, mean, quat, scale, gg);
+        GaussGeom<FT> gg;
+        gauss_geom<FT>(cam, mean, quat, scale, gg);
         if (!gg.degenerate) {
             const float4 *r4 = reinterpret_cast<const float4 *>(recs + g);
             const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
-            const double cn0 = q0.z, cn1 = q0.w, cn2 = q1.x;
-            const double cd1 = q1.y, cd2 = q1.z, cd3 = q1.w, cd4 = q2.x, cd5 = q2.y;
-            const double M0 = m[0], M1 = m[1], M2 = m[2], M3_ = m[3], M4 = m[4], M5 = m[5], M6 = m[6], M7 = m[7],
+            const FT cn0 = q0.z, cn1 = q0.w, cn2 = q1.x;
+            const FT cd1 = q1.y, cd2 = q1.z, cd3 = q1.w, cd4 = q2.x, cd5 = q2.y;
+            const FT M0 = m[0], M1 = m[1], M2 = m[2], M3_ = m[3], M4 = m[4], M5 = m[5], M6 = m[6], M7 = m[7],
                          M8 = m[8], M9 = m[9], M10 = m[10];
-            const double ax = 1.0 / cam.fx, ay = 1.0 / cam.fy;
-            const double id0 = 1.0 / gg.d0;
-            const double kk = -0.5 * 1.4426950408889634;
+            const FT ax = FT(1) / (FT)cam.fx, ay = FT(1) / (FT)cam.fy;
+            const FT id0 = FT(1) / gg.d0;
+            const FT kk = FT(-0.5 * 1.4426950408889634);
             // gradients w.r.t. the projected centre (pixels -> normalised image coordinates)
-            const double vpcx = -(2.0 * cn0 * M0 + cn1 * M1 + cd1 * M5 + 2.0 * cd3 * M6 + cd4 * M7);
-            const double vpcy = -(cn1 * M0 + 2.0 * cn2 * M1 + cd2 * M5 + cd4 * M6 + 2.0 * cd5 * M7);
-            double vuc = cam.fx * vpcx, vvc = cam.fy * vpcy;
+            const FT vpcx = -(FT(2) * cn0 * M0 + cn1 * M1 + cd1 * M5 + FT(2) * cd3 * M6 + cd4 * M7);
+            const FT vpcy = -(cn1 * M0 + FT(2) * cn2 * M1 + cd2 * M5 + cd4 * M6 + FT(2) * cd5 * M7);
+            FT vuc = (FT)cam.fx * vpcx, vvc = (FT)cam.fy * vpcy;
             // gradients w.r.t. the un-normalised quadratic-form coefficients
-            const double vn0 = M2 * kk * ax * ax * id0, vn1 = M3_ * kk * ax * ay * id0, vn2 = M4 * kk * ay * ay * id0;
-            const double vd1 = M6 * ax * id0, vd2 = M7 * ay * id0, vd3 = M8 * ax * ax * id0, vd4 = M9 * ax * ay * id0,
+            const FT vn0 = M2 * kk * ax * ax * id0, vn1 = M3_ * kk * ax * ay * id0, vn2 = M4 * kk * ay * ay * id0;
+            const FT vd1 = M6 * ax * id0, vd2 = M7 * ay * id0, vd3 = M8 * ax * ax * id0, vd4 = M9 * ax * ay * id0,
                          vd5 = M10 * ay * ay * id0;
-            const double vd0 = -(cn0 * M2 + cn1 * M3_ + cn2 * M4 + cd1 * M6 + cd2 * M7 + cd3 * M8 + cd4 * M9 + cd5 * M10) * id0;
+            const FT vd0 = -(cn0 * M2 + cn1 * M3_ + cn2 * M4 + cd1 * M6 + cd2 * M7 + cd3 * M8 + cd4 * M9 + cd5 * M10) * id0;
             // n = (E0.E0, 2 E0.E1, E1.E1), d = (G.G, 2 G.A0, 2 G.A1, A0.A0, 2 A0.A1, A1.A1)
-            const V3<double> vE0 = gg.E0 * (2.0 * vn0) + gg.E1 * (2.0 * vn1);
-            const V3<double> vE1 = gg.E1 * (2.0 * vn2) + gg.E0 * (2.0 * vn1);
-            V3<double> vG = gg.G * (2.0 * vd0) + gg.A0 * (2.0 * vd1) + gg.A1 * (2.0 * vd2);
-            V3<double> vA0 = gg.G * (2.0 * vd1) + gg.A0 * (2.0 * vd3) + gg.A1 * (2.0 * vd4) + cross(gg.gro, vE0);
-            V3<double> vA1 = gg.G * (2.0 * vd2) + gg.A1 * (2.0 * vd5) + gg.A0 * (2.0 * vd4) + cross(gg.gro, vE1);
-            const V3<double> vgro = cross(vE0, gg.A0) + cross(vE1, gg.A1);
+            const V3<FT> vE0 = gg.E0 * (FT(2) * vn0) + gg.E1 * (FT(2) * vn1);
+            const V3<FT> vE1 = gg.E1 * (FT(2) * vn2) + gg.E0 * (FT(2) * vn1);
+            V3<FT> vG = gg.G * (FT(2) * vd0) + gg.A0 * (FT(2) * vd1) + gg.A1 * (FT(2) * vd2);
+            V3<FT> vA0 = gg.G * (FT(2) * vd1) + gg.A0 * (FT(2) * vd3) + gg.A1 * (FT(2) * vd4) + cross(gg.gro, vE0);
+            V3<FT> vA1 = gg.G * (FT(2) * vd2) + gg.A1 * (FT(2) * vd5) + gg.A0 * (FT(2) * vd4) + cross(gg.gro, vE1);
+            const V3<FT> vgro = cross(vE0, gg.A0) + cross(vE1, gg.A1);
             vG = vG - vgro * gg.zc;
-            double vzc = -dot(gg.G, vgro);
+            FT vzc = -dot(gg.G, vgro);
             vA0 = vA0 + vG * gg.uc;
             vA1 = vA1 + vG * gg.vc;
-            const V3<double> vA2 = vG;
+            const V3<FT> vA2 = vG;
             vuc += dot(gg.A0, vG);
             vvc += dot(gg.A1, vG);
-            const double iz = 1.0 / gg.zc;
-            const double vxc = vuc * iz, vyc = vvc * iz;
+            const FT iz = FT(1) / gg.zc;
+            const FT vxc = vuc * iz, vyc = vvc * iz;
             vzc += -(gg.uc * vuc + gg.vc * vvc) * iz;
             // mu_c = Binv mu + t
-            om[0] = (float)(cam.Binv[0][0] * vxc + cam.Binv[1][0] * vyc + cam.Binv[2][0] * vzc);
-            om[1] = (float)(cam.Binv[0][1] * vxc + cam.Binv[1][1] * vyc + cam.Binv[2][1] * vzc);
-            om[2] = (float)(cam.Binv[0][2] * vxc + cam.Binv[1][2] * vyc + cam.Binv[2][2] * vzc);
+            om[0] = (float)((FT)cam.Binv[0][0] * vxc + (FT)cam.Binv[1][0] * vyc + (FT)cam.Binv[2][0] * vzc);
+            om[1] = (float)((FT)cam.Binv[0][1] * vxc + (FT)cam.Binv[1][1] * vyc + (FT)cam.Binv[2][1] * vzc);
+            om[2] = (float)((FT)cam.Binv[0][2] * vxc + (FT)cam.Binv[1][2] * vyc + (FT)cam.Binv[2][2] * vzc);
             // A = M B  ->  vM = vA B^T ;  M[i][k] = Rg[k][i] / s_i
-            const double vA[3][3] = {{vA0.x, vA1.x, vA2.x}, {vA0.y, vA1.y, vA2.y}, {vA0.z, vA1.z, vA2.z}};
-            double vRg[3][3];
+            const FT vA[3][3] = {{vA0.x, vA1.x, vA2.x}, {vA0.y, vA1.y, vA2.y}, {vA0.z, vA1.z, vA2.z}};
+            FT vRg[3][3];
             for (int i = 0; i < 3; ++i) {
-                double vsi = 0.0;
+                FT vsi = FT(0);
                 for (int k = 0; k < 3; ++k) {
-                    const double vM = vA[i][0] * cam.B[k][0] + vA[i][1] * cam.B[k][1] + vA[i][2] * cam.B[k][2];
+                    const FT vM = vA[i][0] * (FT)cam.B[k][0] + vA[i][1] * (FT)cam.B[k][1] + vA[i][2] * (FT)cam.B[k][2];
                     vsi += vM * gg.Rg.m[k][i];
                     vRg[k][i] = vM * gg.inv_s[i];
                 }
                 os[i] = (float)(-vsi * gg.inv_s[i] * gg.inv_s[i]);
             }
             // quaternion VJP including the normalisation (Utils.cuh:104-126)
-            const double w = gg.qn[0], x = gg.qn[1], y = gg.qn[2], z = gg.qn[3];
-            double vq[4];
-            vq[0] = 2.0 * (x * (vRg[2][1] - vRg[1][2]) + y * (vRg[0][2] - vRg[2][0]) + z * (vRg[1][0] - vRg[0][1]));
-            vq[1] = 2.0 * (-2.0 * x * (vRg[1][1] + vRg[2][2]) + y * (vRg[1][0] + vRg[0][1]) + z * (vRg[2][0] + vRg[0][2]) +
+            const FT w = gg.qn[0], x = gg.qn[1], y = gg.qn[2], z = gg.qn[3];
+            FT vq[4];
+            vq[0] = FT(2) * (x * (vRg[2][1] - vRg[1][2]) + y * (vRg[0][2] - vRg[2][0]) + z * (vRg[1][0] - vRg[0][1]));
+            vq[1] = FT(2) * (-FT(2) * x * (vRg[1][1] + vRg[2][2]) + y * (vRg[1][0] + vRg[0][1]) + z * (vRg[2][0] + vRg[0][2]) +
                            w * (vRg[2][1] - vRg[1][2]));
-            vq[2] = 2.0 * (x * (vRg[1][0] + vRg[0][1]) - 2.0 * y * (vRg[0][0] + vRg[2][2]) + z * (vRg[2][1] + vRg[1][2]) +
+            vq[2] = FT(2) * (x * (vRg[1][0] + vRg[0][1]) - FT(2) * y * (vRg[0][0] + vRg[2][2]) + z * (vRg[2][1] + vRg[1][2]) +
                            w * (vRg[0][2] - vRg[2][0]));
-            vq[3] = 2.0 * (x * (vRg[2][0] + vRg[0][2]) + y * (vRg[2][1] + vRg[1][2]) - 2.0 * z * (vRg[0][0] + vRg[1][1]) +
+            vq[3] = FT(2) * (x * (vRg[2][0] + vRg[0][2]) + y * (vRg[2][1] + vRg[1][2]) - FT(2) * z * (vRg[0][0] + vRg[1][1]) +
                            w * (vRg[1][0] - vRg[0][1]));
-            const double dq = vq[0] * w + vq[1] * x + vq[2] * y + vq[3] * z;
+            const FT dq = vq[0] * w + vq[1] * x + vq[2] * y + vq[3] * z;
             for (int k = 0; k < 4; ++k) oq[k] = (float)((vq[k] - dq * gg.qn[k]) * gg.inv_qnorm);
-            oo = (opac > 0.f) ? (float)((double)m[11] / (double)opac) : 0.f; // sum vis * v_alpha
+            oo = (opac > 0.f) ? m[11] / opac : 0.f; // sum vis * v_alpha
         }
     }
     v_means[(size_t)g * 3] = om[0]; v_means[(size_t)g * 3 + 1] = om[1]; v_means[(size_t)g * 3 + 2] = om[2];

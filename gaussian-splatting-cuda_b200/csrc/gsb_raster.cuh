@@ -74,51 +74,54 @@ __device__ inline void cam_const_from(const float *viewmat, const float *K, CamC
     c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
 }
 
-// Geometry of one Gaussian in the camera-relative parametrisation (float64).
+// Geometry of one Gaussian in the camera-relative parametrisation.  T = double in prep (the projected
+// centre is cancellation-sensitive), T = float in finalize (the chain rule is not: see DESIGN.md 4.1).
+template <typename T>
 struct GaussGeom {
-    V3<double> A0, A1, A2, G, gro, E0, E1;
-    M3<double> Rg;       // rotation of the normalised quaternion (row-major math matrix)
-    double inv_s[3];
-    double qn[4], inv_qnorm;
-    double zc, uc, vc;
-    double n[3], d0, d[5];
+    V3<T> A0, A1, A2, G, gro, E0, E1;
+    M3<T> Rg;       // rotation of the normalised quaternion (row-major math matrix)
+    T inv_s[3];
+    T qn[4], inv_qnorm;
+    T zc, uc, vc;
+    T n[3], d0, d[5];
     bool degenerate;
 };
 
+template <typename T>
 __device__ inline void gauss_geom(const CamConst &c, const float *mean, const float *quat, const float *scale,
-                                  GaussGeom &g) {
-    const double qw = quat[0], qx = quat[1], qy = quat[2], qz = quat[3];
-    const double nn = qw * qw + qx * qx + qy * qy + qz * qz;
-    g.inv_qnorm = 1.0 / sqrt(nn);
+                                  GaussGeom<T> &g) {
+    const T qw = quat[0], qx = quat[1], qy = quat[2], qz = quat[3];
+    const T nn = qw * qw + qx * qx + qy * qy + qz * qz;
+    g.inv_qnorm = T(1) / sqrt(nn);
     g.qn[0] = qw * g.inv_qnorm; g.qn[1] = qx * g.inv_qnorm; g.qn[2] = qy * g.inv_qnorm; g.qn[3] = qz * g.inv_qnorm;
-    g.Rg = rotmat_raw<double>(g.qn[0], g.qn[1], g.qn[2], g.qn[3]);
-    g.inv_s[0] = 1.0 / (double)scale[0]; g.inv_s[1] = 1.0 / (double)scale[1]; g.inv_s[2] = 1.0 / (double)scale[2];
+    g.Rg = rotmat_raw<T>(g.qn[0], g.qn[1], g.qn[2], g.qn[3]);
+    g.inv_s[0] = T(1) / (T)scale[0]; g.inv_s[1] = T(1) / (T)scale[1]; g.inv_s[2] = T(1) / (T)scale[2];
     // M = diag(1/s) Rg^T ; A = M B
-    M3<double> A;
+    M3<T> A;
     for (int i = 0; i < 3; ++i)
         for (int j = 0; j < 3; ++j) {
-            double s = 0.0;
-            for (int k = 0; k < 3; ++k) s += g.Rg.m[k][i] * c.B[k][j];
+            T s = T(0);
+            for (int k = 0; k < 3; ++k) s += g.Rg.m[k][i] * (T)c.B[k][j];
             A.m[i][j] = s * g.inv_s[i];
         }
     g.A0 = col(A, 0); g.A1 = col(A, 1); g.A2 = col(A, 2);
-    const double mx = mean[0], my = mean[1], mz = mean[2];
-    const double xc = c.Binv[0][0] * mx + c.Binv[0][1] * my + c.Binv[0][2] * mz + c.t[0];
-    const double yc = c.Binv[1][0] * mx + c.Binv[1][1] * my + c.Binv[1][2] * mz + c.t[1];
-    const double zc = c.Binv[2][0] * mx + c.Binv[2][1] * my + c.Binv[2][2] * mz + c.t[2];
+    const T mx = mean[0], my = mean[1], mz = mean[2];
+    const T xc = (T)c.Binv[0][0] * mx + (T)c.Binv[0][1] * my + (T)c.Binv[0][2] * mz + (T)c.t[0];
+    const T yc = (T)c.Binv[1][0] * mx + (T)c.Binv[1][1] * my + (T)c.Binv[1][2] * mz + (T)c.t[1];
+    const T zc = (T)c.Binv[2][0] * mx + (T)c.Binv[2][1] * my + (T)c.Binv[2][2] * mz + (T)c.t[2];
     g.zc = zc;
-    g.degenerate = !(fabs(zc) > 1e-12 * (fabs(xc) + fabs(yc) + 1e-300)) || !isfinite(zc);
-    const double iz = g.degenerate ? 0.0 : 1.0 / zc;
+    g.degenerate = !(fabs((double)zc) > 1e-12 * (fabs((double)xc) + fabs((double)yc) + 1e-300)) || !isfinite((double)zc);
+    const T iz = g.degenerate ? T(0) : T(1) / zc;
     g.uc = xc * iz; g.vc = yc * iz;
     g.G = g.A0 * g.uc + g.A1 * g.vc + g.A2;
     g.gro = g.G * (-zc);
     g.E0 = cross(g.A0, g.gro);
     g.E1 = cross(g.A1, g.gro);
-    g.n[0] = dot(g.E0, g.E0); g.n[1] = 2.0 * dot(g.E0, g.E1); g.n[2] = dot(g.E1, g.E1);
+    g.n[0] = dot(g.E0, g.E0); g.n[1] = T(2) * dot(g.E0, g.E1); g.n[2] = dot(g.E1, g.E1);
     g.d0 = dot(g.G, g.G);
-    g.d[0] = 2.0 * dot(g.G, g.A0); g.d[1] = 2.0 * dot(g.G, g.A1);
-    g.d[2] = dot(g.A0, g.A0); g.d[3] = 2.0 * dot(g.A0, g.A1); g.d[4] = dot(g.A1, g.A1);
-    if (!(g.d0 > 0.0) || !isfinite(g.d0)) g.degenerate = true;
+    g.d[0] = T(2) * dot(g.G, g.A0); g.d[1] = T(2) * dot(g.G, g.A1);
+    g.d[2] = dot(g.A0, g.A0); g.d[3] = T(2) * dot(g.A0, g.A1); g.d[4] = dot(g.A1, g.A1);
+    if (!(g.d0 > T(0)) || !isfinite((double)g.d0)) g.degenerate = true;
 }
 
 // Per-pair evaluation shared VERBATIM by the forward and backward kernels (explicit rounding

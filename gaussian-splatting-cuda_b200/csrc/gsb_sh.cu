@@ -243,6 +243,141 @@ __global__ void __launch_bounds__(kShThreads) sh_bwd_kernel(uint32_t M, uint32_t
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K == 16 fast path (SH degree <= 3 with the reference's [N,16,3] layout, 192-byte rows).
+// Every thread moves ITS OWN 192-byte coefficient row with one TMA bulk copy (global -> shared
+// through an mbarrier, shared -> global through a bulk group), so all global traffic is full,
+// aligned 32-byte sectors regardless of the 192-byte element stride, and the per-thread shared rows
+// are padded to 208 bytes: float4 slot (13 t + i) mod 8 is conflict-free for 8 consecutive lanes.
+// ------------------------------------------------------------------------------------------
+constexpr int kRow16 = 48;        // floats per row
+constexpr int kRowStride16 = 52;  // padded row stride in floats (208 B)
+
+template <int DEG>
+__global__ void __launch_bounds__(kShThreads) sh_fwd_k16_kernel(uint32_t M, const float *__restrict__ dirs,
+                                                                const float *__restrict__ coeffs,
+                                                                const uint8_t *__restrict__ masks,
+                                                                float *__restrict__ colors) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    extern __shared__ __align__(128) float s_rows[]; // [kShThreads][kRowStride16]
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t e = blockIdx.x * kShThreads + tid;
+    const bool active = (e < M) && (masks == nullptr || masks[e]);
+    if (tid == 0) { mbar_init(&s_bar, kShThreads); mbar_fence_init(); }
+    __syncthreads();
+    float *row = s_rows + tid * kRowStride16;
+    constexpr uint32_t kInBytes = (NB * 12 + 15) / 16 * 16; // only the active degrees' bytes
+    if (active) {
+        mbar_arrive_expect_tx(&s_bar, kInBytes);
+        bulk_g2s(row, coeffs + (size_t)e * kRow16, kInBytes, &s_bar);
+    } else {
+        mbar_arrive(&s_bar);
+    }
+    float b[NB];
+    float x = 0.f, y = 0.f, z = 1.f;
+    if (active) { x = dirs[(size_t)e * 3]; y = dirs[(size_t)e * 3 + 1]; z = dirs[(size_t)e * 3 + 2]; }
+    if constexpr (DEG >= 1) {
+        const float inorm = rsqrtf(x * x + y * y + z * z);
+        x *= inorm; y *= inorm; z *= inorm;
+    }
+    sh_basis<DEG>(x, y, z, b);
+    mbar_wait(&s_bar, 0);
+    if (!active) return; // masked rows stay untouched
+    float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+    const float4 *r4 = reinterpret_cast<const float4 *>(row);
+    float f[(NB * 3 + 3) / 4 * 4];
+#pragma unroll
+    for (int i = 0; i < (NB * 3 + 3) / 4; ++i) {
+        const float4 v = r4[i];
+        f[i * 4] = v.x; f[i * 4 + 1] = v.y; f[i * 4 + 2] = v.z; f[i * 4 + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) { r0 += b[k] * f[k * 3]; r1 += b[k] * f[k * 3 + 1]; r2 += b[k] * f[k * 3 + 2]; }
+    colors[(size_t)e * 3] = r0; colors[(size_t)e * 3 + 1] = r1; colors[(size_t)e * 3 + 2] = r2;
+}
+
+template <int DEG>
+__global__ void __launch_bounds__(kShThreads) sh_bwd_k16_kernel(uint32_t M, const float *__restrict__ dirs,
+                                                                const float *__restrict__ coeffs,
+                                                                const uint8_t *__restrict__ masks,
+                                                                const float *__restrict__ v_colors,
+                                                                float *__restrict__ v_coeffs,
+                                                                float *__restrict__ v_dirs) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    extern __shared__ __align__(128) float s_rows[]; // in rows [T][52] then out rows [T][52]
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t e = blockIdx.x * kShThreads + tid;
+    const bool inside = e < M;
+    const bool active = inside && (masks == nullptr || masks[e]);
+    const bool need_in = active && (v_dirs != nullptr) && (DEG >= 1);
+    if (tid == 0) { mbar_init(&s_bar, kShThreads); mbar_fence_init(); }
+    __syncthreads();
+    float *row_in = s_rows + tid * kRowStride16;
+    float *row_out = s_rows + (kShThreads + tid) * kRowStride16;
+    constexpr uint32_t kInBytes = (NB * 12 + 15) / 16 * 16;
+    if (need_in) {
+        mbar_arrive_expect_tx(&s_bar, kInBytes);
+        bulk_g2s(row_in, coeffs + (size_t)e * kRow16, kInBytes, &s_bar);
+    } else {
+        mbar_arrive(&s_bar);
+    }
+    float b[NB];
+    float x = 0.f, y = 0.f, z = 1.f, inorm = 1.f, g0 = 0.f, g1 = 0.f, g2 = 0.f;
+    if (active) {
+        x = dirs[(size_t)e * 3]; y = dirs[(size_t)e * 3 + 1]; z = dirs[(size_t)e * 3 + 2];
+        g0 = v_colors[(size_t)e * 3]; g1 = v_colors[(size_t)e * 3 + 1]; g2 = v_colors[(size_t)e * 3 + 2];
+    }
+    if constexpr (DEG >= 1) {
+        inorm = rsqrtf(x * x + y * y + z * z);
+        x *= inorm; y *= inorm; z *= inorm;
+    }
+    sh_basis<DEG>(x, y, z, b);
+    // v_coeffs row: b_k * g_c for the active degrees, zeros elsewhere (and for masked elements)
+    float4 *o4 = reinterpret_cast<float4 *>(row_out);
+    {
+        float o[kRow16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float bk = (k < NB) ? b[k < NB ? k : 0] : 0.f;
+            o[k * 3] = bk * g0; o[k * 3 + 1] = bk * g1; o[k * 3 + 2] = bk * g2;
+        }
+#pragma unroll
+        for (int i = 0; i < kRow16 / 4; ++i) o4[i] = make_float4(o[i * 4], o[i * 4 + 1], o[i * 4 + 2], o[i * 4 + 3]);
+    }
+    if (inside) {
+        fence_proxy_async(); // this thread's generic-proxy writes -> visible to its bulk store
+        bulk_s2g(v_coeffs + (size_t)e * kRow16, row_out, kRow16 * 4);
+        bulk_commit();
+    }
+    mbar_wait(&s_bar, 0);
+    if (inside && v_dirs != nullptr) {
+        float vx = 0.f, vy = 0.f, vz = 0.f;
+        if constexpr (DEG >= 1) {
+            if (active) {
+                float w[NB];
+                const float4 *r4 = reinterpret_cast<const float4 *>(row_in);
+                float f[(NB * 3 + 3) / 4 * 4];
+#pragma unroll
+                for (int i = 0; i < (NB * 3 + 3) / 4; ++i) {
+                    const float4 v = r4[i];
+                    f[i * 4] = v.x; f[i * 4 + 1] = v.y; f[i * 4 + 2] = v.z; f[i * 4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int k = 0; k < NB; ++k) w[k] = g0 * f[k * 3] + g1 * f[k * 3 + 1] + g2 * f[k * 3 + 2];
+                sh_basis_vjp<DEG>(x, y, z, w, vx, vy, vz);
+                const float d = vx * x + vy * y + vz * z;
+                vx = (vx - d * x) * inorm; vy = (vy - d * y) * inorm; vz = (vz - d * z) * inorm;
+            }
+        }
+        v_dirs[(size_t)e * 3] = vx; v_dirs[(size_t)e * 3 + 1] = vy; v_dirs[(size_t)e * 3 + 2] = vz;
+    }
+    if (inside) bulk_wait_read_all(); // the row must stay in shared memory until the bulk store has read it
+}
+
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 } // namespace gsb
 
 extern "C" int gsb_sh_fwd(uint32_t M, uint32_t K, uint32_t degree, const float *dirs, const float *coeffs,
@@ -253,6 +388,16 @@ extern "C" int gsb_sh_fwd(uint32_t M, uint32_t K, uint32_t degree, const float *
     const dim3 grid((M + gsb::kShThreads - 1) / gsb::kShThreads);
     cudaStream_t s = gsb::as_stream(stream);
     gsb::ProfScope ps("sh_fwd", s);
+    if (K == 16 && degree >= 1 && degree <= 3 && gsb::aligned16(coeffs)) {
+        const size_t smem = (size_t)gsb::kShThreads * gsb::kRowStride16 * 4;
+        switch (degree) {
+        case 1: gsb::sh_fwd_k16_kernel<1><<<grid, gsb::kShThreads, smem, s>>>(M, dirs, coeffs, masks, colors); break;
+        case 2: gsb::sh_fwd_k16_kernel<2><<<grid, gsb::kShThreads, smem, s>>>(M, dirs, coeffs, masks, colors); break;
+        default: gsb::sh_fwd_k16_kernel<3><<<grid, gsb::kShThreads, smem, s>>>(M, dirs, coeffs, masks, colors); break;
+        }
+        GSB_LAUNCH_CHECK();
+        return GSB_OK;
+    }
     switch (degree) {
     case 0: gsb::sh_fwd_kernel<0><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, colors); break;
     case 1: gsb::sh_fwd_kernel<1><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, colors); break;
@@ -273,6 +418,21 @@ extern "C" int gsb_sh_bwd(uint32_t M, uint32_t K, uint32_t degree, const float *
     const dim3 grid((M + gsb::kShThreads - 1) / gsb::kShThreads);
     cudaStream_t s = gsb::as_stream(stream);
     gsb::ProfScope ps("sh_bwd", s);
+    if (K == 16 && degree <= 3 && gsb::aligned16(coeffs) && gsb::aligned16(v_coeffs)) {
+        const size_t smem = (size_t)2 * gsb::kShThreads * gsb::kRowStride16 * 4; // 53 248 B
+        #define GSB_SH_BWD16(D)                                                                                        \
+            cudaFuncSetAttribute(gsb::sh_bwd_k16_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+            gsb::sh_bwd_k16_kernel<D><<<grid, gsb::kShThreads, smem, s>>>(M, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs)
+        switch (degree) {
+        case 0: GSB_SH_BWD16(0); break;
+        case 1: GSB_SH_BWD16(1); break;
+        case 2: GSB_SH_BWD16(2); break;
+        default: GSB_SH_BWD16(3); break;
+        }
+        #undef GSB_SH_BWD16
+        GSB_LAUNCH_CHECK();
+        return GSB_OK;
+    }
     switch (degree) {
     case 0: gsb::sh_bwd_kernel<0><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
     case 1: gsb::sh_bwd_kernel<1><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
