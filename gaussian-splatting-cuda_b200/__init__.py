@@ -269,7 +269,9 @@ def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K,
             means.detach().contiguous(), quats.detach().contiguous(), scaled.detach().contiguous(),
             opacities.detach().contiguous(), viewmat, K, width, height, eps2d, near_plane, far_plane, radius_clip,
             **camera)
-        campos = torch.linalg.inv(viewmat)[:, :3, 3]                     # rasterizer.cpp:250-251
+        # rasterizer.cpp:250-251 (torch::inverse).  inv_ex is the same LU inverse without the host-side
+        # singularity check, i.e. without a device->host sync in the middle of the step.
+        campos = torch.linalg.inv_ex(viewmat).inverse[:, :3, 3]
         masks = (radii > 0).all(-1)                                      # :257
     dirs = means.unsqueeze(0) - campos.unsqueeze(1)                      # :254
     colors = SphericalHarmonicsFunction.apply(be, sh_degree, dirs, sh_coeffs.unsqueeze(0), masks)

@@ -215,4 +215,42 @@ __device__ __forceinline__ float fast_ex2(float x) {
     return r;
 }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FMUL2 / FADD2: two IEEE-rn fp32 results per issue slot) ----
+// A scalar operand built with f2_bc() is folded by ptxas into the instruction's broadcast modifier,
+// so mixing per-Gaussian scalars with per-pixel pairs costs no extra moves.
+struct f2 {
+    unsigned long long v;
+};
+__device__ __forceinline__ f2 f2_make(float lo, float hi) {
+    f2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ f2 f2_bc(float a) { return f2_make(a, a); }
+__device__ __forceinline__ float f2_lo(f2 a) {
+    float lo;
+    asm("{ .reg .b32 t; mov.b64 {%0, t}, %1; }" : "=f"(lo) : "l"(a.v));
+    return lo;
+}
+__device__ __forceinline__ float f2_hi(f2 a) {
+    float hi;
+    asm("{ .reg .b32 t; mov.b64 {t, %0}, %1; }" : "=f"(hi) : "l"(a.v));
+    return hi;
+}
+__device__ __forceinline__ f2 f2_fma(f2 a, f2 b, f2 c) {
+    f2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_mul(f2 a, f2 b) {
+    f2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ f2 f2_add(f2 a, f2 b) {
+    f2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+
 } // namespace gsb

@@ -10,7 +10,7 @@
 // (ascending flattened Gaussian index), which is what the reference's stable
 // cub::DeviceRadixSort::SortPairs over 32+tile_bits+cam_bits key bits produces.
 //
-// How the sorted lists are built (gsb_isect_emit_sorted): the reference radix-sorts all I
+// How the sorted lists are built (gsb_isect_plan + gsb_isect_emit_planned): the reference radix-sorts all I
 // intersections on 46 bits (six 8-bit passes over 12-byte pairs, ~150 B of HBM traffic per
 // intersection).  Here the depth order is established ONCE per Gaussian instead of once per
 // intersection:
@@ -99,17 +99,23 @@ __global__ void __launch_bounds__(kIsectThreads) isect_emit_kernel(uint64_t n, u
         }
 }
 
-// (camera, depth bits) key and identity value for every Gaussian
-__global__ void __launch_bounds__(kIsectThreads) depth_keys_kernel(uint64_t n, uint32_t N,
+// Count and depth key in one pass over the Gaussians (the plan phase of the two-phase sorted path).
+__global__ void __launch_bounds__(kIsectThreads) isect_plan_kernel(uint64_t n, uint32_t N,
+                                                                    const float *__restrict__ means2d,
+                                                                    const int32_t *__restrict__ radii,
                                                                     const float *__restrict__ depths,
-                                                                    const int32_t *__restrict__ tiles_per_gauss,
+                                                                    uint32_t tile_size, uint32_t tile_width,
+                                                                    uint32_t tile_height,
+                                                                    int32_t *__restrict__ tiles_per_gauss,
                                                                     uint64_t *__restrict__ keys64,
                                                                     uint32_t *__restrict__ keys32,
                                                                     uint32_t *__restrict__ vals) {
     const uint64_t idx = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
     if (idx >= n) return;
-    // Gaussians without intersections never emit; park them at the end (any order is fine)
-    const uint32_t d = tiles_per_gauss[idx] > 0 ? __float_as_uint(depths[idx]) : 0xffffffffu;
+    const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
+    const int32_t cnt = b.active ? (int32_t)((b.y1 - b.y0) * (b.x1 - b.x0)) : 0;
+    tiles_per_gauss[idx] = cnt;
+    const uint32_t d = cnt > 0 ? __float_as_uint(depths[idx]) : 0xffffffffu;
     if (keys64) keys64[idx] = ((uint64_t)(idx / N) << 32) | d;
     else keys32[idx] = d;
     vals[idx] = (uint32_t)idx;
@@ -145,38 +151,6 @@ using PermCountIter =
     thrust::transform_iterator<CastI64, thrust::permutation_iterator<const int32_t *, const uint32_t *>, int64_t>;
 
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
-
-// Workspace carve-up of gsb_isect_emit_sorted
-struct SortedWs {
-    size_t keys_a, keys_b, vals_a, vals_b, cum, tmp_keys, tmp_vals, cub, cub_bytes, total;
-};
-static SortedWs sorted_ws(uint64_t n, uint64_t n_isects, bool multi_cam) {
-    SortedWs w;
-    const size_t kb = multi_cam ? 8 : 4;
-    size_t off = 0;
-    w.keys_a = off; off += align256(n * kb);
-    w.keys_b = off; off += align256(n * kb);
-    w.vals_a = off; off += align256(n * 4);
-    w.vals_b = off; off += align256(n * 4);
-    w.cum = off; off += align256(n * 8);
-    w.tmp_keys = off; off += align256(n_isects * 8);
-    w.tmp_vals = off; off += align256(n_isects * 4);
-    size_t b1 = 0, b2 = 0, b3 = 0;
-    if (multi_cam)
-        cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n, 0, 64);
-    else
-        cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n, 0, 32);
-    PermCountIter it(thrust::permutation_iterator<const int32_t *, const uint32_t *>(nullptr, nullptr), CastI64());
-    cub::DeviceScan::InclusiveSum(nullptr, b2, it, (int64_t *)nullptr, (int64_t)n);
-    cub::DeviceRadixSort::SortPairs(nullptr, b3, (const int64_t *)nullptr, (int64_t *)nullptr, (const int32_t *)nullptr,
-                                    (int32_t *)nullptr, (int64_t)n_isects, 32, 64);
-    w.cub_bytes = align256(b1 > b2 ? (b1 > b3 ? b1 : b3) : (b2 > b3 ? b2 : b3)) + 256;
-    w.cub = off; off += w.cub_bytes;
-    w.total = off + 256;
-    return w;
-}
 
 } // namespace gsb
 
@@ -250,67 +224,146 @@ extern "C" int gsb_isect_sort(uint64_t n_isects, uint32_t C, uint32_t tile_width
     return GSB_OK;
 }
 
-extern "C" size_t gsb_isect_emit_sorted_workspace(uint32_t C, uint32_t N, uint64_t n_isects) {
-    return gsb::sorted_ws((uint64_t)C * N, n_isects, C > 1).total;
+namespace gsb {
+// Workspace of the plan: [perm N u32][cum N i64] survive until the emit; the rest is scratch.
+struct PlanWs {
+    size_t perm, cum, keys_a, keys_b, vals_a, cub, cub_bytes, total;
+};
+static PlanWs plan_ws(uint64_t n, bool multi_cam) {
+    PlanWs w;
+    const size_t kb = multi_cam ? 8 : 4;
+    size_t off = 0;
+    w.perm = off; off += align256(n * 4);
+    w.cum = off; off += align256(n * 8);
+    w.keys_a = off; off += align256(n * kb);
+    w.keys_b = off; off += align256(n * kb);
+    w.vals_a = off; off += align256(n * 4);
+    size_t b1 = 0, b2 = 0;
+    if (multi_cam)
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n, 0, 64);
+    else
+        cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n, 0, 32);
+    PermCountIter it(thrust::permutation_iterator<const int32_t *, const uint32_t *>(nullptr, nullptr), CastI64());
+    cub::DeviceScan::InclusiveSum(nullptr, b2, it, (int64_t *)nullptr, (int64_t)n);
+    w.cub_bytes = align256(b1 > b2 ? b1 : b2) + 256;
+    w.cub = off; off += w.cub_bytes;
+    w.total = off + 256;
+    return w;
+}
+struct PlannedWs {
+    size_t tmp_keys, tmp_vals, cub, cub_bytes, total;
+};
+static PlannedWs planned_ws(uint64_t n_isects) {
+    PlannedWs w;
+    size_t off = 0;
+    w.tmp_keys = off; off += align256(n_isects * 8);
+    w.tmp_vals = off; off += align256(n_isects * 4);
+    size_t b = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, b, (const int64_t *)nullptr, (int64_t *)nullptr, (const int32_t *)nullptr,
+                                    (int32_t *)nullptr, (int64_t)n_isects, 32, 64);
+    w.cub_bytes = align256(b) + 256;
+    w.cub = off; off += w.cub_bytes;
+    w.total = off + 256;
+    return w;
+}
+} // namespace gsb
+
+extern "C" size_t gsb_isect_plan_workspace(uint32_t C, uint32_t N) {
+    return gsb::plan_ws((uint64_t)C * N, C > 1).total;
 }
 
-extern "C" int gsb_isect_emit_sorted(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
-                                     const float *depths, const int32_t *tiles_per_gauss, uint32_t tile_size,
-                                     uint32_t tile_width, uint32_t tile_height, uint64_t n_isects,
-                                     int64_t *isect_ids, int32_t *flatten_ids, void *workspace,
-                                     size_t workspace_bytes, gsb_stream_t stream) {
+extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii, const float *depths,
+                              uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                              int32_t *tiles_per_gauss, int64_t *n_isects_out, void *plan_workspace,
+                              size_t plan_workspace_bytes, gsb_stream_t stream) {
     using namespace gsb;
     const uint64_t n = (uint64_t)C * N;
-    if (n == 0 || n_isects == 0) return GSB_OK;
-    if (!means2d || !radii || !depths || !tiles_per_gauss || !isect_ids || !flatten_ids) return GSB_E_INVALID;
+    if (!n_isects_out) return GSB_E_INVALID;
+    cudaStream_t s = as_stream(stream);
+    if (n == 0) {
+        GSB_CUDA_TRY(cudaMemsetAsync(n_isects_out, 0, sizeof(int64_t), s));
+        return GSB_OK;
+    }
+    if (!means2d || !radii || !depths || !tiles_per_gauss || tile_size == 0) return GSB_E_INVALID;
     const uint32_t tile_n_bits = bit_width_u32(tile_width * tile_height);
     const uint32_t cam_n_bits = bit_width_u32(C);
-    if (tile_n_bits + cam_n_bits > 32) return GSB_E_INVALID;
+    if (tile_n_bits + cam_n_bits > 32) return GSB_E_INVALID; // Intersect.cpp:50
     const bool multi = C > 1;
-    const SortedWs w = sorted_ws(n, n_isects, multi);
-    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < w.total)
+    const PlanWs w = plan_ws(n, multi);
+    if (!plan_workspace || (reinterpret_cast<uintptr_t>(plan_workspace) & 255) || plan_workspace_bytes < w.total)
         return GSB_E_WORKSPACE;
-    cudaStream_t s = as_stream(stream);
-    char *base = reinterpret_cast<char *>(workspace);
-    uint32_t *vals_a = reinterpret_cast<uint32_t *>(base + w.vals_a);
-    uint32_t *perm = reinterpret_cast<uint32_t *>(base + w.vals_b);
+    char *base = reinterpret_cast<char *>(plan_workspace);
+    uint32_t *perm = reinterpret_cast<uint32_t *>(base + w.perm);
     int64_t *cum = reinterpret_cast<int64_t *>(base + w.cum);
-    int64_t *tmp_keys = reinterpret_cast<int64_t *>(base + w.tmp_keys);
-    int32_t *tmp_vals = reinterpret_cast<int32_t *>(base + w.tmp_vals);
+    uint32_t *vals_a = reinterpret_cast<uint32_t *>(base + w.vals_a);
     void *cub_tmp = base + w.cub;
     const uint32_t grid = (uint32_t)((n + kIsectThreads - 1) / kIsectThreads);
     {
-        // 1. stable sort of the Gaussians by (camera, depth bits); input order = flattened index
+        ProfScope ps("isect_count", s);
+        uint64_t *k64 = multi ? reinterpret_cast<uint64_t *>(base + w.keys_a) : nullptr;
+        uint32_t *k32 = multi ? nullptr : reinterpret_cast<uint32_t *>(base + w.keys_a);
+        isect_plan_kernel<<<grid, kIsectThreads, 0, s>>>(n, N, means2d, radii, depths, tile_size, tile_width,
+                                                        tile_height, tiles_per_gauss, k64, k32, vals_a);
+        GSB_LAUNCH_CHECK();
+    }
+    {
         ProfScope ps("isect_depth_sort", s);
         size_t bytes = w.cub_bytes;
         if (multi) {
             uint64_t *ka = reinterpret_cast<uint64_t *>(base + w.keys_a), *kb = reinterpret_cast<uint64_t *>(base + w.keys_b);
-            depth_keys_kernel<<<grid, kIsectThreads, 0, s>>>(n, N, depths, tiles_per_gauss, ka, nullptr, vals_a);
-            GSB_LAUNCH_CHECK();
             GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, ka, kb, vals_a, perm, (int64_t)n, 0,
                                                          (int)(32 + cam_n_bits), s));
         } else {
             uint32_t *ka = reinterpret_cast<uint32_t *>(base + w.keys_a), *kb = reinterpret_cast<uint32_t *>(base + w.keys_b);
-            depth_keys_kernel<<<grid, kIsectThreads, 0, s>>>(n, N, depths, tiles_per_gauss, nullptr, ka, vals_a);
-            GSB_LAUNCH_CHECK();
             GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, ka, kb, vals_a, perm, (int64_t)n, 0, 32, s));
         }
-    }
-    {
-        // 2. offsets of every Gaussian's run in depth order, then emit in that order
-        ProfScope ps("isect_emit", s);
-        size_t bytes = w.cub_bytes;
+        bytes = w.cub_bytes;
         PermCountIter it(thrust::permutation_iterator<const int32_t *, const uint32_t *>(tiles_per_gauss, perm), CastI64());
         GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_tmp, bytes, it, cum, (int64_t)n, s));
+    }
+    // device or pinned-host destination alike
+    GSB_CUDA_TRY(cudaMemcpyAsync(n_isects_out, cum + (n - 1), sizeof(int64_t), cudaMemcpyDefault, s));
+    return GSB_OK;
+}
+
+extern "C" size_t gsb_isect_emit_planned_workspace(uint64_t n_isects) { return gsb::planned_ws(n_isects).total; }
+
+extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
+                                      const float *depths, uint32_t tile_size, uint32_t tile_width,
+                                      uint32_t tile_height, uint64_t n_isects, const void *plan_workspace,
+                                      int64_t *isect_ids, int32_t *flatten_ids, void *workspace,
+                                      size_t workspace_bytes, gsb_stream_t stream) {
+    using namespace gsb;
+    const uint64_t n = (uint64_t)C * N;
+    if (n == 0 || n_isects == 0) return GSB_OK;
+    if (!means2d || !radii || !depths || !plan_workspace || !isect_ids || !flatten_ids) return GSB_E_INVALID;
+    const uint32_t tile_n_bits = bit_width_u32(tile_width * tile_height);
+    const uint32_t cam_n_bits = bit_width_u32(C);
+    if (tile_n_bits + cam_n_bits > 32) return GSB_E_INVALID;
+    const PlanWs pw = plan_ws(n, C > 1);
+    const PlannedWs w = planned_ws(n_isects);
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < w.total)
+        return GSB_E_WORKSPACE;
+    cudaStream_t s = as_stream(stream);
+    const char *pbase = reinterpret_cast<const char *>(plan_workspace);
+    const uint32_t *perm = reinterpret_cast<const uint32_t *>(pbase + pw.perm);
+    const int64_t *cum = reinterpret_cast<const int64_t *>(pbase + pw.cum);
+    char *base = reinterpret_cast<char *>(workspace);
+    int64_t *tmp_keys = reinterpret_cast<int64_t *>(base + w.tmp_keys);
+    int32_t *tmp_vals = reinterpret_cast<int32_t *>(base + w.tmp_vals);
+    const uint32_t grid = (uint32_t)((n + kIsectThreads - 1) / kIsectThreads);
+    {
+        ProfScope ps("isect_emit", s);
         isect_emit_kernel<<<grid, kIsectThreads, 0, s>>>(n, N, means2d, radii, depths, perm, cum, tile_size, tile_width,
                                                         tile_height, tile_n_bits, tmp_keys, tmp_vals);
         GSB_LAUNCH_CHECK();
     }
     {
-        // 3. stable partition by (camera, tile): key bits [32, 32 + tile_bits + cam_bits)
         ProfScope ps("isect_sort", s);
         size_t bytes = w.cub_bytes;
-        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, tmp_keys, isect_ids, tmp_vals, flatten_ids,
+        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(base + w.cub, bytes, tmp_keys, isect_ids, tmp_vals, flatten_ids,
                                                      (int64_t)n_isects, 32, (int)(32 + tile_n_bits + cam_n_bits), s));
     }
     return GSB_OK;

@@ -39,12 +39,18 @@ __global__ void __launch_bounds__(kPrepThreads) prep_records_kernel(uint32_t N, 
                                                                      const float *__restrict__ opacities,
                                                                      const float *__restrict__ viewmat,
                                                                      const float *__restrict__ K,
-                                                                     GaussRec *__restrict__ recs) {
+                                                                     GaussRec *__restrict__ recs,
+                                                                     float *__restrict__ moments /* nullable */) {
     __shared__ CamConst cam;
     if (threadIdx.x == 0) cam_const_from(viewmat, K, cam);
     __syncthreads();
     const uint32_t g = blockIdx.x * kPrepThreads + threadIdx.x;
     if (g >= N) return;
+    if (moments) { // the backward's accumulation rows start at zero (saves a separate 64 B/Gaussian memset pass)
+        float4 *m4 = reinterpret_cast<float4 *>(moments + (size_t)g * kMomFloats);
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+        m4[0] = z; m4[1] = z; m4[2] = z; m4[3] = z;
+    }
     const float mean[3] = {means[(size_t)g * 3], means[(size_t)g * 3 + 1], means[(size_t)g * 3 + 2]};
     const float quat[4] = {quats[(size_t)g * 4], quats[(size_t)g * 4 + 1], quats[(size_t)g * 4 + 2],
                            quats[(size_t)g * 4 + 3]};
@@ -212,6 +218,7 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
     float c0r = 0.f, c0g = 0.f, c0b = 0.f, c1r = 0.f, c1g = 0.f, c1b = 0.f;
     int32_t last0 = 0, last1 = 0;
     bool done0 = !pm.in0 || !pc.ok0, done1 = !pm.in1 || !pc.ok1;
+    const f2 PX = f2_make(pc.px0, pc.px1), PY = f2_make(pc.py0, pc.py1);
 
     // prologue: batch 0 in flight, ids of batch 1 prefetched into a register
     int32_t gid_next = 0;
@@ -250,14 +257,12 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
                 const int32_t t = c0 + __ffs(cmask) - 1;
                 cmask &= cmask - 1;
                 const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
-                const PairEval e0 = pair_eval(q0, q1, q2, pc.px0 - q0.x, pc.py0 - q0.y);
-                const PairEval e1 = pair_eval(q0, q1, q2, pc.px1 - q0.x, pc.py1 - q0.y);
-                const bool p0 = e0.pass && !done0, p1 = e1.pass && !done1;
+                const PairEval2 e = pair_eval2(q0, q1, q2, f2_add(PX, f2_bc(-q0.x)), f2_add(PY, f2_bc(-q0.y)));
+                const bool p0 = e.pass0 && !done0, p1 = e.pass1 && !done1;
                 if (!__any_sync(0xffffffffu, p0 || p1)) continue;
                 const float4 q3 = rec4[t * 4 + 3];
                 if (p0) {
-                    float ex;
-                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw(e0, q2.z, ex));
+                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw(f2_lo(e.Ns), f2_lo(e.Ds), q2.z));
                     if (alpha >= kAlphaThreshold) {
                         const float nT = T0 * (1.0f - alpha);
                         if (nT <= kMinTransmittance) {
@@ -271,8 +276,7 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
                     }
                 }
                 if (p1) {
-                    float ex;
-                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw(e1, q2.z, ex));
+                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw(f2_hi(e.Ns), f2_hi(e.Ds), q2.z));
                     if (alpha >= kAlphaThreshold) {
                         const float nT = T1 * (1.0f - alpha);
                         if (nT <= kMinTransmittance) {
@@ -315,19 +319,22 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
 // backward
 // ------------------------------------------------------------------------------------------
 
-// Sum 16 per-lane values across the warp: after the call lane L holds in v[0] the warp-wide
-// total of slot (L >> 1).  16 shuffles (8+4+2+1+1) instead of 16 x 5.
-__device__ __forceinline__ void butterfly16(float (&v)[16]) {
+// Moment row of a Gaussian (16 floats, kMomFloats), x / y in pixels relative to (pcx, pcy):
+//   w1 = dL/dNs, w2 = dL/dDs, g = dL/d(power) summed, c = dL/d(colour).
+// Slot s and slot s ^ 8 are partners in the first stage of the warp reduction: they differ only in the
+// weight (w1 <-> w2) or in a per-pixel constant, which is what makes that stage select-free.
+enum MomentSlot : int {
+    kS_G = 0, kS_W1X = 1, kS_W1Y = 2, kS_W1XX = 3, kS_W1XY = 4, kS_W1YY = 5, kS_CR = 6, kS_CB = 7,
+    kS_W2 = 8, kS_W2X = 9, kS_W2Y = 10, kS_W2XX = 11, kS_W2XY = 12, kS_W2YY = 13, kS_CG = 14, kS_PAD = 15
+};
+
+// Sum 16 per-lane values across the warp: after the call lane L holds in v[0] the warp-wide total of
+// slot (L >> 1).  16 shuffles (8+4+2+1+1) instead of 16 x 5.  On entry lanes 16..31 hold slot (i ^ 8) in
+// v[i] (they built their registers pre-swapped), so stage one needs no lane-dependent selects.
+__device__ __forceinline__ void butterfly16_preswapped(float (&v)[16]) {
     const uint32_t lane = threadIdx.x & 31;
-    {
-        const bool hi = lane & 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float send = hi ? v[i] : v[i + 8];
-            const float keep = hi ? v[i + 8] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-        }
-    }
+    for (int i = 0; i < 8; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i + 8], 16);
     {
         const bool hi = lane & 8;
 #pragma unroll
@@ -355,41 +362,58 @@ __device__ __forceinline__ void butterfly16(float (&v)[16]) {
     v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
 }
 
-struct BwdPixel {
-    float T, br, bgc, bb; // running transmittance and colour accumulated behind
-    float vr, vg, vb;     // dL/d(render colour)
-    float tfva;           // T_final * (dL/d(alpha) - bg . dL/d(colour))
-    int32_t last;
-    bool in;
+// Per-thread state of the backward sweep for the thread's two pixels (lo = pixel 0, hi = pixel 1).
+struct BwdState {
+    f2 T;      // running transmittance (restored front-to-back value at the current Gaussian)
+    f2 bdot;   // (colour accumulated behind) . dL/d(colour)
+    f2 tfva;   // T_final * (dL/d(alpha) - bg . dL/d(colour))
+    f2 vr, vg, vb; // dL/d(render colour)
+    f2 vA, vB, vC, vD; // the colour slots' per-pixel factors, pre-swapped for lanes 16..31 (see MomentSlot)
+    int32_t last0, last1;
+    bool in0, in1;
 };
 
-// Moment layout (row of 16 floats per Gaussian), x/y in pixels relative to (pcx, pcy):
-//  0: w1 x   1: w1 y   2: w1 xx  3: w1 xy  4: w1 yy
-//  5: w2     6: w2 x   7: w2 y   8: w2 xx  9: w2 xy  10: w2 yy
-//  11: g (= dL/dpower summed)    12..14: dL/d(colour)      15: unused
-__device__ __forceinline__ void bwd_pair(BwdPixel &s, const PairEval &e, float lop, float x, float y, float cr,
-                                         float cg, float cb, float (&acc)[16]) {
-    float ex;
-    const float rD = fast_rcp(e.Ds);
-    ex = __fmaf_rn(e.Ns, rD, lop);
-    const float a_raw = fast_ex2(ex);
-    const float alpha = fminf(kMaxAlpha, a_raw);
-    if (alpha < kAlphaThreshold) return;
+__device__ __forceinline__ float f2_sum(f2 a) { return f2_lo(a) + f2_hi(a); }
+
+// One (record, pixel pair) event of the backward sweep, branch-free over the two pixels: a pixel that
+// does not contribute gets alpha = 0, which leaves its state untouched and adds zeros to the moments.
+__device__ __forceinline__ void bwd_event(BwdState &s, const PairEval2 &e, bool p0, bool p1, float lop, f2 x, f2 y,
+                                          float cr, float cg, float cb, bool hi16, float (&R)[16]) {
+    const f2 rD = f2_make(fast_rcp(f2_lo(e.Ds)), fast_rcp(f2_hi(e.Ds)));
+    const f2 ex = f2_fma(e.Ns, rD, f2_bc(lop)); // same rounding as the forward's pair_alpha_raw
+    const float ar0 = fast_ex2(f2_lo(ex)), ar1 = fast_ex2(f2_hi(ex));
+    const float al0 = fminf(kMaxAlpha, ar0), al1 = fminf(kMaxAlpha, ar1);
+    const bool ok0 = p0 && al0 >= kAlphaThreshold, ok1 = p1 && al1 >= kAlphaThreshold;
+    const f2 alpha = f2_make(ok0 ? al0 : 0.0f, ok1 ? al1 : 0.0f);
+    // Bwd.cu:318: the gradient reaches the Gaussian through alpha only when alpha was not clamped
+    const f2 araw_g = f2_make((ok0 && ar0 <= kMaxAlpha) ? ar0 : 0.0f, (ok1 && ar1 <= kMaxAlpha) ? ar1 : 0.0f);
+    const f2 om = f2_fma(alpha, f2_bc(-1.0f), f2_bc(1.0f));
     // the reference evaluates 1/(1-alpha) with the fast-math reciprocal too (Bwd.cu:291 under --use_fast_math)
-    const float ra = fast_rcp(1.0f - alpha);
-    s.T *= ra;
-    const float fac = alpha * s.T;
-    float v_alpha = (cr * s.T - s.br * ra) * s.vr + (cg * s.T - s.bgc * ra) * s.vg + (cb * s.T - s.bb * ra) * s.vb;
-    v_alpha += s.tfva * ra;
-    acc[12] += fac * s.vr; acc[13] += fac * s.vg; acc[14] += fac * s.vb;
-    // Bwd.cu:318: gradient through opacity*vis only when alpha was not clamped (branch-free select)
-    const float g = (a_raw <= kMaxAlpha) ? a_raw * v_alpha : 0.0f;
-    const float w1 = g * kLn2 * rD;
-    const float w2 = -w1 * (e.Ns * rD);
-    acc[0] += w1 * x; acc[1] += w1 * y; acc[2] += w1 * e.xx; acc[3] += w1 * e.xy; acc[4] += w1 * e.yy;
-    acc[5] += w2; acc[6] += w2 * x; acc[7] += w2 * y; acc[8] += w2 * e.xx; acc[9] += w2 * e.xy; acc[10] += w2 * e.yy;
-    acc[11] += g;
-    s.br += cr * fac; s.bgc += cg * fac; s.bb += cb * fac;
+    float ra0 = 1.0f, ra1 = 1.0f;
+    if (ok0) ra0 = fast_rcp(f2_lo(om));
+    if (ok1) ra1 = fast_rcp(f2_hi(om));
+    const f2 ra = f2_make(ra0, ra1);
+    s.T = f2_mul(s.T, ra);
+    const f2 fac = f2_mul(alpha, s.T);
+    // v_alpha = sum_c (c_c T - behind_c / (1-alpha)) v_c + T_final (...) / (1-alpha)     (Bwd.cu:296-316)
+    const f2 cv = f2_fma(f2_bc(cr), s.vr, f2_fma(f2_bc(cg), s.vg, f2_mul(f2_bc(cb), s.vb)));
+    const f2 v_alpha = f2_fma(s.T, cv, f2_mul(ra, f2_fma(s.bdot, f2_bc(-1.0f), s.tfva)));
+    s.bdot = f2_fma(fac, cv, s.bdot);
+    const f2 g = f2_mul(araw_g, v_alpha);
+    const f2 gr = f2_mul(g, rD);
+    const f2 w1 = f2_mul(gr, f2_bc(kLn2));
+    const f2 w2 = f2_mul(f2_mul(gr, f2_bc(-kLn2)), f2_mul(e.Ns, rD));
+    // lanes 16..31 build every register pair (i, i + 8) swapped
+    const f2 wA = hi16 ? w2 : w1, wB = hi16 ? w1 : w2;
+    const float gs = f2_sum(g), w2s = f2_sum(w2);
+    R[0] = hi16 ? w2s : gs;
+    R[8] = hi16 ? gs : w2s;
+    R[1] = f2_sum(f2_mul(wA, x)); R[2] = f2_sum(f2_mul(wA, y));
+    R[3] = f2_sum(f2_mul(wA, e.xx)); R[4] = f2_sum(f2_mul(wA, e.xy)); R[5] = f2_sum(f2_mul(wA, e.yy));
+    R[9] = f2_sum(f2_mul(wB, x)); R[10] = f2_sum(f2_mul(wB, y));
+    R[11] = f2_sum(f2_mul(wB, e.xx)); R[12] = f2_sum(f2_mul(wB, e.xy)); R[13] = f2_sum(f2_mul(wB, e.yy));
+    R[6] = f2_sum(f2_mul(fac, s.vA)); R[14] = f2_sum(f2_mul(fac, s.vB));
+    R[7] = f2_sum(f2_mul(fac, s.vC)); R[15] = f2_sum(f2_mul(fac, s.vD));
 }
 
 template <bool kGeneral>
@@ -409,42 +433,58 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
     const uint32_t tile_y = tile_id / p.tile_w, tile_x = tile_id % p.tile_w;
     const PixelMap pm = pixel_map(tile_x, tile_y, p.W, p.H);
     const uint32_t tid = threadIdx.x;
+    const bool hi16 = (tid & 16) != 0;
 
     const int32_t range_start = p.tile_offsets[tile_id];
     const int32_t range_end = (tile_id == p.tile_w * p.tile_h - 1) ? (int32_t)p.n_isects : p.tile_offsets[tile_id + 1];
 
-    float bgdot_scale[3] = {0.f, 0.f, 0.f};
-    if (p.backgrounds) { bgdot_scale[0] = p.backgrounds[0]; bgdot_scale[1] = p.backgrounds[1]; bgdot_scale[2] = p.backgrounds[2]; }
+    float bg[3] = {0.f, 0.f, 0.f};
+    if (p.backgrounds) { bg[0] = p.backgrounds[0]; bg[1] = p.backgrounds[1]; bg[2] = p.backgrounds[2]; }
 
-    BwdPixel s0, s1;
-    auto load_pixel = [&](BwdPixel &s, bool in, uint32_t y) {
-        s.in = in; s.br = s.bgc = s.bb = 0.f;
+    struct PixelIn { float T, vr, vg, vb, tfva; int32_t last; };
+    auto load_pixel = [&](bool in, uint32_t y) {
+        PixelIn r;
         if (in) {
             const size_t pix = (size_t)y * p.W + pm.x;
             const float Tf = 1.0f - render_alphas[pix];
-            s.T = Tf;
-            s.last = last_ids[pix];
-            s.vr = v_render_colors[pix * 3]; s.vg = v_render_colors[pix * 3 + 1]; s.vb = v_render_colors[pix * 3 + 2];
+            r.T = Tf;
+            r.last = last_ids[pix];
+            r.vr = v_render_colors[pix * 3]; r.vg = v_render_colors[pix * 3 + 1]; r.vb = v_render_colors[pix * 3 + 2];
             const float va = v_render_alphas[pix];
-            const float bgd = bgdot_scale[0] * s.vr + bgdot_scale[1] * s.vg + bgdot_scale[2] * s.vb;
-            s.tfva = Tf * va - Tf * bgd; // Bwd.cu:307-316
+            const float bgd = bg[0] * r.vr + bg[1] * r.vg + bg[2] * r.vb;
+            r.tfva = Tf * va - Tf * bgd; // Bwd.cu:307-316
         } else {
-            s.T = 1.f; s.last = -1; s.vr = s.vg = s.vb = 0.f; s.tfva = 0.f;
+            r.T = 1.f; r.last = -1; r.vr = r.vg = r.vb = 0.f; r.tfva = 0.f;
         }
+        return r;
     };
     if constexpr (kGeneral) {
         if (tid == 0) tile_cam_build(p, s_cm);
         __syncthreads();
     }
     const PixelCoords pc = pixel_coords<kGeneral>(p, pm, tile_x, tile_y, &s_cm);
-    load_pixel(s0, pm.in0 && pc.ok0, pm.y0);
-    load_pixel(s1, pm.in1 && pc.ok1, pm.y1);
+    BwdState s;
+    s.in0 = pm.in0 && pc.ok0;
+    s.in1 = pm.in1 && pc.ok1;
+    {
+        const PixelIn a = load_pixel(s.in0, pm.y0), b = load_pixel(s.in1, pm.y1);
+        s.T = f2_make(a.T, b.T);
+        s.bdot = f2_bc(0.0f);
+        s.tfva = f2_make(a.tfva, b.tfva);
+        s.vr = f2_make(a.vr, b.vr); s.vg = f2_make(a.vg, b.vg); s.vb = f2_make(a.vb, b.vb);
+        s.vA = hi16 ? s.vg : s.vr;
+        s.vB = hi16 ? s.vr : s.vg;
+        s.vC = hi16 ? f2_bc(0.0f) : s.vb;
+        s.vD = hi16 ? s.vb : f2_bc(0.0f);
+        s.last0 = a.last; s.last1 = b.last;
+    }
+    const f2 PX = f2_make(pc.px0, pc.px1), PY = f2_make(pc.py0, pc.py1);
 
     // CTA-wide newest contributor: nothing behind it can receive gradient
-    int32_t wmax = __reduce_max_sync(0xffffffffu, max(s0.last, s1.last));
+    int32_t wmax = __reduce_max_sync(0xffffffffu, max(s.last0, s.last1));
     if ((tid & 31) == 0) s_warp_max[tid >> 5] = wmax;
     if (tid == 0) {
-        for (int s = 0; s < kStages; ++s) mbar_init(&s_full[s], 1);
+        for (int st = 0; st < kStages; ++st) mbar_init(&s_full[st], 1);
         mbar_fence_init();
     }
     __syncthreads();
@@ -492,23 +532,19 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
             cmask &= cmask - 1;
             const int32_t idx = top - t;
             const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
-            const float x0 = pc.px0 - q0.x, x1 = pc.px1 - q0.x;
-            const float y0 = pc.py0 - q0.y, y1 = pc.py1 - q0.y;
-            const PairEval e0 = pair_eval(q0, q1, q2, x0, y0);
-            const PairEval e1 = pair_eval(q0, q1, q2, x1, y1);
-            const bool p0 = e0.pass && s0.in && idx <= s0.last;
-            const bool p1 = e1.pass && s1.in && idx <= s1.last;
+            const f2 x = f2_add(PX, f2_bc(-q0.x)), y = f2_add(PY, f2_bc(-q0.y));
+            const PairEval2 e = pair_eval2(q0, q1, q2, x, y);
+            const bool p0 = e.pass0 && s.in0 && idx <= s.last0;
+            const bool p1 = e.pass1 && s.in1 && idx <= s.last1;
             if (!__any_sync(0xffffffffu, p0 || p1)) continue;
             const float4 q3 = rec4[t * 4 + 3];
-            float acc[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-            if (p0) bwd_pair(s0, e0, q2.z, x0, y0, q3.x, q3.y, q3.z, acc);
-            if (p1) bwd_pair(s1, e1, q2.z, x1, y1, q3.x, q3.y, q3.z, acc);
-            butterfly16(acc);
+            float R[16];
+            bwd_event(s, e, p0, p1, q2.z, x, y, q3.x, q3.y, q3.z, hi16, R);
+            butterfly16_preswapped(R);
             if ((tid & 1) == 0) {
                 const uint32_t slot = (tid & 31) >> 1;
-                if (slot < 15) red_add_f32(moments + (size_t)__float_as_int(q3.w) * kMomFloats + slot, acc[0]);
+                if (slot != (uint32_t)kS_PAD)
+                    red_add_f32(moments + (size_t)__float_as_int(q3.w) * kMomFloats + slot, R[0]);
             }
           }
         }
@@ -543,11 +579,12 @@ __global__ void __launch_bounds__(kPrepThreads) finalize_grads_kernel(
             m[i * 4] = v.x; m[i * 4 + 1] = v.y; m[i * 4 + 2] = v.z; m[i * 4 + 3] = v.w;
         }
     }
-    v_colors[(size_t)g * 3] = m[12]; v_colors[(size_t)g * 3 + 1] = m[13]; v_colors[(size_t)g * 3 + 2] = m[14];
+    v_colors[(size_t)g * 3] = m[kS_CR]; v_colors[(size_t)g * 3 + 1] = m[kS_CG]; v_colors[(size_t)g * 3 + 2] = m[kS_CB];
     const float opac = opacities[g];
     bool any = false;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) any = any || (m[i] != 0.f);
+    for (int i = 0; i < 16; ++i)
+        if (i != kS_CR && i != kS_CG && i != kS_CB && i != kS_PAD) any = any || (m[i] != 0.f);
     float om[3] = {0.f, 0.f, 0.f}, oq[4] = {0.f, 0.f, 0.f, 0.f}, os[3] = {0.f, 0.f, 0.f}, oo = 0.f;
     if (any) {
         const float mean[3] = {means[(size_t)g * 3], means[(size_t)g * 3 + 1], means[(size_t)g * 3 + 2]};
@@ -561,8 +598,8 @@ __global__ void __launch_bounds__(kPrepThreads) finalize_grads_kernel(
             const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
             const FT cn0 = q0.z, cn1 = q0.w, cn2 = q1.x;
             const FT cd1 = q1.y, cd2 = q1.z, cd3 = q1.w, cd4 = q2.x, cd5 = q2.y;
-            const FT M0 = m[0], M1 = m[1], M2 = m[2], M3_ = m[3], M4 = m[4], M5 = m[5], M6 = m[6], M7 = m[7],
-                         M8 = m[8], M9 = m[9], M10 = m[10];
+            const FT M0 = m[kS_W1X], M1 = m[kS_W1Y], M2 = m[kS_W1XX], M3_ = m[kS_W1XY], M4 = m[kS_W1YY], M5 = m[kS_W2],
+                     M6 = m[kS_W2X], M7 = m[kS_W2Y], M8 = m[kS_W2XX], M9 = m[kS_W2XY], M10 = m[kS_W2YY];
             const FT ax = FT(1) / (FT)cam.fx, ay = FT(1) / (FT)cam.fy;
             const FT id0 = FT(1) / gg.d0;
             const FT kk = FT(-0.5 * 1.4426950408889634);
@@ -620,7 +657,7 @@ __global__ void __launch_bounds__(kPrepThreads) finalize_grads_kernel(
                            w * (vRg[1][0] - vRg[0][1]));
             const FT dq = vq[0] * w + vq[1] * x + vq[2] * y + vq[3] * z;
             for (int k = 0; k < 4; ++k) oq[k] = (float)((vq[k] - dq * gg.qn[k]) * gg.inv_qnorm);
-            oo = (opac > 0.f) ? m[11] / opac : 0.f; // sum vis * v_alpha
+            oo = (opac > 0.f) ? m[kS_G] / opac : 0.f; // sum vis * v_alpha
         }
     }
     v_means[(size_t)g * 3] = om[0]; v_means[(size_t)g * 3 + 1] = om[1]; v_means[(size_t)g * 3 + 2] = om[2];
@@ -681,7 +718,7 @@ extern "C" int gsb_raster_fwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
         {
             ProfScope ps("raster_prep", s);
             prep_records_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
-                N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs);
+                N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs, nullptr);
         }
         GSB_LAUNCH_CHECK();
     }
@@ -734,11 +771,10 @@ extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
         return GSB_E_WORKSPACE;
     GaussRec *recs = reinterpret_cast<GaussRec *>(workspace);
     float *moments = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align256((size_t)N * sizeof(GaussRec)));
-    GSB_CUDA_TRY(cudaMemsetAsync(moments, 0, (size_t)N * kMomFloats * 4, s));
     {
         ProfScope ps("raster_prep", s);
         prep_records_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
-            N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs);
+            N, means, quats, scales, colors, opacities, cam->viewmats0, cam->Ks, recs, moments);
     }
     GSB_LAUNCH_CHECK();
     TileParams p;

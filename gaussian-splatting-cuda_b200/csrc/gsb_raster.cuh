@@ -144,6 +144,28 @@ __device__ __forceinline__ PairEval pair_eval(const float4 q0, const float4 q1, 
     r.pass = __fmaf_rn(-q2.w, r.Ds, r.Ns) >= 0.0f; // Ns >= tau * Ds
     return r;
 }
+// The same evaluation for a thread's two pixels at once on packed fp32 pairs (lo = pixel 0, hi = pixel 1).
+// Every component goes through exactly the rounding sequence of pair_eval (mul.rn / fma.rn), so the
+// packed and the scalar form agree bit for bit.
+struct PairEval2 {
+    f2 Ns, Ds;
+    f2 xx, xy, yy;
+    bool pass0, pass1;
+};
+__device__ __forceinline__ PairEval2 pair_eval2(const float4 q0, const float4 q1, const float4 q2, f2 x, f2 y) {
+    PairEval2 r;
+    r.xx = f2_mul(x, x); r.xy = f2_mul(x, y); r.yy = f2_mul(y, y);
+    r.Ns = f2_fma(f2_bc(q1.x), r.yy, f2_fma(f2_bc(q0.w), r.xy, f2_mul(f2_bc(q0.z), r.xx)));
+    f2 D = f2_fma(f2_bc(q1.y), x, f2_bc(1.0f));
+    D = f2_fma(f2_bc(q1.z), y, D);
+    D = f2_fma(f2_bc(q1.w), r.xx, D);
+    D = f2_fma(f2_bc(q2.x), r.xy, D);
+    r.Ds = f2_fma(f2_bc(q2.y), r.yy, D);
+    const f2 t = f2_fma(f2_bc(-q2.w), r.Ds, r.Ns); // Ns >= tau * Ds
+    r.pass0 = f2_lo(t) >= 0.0f;
+    r.pass1 = f2_hi(t) >= 0.0f;
+    return r;
+}
 // Warp-level culling: can ANY pixel of the warp's block, whose (undistorted) pixel coordinates lie
 // in the box [bx0, bx1] x [by0, by1], pass the rejection test of this record?  The pass region {Ns - tau Ds >= 0} is the interior of an
 // ellipse (the form F = A x^2 + B xy + C y^2 + D x + E y + F0 is concave for every realistic
@@ -184,9 +206,8 @@ __device__ __forceinline__ bool block_may_pass(const float4 q0, const float4 q1,
 }
 
 // alpha_raw = opac * exp(power) = 2^(Ns/Ds + lop)
-__device__ __forceinline__ float pair_alpha_raw(const PairEval &e, float lop, float &ex) {
-    ex = __fmaf_rn(e.Ns, fast_rcp(e.Ds), lop);
-    return fast_ex2(ex);
+__device__ __forceinline__ float pair_alpha_raw(float Ns, float Ds, float lop) {
+    return fast_ex2(__fmaf_rn(Ns, fast_rcp(Ds), lop));
 }
 
 } // namespace gsb

@@ -147,6 +147,33 @@ GSB_EXPORT std::tuple<at::Tensor, at::Tensor, at::Tensor> intersect_tile(
 
     at::Tensor tiles_per_gauss = at::empty_like(depths, depths.options().dtype(at::kInt));
     int64_t n_isects = 0;
+    if (n_elements && sort) {
+        // Two-phase sorted path (gsb_intersect.cu): count, depth order and run offsets are enqueued before
+        // the one host read-back the API forces (Intersect.cpp:76); the number lands in pinned memory.
+        const size_t plan_bytes = gsb_isect_plan_workspace(C, N);
+        at::Tensor plan_ws = byte_workspace(plan_bytes, depths);
+        at::Tensor n_host = at::empty({1}, at::TensorOptions().dtype(at::kLong).pinned_memory(true));
+        gsb_check(gsb_isect_plan(C, N, means2d.data_ptr<float>(), radii.data_ptr<int32_t>(), depths.data_ptr<float>(),
+                                 tile_size, tile_width, tile_height, tiles_per_gauss.data_ptr<int32_t>(),
+                                 n_host.data_ptr<int64_t>(), plan_ws.data_ptr(), plan_bytes, cur_stream()),
+                  "intersect_tile/plan");
+        c10::cuda::getCurrentCUDAStream().synchronize();
+        n_isects = n_host.data_ptr<int64_t>()[0];
+        at::Tensor isect_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kLong));
+        at::Tensor flatten_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kInt));
+        if (n_isects) {
+            const size_t ws_bytes = gsb_isect_emit_planned_workspace((uint64_t)n_isects);
+            at::Tensor ws = byte_workspace(ws_bytes, depths);
+            gsb_check(gsb_isect_emit_planned(C, N, means2d.data_ptr<float>(), radii.data_ptr<int32_t>(),
+                                             depths.data_ptr<float>(), tile_size, tile_width, tile_height,
+                                             (uint64_t)n_isects, plan_ws.data_ptr(),
+                                             isect_ids_sorted.data_ptr<int64_t>(),
+                                             flatten_ids_sorted.data_ptr<int32_t>(), ws.data_ptr(), ws_bytes,
+                                             cur_stream()),
+                      "intersect_tile/emit_planned");
+        }
+        return std::make_tuple(tiles_per_gauss, isect_ids_sorted, flatten_ids_sorted);
+    }
     at::Tensor cum_tiles;
     if (n_elements) {
         cum_tiles = at::empty({(int64_t)n_elements}, depths.options().dtype(at::kLong));
@@ -157,20 +184,6 @@ GSB_EXPORT std::tuple<at::Tensor, at::Tensor, at::Tensor> intersect_tile(
                                   ws.data_ptr(), ws_bytes, cur_stream()),
                   "intersect_tile/count");
         n_isects = cum_tiles[-1].item<int64_t>(); // the one host sync the API forces (Intersect.cpp:76)
-    }
-    if (n_isects && sort) {
-        // depth order per Gaussian first, then a stable sort on the tile bits only (gsb_intersect.cu)
-        at::Tensor isect_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kLong));
-        at::Tensor flatten_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kInt));
-        const size_t ws_bytes = gsb_isect_emit_sorted_workspace(C, N, (uint64_t)n_isects);
-        at::Tensor ws = byte_workspace(ws_bytes, depths);
-        gsb_check(gsb_isect_emit_sorted(C, N, means2d.data_ptr<float>(), radii.data_ptr<int32_t>(),
-                                        depths.data_ptr<float>(), tiles_per_gauss.data_ptr<int32_t>(), tile_size,
-                                        tile_width, tile_height, (uint64_t)n_isects,
-                                        isect_ids_sorted.data_ptr<int64_t>(), flatten_ids_sorted.data_ptr<int32_t>(),
-                                        ws.data_ptr(), ws_bytes, cur_stream()),
-                  "intersect_tile/emit_sorted");
-        return std::make_tuple(tiles_per_gauss, isect_ids_sorted, flatten_ids_sorted);
     }
     at::Tensor isect_ids = at::empty({n_isects}, depths.options().dtype(at::kLong));
     at::Tensor flatten_ids = at::empty({n_isects}, depths.options().dtype(at::kInt));

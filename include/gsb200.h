@@ -154,17 +154,29 @@ GSB_API int gsb_isect_sort(uint64_t n_isects, uint32_t C, uint32_t tile_width, u
                            int64_t *isect_ids_out, int32_t *flatten_ids_out,
                            void *workspace, size_t workspace_bytes, gsb_stream_t stream);
 
-/* Fused emit + sort for sort == true (same outputs as gsb_isect_emit + gsb_isect_sort, bit for
+/* Two-phase sorted path for sort == true (same outputs as gsb_isect_emit + gsb_isect_sort, bit for
  * bit, with a third of the sort traffic): the Gaussians are first ordered by (camera, depth bits)
  * -- N elements instead of I -- the intersections are emitted in that order, and a stable radix
- * sort on the (camera, tile) key bits only finishes the job.  tiles_per_gauss is the output of
- * gsb_isect_count; n_isects the value read back from cum_tiles. */
-GSB_API size_t gsb_isect_emit_sorted_workspace(uint32_t C, uint32_t N, uint64_t n_isects);
-GSB_API int gsb_isect_emit_sorted(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
-                                  const float *depths, const int32_t *tiles_per_gauss, uint32_t tile_size,
-                                  uint32_t tile_width, uint32_t tile_height, uint64_t n_isects,
-                                  int64_t *isect_ids, int32_t *flatten_ids, void *workspace,
-                                  size_t workspace_bytes, gsb_stream_t stream);
+ * sort on the (camera, tile) key bits only finishes the job.  It is arranged around the host
+ * read-back: everything that does not need the host to know n_isects (count, depth order, run
+ * offsets) runs in the PLAN, so only the emit and the tile partition are left to enqueue once the
+ * host has the number.
+ *   gsb_isect_plan          tiles_per_gauss [C*N]; *n_isects_out (device OR pinned host int64,
+ *                           written asynchronously on `stream`); plan_workspace keeps the depth
+ *                           permutation and the run offsets for the emit.
+ *   gsb_isect_emit_planned  isect_ids / flatten_ids [n_isects], sorted; identical to
+ *                           gsb_isect_emit + gsb_isect_sort bit for bit. */
+GSB_API size_t gsb_isect_plan_workspace(uint32_t C, uint32_t N);
+GSB_API int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
+                           const float *depths, uint32_t tile_size, uint32_t tile_width,
+                           uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *n_isects_out,
+                           void *plan_workspace, size_t plan_workspace_bytes, gsb_stream_t stream);
+GSB_API size_t gsb_isect_emit_planned_workspace(uint64_t n_isects);
+GSB_API int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
+                                   const float *depths, uint32_t tile_size, uint32_t tile_width,
+                                   uint32_t tile_height, uint64_t n_isects, const void *plan_workspace,
+                                   int64_t *isect_ids, int32_t *flatten_ids, void *workspace,
+                                   size_t workspace_bytes, gsb_stream_t stream);
 
 /* ---- a6: gsplat::intersect_offset (Ops.h:39-43, IntersectTile.cu:206-288) --------
  * offsets [C,tile_height,tile_width] int32; all zero when n_isects == 0. */

@@ -18,7 +18,7 @@ def _declared():
 
 def test_header_declares_expected_entry_points():
     names = _declared()
-    for n in ("gsb_projection_ut", "gsb_sh_fwd", "gsb_sh_bwd", "gsb_isect_count", "gsb_isect_emit", "gsb_isect_sort",
+    for n in ("gsb_projection_ut", "gsb_sh_fwd", "gsb_sh_bwd", "gsb_isect_count", "gsb_isect_emit", "gsb_isect_sort", "gsb_isect_plan", "gsb_isect_emit_planned",
               "gsb_isect_offsets", "gsb_raster_fwd", "gsb_raster_bwd", "gsb_quat_to_rotmat", "gsb_relocation",
               "gsb_add_noise"):
         assert n in names
@@ -49,6 +49,7 @@ def test_cabi_has_sm100a_sass_and_tma(pkg):
     assert "sm_100a" in out
     assert "UBLKCP" in out
     assert "SYNCS" in out  # mbarrier
+    assert "FFMA2" in out  # packed fp32 pairs in the blend kernels
 
 
 def test_shim_exports_reference_operator_symbols(pkg):
