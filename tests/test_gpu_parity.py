@@ -282,6 +282,43 @@ def test_pipeline_autograd_vs_oracle(native, orc, cuda_device, name):
     assert rel(leaves["sh_coeffs"].grad.cpu().numpy(), ref["v_sh_coeffs"]) < 1e-3
 
 
+def test_host_staged_steps_match_sequential_steps(native, cuda_device):
+    """The three-stream host pipeline (hoststream.py) returns, for every step, exactly what a blocking
+    copy-in / step / copy-out sequence returns: same loss, same image, same gradients (bit for bit -- the
+    kernels and their inputs are the same; only the copies overlap)."""
+    from gsplat_b200 import hoststream
+    sc = _blend_case("small_rot")
+    W, H = sc["width"], sc["height"]
+    names = ("means", "quats", "scales", "opacities", "sh_coeffs")
+    host = {k: torch.from_numpy(np.ascontiguousarray(sc[k])).pin_memory()
+            for k in names + ("viewmats", "Ks", "background")}
+    host["target"] = torch.from_numpy(np.random.default_rng(9).random((1, H, W, 3), dtype=np.float32)).pin_memory()
+
+    def step(Pd):
+        for k in names:
+            Pd[k].grad = None
+        out = native.rasterize(Pd["means"], Pd["quats"], Pd["scales"], Pd["opacities"], Pd["sh_coeffs"],
+                               sc["sh_degree"], Pd["viewmats"], Pd["Ks"], W, H, bg_color=Pd["background"])
+        loss = (out.render_colors - Pd["target"]).abs().mean()
+        loss.backward()
+        return loss, out.render_colors
+
+    Pd = {k: host[k].to(cuda_device).requires_grad_(k in names) for k in host}
+    loss, img = step(Pd)
+    want = {k: Pd[k].grad.cpu() for k in names}
+    staged = hoststream.HostStagedSteps(cuda_device, host, names, step)
+    losses = staged.run(5)
+    assert len(losses) == 5
+    # blend gradients are accumulated with float atomics: equal up to summation order
+    want_loss = float(loss.item())
+    assert all(abs(l - want_loss) <= 1e-6 * abs(want_loss) for l in losses)
+    for slot in (0, 1):
+        assert torch.equal(staged.host_img[slot], img.detach().cpu())
+        for k in names:
+            assert rel(staged.host_grads[slot][k].numpy(), want[k].numpy()) < 1e-5
+    assert staged.h2d_bytes == sum(t.numel() * t.element_size() for t in host.values())
+
+
 # ------------------------------------------------------------------------------------------
 # link-surface ops
 # ------------------------------------------------------------------------------------------
