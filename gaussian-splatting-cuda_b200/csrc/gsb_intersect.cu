@@ -99,6 +99,100 @@ __global__ void __launch_bounds__(kIsectThreads) isect_emit_kernel(uint64_t n, u
         }
 }
 
+// Load-balanced emit for the sorted path: one CTA per kEmitSpan consecutive OUTPUT slots instead of one
+// thread per Gaussian, so a Gaussian covering 400 tiles costs 400 slots of work spread over 50 threads
+// rather than one thread's 400-iteration loop, and the span leaves through coalesced warp stores.
+// Run i (Gaussian perm[i]) owns the slots [cum[i-1], cum[i]); Gaussians without tiles are parked behind
+// all others by their depth key, so every run that intersects [0, I) is non-empty.
+constexpr int kEmitItems = 8;
+constexpr int kEmitSpan = kIsectThreads * kEmitItems;
+
+__global__ void __launch_bounds__(kIsectThreads) isect_emit_balanced_kernel(
+    uint64_t n, uint32_t N, uint64_t n_isects, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
+    const float *__restrict__ depths, const uint32_t *__restrict__ perm, const int64_t *__restrict__ cum,
+    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, uint32_t tile_n_bits,
+    int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
+    __shared__ int32_t s_end[kEmitSpan + 1]; // run ends relative to the CTA's first slot, clamped to the span
+    __shared__ int64_t s_keys[kEmitSpan];
+    __shared__ int32_t s_vals[kEmitSpan];
+    __shared__ uint64_t s_first;             // index of the run that owns the CTA's first slot
+    __shared__ int64_t s_first_start;        // and its first slot
+    const int64_t o0 = (int64_t)blockIdx.x * kEmitSpan;
+    const int32_t span = (int32_t)min((int64_t)kEmitSpan, (int64_t)n_isects - o0);
+    const uint32_t tid = threadIdx.x;
+
+    if (tid < 32) {
+        // first i with cum[i] > o0: 32-ary search, one probe per lane per round
+        uint64_t lo = 0, hi = n; // answer in [lo, hi), cum[n-1] = n_isects > o0
+        while (hi - lo > 1) {
+            const uint64_t len = hi - lo;
+            const uint64_t step = (len + 32) / 33; // 32 interior probes split the range into <= 33 pieces
+            const uint64_t p = lo + (uint64_t)(tid + 1) * step - 1; // probe positions lo+step-1, lo+2step-1, ...
+            const bool le = (p < hi - 1) ? (cum[p] <= o0) : false;   // position hi-1 is known to be > o0
+            const uint32_t m = __ballot_sync(0xffffffffu, le);
+            const uint32_t k = __popc(m); // probes are monotone: the first k satisfy cum <= o0
+            const uint64_t nlo = (k == 0) ? lo : lo + (uint64_t)k * step;
+            const uint64_t nhi = (k == 32) ? hi : min(hi, lo + (uint64_t)(k + 1) * step);
+            lo = nlo; hi = nhi;
+        }
+        if (tid == 0) {
+            s_first = lo;
+            s_first_start = (lo == 0) ? 0 : cum[lo - 1];
+        }
+    }
+    __syncthreads();
+    const uint64_t g_lo = s_first;
+    for (int32_t r = (int32_t)tid; r <= kEmitSpan; r += kIsectThreads) {
+        const uint64_t g = g_lo + (uint64_t)r;
+        int64_t e = (g < n) ? cum[g] - o0 : (int64_t)kEmitSpan;
+        s_end[r] = (int32_t)min(e, (int64_t)kEmitSpan);
+    }
+    __syncthreads();
+
+    // Each thread walks its kEmitItems consecutive slots (one run lookup, then increments) into shared
+    // memory; the CTA then writes the span out with fully coalesced 256-byte warp stores -- per-thread
+    // 8-byte global stores would touch one 32-byte sector each and run at the L2's transaction rate.
+    auto phys = [](int32_t e) { return (e & ~7) | ((e & 7) ^ ((e >> 3) & 7)); }; // bank swizzle
+    int32_t o = (int32_t)tid * kEmitItems;
+    if (o < span) {
+        // run of this thread's first slot: first r with s_end[r] > o
+        int32_t lo = 0, hi = kEmitSpan;
+        while (lo < hi) {
+            const int32_t mid = (lo + hi) >> 1;
+            if (s_end[mid] > o) hi = mid; else lo = mid + 1;
+        }
+        int32_t r = lo;
+        const int32_t o_stop = min(o + kEmitItems, span);
+        while (o < o_stop) {
+            const uint64_t idx = perm[g_lo + (uint64_t)r];
+            const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
+            const uint32_t w = b.x1 - b.x0;
+            const int64_t run_start = (r == 0) ? s_first_start - o0 : (int64_t)s_end[r - 1];
+            const uint32_t j = (uint32_t)((int64_t)o - run_start);
+            uint32_t y = b.y0 + j / w, x = b.x0 + j % w;
+            const int64_t cid_enc = (int64_t)(idx / N) << (32 + tile_n_bits);
+            const int64_t depth_enc = (int64_t)__float_as_uint(depths[idx]);
+            const int32_t run_stop = min(s_end[r], o_stop);
+            for (; o < run_stop; ++o) {
+                const int64_t tile_id = (int64_t)y * tile_width + x;
+                s_keys[phys(o)] = cid_enc | (tile_id << 32) | depth_enc;
+                s_vals[phys(o)] = (int32_t)idx;
+                if (++x == b.x1) { x = b.x0; ++y; }
+            }
+            ++r;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kEmitItems; ++k) {
+        const int32_t e = k * kIsectThreads + (int32_t)tid;
+        if (e < span) {
+            isect_ids[o0 + e] = s_keys[phys(e)];
+            flatten_ids[o0 + e] = s_vals[phys(e)];
+        }
+    }
+}
+
 // Count and depth key in one pass over the Gaussians (the plan phase of the two-phase sorted path).
 __global__ void __launch_bounds__(kIsectThreads) isect_plan_kernel(uint64_t n, uint32_t N,
                                                                     const float *__restrict__ means2d,
@@ -115,8 +209,10 @@ __global__ void __launch_bounds__(kIsectThreads) isect_plan_kernel(uint64_t n, u
     const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
     const int32_t cnt = b.active ? (int32_t)((b.y1 - b.y0) * (b.x1 - b.x0)) : 0;
     tiles_per_gauss[idx] = cnt;
+    // Gaussians without tiles never emit: park them behind ALL others (camera field = C, one past the last)
     const uint32_t d = cnt > 0 ? __float_as_uint(depths[idx]) : 0xffffffffu;
-    if (keys64) keys64[idx] = ((uint64_t)(idx / N) << 32) | d;
+    const uint64_t cam = cnt > 0 ? idx / N : n / N;
+    if (keys64) keys64[idx] = (cam << 32) | d;
     else keys32[idx] = d;
     vals[idx] = (uint32_t)idx;
 }
@@ -353,11 +449,12 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *means
     char *base = reinterpret_cast<char *>(workspace);
     int64_t *tmp_keys = reinterpret_cast<int64_t *>(base + w.tmp_keys);
     int32_t *tmp_vals = reinterpret_cast<int32_t *>(base + w.tmp_vals);
-    const uint32_t grid = (uint32_t)((n + kIsectThreads - 1) / kIsectThreads);
     {
         ProfScope ps("isect_emit", s);
-        isect_emit_kernel<<<grid, kIsectThreads, 0, s>>>(n, N, means2d, radii, depths, perm, cum, tile_size, tile_width,
-                                                        tile_height, tile_n_bits, tmp_keys, tmp_vals);
+        const uint32_t egrid = (uint32_t)((n_isects + kEmitSpan - 1) / kEmitSpan);
+        isect_emit_balanced_kernel<<<egrid, kIsectThreads, 0, s>>>(n, N, n_isects, means2d, radii, depths, perm, cum,
+                                                                  tile_size, tile_width, tile_height, tile_n_bits,
+                                                                  tmp_keys, tmp_vals);
         GSB_LAUNCH_CHECK();
     }
     {
