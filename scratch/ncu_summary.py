@@ -55,7 +55,7 @@ def full(kernel):
     st.sort(key=lambda t: -t[1])
     out.append("\nTop warp-stall reasons (warps per issue-active cycle): " + ", ".join(f"{n} {v:.2f}" for n, v in st[:7]) + "\n")
 launches()
-for k in ('raster_bwd_kernel', 'raster_fwd_kernel'):
+for k in ('raster_bwd_kernel', 'raster_fwd_kernel', 'isect_emit_balanced_kernel'):
     full(k)
 open(f'profiles/{tag}_ncu_summary.md', 'w').write(f"# ncu summary {tag}\n\nSource artefacts: `gpurun_out/launches_{tag}.csv`, `gpurun_out/prof_raster_*_{tag}.ncu-rep` "
      f"(scratch, not tracked); this file is the tracked digest.\n\n" + "\n".join(out) + "\n")

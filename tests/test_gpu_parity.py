@@ -282,6 +282,31 @@ def test_pipeline_autograd_vs_oracle(native, orc, cuda_device, name):
     assert rel(leaves["sh_coeffs"].grad.cpu().numpy(), ref["v_sh_coeffs"]) < 1e-3
 
 
+def test_blend_bwd_tensor_core_reduction_matches_shuffle_reduction(native, orc, cuda_device, monkeypatch):
+    """GSB_BWD_REDUCE=mma: the ten geometric moments of eight events at a time go through mma.sync (tf32 hi/lo
+    split, fp32 accumulate) instead of warp shuffles.  Same gradients to fp32 summation-order noise."""
+    sc = _blend_case("b30k")
+    W, H = sc["width"], sc["height"]
+    rng = np.random.default_rng(11)
+    vrc = torch.from_numpy(rng.standard_normal((1, H, W, 3)).astype(np.float32)).to(cuda_device)
+    vra = torch.from_numpy(rng.standard_normal((1, H, W, 1)).astype(np.float32)).to(cuda_device)
+    ref = orc.render_pipeline(sc, "f32", False)
+    t = to_dev(sc, cuda_device)
+    colors = torch.from_numpy(ref["colors"]).to(cuda_device)
+    off = torch.from_numpy(ref["tile_offsets"]).to(cuda_device)
+    flat = torch.from_numpy(ref["flatten_ids"]).to(cuda_device)
+    args = (t["means"], t["quats"], t["scales"], colors, t["opacities"][None], t.get("background"), None, W, H, 16,
+            t["viewmats"], t["Ks"], off, flat)
+    _, alphas, last_ids = native.rasterize_to_pixels_from_world_3dgs_fwd(*args)
+    out = {}
+    for mode in ("shuffle", "mma"):
+        monkeypatch.setenv("GSB_BWD_REDUCE", mode)
+        out[mode] = native.rasterize_to_pixels_from_world_3dgs_bwd(*args, alphas, last_ids, vrc, vra)
+        torch.cuda.synchronize()
+    for a, b, name in zip(out["shuffle"], out["mma"], ("v_means", "v_quats", "v_scales", "v_colors", "v_opacities")):
+        assert rel(b.cpu().numpy(), a.cpu().numpy()) < 2e-5, name
+
+
 def test_host_staged_steps_match_sequential_steps(native, cuda_device):
     """The three-stream host pipeline (hoststream.py) returns, for every step, exactly what a blocking
     copy-in / step / copy-out sequence returns: same loss, same image, same gradients (bit for bit -- the
