@@ -223,14 +223,22 @@ def run_b200(args):
 
     stats = {}
 
+    compact = world > 1 and args.exchange == "compact"
+
     def step(Pd, backend=None):
         for k in names:
             Pd[k].grad = None
+        deferred = pkg.DeferredSHBackward() if compact else None
         out = pkg.rasterize(Pd["means"], Pd["quats"], Pd["scales"], Pd["opacities"], Pd["sh_coeffs"], deg,
-                            Pd["viewmats"], Pd["Ks"], W, H, bg_color=Pd["background"], backend=backend)
+                            Pd["viewmats"], Pd["Ks"], W, H, bg_color=Pd["background"], backend=backend,
+                            sh_exchange=deferred)
         loss = (out.render_colors - Pd["target"]).abs().mean()
         loss.backward()
-        if world > 1:
+        if compact:
+            # all-gather of the 12-byte colour gradients + all-reduce of the 44 B of geometry gradients + local
+            # expansion of all views (gsb_sh_bwd_views): the same sums as the all-reduce below, 1/2-1/3 of the bytes
+            multiview.exchange_gradients_compact(Pd, deferred)
+        elif world > 1:
             # one fused NCCL launch for the five gradient tensors (236 B/Gaussian)
             multiview.allreduce_gradients([Pd[k].grad for k in names])
         stats["n_isects"], stats["vis"] = out.n_isects, out.visibility
@@ -266,7 +274,7 @@ def run_b200(args):
     prof = {}
     for kname in ("projection_ut", "sh_fwd", "isect_count", "isect_depth_sort", "isect_emit", "isect_sort",
                   "isect_offsets", "raster_prep",
-                  "raster_fwd", "raster_bwd", "raster_finalize", "sh_bwd"):
+                  "raster_fwd", "raster_bwd", "raster_finalize", "sh_bwd", "sh_bwd_views"):
         tot = ctypes.c_double(0.0)
         n = cabi.gsb_profile_read(kname.encode(), ctypes.byref(tot))
         if n:
@@ -361,8 +369,8 @@ def run_b200(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": ("1M synthetic Gaussians, 1920x1080, SH deg 3, 16x16 tiles, fwd+bwd on 1xB200 "
                                 "(BASELINE.json configs[1])" if world == 1 else
-                                f"1M Gaussians x {world} synthetic cameras/step, per-view shard + NCCL grad "
-                                "all-reduce (BASELINE.json configs[4])"),
+                                f"1M Gaussians x {world} synthetic cameras/step, per-view shard + NCCL gradient "
+                                f"exchange ({args.exchange}) (BASELINE.json configs[4])"),
                    "gaussians": N, "visible": int(stats["vis"].sum().item()), "intersections": I, "image": [W, H],
                    "loss": "L1 vs synthetic target", "parallelism": f"view-dp{world}",
                    "l2": "per-step working set (236 MB parameters + 64 MB records + ~0.35 GB intersection "
@@ -394,6 +402,9 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--exchange", choices=("compact", "allreduce"), default="compact",
+                    help="N>1 gradient exchange: compact (all-gather colour gradients + multi-view SH backward) or "
+                         "plain all-reduce of the five gradient tensors")
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

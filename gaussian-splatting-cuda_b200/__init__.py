@@ -103,6 +103,11 @@ class OpsBackend:
                                                            compute_v_dirs)
         return v_coeffs, (v_dirs if compute_v_dirs else None)
 
+    def spherical_harmonics_bwd_views(self, degrees_to_use, means, campos, coeffs, v_colors, v_means):
+        """Extension (multi-GPU exchange step, include/gsb200.h gsb_sh_bwd_views): SH backward of V views at
+        once from their gathered colour gradients; returns v_coeffs, accumulates into v_means."""
+        return self.ns.spherical_harmonics_bwd_views(degrees_to_use, means, campos, coeffs, v_colors, v_means)
+
     def intersect_tile(self, means2d, radii, depths, C, tile_size, tile_width, tile_height, sort=True):
         return self.ns.intersect_tile(means2d, radii, depths, C, tile_size, tile_width, tile_height, sort)
 
@@ -200,6 +205,37 @@ class SphericalHarmonicsFunction(torch.autograd.Function):
                 v_coeffs.reshape(coeffs.shape) if ctx.needs_input_grad[3] else None, None)
 
 
+class DeferredSHBackward:
+    """Filled by rasterize(..., sh_exchange=...) during backward(): the view's colour gradient as the SH
+    backward would receive it (12 B/Gaussian), instead of the expanded 192 B/Gaussian coefficient gradient.
+    multiview.exchange_gradients_compact() gathers these over the ranks and expands all views at once."""
+
+    def __init__(self):
+        self.v_colors = None  # [N, 3], zero where the Gaussian was masked / not blended
+        self.campos = None    # [3] camera position of this rank's view
+        self.sh_degree = None
+
+
+class DeferredSphericalHarmonicsFunction(torch.autograd.Function):
+    """Same forward as SphericalHarmonicsFunction; the backward only records v_colors (see DeferredSHBackward)
+    and lets no gradient flow to coeffs / dirs -- the exchange step supplies both, summed over all views."""
+
+    @staticmethod
+    def forward(ctx, backend: OpsBackend, sh_degree: int, dirs, coeffs, masks, sink: DeferredSHBackward):
+        colors = backend.spherical_harmonics_fwd(sh_degree, dirs.contiguous().reshape(-1, 3),
+                                                 coeffs.contiguous().reshape(-1, coeffs.shape[-2], 3),
+                                                 masks.reshape(-1).contiguous())
+        ctx.save_for_backward(masks)
+        ctx.sink = sink
+        return colors.reshape(dirs.shape)
+
+    @staticmethod
+    def backward(ctx, v_colors):
+        (masks,) = ctx.saved_tensors
+        ctx.sink.v_colors = (v_colors.reshape(-1, 3) * masks.reshape(-1, 1)).contiguous()
+        return None, None, None, None, None, None
+
+
 class GUTRasterizationFunction(torch.autograd.Function):
     """rasterizer_autograd.cpp:267-391."""
 
@@ -252,7 +288,8 @@ class RenderOutput:
 def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K, width, height, bg_color=None,
               scaling_modifier=1.0, tile_size=16, eps2d=0.3, near_plane=0.01, far_plane=10000.0,
               radius_clip=0.0, backend: OpsBackend | None = None, camera_model=PINHOLE, radial_coeffs=None,
-              tangential_coeffs=None, thin_prism_coeffs=None) -> RenderOutput:
+              tangential_coeffs=None, thin_prism_coeffs=None,
+              sh_exchange: DeferredSHBackward | None = None) -> RenderOutput:
     """gs::training::rasterize for RenderMode::RGB, perfect pinhole, C == 1 (rasterizer.cpp:46-437).
 
     Inputs are the ACTIVATED parameters (get_means/get_rotation/get_scaling/get_opacity/get_shs of
@@ -274,7 +311,12 @@ def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K,
         campos = torch.linalg.inv_ex(viewmat).inverse[:, :3, 3]
         masks = (radii > 0).all(-1)                                      # :257
     dirs = means.unsqueeze(0) - campos.unsqueeze(1)                      # :254
-    colors = SphericalHarmonicsFunction.apply(be, sh_degree, dirs, sh_coeffs.unsqueeze(0), masks)
+    if sh_exchange is not None:  # multi-GPU step: the SH backward happens in the exchange (multiview.py)
+        sh_exchange.campos, sh_exchange.sh_degree = campos[0], sh_degree
+        colors = DeferredSphericalHarmonicsFunction.apply(be, sh_degree, dirs, sh_coeffs.unsqueeze(0), masks,
+                                                          sh_exchange)
+    else:
+        colors = SphericalHarmonicsFunction.apply(be, sh_degree, dirs, sh_coeffs.unsqueeze(0), masks)
     colors = torch.clamp_min(colors + 0.5, 0.0)                          # :266
     tile_w = (width + tile_size - 1) // tile_size
     tile_h = (height + tile_size - 1) // tile_size

@@ -376,6 +376,113 @@ __global__ void __launch_bounds__(kShThreads) sh_bwd_k16_kernel(uint32_t M, cons
     if (inside) bulk_wait_read_all(); // the row must stay in shared memory until the bulk store has read it
 }
 
+// ------------------------------------------------------------------------------------------
+// Multi-view SH backward (the multi-GPU exchange step).  The SH gradient of one view is the
+// rank-1 row  v_coeffs[n] = Y(dir_v(n)) (x) v_color_v[n]  -- 192 B per Gaussian made from 12 B.  Ranks
+// therefore exchange the 12-byte colour gradients (all-gather) instead of all-reducing the 192-byte rows,
+// and every rank expands and sums all V views here: one thread per Gaussian, the coefficient row comes in
+// and the summed gradient row goes out with one TMA bulk copy each (K = 16), views whose colour gradient is
+// exactly zero (Gaussian not blended in that view) cost one 12-byte load.  The gradient w.r.t. the view
+// directions is chained to the Gaussian's position (dir = mean - campos) and ACCUMULATED into v_means.
+// ------------------------------------------------------------------------------------------
+template <int DEG, bool kRow16Path>
+__global__ void __launch_bounds__(kShThreads) sh_bwd_views_kernel(uint32_t M, uint32_t K, uint32_t V,
+                                                                  const float *__restrict__ means,
+                                                                  const float *__restrict__ campos,
+                                                                  const float *__restrict__ coeffs,
+                                                                  const float *__restrict__ v_colors,
+                                                                  float *__restrict__ v_coeffs,
+                                                                  float *__restrict__ v_means) {
+    constexpr int NB = (DEG + 1) * (DEG + 1);
+    extern __shared__ __align__(128) float s_rows[]; // row path: in rows [T][52] then out rows [T][52]
+    __shared__ __align__(8) uint64_t s_bar;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t e = blockIdx.x * kShThreads + tid;
+    const bool inside = e < M;
+    float *row_in = nullptr, *row_out = nullptr;
+    if constexpr (kRow16Path) {
+        if (tid == 0) { mbar_init(&s_bar, kShThreads); mbar_fence_init(); }
+        __syncthreads();
+        row_in = s_rows + tid * kRowStride16;
+        row_out = s_rows + (kShThreads + tid) * kRowStride16;
+        constexpr uint32_t kInBytes = (NB * 12 + 15) / 16 * 16;
+        if (inside && DEG >= 1) {
+            mbar_arrive_expect_tx(&s_bar, kInBytes);
+            bulk_g2s(row_in, coeffs + (size_t)e * kRow16, kInBytes, &s_bar);
+        } else {
+            mbar_arrive(&s_bar);
+        }
+    }
+    float acc[NB * 3];
+#pragma unroll
+    for (int i = 0; i < NB * 3; ++i) acc[i] = 0.f;
+    float mx = 0.f, my = 0.f, mz = 0.f, vmx = 0.f, vmy = 0.f, vmz = 0.f;
+    if (inside) { mx = means[(size_t)e * 3]; my = means[(size_t)e * 3 + 1]; mz = means[(size_t)e * 3 + 2]; }
+    if constexpr (kRow16Path) mbar_wait(&s_bar, 0);
+    if (inside) {
+        for (uint32_t v = 0; v < V; ++v) {
+            const float *gc = v_colors + ((size_t)v * M + e) * 3;
+            const float g0 = gc[0], g1 = gc[1], g2 = gc[2];
+            if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
+            float x = mx - campos[v * 3], y = my - campos[v * 3 + 1], z = mz - campos[v * 3 + 2], inorm = 1.f;
+            if constexpr (DEG >= 1) {
+                inorm = rsqrtf(x * x + y * y + z * z);
+                x *= inorm; y *= inorm; z *= inorm;
+            }
+            float b[NB];
+            sh_basis<DEG>(x, y, z, b);
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                acc[k * 3] = fmaf(b[k], g0, acc[k * 3]);
+                acc[k * 3 + 1] = fmaf(b[k], g1, acc[k * 3 + 1]);
+                acc[k * 3 + 2] = fmaf(b[k], g2, acc[k * 3 + 2]);
+            }
+            if constexpr (DEG >= 1) {
+                float w[NB];
+#pragma unroll
+                for (int k = 0; k < NB; ++k) {
+                    float f0, f1, f2;
+                    if constexpr (kRow16Path) { f0 = row_in[k * 3]; f1 = row_in[k * 3 + 1]; f2 = row_in[k * 3 + 2]; }
+                    else {
+                        const float *f = coeffs + ((size_t)e * K + k) * 3;
+                        f0 = f[0]; f1 = f[1]; f2 = f[2];
+                    }
+                    w[k] = g0 * f0 + g1 * f1 + g2 * f2;
+                }
+                float vx = 0.f, vy = 0.f, vz = 0.f;
+                sh_basis_vjp<DEG>(x, y, z, w, vx, vy, vz);
+                const float d = vx * x + vy * y + vz * z;
+                vmx += (vx - d * x) * inorm; vmy += (vy - d * y) * inorm; vmz += (vz - d * z) * inorm;
+            }
+        }
+    }
+    if constexpr (kRow16Path) {
+        float4 *o4 = reinterpret_cast<float4 *>(row_out);
+#pragma unroll
+        for (int i = 0; i < kRow16 / 4; ++i) {
+            float t[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) t[j] = (i * 4 + j < NB * 3) ? acc[(i * 4 + j < NB * 3) ? i * 4 + j : 0] : 0.f;
+            o4[i] = make_float4(t[0], t[1], t[2], t[3]);
+        }
+        if (inside) {
+            fence_proxy_async();
+            bulk_s2g(v_coeffs + (size_t)e * kRow16, row_out, kRow16 * 4);
+            bulk_commit();
+        }
+    } else if (inside) {
+        float *o = v_coeffs + (size_t)e * K * 3;
+        for (uint32_t k = 0; k < K; ++k)
+            for (int c = 0; c < 3; ++c) o[k * 3 + c] = (k < (uint32_t)NB) ? acc[(k < (uint32_t)NB ? k : 0) * 3 + c] : 0.f;
+    }
+    if (inside && DEG >= 1) {
+        v_means[(size_t)e * 3] += vmx; v_means[(size_t)e * 3 + 1] += vmy; v_means[(size_t)e * 3 + 2] += vmz;
+    }
+    if constexpr (kRow16Path) {
+        if (inside) bulk_wait_read_all();
+    }
+}
+
 static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 } // namespace gsb
@@ -440,6 +547,47 @@ extern "C" int gsb_sh_bwd(uint32_t M, uint32_t K, uint32_t degree, const float *
     case 3: gsb::sh_bwd_kernel<3><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
     default: gsb::sh_bwd_kernel<4><<<grid, gsb::kShThreads, 0, s>>>(M, K, dirs, coeffs, masks, v_colors, v_coeffs, v_dirs); break;
     }
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
+extern "C" int gsb_sh_bwd_views(uint32_t M, uint32_t K, uint32_t degree, uint32_t V, const float *means,
+                                const float *campos, const float *coeffs, const float *v_colors, float *v_coeffs,
+                                float *v_means, gsb_stream_t stream) {
+    if (M == 0) return GSB_OK;
+    if (!means || !coeffs || !v_coeffs || !v_means || (V > 0 && (!campos || !v_colors))) return GSB_E_INVALID;
+    if (degree > 4 || (degree + 1) * (degree + 1) > K) return GSB_E_INVALID;
+    const dim3 grid((M + gsb::kShThreads - 1) / gsb::kShThreads);
+    cudaStream_t s = gsb::as_stream(stream);
+    gsb::ProfScope ps("sh_bwd_views", s);
+    if (K == 16 && degree <= 3 && gsb::aligned16(coeffs) && gsb::aligned16(v_coeffs)) {
+        const size_t smem = (size_t)2 * gsb::kShThreads * gsb::kRowStride16 * 4;
+        #define GSB_SH_VIEWS16(D)                                                                                      \
+            cudaFuncSetAttribute(gsb::sh_bwd_views_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                 (int)smem);                                                                           \
+            gsb::sh_bwd_views_kernel<D, true><<<grid, gsb::kShThreads, smem, s>>>(M, K, V, means, campos, coeffs,      \
+                                                                                  v_colors, v_coeffs, v_means)
+        switch (degree) {
+        case 0: GSB_SH_VIEWS16(0); break;
+        case 1: GSB_SH_VIEWS16(1); break;
+        case 2: GSB_SH_VIEWS16(2); break;
+        default: GSB_SH_VIEWS16(3); break;
+        }
+        #undef GSB_SH_VIEWS16
+        GSB_LAUNCH_CHECK();
+        return GSB_OK;
+    }
+    #define GSB_SH_VIEWS(D)                                                                                            \
+        gsb::sh_bwd_views_kernel<D, false><<<grid, gsb::kShThreads, 0, s>>>(M, K, V, means, campos, coeffs, v_colors,  \
+                                                                            v_coeffs, v_means)
+    switch (degree) {
+    case 0: GSB_SH_VIEWS(0); break;
+    case 1: GSB_SH_VIEWS(1); break;
+    case 2: GSB_SH_VIEWS(2); break;
+    case 3: GSB_SH_VIEWS(3); break;
+    default: GSB_SH_VIEWS(4); break;
+    }
+    #undef GSB_SH_VIEWS
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }

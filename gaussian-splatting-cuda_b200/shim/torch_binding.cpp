@@ -4,7 +4,11 @@
 // to ints/floats because the dispatcher only carries primitive types).
 #include <torch/library.h>
 
+#include <c10/cuda/CUDAGuard.h>
+#include <c10/cuda/CUDAStream.h>
+
 #include "Ops.h"
+#include "gsb200.h"
 
 namespace {
 
@@ -87,6 +91,32 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor> raster_bwd(
         flatten_ids, render_alphas, last_ids, v_render_colors, v_render_alphas);
 }
 
+// Extension for the multi-GPU exchange step (not part of the reference's Ops.h): include/gsb200.h, gsb_sh_bwd_views.
+// Returns v_coeffs [M, K, 3]; v_means [M, 3] is accumulated in place.
+Tensor sh_bwd_views(int64_t degree, const Tensor &means, const Tensor &campos, const Tensor &coeffs,
+                    const Tensor &v_colors, Tensor v_means) {
+    TORCH_CHECK(means.is_cuda() && campos.is_cuda() && coeffs.is_cuda() && v_colors.is_cuda() && v_means.is_cuda(),
+                "sh_bwd_views: CUDA tensors expected");
+    TORCH_CHECK(means.is_contiguous() && campos.is_contiguous() && coeffs.is_contiguous() && v_colors.is_contiguous() &&
+                    v_means.is_contiguous(),
+                "sh_bwd_views: contiguous tensors expected");
+    TORCH_CHECK(means.scalar_type() == at::kFloat && coeffs.scalar_type() == at::kFloat &&
+                    v_colors.scalar_type() == at::kFloat && campos.scalar_type() == at::kFloat &&
+                    v_means.scalar_type() == at::kFloat,
+                "sh_bwd_views: float32 tensors expected");
+    const int64_t M = means.size(0), V = campos.size(0), K = coeffs.size(-2);
+    TORCH_CHECK(coeffs.numel() == M * K * 3 && v_colors.numel() == V * M * 3 && v_means.numel() == M * 3,
+                "sh_bwd_views: shape mismatch");
+    const c10::cuda::CUDAGuard guard(means.device());
+    Tensor v_coeffs = at::empty_like(coeffs);
+    const int rc = gsb_sh_bwd_views((uint32_t)M, (uint32_t)K, (uint32_t)degree, (uint32_t)V, means.data_ptr<float>(),
+                                    campos.data_ptr<float>(), coeffs.data_ptr<float>(), v_colors.data_ptr<float>(),
+                                    v_coeffs.data_ptr<float>(), v_means.data_ptr<float>(),
+                                    c10::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == 0, "gsb_sh_bwd_views failed: ", gsb_error_string(rc));
+    return v_coeffs;
+}
+
 Tensor quats_to_rotmats(const Tensor &quats) { return gsplat::quats_to_rotmats(quats); }
 
 std::tuple<Tensor, Tensor> relocation(const Tensor &opacities, const Tensor &scales, const Tensor &ratios,
@@ -109,6 +139,9 @@ TORCH_LIBRARY(gsplat_b200, m) {
     m.def("projection_ut_3dgs_fused", &projection_ut);
     m.def("rasterize_to_pixels_from_world_3dgs_fwd", &raster_fwd);
     m.def("rasterize_to_pixels_from_world_3dgs_bwd", &raster_bwd);
+    m.def("spherical_harmonics_bwd_views(int degree, Tensor means, Tensor campos, Tensor coeffs, Tensor v_colors, "
+          "Tensor(a!) v_means) -> Tensor",
+          &sh_bwd_views);
     m.def("quats_to_rotmats", &quats_to_rotmats);
     m.def("relocation", &relocation);
     m.def("add_noise(Tensor raw_opacities, Tensor raw_scales, Tensor raw_quats, Tensor noise, Tensor(a!) means, float current_lr) -> ()",

@@ -128,6 +128,19 @@ GSB_API int gsb_sh_bwd(uint32_t M, uint32_t K, uint32_t degrees_to_use, const fl
                        const float *coeffs, const uint8_t *masks, const float *v_colors,
                        float *v_coeffs, float *v_dirs /*nullable*/, gsb_stream_t stream);
 
+/* ---- (e) multi-GPU exchange step: SH backward of V views at once ------------------------------
+ * The reference has no distributed mode; this entry point belongs to the view-sharded
+ * data-parallel step of SURVEY.md 8(e).  Per view the SH gradient row is the outer product of the basis
+ * at that view's direction and a 12-byte colour gradient, so ranks all-gather the colour gradients
+ * (v_colors [V, M, 3], zero where a Gaussian was not blended) and each expands and sums all views:
+ *   v_coeffs [M, K, 3]  = sum_v Y(normalize(means - campos[v])) (x) v_colors[v]      (fully written)
+ *   v_means  [M, 3]    += sum_v d(colour_v)/d(mean)                                   (accumulated)
+ * Equal to summing gsb_sh_bwd over the views with dirs = means - campos[v]. */
+GSB_API int gsb_sh_bwd_views(uint32_t M, uint32_t K, uint32_t degrees_to_use, uint32_t V,
+                             const float *means, const float *campos /* [V,3] */, const float *coeffs,
+                             const float *v_colors /* [V,M,3] */, float *v_coeffs, float *v_means,
+                             gsb_stream_t stream);
+
 /* ---- a5: gsplat::intersect_tile (Ops.h:28-38, Intersect.cpp:15-122,
  *      IntersectTile.cu:24-114,290-328) ----------------------------------------------
  * Three device steps around the one host read-back the API forces (the op

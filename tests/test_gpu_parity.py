@@ -345,6 +345,63 @@ def test_host_staged_steps_match_sequential_steps(native, cuda_device):
 
 
 # ------------------------------------------------------------------------------------------
+# multi-GPU exchange step: multi-view SH backward and the deferred L3 path
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K,deg", [(16, 3), (16, 1), (16, 0), (25, 4), (9, 2)])
+def test_sh_bwd_views_equals_sum_of_single_view_backwards(native, orc, cuda_device, K, deg):
+    rng = np.random.default_rng(21)
+    M, V = 5003, 3
+    means = rng.standard_normal((M, 3)).astype(np.float32) * 3
+    campos = rng.standard_normal((V, 3)).astype(np.float32) * 6
+    coeffs = rng.standard_normal((M, K, 3)).astype(np.float32)
+    vc = rng.standard_normal((V, M, 3)).astype(np.float32)
+    vc[rng.random((V, M)) < 0.5] = 0.0  # not blended in that view
+    vm0 = rng.standard_normal((M, 3)).astype(np.float32)
+    want_c = np.zeros_like(coeffs, dtype=np.float64)
+    want_m = vm0.astype(np.float64)
+    for v in range(V):
+        a, b = orc.sh_bwd(deg, means - campos[v], coeffs, None, vc[v], True, precision="f64")
+        want_c += a
+        want_m += b
+    d = lambda x: torch.from_numpy(x).to(cuda_device)
+    v_means = d(vm0.copy())
+    got_c = native.default_backend().spherical_harmonics_bwd_views(deg, d(means), d(campos), d(coeffs), d(vc), v_means)
+    assert rel(got_c.cpu().numpy(), want_c) < 1e-5
+    assert rel(v_means.cpu().numpy(), want_m) < 1e-5
+    # also against the product's own single-view op (same arithmetic per view, sums in a different order)
+    acc = torch.zeros_like(got_c)
+    for v in range(V):
+        a, _ = native.spherical_harmonics_bwd(K, deg, d(means - campos[v]), d(coeffs), None, d(vc[v]), True)
+        acc += a
+    assert rel(got_c.cpu().numpy(), acc.cpu().numpy()) < 1e-6
+
+
+def test_deferred_sh_exchange_single_rank_equals_plain_backward(native, cuda_device):
+    """rasterize(..., sh_exchange=...) + exchange_gradients_compact at world size 1 == the plain autograd path."""
+    from gsplat_b200 import multiview as mv
+    sc = _blend_case("small_rot")
+    W, H = sc["width"], sc["height"]
+    names = ("means", "quats", "scales", "opacities", "sh_coeffs")
+    t = to_dev(sc, cuda_device)
+    target = torch.rand((1, H, W, 3), device=cuda_device, generator=torch.Generator(cuda_device).manual_seed(3))
+
+    def run(deferred):
+        P = {k: t[k].clone().requires_grad_(True) for k in names}
+        out = native.rasterize(P["means"], P["quats"], P["scales"], P["opacities"], P["sh_coeffs"], sc["sh_degree"],
+                               t["viewmats"], t["Ks"], W, H, bg_color=t.get("background"), sh_exchange=deferred)
+        (out.render_colors - target).abs().mean().backward()
+        if deferred is not None:
+            assert P["sh_coeffs"].grad is None and deferred.v_colors.shape == (P["means"].shape[0], 3)
+            mv.exchange_gradients_compact(P, deferred)
+        return {k: P[k].grad.cpu().numpy() for k in names}
+
+    plain = run(None)
+    compact = run(native.DeferredSHBackward())
+    for k in names:
+        assert rel(compact[k], plain[k]) < 2e-5, k
+
+
+# ------------------------------------------------------------------------------------------
 # link-surface ops
 # ------------------------------------------------------------------------------------------
 def test_strategy_helpers_vs_oracle(native, orc, cuda_device):
