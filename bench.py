@@ -185,6 +185,11 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
+# (kernel, gaussians, width, height) -> DRAM bytes per launch measured by ncu (profiles/r1c_ncu_summary.md)
+NCU_DRAM_BYTES = {("raster_bwd", 1_000_000, 1920, 1080): 89_998_592 + 4_392_448,
+                  ("raster_fwd", 1_000_000, 1920, 1080): 50_757_632 + 9_520_640}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -336,8 +341,11 @@ def run_b200(args):
     roof = None
     if dom in algo:
         achieved = algo[dom] / (prof[dom]["avg_ms"] * 1e-3) / 1e9
+        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this
+        # workload (profiles/r1c_ncu_summary.md); other sizes have no capture
+        traffic = NCU_DRAM_BYTES.get((dom, N, W, H))
         roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo[dom], "avg_kernel_ms": prof[dom]["avg_ms"],
                 "note": "the blend is FP32-issue/LSU/atomic bound by construction (SURVEY.md 8d): the HBM fraction is "
                         "the figure north_star asks for, the pipe utilisations are in profiles/"}
