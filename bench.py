@@ -392,6 +392,8 @@ def run_b200(args):
         "e2e_resident": {"value": N * world / (ms_e2e_res * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_res,
                          "what": "parameters resident (as in training); camera + target image H2D, loss D2H per step"},
         "gpu_launches": launches,
+        # the quantity the blend's cost is proportional to; rank 0's count x ranks
+        "intersections_per_sec": I * world / (ms_step * 1e-3),
         "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in prof.items()},
         "clocks": clocks,
     }

@@ -543,8 +543,6 @@ ORC_API int orc_projection_ut(
         return ORC_E_UNSUPPORTED; /* rolling shutter / ortho: not restated */
     const real eps2d = eps2d_f;
     for (uint32_t cid = 0; cid < C; ++cid) {
-        const real fx = Ks[cid * 9 + 0], fy = Ks[cid * 9 + 4];
-        const real cx = Ks[cid * 9 + 2], cy = Ks[cid * 9 + 5];
         const Pose start = pose_from_viewmat(viewmats0 + cid * 16);
         const Pose mid = interpolate_pose_global(start, (real)0.5);
         const CamModel cm = cam_model_make(camera_model, image_width, image_height, Ks + cid * 9,
@@ -1053,8 +1051,6 @@ ORC_API int orc_raster_fwd(
     const uint32_t tile_width = (image_width + tile_size - 1) / tile_size;
     const uint32_t tile_height = (image_height + tile_size - 1) / tile_size;
     for (uint32_t cid = 0; cid < C; ++cid) {
-        const real fx = Ks[cid * 9 + 0], fy = Ks[cid * 9 + 4];
-        const real cx = Ks[cid * 9 + 2], cy = Ks[cid * 9 + 5];
         const Pose start = pose_from_viewmat(viewmats0 + cid * 16);
         const CamModel cm = cam_model_make(camera_model, image_width, image_height, Ks + cid * 9,
                                            radial ? radial + cid * n_radial : NULL, n_radial,
@@ -1183,8 +1179,6 @@ ORC_API int orc_raster_bwd(
     const uint32_t tile_width = (image_width + tile_size - 1) / tile_size;
     const uint32_t tile_height = (image_height + tile_size - 1) / tile_size;
     for (uint32_t cid = 0; cid < C; ++cid) {
-        const real fx = Ks[cid * 9 + 0], fy = Ks[cid * 9 + 4];
-        const real cx = Ks[cid * 9 + 2], cy = Ks[cid * 9 + 5];
         const Pose start = pose_from_viewmat(viewmats0 + cid * 16);
         const CamModel cm = cam_model_make(camera_model, image_width, image_height, Ks + cid * 9,
                                            radial ? radial + cid * n_radial : NULL, n_radial,
