@@ -199,11 +199,6 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void red_add_f32(float *addr, float v) {
     asm volatile("red.global.add.f32 [%0], %1;" ::"l"(addr), "f"(v) : "memory");
 }
-__device__ __forceinline__ void red_add_v4_f32(float *addr, float a, float b, float c, float d) {
-    // sm_90+: 128-bit vector reduction, addr 16-byte aligned
-    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
-}
-
 __device__ __forceinline__ float fast_rcp(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));

@@ -124,29 +124,12 @@ __device__ inline void gauss_geom(const CamConst &c, const float *mean, const fl
     if (!(g.d0 > T(0)) || !isfinite((double)g.d0)) g.degenerate = true;
 }
 
-// Per-pair evaluation shared VERBATIM by the forward and backward kernels (explicit rounding
-// intrinsics: the two kernels must agree bit-for-bit on which pairs pass the alpha test).
-struct PairEval {
-    float Ns, Ds;
-    float xx, xy, yy; // monomials, reused by the backward's moment accumulation
-    bool pass;
-};
-__device__ __forceinline__ PairEval pair_eval(const float4 q0, const float4 q1, const float4 q2, float x, float y) {
-    PairEval r;
-    const float xx = __fmul_rn(x, x), xy = __fmul_rn(x, y), yy = __fmul_rn(y, y);
-    r.xx = xx; r.xy = xy; r.yy = yy;
-    r.Ns = __fmaf_rn(q1.x, yy, __fmaf_rn(q0.w, xy, __fmul_rn(q0.z, xx)));
-    float D = __fmaf_rn(q1.y, x, 1.0f);
-    D = __fmaf_rn(q1.z, y, D);
-    D = __fmaf_rn(q1.w, xx, D);
-    D = __fmaf_rn(q2.x, xy, D);
-    r.Ds = __fmaf_rn(q2.y, yy, D);
-    r.pass = __fmaf_rn(-q2.w, r.Ds, r.Ns) >= 0.0f; // Ns >= tau * Ds
-    return r;
-}
-// The same evaluation for a thread's two pixels at once on packed fp32 pairs (lo = pixel 0, hi = pixel 1).
-// Every component goes through exactly the rounding sequence of pair_eval (mul.rn / fma.rn), so the
-// packed and the scalar form agree bit for bit.
+// Per-pair evaluation, shared VERBATIM by the forward and backward kernels (explicitly rounded
+// operations: the two kernels must agree bit-for-bit on which pairs pass the alpha test), for a
+// thread's two pixels at once on packed fp32 pairs (lo = pixel 0, hi = pixel 1):
+//   Ns = n0 x^2 + n1 xy + n2 y^2          (pre-scaled by -1/2 log2 e / d0)
+//   Ds = 1 + d1 x + d2 y + d3 x^2 + d4 xy + d5 y^2
+//   pass <=> Ns >= tau Ds                  (MUFU-free rejection, tau carries a safety margin)
 struct PairEval2 {
     f2 Ns, Ds;
     f2 xx, xy, yy;
