@@ -519,7 +519,90 @@ __device__ __forceinline__ float butterfly4(const BwdState &s, const EventWeight
     return v; // (hi16, hi8) = (0,0): cr  (0,1): g  (1,0): cg  (1,1): cb
 }
 
-template <bool kGeneral, bool kMma>
+// ---- transposed reduction (perfect pinhole): lanes own events --------------------------------------
+// Same idea as the tensor-core variant -- stash the per-pair weights of eight events, then reduce them with
+// the roles transposed -- but on the CUDA cores: in the flush a quad of lanes owns ONE event and walks the
+// block's 64 pixels (16 each) with loop-constant pixel offsets, accumulating the raw moments in registers
+// (packed (w1, w2) pairs: seven FFMA2/FADD2 per pixel for both weights, four scalar FMAs for the colour
+// gradient and g).  No shuffle is needed until the four partial sums of a quad are combined (two xor
+// stages), after which lane 0 of the quad shifts and adds the w1 moments, lane 1 the w2 moments, lane 2 the
+// colour gradient and g.  Stash layout per warp: row e (event) of kTrStride float4, slot p < 32 = first
+// pixel of lane p, slot p >= 32 = second pixel of lane p - 32, each (w1, w2, fac, g); s_v[p] = dL/d(colour)
+// of pixel slot p.  Flush lane (e, q) reads slots p = 4 i + q, i = 0..15: x' = q + 4 (i & 1) - 3.5,
+// y' = ((i & 7) >> 1) - 3.5 (+ 4 for i >= 8).
+// NOT the default: written at the end of round 1 without a GPU at hand; to be measured.
+constexpr int kTrEvents = 8;
+constexpr int kTrStride = 68; // float4 units: 64 pixel slots + 4 of padding (odd events land 16 banks away)
+
+__device__ __forceinline__ f2 f2_shfl_xor(f2 a, int m) {
+    return f2_make(__shfl_xor_sync(0xffffffffu, f2_lo(a), m), __shfl_xor_sync(0xffffffffu, f2_hi(a), m));
+}
+
+__device__ __forceinline__ void transpose_flush(const float4 *__restrict__ s_t, const float4 *__restrict__ s_ev,
+                                                const float4 *__restrict__ s_v, int n_ev,
+                                                float *__restrict__ moments) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t e = lane >> 2, q = lane & 3;
+    __syncwarp();
+    const float xq0 = (float)q - 3.5f, xq1 = (float)q + 0.5f;
+    f2 S1 = f2_bc(0.f), Sx = f2_bc(0.f), Sy = f2_bc(0.f), Sxx = f2_bc(0.f), Sxy = f2_bc(0.f), Syy = f2_bc(0.f);
+    float cr = 0.f, cg = 0.f, cb = 0.f, gs = 0.f;
+    const float4 *row = s_t + e * kTrStride + q;
+    const float4 *vrow = s_v + q;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const float4 w = row[4 * i];
+        const float4 v = vrow[4 * i];
+        const float x = (i & 1) ? xq1 : xq0;
+        const float yc = (float)((i & 7) >> 1) - 3.5f + ((i >= 8) ? 4.0f : 0.0f);
+        const f2 W = f2_make(w.x, w.y);
+        const f2 t = f2_mul(W, f2_bc(x));
+        S1 = f2_add(S1, W);
+        Sx = f2_add(Sx, t);
+        Sy = f2_fma(W, f2_bc(yc), Sy);
+        Sxx = f2_fma(t, f2_bc(x), Sxx);
+        Sxy = f2_fma(t, f2_bc(yc), Sxy);
+        Syy = f2_fma(W, f2_bc(yc * yc), Syy);
+        cr = fmaf(w.z, v.x, cr); cg = fmaf(w.z, v.y, cg); cb = fmaf(w.z, v.z, cb);
+        gs += w.w;
+    }
+#pragma unroll
+    for (int m = 1; m <= 2; m <<= 1) {
+        S1 = f2_add(S1, f2_shfl_xor(S1, m)); Sx = f2_add(Sx, f2_shfl_xor(Sx, m)); Sy = f2_add(Sy, f2_shfl_xor(Sy, m));
+        Sxx = f2_add(Sxx, f2_shfl_xor(Sxx, m)); Sxy = f2_add(Sxy, f2_shfl_xor(Sxy, m));
+        Syy = f2_add(Syy, f2_shfl_xor(Syy, m));
+        cr += __shfl_xor_sync(0xffffffffu, cr, m); cg += __shfl_xor_sync(0xffffffffu, cg, m);
+        cb += __shfl_xor_sync(0xffffffffu, cb, m); gs += __shfl_xor_sync(0xffffffffu, gs, m);
+    }
+    if ((int)e < n_ev && q < 3) {
+        const float4 ev = s_ev[e]; // (a, b) = Gaussian centre - block centre, bits of the Gaussian index
+        float *mrow = moments + (size_t)__float_as_int(ev.z) * kMomFloats;
+        if (q == 2) {
+            red_add_f32(mrow + kS_G, gs); red_add_f32(mrow + kS_CR, cr);
+            red_add_f32(mrow + kS_CG, cg); red_add_f32(mrow + kS_CB, cb);
+        } else {
+            const float a = ev.x, b = ev.y;
+            const bool hi = q == 1; // lane 0 of the quad finishes w1 (lo halves), lane 1 finishes w2 (hi halves)
+            const float s1 = hi ? f2_hi(S1) : f2_lo(S1), sx = hi ? f2_hi(Sx) : f2_lo(Sx), sy = hi ? f2_hi(Sy) : f2_lo(Sy);
+            const float sxx = hi ? f2_hi(Sxx) : f2_lo(Sxx), sxy = hi ? f2_hi(Sxy) : f2_lo(Sxy);
+            const float syy = hi ? f2_hi(Syy) : f2_lo(Syy);
+            // shift the raw moments about the block centre to the Gaussian's centre: x = x' - a, y = y' - b
+            const float mx = fmaf(-a, s1, sx), my = fmaf(-b, s1, sy);
+            const float mxx = fmaf(a * a, s1, fmaf(-2.f * a, sx, sxx));
+            const float mxy = fmaf(a * b, s1, fmaf(-b, sx, fmaf(-a, sy, sxy)));
+            const float myy = fmaf(b * b, s1, fmaf(-2.f * b, sy, syy));
+            float *dst = mrow + (hi ? kS_W2 : 0); // W1X..W1YY = 1..5, W2, W2X..W2YY = 8, 9..13
+            if (hi) red_add_f32(dst, s1);
+            red_add_f32(dst + 1, mx); red_add_f32(dst + 2, my); red_add_f32(dst + 3, mxx);
+            red_add_f32(dst + 4, mxy); red_add_f32(dst + 5, myy);
+        }
+    }
+    __syncwarp();
+}
+
+constexpr int kReduceShuffle = 0, kReduceMma = 1, kReduceTranspose = 2;
+
+template <bool kGeneral, int kReduce>
 __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TileParams p,
                                                                    const float *__restrict__ render_alphas,
                                                                    const int32_t *__restrict__ last_ids,
@@ -532,10 +615,14 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
     __shared__ CamModel s_cm;
     // tensor-core reduction: per-warp stash of eight events' weights, their (centre offset, index), and
     // the CTA-wide monomial fragments
+    constexpr bool kMma = kReduce == kReduceMma, kTr = kReduce == kReduceTranspose;
     __shared__ __align__(16) float4 s_w[kMma ? (kTileThreads / 32) * kMmaEvents * kMmaRowStride : 1];
-    __shared__ __align__(16) float4 s_ev[kMma ? (kTileThreads / 32) * kMmaEvents : 1];
+    __shared__ __align__(16) float4 s_ev[(kMma || kTr) ? (kTileThreads / 32) * kMmaEvents : 1];
     __shared__ __align__(8) float2 s_mono[kMma ? 8 * 32 : 1];
-    static_assert(!(kGeneral && kMma), "the monomial table assumes pixel-centre coordinates");
+    // transposed reduction: the weight stash is dynamic shared memory (with the ring it exceeds 48 KB)
+    extern __shared__ __align__(16) float4 s_dyn[]; // [warps][kTrEvents][kTrStride] then [warps][64]
+    static_assert(!(kGeneral && kReduce != kReduceShuffle), "the stash variants assume pixel-centre coordinates");
+    static_assert(kTrEvents == kMmaEvents, "s_ev is shared by the two stash variants");
 
     const uint32_t tile_id = blockIdx.x;
     if (p.masks != nullptr && !p.masks[tile_id]) return; // Bwd.cu:84-86
@@ -590,7 +677,13 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
     const f2 PX = f2_make(pc.px0, pc.px1), PY = f2_make(pc.py0, pc.py1);
     const bool hi8 = (tid & 8) != 0;
     float4 *const my_w = s_w + (kMma ? (tid >> 5) * kMmaEvents * kMmaRowStride : 0);
-    float4 *const my_ev = s_ev + (kMma ? (tid >> 5) * kMmaEvents : 0);
+    float4 *const my_ev = s_ev + ((kMma || kTr) ? (tid >> 5) * kMmaEvents : 0);
+    float4 *const my_t = s_dyn + (kTr ? (tid >> 5) * kTrEvents * kTrStride : 0);
+    float4 *const my_v = s_dyn + (kTr ? (kTileThreads / 32) * kTrEvents * kTrStride + (tid >> 5) * 64 : 0);
+    if constexpr (kTr) {
+        my_v[tid & 31] = make_float4(f2_lo(s.vr), f2_lo(s.vg), f2_lo(s.vb), 0.f);
+        my_v[32 + (tid & 31)] = make_float4(f2_hi(s.vr), f2_hi(s.vg), f2_hi(s.vb), 0.f);
+    }
     const float cxb = pc.bx0 + 3.5f, cyb = pc.by0 + 3.5f; // centre of the warp's 8x8 block
     int n_ev = 0;
     if constexpr (kMma) {
@@ -684,6 +777,14 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
                     mma_flush(my_w, my_ev, s_mono, kMmaEvents, moments);
                     n_ev = 0;
                 }
+            } else if constexpr (kTr) {
+                my_t[n_ev * kTrStride + (tid & 31)] = make_float4(f2_lo(w.w1), f2_lo(w.w2), f2_lo(w.fac), f2_lo(w.g));
+                my_t[n_ev * kTrStride + 32 + (tid & 31)] = make_float4(f2_hi(w.w1), f2_hi(w.w2), f2_hi(w.fac), f2_hi(w.g));
+                my_ev[n_ev] = make_float4(q0.x - cxb, q0.y - cyb, q3.w, 0.f); // same value from every lane
+                if (++n_ev == kTrEvents) {
+                    transpose_flush(my_t, my_ev, my_v, kTrEvents, moments);
+                    n_ev = 0;
+                }
             } else {
                 float R[16];
                 event_registers(s, w, e, x, y, hi16, R);
@@ -700,6 +801,9 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
     }
     if constexpr (kMma) {
         if (n_ev > 0) mma_flush(my_w, my_ev, s_mono, n_ev, moments);
+    }
+    if constexpr (kTr) {
+        if (n_ev > 0) transpose_flush(my_t, my_ev, my_v, n_ev, moments);
     }
 }
 
@@ -827,15 +931,20 @@ static int check_camera(const GsbCamera *cam) {
     return GSB_OK;
 }
 
-// GSB_BWD_REDUCE=mma selects the tensor-core reduction of the geometric moments for the perfect pinhole
-// (mma_flush above).  It executes 14 % fewer instructions per event than the all-shuffle reduction but
-// measures 4 % SLOWER on the B200 (0.825 vs 0.790 ms, config B: the flush's LDS -> HMMA -> shuffle chain and
-// the lower occupancy cost more than the saved issue slots), so the shuffle reduction stays the default.
-// Read on every call so a test can exercise both.
-static bool bwd_use_mma() {
+// GSB_BWD_REDUCE selects the reduction of the backward's moments for the perfect pinhole; read on every call
+// so a test can exercise the variants.
+//   (unset) / shuffle : 16-value butterfly per event -- the default, the fastest measured.
+//   mma       : tensor-core reduction of the geometric moments (mma_flush).  14 % fewer instructions per event,
+//               but 4 % SLOWER on the B200 (0.825 vs 0.790 ms, config B): the flush's LDS -> HMMA -> shuffle chain
+//               and the lower occupancy cost more than the saved issue slots.
+//   transpose : lane-per-event reduction on the CUDA cores (transpose_flush); not yet measured.
+static int bwd_reduce_mode() {
     const char *e = getenv("GSB_BWD_REDUCE");
-    return e && strcmp(e, "mma") == 0;
+    if (e && strcmp(e, "mma") == 0) return kReduceMma;
+    if (e && strcmp(e, "transpose") == 0) return kReduceTranspose;
+    return kReduceShuffle;
 }
+static constexpr size_t kTrDynSmem = (size_t)(kTileThreads / 32) * (kTrEvents * kTrStride + 64) * sizeof(float4);
 
 static bool general_camera(const GsbCamera *cam) {
     return cam->camera_model == GSB_CAMERA_FISHEYE || cam->radial_coeffs || cam->tangential_coeffs ||
@@ -947,14 +1056,20 @@ extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     {
         ProfScope ps("raster_bwd", s);
         fill_camera(p, cam);
+        const int mode = bwd_reduce_mode();
         if (general_camera(cam))
-            raster_bwd_kernel<true, false><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(
+            raster_bwd_kernel<true, kReduceShuffle><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(
                 p, render_alphas, last_ids, v_render_colors, v_render_alphas, moments);
-        else if (bwd_use_mma())
-            raster_bwd_kernel<false, true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(
+        else if (mode == kReduceMma)
+            raster_bwd_kernel<false, kReduceMma><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(
                 p, render_alphas, last_ids, v_render_colors, v_render_alphas, moments);
-        else
-            raster_bwd_kernel<false, false><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(
+        else if (mode == kReduceTranspose) {
+            GSB_CUDA_TRY(cudaFuncSetAttribute(raster_bwd_kernel<false, kReduceTranspose>,
+                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrDynSmem));
+            raster_bwd_kernel<false, kReduceTranspose><<<p.tile_w * p.tile_h, kTileThreads, kTrDynSmem, s>>>(
+                p, render_alphas, last_ids, v_render_colors, v_render_alphas, moments);
+        } else
+            raster_bwd_kernel<false, kReduceShuffle><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(
                 p, render_alphas, last_ids, v_render_colors, v_render_alphas, moments);
     }
     GSB_LAUNCH_CHECK();
