@@ -92,3 +92,64 @@ def test_backward_matches_finite_differences(orc, small):
             assert ok, (name, g, nums, ana)
             checked += 1
     assert checked >= 6
+
+
+# ------------------------------------------------------------------------------------------
+# a2: camera models of the oracle (the checker of the GPU's distorted-camera tests)
+# ------------------------------------------------------------------------------------------
+OPENCV = dict(camera_model=0, radial=np.array([[-0.12, 0.05, 0.002, 0.01, -0.003, 0.0005]], np.float32),
+              tangential=np.array([[0.002, -0.001]], np.float32),
+              thin_prism=np.array([[0.001, 0.0002, -0.0005, 0.0001]], np.float32))
+FISHEYE = dict(camera_model=2, radial=np.array([[0.03, -0.004, 0.0007, -0.0001]], np.float32), tangential=None,
+               thin_prism=None)
+
+
+def _project_and_blend(orc, sc, colors, **cam):
+    W, H = sc["width"], sc["height"]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    radii, m2d, depths, _, _ = orc.projection_ut(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["viewmats"],
+                                                 sc["Ks"], W, H, 0.3, 0.01, 1e4, 0.0, **cam)
+    _, ids, flat = orc.isect_tiles(m2d, radii, depths, 1, 16, tw, th)
+    off = orc.isect_offsets(ids, 1, tw, th)
+    img, alp, _ = orc.raster_fwd(sc["means"], sc["quats"], sc["scales"], colors, sc["opacities"][None], None, None, W, H,
+                                 16, sc["viewmats"], sc["Ks"], off, flat, **cam)
+    return radii, m2d, img, alp
+
+
+def test_zero_distortion_is_the_perfect_pinhole(orc):
+    """All-zero OpenCV coefficients go through the general camera code (Newton undistortion included) and must
+    reproduce the perfect-pinhole results."""
+    sc = scenes.scene_small(N=400, width=96, height=64, sh_degree=0, view=2)
+    colors = np.random.default_rng(5).random((1, 400, 3), dtype=np.float32)
+    zero = dict(camera_model=0, radial=np.zeros((1, 6), np.float32), tangential=np.zeros((1, 2), np.float32),
+                thin_prism=np.zeros((1, 4), np.float32))
+    r0, m0, i0, a0 = _project_and_blend(orc, sc, colors, camera_model=0)
+    r1, m1, i1, a1 = _project_and_blend(orc, sc, colors, **zero)
+    assert np.array_equal(r0, r1)
+    assert rel(m1, m0) < 1e-6 and rel(i1, i0) < 1e-5 and rel(a1, a0) < 1e-5
+
+
+@pytest.mark.parametrize("cam", [OPENCV, FISHEYE], ids=["opencv", "fisheye"])
+def test_blend_unprojection_inverts_the_projection(orc, cam):
+    """The UT projection maps world -> distorted image, the blend maps pixel -> ray by undistorting; for a small
+    isotropic Gaussian the alpha image must peak at the projected centre under every camera model."""
+    W, H = 160, 112
+    Ks = np.array([[[140.0, 0, 80.0], [0, 150.0, 56.0], [0, 0, 1]]], np.float32)
+    viewmats = np.eye(4, dtype=np.float32)[None]
+    pts = np.array([[0.9, 0.5, 3.0], [-1.0, -0.55, 2.5], [0.2, -0.6, 4.0], [-0.7, 0.6, 3.5]], np.float32)
+    moved = 0.0
+    for pt in pts:
+        sc = dict(means=pt[None].copy(), quats=np.array([[1, 0, 0, 0]], np.float32),
+                  scales=np.full((1, 3), 0.03, np.float32), opacities=np.array([0.9], np.float32), viewmats=viewmats,
+                  Ks=Ks, width=W, height=H)
+        radii, m2d, _, alp = _project_and_blend(orc, sc, np.ones((1, 1, 3), np.float32), **cam)
+        assert (radii > 0).all(), "test point must be visible"
+        a = alp[0, :, :, 0]
+        ys, xs = np.mgrid[0:H, 0:W]
+        wsum = a.sum()
+        assert wsum > 0
+        cx, cy = ((xs + 0.5) * a).sum() / wsum, ((ys + 0.5) * a).sum() / wsum  # alpha-weighted centroid
+        assert abs(cx - m2d[0, 0, 0]) < 0.35 and abs(cy - m2d[0, 0, 1]) < 0.35, (pt, (cx, cy), m2d[0, 0])
+        ideal = np.array([Ks[0, 0, 0] * pt[0] / pt[2] + Ks[0, 0, 2], Ks[0, 1, 1] * pt[1] / pt[2] + Ks[0, 1, 2]])
+        moved = max(moved, float(np.linalg.norm(ideal - m2d[0, 0])))
+    assert moved > 1.0  # the distortion is not a no-op: off-centre points land more than a pixel from the ideal pinhole
