@@ -74,6 +74,18 @@ typedef float real;
 #define R_EPS 1.1920929e-07f
 #endif
 
+/* The blend's two cut-offs (Fwd.cu:240-248, Bwd.cu:281).  ORC_SMOOTH is a TEST-ONLY build without them: the
+ * forward becomes a smooth function of the parameters (for fixed intersection lists), so central differences
+ * validate the analytic backward to rounding instead of "up to a threshold crossing". */
+#ifdef ORC_SMOOTH
+#define ORC_ALPHA_MIN ((real)0)
+#define ORC_T_MIN ((real)-1)
+#else
+#define ORC_ALPHA_MIN ((real)(1.f / 255.f))
+#define ORC_T_MIN ((real)1e-4)
+#endif
+
+
 #define ORC_API __attribute__((visibility("default")))
 
 #ifdef _OPENMP
@@ -1100,9 +1112,9 @@ ORC_API int orc_raster_fwd(
                             const real power = (real)-0.5 * grayDist;
                             real alpha = opac * R_EXP(power);
                             if (alpha > (real)0.999) alpha = (real)0.999;
-                            if (alpha < (real)(1.f / 255.f)) continue;
+                            if (alpha < ORC_ALPHA_MIN) continue;
                             const real next_T = T * ((real)1 - alpha);
-                            if (next_T <= (real)1e-4) break;
+                            if (next_T <= ORC_T_MIN) break;
                             const real vis = alpha * T;
                             for (int c = 0; c < 3; ++c) pix_out[c] += (real)colors[(uint64_t)g * 3 + c] * vis;
                             cur_idx = (uint32_t)(range_start + k);
@@ -1234,7 +1246,7 @@ ORC_API int orc_raster_bwd(
                             const real vis = R_EXP(power);
                             real alpha = opac * vis;
                             if (alpha > (real)0.999) alpha = (real)0.999;
-                            if (power > (real)0 || alpha < (real)(1.f / 255.f)) continue;
+                            if (power > (real)0 || alpha < ORC_ALPHA_MIN) continue;
 
                             const real ra = (real)1 / ((real)1 - alpha);
                             T *= ra;

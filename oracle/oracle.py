@@ -51,11 +51,11 @@ class UTParams:
 def build(force: bool = False) -> None:
     """Compile the two oracle libraries with the committed Makefile."""
     need = force or not all(
-        os.path.exists(os.path.join(_HERE, f"libgut_oracle_{p}.so")) for p in ("f32", "f64"))
+        os.path.exists(os.path.join(_HERE, f"libgut_oracle_{p}.so")) for p in ("f32", "f64", "f64s"))
     src = os.path.join(_HERE, "gut_oracle.c")
     if not need:
         need = any(os.path.getmtime(os.path.join(_HERE, f"libgut_oracle_{p}.so")) < os.path.getmtime(src)
-                   for p in ("f32", "f64"))
+                   for p in ("f32", "f64", "f64s"))
     if need:
         subprocess.run(["make", "-C", _HERE, "-s", "-B"], check=True)
 

@@ -153,3 +153,57 @@ def test_blend_unprojection_inverts_the_projection(orc, cam):
         ideal = np.array([Ks[0, 0, 0] * pt[0] / pt[2] + Ks[0, 0, 2], Ks[0, 1, 1] * pt[1] / pt[2] + Ks[0, 1, 2]])
         moved = max(moved, float(np.linalg.norm(ideal - m2d[0, 0])))
     assert moved > 1.0  # the distortion is not a no-op: off-centre points land more than a pixel from the ideal pinhole
+
+
+@pytest.mark.parametrize("cam", [dict(camera_model=0), OPENCV, FISHEYE], ids=["pinhole", "opencv", "fisheye"])
+def test_backward_matches_finite_differences_without_cutoffs(orc, cam):
+    """The analytic backward against central differences of the forward, camera model by camera model, on the
+    test-only ORC_SMOOTH float64 build of the oracle (no 1/255 cut, no T <= 1e-4 stop): with fixed intersection
+    lists the forward is then smooth, so the comparison is tight (1 %) on EVERY checked component instead of
+    "some step size agrees up to a threshold crossing".  The cut-offs themselves only gate which pairs contribute."""
+    sc = scenes.scene_small(N=300, width=80, height=64, sh_degree=0, view=2)
+    W, H = sc["width"], sc["height"]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    rng = np.random.default_rng(8)
+    colors = rng.random((1, 300, 3), dtype=np.float32)
+    vrc = rng.standard_normal((1, H, W, 3))
+    vra = rng.standard_normal((1, H, W, 1))
+    radii, m2d, depths, _, _ = orc.projection_ut(sc["means"], sc["quats"], sc["scales"], sc["opacities"], sc["viewmats"],
+                                                 sc["Ks"], W, H, 0.3, 0.01, 1e4, 0.0, precision="f64", **cam)
+    _, ids, flat = orc.isect_tiles(m2d, radii, depths, 1, 16, tw, th)
+    off = orc.isect_offsets(ids, 1, tw, th)
+
+    def fwd(P):
+        return orc.raster_fwd(P["means"], P["quats"], P["scales"], colors, P["opacities"][None], sc["background"], None, W,
+                              H, 16, sc["viewmats"], sc["Ks"], off, flat, precision="f64s", **cam)
+
+    base = {k: sc[k].copy() for k in ("means", "quats", "scales", "opacities")}
+    img, alp, li = fwd(base)
+    g = orc.raster_bwd(base["means"], base["quats"], base["scales"], colors, base["opacities"][None], sc["background"],
+                       None, W, H, 16, sc["viewmats"], sc["Ks"], off, flat, alp, li, vrc.astype(np.float32),
+                       vra.astype(np.float32), precision="f64s", **cam)
+    ana = dict(means=g[0], quats=g[1], scales=g[2], opacities=g[4][0])
+
+    def loss(P):
+        r, a, _ = fwd(P)
+        return float((r.astype(np.float64) * vrc).sum() + (a.astype(np.float64) * vra).sum())
+
+    cand = np.argsort(-np.abs(ana["means"]).sum(-1))[:10]
+    checked = 0
+    for gi in cand:
+        for name, dim in (("means", 0), ("means", 1), ("means", 2), ("scales", 0), ("scales", 1), ("scales", 2),
+                          ("quats", 0), ("quats", 1), ("quats", 2), ("quats", 3), ("opacities", None)):
+            a_ = float(ana[name][gi] if dim is None else ana[name][gi, dim])
+            eps = 1e-3 if name != "opacities" else 2e-3
+            p = {k: v.copy() for k, v in base.items()}
+            m = {k: v.copy() for k, v in base.items()}
+            if dim is None:
+                p[name][gi] += eps; m[name][gi] -= eps
+                h = float(p[name][gi]) - float(m[name][gi])
+            else:
+                p[name][gi, dim] += eps; m[name][gi, dim] -= eps
+                h = float(p[name][gi, dim]) - float(m[name][gi, dim])
+            num = (loss(p) - loss(m)) / h
+            assert abs(num - a_) <= 0.01 * abs(a_) + 2e-3, (name, int(gi), dim, num, a_)
+            checked += 1
+    assert checked == 110
