@@ -1,0 +1,183 @@
+"""CPU: the error convention of the C ABI (include/gsb200.h).  Every entry point validates its arguments
+before it touches the device, so these paths run without a GPU: 0 for the empty cases the reference
+treats as no-ops, GSB_E_INVALID (-1) for null / inconsistent arguments, GSB_E_UNSUPPORTED (-2) for what
+the reference's API allows but this backend does not implement, GSB_E_WORKSPACE (-3) for a short or
+misaligned workspace.  No compute call is made."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OK, E_INVALID, E_UNSUPPORTED, E_WORKSPACE = 0, -1, -2, -3
+PINHOLE, ORTHO, FISHEYE = 0, 1, 2
+SHUTTER_ROLLING, SHUTTER_GLOBAL = 0, 4  # ShutterType values of the reference (Cameras.h)
+
+
+class GsbUTParams(C.Structure):
+    _fields_ = [("alpha", C.c_float), ("beta", C.c_float), ("kappa", C.c_float),
+                ("in_image_margin_factor", C.c_float), ("require_all_sigma_points_valid", C.c_int32)]
+
+
+class GsbCamera(C.Structure):
+    _fields_ = [("viewmats0", C.c_void_p), ("viewmats1", C.c_void_p), ("Ks", C.c_void_p),
+                ("camera_model", C.c_int32), ("shutter_type", C.c_int32),
+                ("radial_coeffs", C.c_void_p), ("radial_count", C.c_int32),
+                ("tangential_coeffs", C.c_void_p), ("tangential_count", C.c_int32),
+                ("thin_prism_coeffs", C.c_void_p), ("thin_prism_count", C.c_int32), ("ut", GsbUTParams)]
+
+
+@pytest.fixture(scope="module")
+def lib(pkg):
+    path = os.path.join(ROOT, "gaussian-splatting-cuda_b200", "lib", "libgsb200.so")
+    if not os.path.exists(path):
+        pkg.build()
+    L = C.CDLL(path)
+    L.gsb_error_string.restype = C.c_char_p
+    for n in ("gsb_raster_fwd_workspace", "gsb_raster_bwd_workspace", "gsb_isect_count_workspace",
+              "gsb_isect_plan_workspace", "gsb_isect_emit_planned_workspace", "gsb_isect_sort_workspace"):
+        getattr(L, n).restype = C.c_size_t
+    return L
+
+
+# any non-null address will do: the calls below return before dereferencing it on the device
+_buf = np.zeros(4096, np.uint8)
+PTR = C.c_void_p(_buf.ctypes.data)
+NULL = C.c_void_p(None)
+u32, u64, f32, i32, sz = C.c_uint32, C.c_uint64, C.c_float, C.c_int32, C.c_size_t
+
+
+def camera(model=PINHOLE, shutter=SHUTTER_GLOBAL, viewmats1=None):
+    cam = GsbCamera()
+    cam.viewmats0, cam.Ks = PTR.value, PTR.value
+    cam.viewmats1 = viewmats1
+    cam.camera_model, cam.shutter_type = model, shutter
+    cam.ut = GsbUTParams(0.1, 2.0, 0.0, 0.1, 1)
+    return cam
+
+
+def test_error_strings(lib):
+    assert lib.gsb_error_string(OK) == b"ok"
+    for code in (E_INVALID, E_UNSUPPORTED, E_WORKSPACE):
+        assert len(lib.gsb_error_string(code)) > 3
+
+
+def test_sh_argument_validation(lib):
+    assert lib.gsb_sh_fwd(u32(0), u32(16), u32(3), NULL, NULL, NULL, NULL, NULL) == OK  # empty: no-op
+    assert lib.gsb_sh_fwd(u32(5), u32(16), u32(3), NULL, PTR, NULL, PTR, NULL) == E_INVALID
+    assert lib.gsb_sh_fwd(u32(5), u32(4), u32(3), PTR, PTR, NULL, PTR, NULL) == E_INVALID  # 16 bases > K = 4
+    assert lib.gsb_sh_fwd(u32(5), u32(36), u32(5), PTR, PTR, NULL, PTR, NULL) == E_INVALID  # degree > 4
+    assert lib.gsb_sh_bwd(u32(0), u32(16), u32(3), NULL, NULL, NULL, NULL, NULL, NULL, NULL) == OK
+    assert lib.gsb_sh_bwd(u32(5), u32(16), u32(3), PTR, PTR, NULL, NULL, PTR, PTR, NULL) == E_INVALID
+    assert lib.gsb_sh_bwd_views(u32(0), u32(16), u32(3), u32(2), NULL, NULL, NULL, NULL, NULL, NULL, NULL) == OK
+    assert lib.gsb_sh_bwd_views(u32(5), u32(16), u32(3), u32(2), PTR, NULL, PTR, PTR, PTR, PTR, NULL) == E_INVALID
+    assert lib.gsb_sh_bwd_views(u32(5), u32(9), u32(3), u32(2), PTR, PTR, PTR, PTR, PTR, PTR, NULL) == E_INVALID
+
+
+def test_projection_argument_validation(lib):
+    args = (f32(0.3), f32(0.01), f32(1e4), f32(0.0), PTR, PTR, PTR, PTR, NULL, NULL)
+    assert lib.gsb_projection_ut(u32(1), u32(8), PTR, PTR, PTR, PTR, NULL, u32(64), u32(64), *args) == E_INVALID
+    cam = camera()
+    assert lib.gsb_projection_ut(u32(1), u32(0), NULL, NULL, NULL, NULL, C.byref(cam), u32(64), u32(64), *args) == OK
+    assert lib.gsb_projection_ut(u32(1), u32(8), NULL, PTR, PTR, PTR, C.byref(cam), u32(64), u32(64), *args) == E_INVALID
+    for bad in (camera(model=ORTHO), camera(shutter=SHUTTER_ROLLING), camera(viewmats1=PTR.value)):
+        assert lib.gsb_projection_ut(u32(1), u32(8), PTR, PTR, PTR, PTR, C.byref(bad), u32(64), u32(64),
+                                     *args) == E_UNSUPPORTED
+
+
+def test_intersect_argument_validation(lib):
+    assert lib.gsb_isect_count(u32(1), u32(0), NULL, NULL, u32(16), u32(4), u32(4), NULL, NULL, NULL, sz(0), NULL) == OK
+    assert lib.gsb_isect_count(u32(1), u32(8), NULL, PTR, u32(16), u32(4), u32(4), PTR, PTR, PTR, sz(4096),
+                               NULL) == E_INVALID
+    assert lib.gsb_isect_count(u32(1), u32(8), PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, PTR, sz(8),
+                               NULL) == E_WORKSPACE
+    assert lib.gsb_isect_count_workspace(u64(1000)) >= 256
+    # plan: the host needs somewhere to read n_isects from; the key must fit 64 bits (Intersect.cpp:50)
+    need = lib.gsb_isect_plan_workspace(u32(1), u32(8))
+    assert need >= 8 * (4 + 8)
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, NULL, PTR, sz(need),
+                              NULL) == E_INVALID
+    assert lib.gsb_isect_plan(u32(1), u32(8), NULL, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, PTR, sz(need),
+                              NULL) == E_INVALID
+    assert lib.gsb_isect_plan(u32(4), u32(8), PTR, PTR, PTR, u32(16), u32(1 << 16), u32(1 << 15), PTR, PTR, PTR,
+                              sz(1 << 20), NULL) == E_INVALID  # 32 tile bits + 3 camera bits > 32
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, PTR, sz(16),
+                              NULL) == E_WORKSPACE
+    misaligned = C.c_void_p(PTR.value + 8)
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, misaligned, sz(need),
+                              NULL) == E_WORKSPACE
+    # emit: nothing to do without intersections; a short workspace is refused
+    assert lib.gsb_isect_emit_planned(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), u64(0), PTR, PTR, PTR,
+                                      PTR, sz(0), NULL) == OK
+    assert lib.gsb_isect_emit_planned(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), u64(100), PTR, PTR, PTR,
+                                      PTR, sz(64), NULL) == E_WORKSPACE
+    assert lib.gsb_isect_emit_planned_workspace(u64(100)) >= 100 * 12
+    assert lib.gsb_isect_sort(u64(0), u32(1), u32(4), u32(4), NULL, NULL, NULL, NULL, NULL, sz(0), NULL) == OK
+    assert lib.gsb_isect_sort(u64(10), u32(1), u32(4), u32(4), PTR, PTR, PTR, PTR, PTR, sz(8), NULL) == E_WORKSPACE
+
+
+def test_blend_argument_validation(lib):
+    fwd_tail = (PTR, PTR, PTR, PTR, PTR, PTR, sz(1 << 20), NULL)
+
+    def fwd(C_=1, N=8, n_isects=10, W=64, H=64, tile=16, cam=None, ws_bytes=None, means=PTR):
+        cam = cam if cam is not None else camera()
+        ws = sz(ws_bytes if ws_bytes is not None else lib.gsb_raster_fwd_workspace(u32(N)))
+        return lib.gsb_raster_fwd(u32(C_), u32(N), u64(n_isects), means, PTR, PTR, PTR, PTR, NULL, NULL, u32(W), u32(H),
+                                  u32(tile), C.byref(cam), PTR, PTR, PTR, PTR, PTR,
+                                  C.c_void_p((_buf.ctypes.data + 255) & ~255), ws, NULL)
+
+    assert lib.gsb_raster_fwd(u32(1), u32(8), u64(10), PTR, PTR, PTR, PTR, PTR, NULL, NULL, u32(64), u32(64), u32(16), NULL,
+                              *fwd_tail) == E_INVALID  # no camera
+    assert fwd(W=0) == OK                              # empty image: no-op
+    assert fwd(C_=2) == E_UNSUPPORTED                  # the reference's kernels are single-camera too
+    assert fwd(tile=8) == E_UNSUPPORTED
+    assert fwd(cam=camera(model=ORTHO)) == E_UNSUPPORTED
+    assert fwd(cam=camera(shutter=SHUTTER_ROLLING)) == E_UNSUPPORTED
+    assert fwd(means=NULL) == E_INVALID
+    assert fwd(n_isects=1 << 31) == E_INVALID          # int32 tile offsets
+    assert fwd(ws_bytes=64) == E_WORKSPACE
+    assert lib.gsb_raster_fwd_workspace(u32(1000)) >= 64 * 1000
+    assert lib.gsb_raster_bwd_workspace(u32(1000)) >= 2 * 64 * 1000
+    # backward: same camera / shape rules
+    cam = camera()
+    bwd = lambda C_, tile, cm: lib.gsb_raster_bwd(
+        u32(C_), u32(8), u64(10), PTR, PTR, PTR, PTR, PTR, NULL, NULL, u32(64), u32(64), u32(tile), C.byref(cm), PTR, PTR,
+        PTR, PTR, PTR, PTR, PTR, PTR, PTR, PTR, PTR, PTR, sz(64), NULL)
+    assert bwd(2, 16, cam) == E_UNSUPPORTED
+    assert bwd(1, 32, cam) == E_UNSUPPORTED
+    assert bwd(1, 16, camera(model=ORTHO)) == E_UNSUPPORTED
+    assert bwd(1, 16, cam) == E_WORKSPACE              # 64-byte workspace for 8 Gaussians
+
+
+def test_strategy_helpers_argument_validation(lib):
+    assert lib.gsb_quat_to_rotmat(u32(0), NULL, NULL, NULL) == OK
+    assert lib.gsb_quat_to_rotmat(u32(4), NULL, PTR, NULL) == E_INVALID
+    assert lib.gsb_relocation(u32(0), NULL, NULL, NULL, NULL, i32(51), NULL, NULL, NULL) == OK
+    assert lib.gsb_relocation(u32(4), PTR, PTR, NULL, PTR, i32(51), PTR, PTR, NULL) == E_INVALID
+    assert lib.gsb_add_noise(u32(0), NULL, NULL, NULL, NULL, NULL, f32(1e-3), NULL) == OK
+    assert lib.gsb_add_noise(u32(4), PTR, PTR, PTR, NULL, PTR, f32(1e-3), NULL) == E_INVALID
+
+
+def test_shim_rejects_cpu_tensors_like_the_reference(pkg):
+    """CHECK_INPUT of the reference (Common.h:12-17): every operator insists on CUDA, contiguous tensors and throws
+    c10::Error (RuntimeError in Python) otherwise -- checked here with CPU tensors, no device needed."""
+    import torch
+    pkg.load()
+    N = 8
+    means, quats, scales = torch.randn(N, 3), torch.randn(N, 4), torch.rand(N, 3)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pkg.spherical_harmonics_fwd(3, torch.randn(N, 3), torch.randn(N, 16, 3), None)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pkg.spherical_harmonics_bwd(16, 3, torch.randn(N, 3), torch.randn(N, 16, 3), None, torch.randn(N, 3), True)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pkg.intersect_tile(torch.randn(1, N, 2), torch.ones(1, N, 2, dtype=torch.int32), torch.rand(1, N), 1, 16, 4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pkg.intersect_offset(torch.zeros(4, dtype=torch.int64), 1, 4, 4)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pkg.projection_ut_3dgs_fused(means, quats, scales, torch.rand(N), torch.eye(4)[None], torch.eye(3)[None], 64, 64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pkg.quats_to_rotmats(quats)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        pkg.default_backend().spherical_harmonics_bwd_views(3, means, torch.zeros(1, 3), torch.randn(N, 16, 3),
+                                                           torch.randn(1, N, 3), torch.zeros(N, 3))
