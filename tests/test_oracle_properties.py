@@ -207,3 +207,40 @@ def test_backward_matches_finite_differences_without_cutoffs(orc, cam):
             assert abs(num - a_) <= 0.01 * abs(a_) + 2e-3, (name, int(gi), dim, num, a_)
             checked += 1
     assert checked == 110
+
+
+def test_ut_projection_tends_to_the_linearised_projection_for_small_gaussians(orc):
+    """Independent check of the unscented transform (sigma points, weights lambda/(D+lambda) and 1/(2(D+lambda)),
+    ProjectionUT3DGSFused.cu:84-150): for a Gaussian that is small compared with its depth the UT mean is the
+    projected centre and the UT covariance is J Sigma J^T of the pinhole Jacobian, up to O((sigma/z)^2)."""
+    rng = np.random.default_rng(12)
+    N, W, H = 200, 320, 240
+    fx, fy, cx, cy = 260.0, 250.0, 160.0, 120.0
+    Ks = np.array([[[fx, 0, cx], [0, fy, cy], [0, 0, 1]]], np.float32)
+    vm = scenes.look_at(np.array([0.4, -0.3, -0.5]), (0.0, 0.0, 3.0)).astype(np.float32)[None]
+    means = np.stack([rng.uniform(-1, 1, N), rng.uniform(-0.7, 0.7, N), rng.uniform(2.5, 4.0, N)], -1).astype(np.float32)
+    quats = rng.standard_normal((N, 4)).astype(np.float32)
+    quats /= np.linalg.norm(quats, axis=-1, keepdims=True)
+    scales = rng.uniform(0.004, 0.012, (N, 3)).astype(np.float32)
+    eps2d = 1e-4
+    radii, m2d, depths, conics, _ = orc.projection_ut(means, quats, scales, np.full(N, 0.9, np.float32), vm, Ks, W, H,
+                                                      eps2d, 0.01, 1e4, 0.0, precision="f64")
+    vis = (radii[0] > 0).all(-1)
+    assert vis.sum() > 100
+    R, t = vm[0, :3, :3].astype(np.float64), vm[0, :3, 3].astype(np.float64)
+    for i in np.nonzero(vis)[0][:60]:
+        pc = R @ means[i].astype(np.float64) + t
+        uv = np.array([fx * pc[0] / pc[2] + cx, fy * pc[1] / pc[2] + cy])
+        w, x, y, z = quats[i].astype(np.float64)
+        Rg = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)],
+                       [2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)],
+                       [2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)]])
+        S3 = Rg @ np.diag(scales[i].astype(np.float64) ** 2) @ Rg.T
+        J = np.array([[fx / pc[2], 0, -fx * pc[0] / pc[2] ** 2], [0, fy / pc[2], -fy * pc[1] / pc[2] ** 2]])
+        S2 = J @ (R @ S3 @ R.T) @ J.T + eps2d * np.eye(2)
+        inv = np.linalg.inv(S2)
+        assert np.abs(m2d[0, i] - uv).max() < 2e-3, (i, m2d[0, i], uv)
+        assert abs(depths[0, i] - pc[2]) < 1e-5
+        got = conics[0, i].astype(np.float64)
+        want = np.array([inv[0, 0], inv[0, 1], inv[1, 1]])
+        assert np.abs(got - want).max() <= 2e-3 * np.abs(want).max(), (i, got, want)
