@@ -277,7 +277,7 @@ def run_b200(args):
     cabi.gsb_profile_enable(1)
     timed(lambda: step(P), args.steps)
     prof = {}
-    for kname in ("projection_ut", "sh_fwd", "isect_count", "isect_depth_sort", "isect_emit", "isect_sort",
+    for kname in ("projection_ut", "sh_fwd", "isect_count", "isect_depth_sort", "isect_tile_hist", "isect_emit", "isect_sort",
                   "isect_offsets", "raster_prep",
                   "raster_fwd", "raster_bwd", "raster_finalize", "sh_bwd", "sh_bwd_views"):
         tot = ctypes.c_double(0.0)

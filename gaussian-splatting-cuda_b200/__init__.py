@@ -289,23 +289,28 @@ def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K,
               scaling_modifier=1.0, tile_size=16, eps2d=0.3, near_plane=0.01, far_plane=10000.0,
               radius_clip=0.0, backend: OpsBackend | None = None, camera_model=PINHOLE, radial_coeffs=None,
               tangential_coeffs=None, thin_prism_coeffs=None,
-              sh_exchange: DeferredSHBackward | None = None) -> RenderOutput:
+              sh_exchange: DeferredSHBackward | None = None, projection=None) -> RenderOutput:
     """gs::training::rasterize for RenderMode::RGB, perfect pinhole, C == 1 (rasterizer.cpp:46-437).
 
     Inputs are the ACTIVATED parameters (get_means/get_rotation/get_scaling/get_opacity/get_shs of
     SplatData): means [N,3], unit quats [N,4] (w,x,y,z), scales [N,3] > 0, opacities [N] in (0,1),
     sh_coeffs [N,K,3]; viewmat [1,4,4], K [1,3,3]; bg_color [1,3] or None.  Distortion coefficients as the
     reference's Camera supplies them (rasterizer.cpp:183-206); camera_model PINHOLE or FISHEYE.
+    `projection` = (radii, means2d, depths) replaces the projection step (the op is not differentiable, Ops.h:67):
+    parity tests feed two backends the SAME projection so that their intersection lists are identical.
     """
     be = backend or _DEFAULT
     camera = dict(camera_model=camera_model, radial_coeffs=radial_coeffs, tangential_coeffs=tangential_coeffs,
                   thin_prism_coeffs=thin_prism_coeffs)
     scaled = scales * scaling_modifier if scaling_modifier != 1.0 else scales
     with torch.no_grad():  # "none differentiable" (Ops.h:67)
-        radii, means2d, depths, _conics, _ = be.projection_ut_3dgs_fused(
-            means.detach().contiguous(), quats.detach().contiguous(), scaled.detach().contiguous(),
-            opacities.detach().contiguous(), viewmat, K, width, height, eps2d, near_plane, far_plane, radius_clip,
-            **camera)
+        if projection is not None:
+            radii, means2d, depths = projection
+        else:
+            radii, means2d, depths, _conics, _ = be.projection_ut_3dgs_fused(
+                means.detach().contiguous(), quats.detach().contiguous(), scaled.detach().contiguous(),
+                opacities.detach().contiguous(), viewmat, K, width, height, eps2d, near_plane, far_plane,
+                radius_clip, **camera)
         # rasterizer.cpp:250-251 (torch::inverse).  inv_ex is the same LU inverse without the host-side
         # singularity check, i.e. without a device->host sync in the middle of the step.
         campos = torch.linalg.inv_ex(viewmat).inverse[:, :3, 3]

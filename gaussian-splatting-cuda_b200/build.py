@@ -37,7 +37,7 @@ CUDA_SOURCES = [
     ("gsb_raster.cu", []),
     ("gsb_misc.cu", []),
 ]
-CUDA_HEADERS = ["gsb_common.cuh", "gsb_raster.cuh", "gsb_camera.cuh"]
+CUDA_HEADERS = ["gsb_common.cuh", "gsb_raster.cuh", "gsb_camera.cuh", "gsb_devsort.cuh"]
 SHIM_SOURCES = ["Ops.cpp", "torch_binding.cpp"]
 
 

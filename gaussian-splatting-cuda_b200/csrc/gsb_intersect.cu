@@ -10,22 +10,26 @@
 // (ascending flattened Gaussian index), which is what the reference's stable
 // cub::DeviceRadixSort::SortPairs over 32+tile_bits+cam_bits key bits produces.
 //
-// How the sorted lists are built (gsb_isect_plan + gsb_isect_emit_planned): the reference radix-sorts all I
-// intersections on 46 bits (six 8-bit passes over 12-byte pairs, ~150 B of HBM traffic per
-// intersection).  Here the depth order is established ONCE per Gaussian instead of once per
-// intersection:
-//   1. stable radix sort of the C*N Gaussians by (camera, depth bits)      [N elements, not I]
-//   2. scan of tiles_per_gauss in that order, emit the intersections in that order
-//   3. stable radix sort of the I intersections on the (camera, tile) bits ONLY (13-14 bits:
-//      two passes instead of six).
-// A stable sort by tile of a sequence already ordered by (depth, index) is ordered by
-// (tile, depth, index): the same permutation as the reference's single 46-bit sort.
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-#include <thrust/iterator/permutation_iterator.h>
-#include <thrust/iterator/transform_iterator.h>
-
-#include "gsb_common.cuh"
+// How the sorted lists are built (gsb_isect_plan + gsb_isect_emit_planned).  The reference radix-sorts
+// all I intersections on 46 bits (six 8-bit passes over 12-byte pairs, ~150 B of HBM traffic per
+// intersection).  Here no intersection is ever sorted:
+//   1. plan      one thread per Gaussian: tile box, tile count, depth key.
+//   2. depth     stable LSD radix sort of the C*N Gaussians by depth bits (N elements, not I;
+//                gsb_devsort.cuh), passes whose digit is constant are skipped.
+//   3. runs      scan of the tile counts in depth order -> compact run table (Gaussians with >= 1 tile:
+//                cumulative end slot, index, box, depth key); n_isects goes to the host here.
+//   4. histogram the I intersection slots, in depth order, are cut into P equal chunks, one warp each.  A
+//                warp walks its chunk 32 slots per step (slot -> run by a ballot over the run ends, run ->
+//                tile by the box) and counts the tiles in shared-memory counters: matrix M[P][tiles].
+//   5. column scan over (tile, chunk): M[p][t] becomes the first output slot of chunk p in tile t;
+//                the tile offsets (a6) fall out of the same scan.
+//   -- host reads n_isects, allocates the outputs --
+//   6. scatter   the same walk again; slot ranks within a step come from match.any on the tile id, so
+//                every (tile, depth, index) lands DIRECTLY in its final position: 4 (+8 for the key) bytes
+//                written per intersection, nothing read back.
+// A stable placement by tile of a sequence ordered by (depth, index) is ordered by (tile, depth, index):
+// the same permutation as the reference's single 46-bit sort, ties included.
+#include "gsb_devsort.cuh"
 
 namespace gsb {
 
@@ -70,26 +74,23 @@ __global__ void __launch_bounds__(kIsectThreads) isect_count_kernel(uint64_t n, 
     tiles_per_gauss[idx] = b.active ? (int32_t)((b.y1 - b.y0) * (b.x1 - b.x0)) : 0;
 }
 
-// Emits the intersections of Gaussian perm[i] (or i when perm == nullptr) at cum[i-1].
+// Unsorted path (sort == false): Gaussian i writes its intersections at cum[i-1], row-major over its box.
 __global__ void __launch_bounds__(kIsectThreads) isect_emit_kernel(uint64_t n, uint32_t N,
                                                                     const float *__restrict__ means2d,
                                                                     const int32_t *__restrict__ radii,
                                                                     const float *__restrict__ depths,
-                                                                    const uint32_t *__restrict__ perm,
                                                                     const int64_t *__restrict__ cum_tiles,
                                                                     uint32_t tile_size, uint32_t tile_width,
                                                                     uint32_t tile_height, uint32_t tile_n_bits,
                                                                     int64_t *__restrict__ isect_ids,
                                                                     int32_t *__restrict__ flatten_ids) {
-    const uint64_t i = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
-    if (i >= n) return;
-    const uint64_t idx = perm ? (uint64_t)perm[i] : i;
+    const uint64_t idx = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
+    if (idx >= n) return;
     const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
     if (!b.active) return;
-    const int64_t cid = (int64_t)(idx / N);
-    const int64_t cid_enc = cid << (32 + tile_n_bits);
+    const int64_t cid_enc = (int64_t)(idx / N) << (32 + tile_n_bits);
     const int64_t depth_enc = (int64_t)__float_as_uint(depths[idx]); // zero-extended bit pattern (:98-99)
-    int64_t cur = (i == 0) ? 0 : cum_tiles[i - 1];
+    int64_t cur = (idx == 0) ? 0 : cum_tiles[idx - 1];
     for (uint32_t y = b.y0; y < b.y1; ++y)
         for (uint32_t x = b.x0; x < b.x1; ++x) {
             const int64_t tile_id = (int64_t)y * tile_width + x;
@@ -99,122 +100,322 @@ __global__ void __launch_bounds__(kIsectThreads) isect_emit_kernel(uint64_t n, u
         }
 }
 
-// Load-balanced emit for the sorted path: one CTA per kEmitSpan consecutive OUTPUT slots instead of one
-// thread per Gaussian, so a Gaussian covering 400 tiles costs 400 slots of work spread over 50 threads
-// rather than one thread's 400-iteration loop, and the span leaves through coalesced warp stores.
-// Run i (Gaussian perm[i]) owns the slots [cum[i-1], cum[i]); Gaussians without tiles are parked behind
-// all others by their depth key, so every run that intersects [0, I) is non-empty.
-constexpr int kEmitItems = 8;
-constexpr int kEmitSpan = kIsectThreads * kEmitItems;
-
-__global__ void __launch_bounds__(kIsectThreads) isect_emit_balanced_kernel(
-    uint64_t n, uint32_t N, uint64_t n_isects, const float *__restrict__ means2d, const int32_t *__restrict__ radii,
-    const float *__restrict__ depths, const uint32_t *__restrict__ perm, const int64_t *__restrict__ cum,
-    uint32_t tile_size, uint32_t tile_width, uint32_t tile_height, uint32_t tile_n_bits,
-    int64_t *__restrict__ isect_ids, int32_t *__restrict__ flatten_ids) {
-    __shared__ int32_t s_end[kEmitSpan + 1]; // run ends relative to the CTA's first slot, clamped to the span
-    __shared__ int64_t s_keys[kEmitSpan];
-    __shared__ int32_t s_vals[kEmitSpan];
-    __shared__ uint64_t s_first;             // index of the run that owns the CTA's first slot
-    __shared__ int64_t s_first_start;        // and its first slot
-    const int64_t o0 = (int64_t)blockIdx.x * kEmitSpan;
-    const int32_t span = (int32_t)min((int64_t)kEmitSpan, (int64_t)n_isects - o0);
-    const uint32_t tid = threadIdx.x;
-
-    if (tid < 32) {
-        // first i with cum[i] > o0: 32-ary search, one probe per lane per round
-        uint64_t lo = 0, hi = n; // answer in [lo, hi), cum[n-1] = n_isects > o0
-        while (hi - lo > 1) {
-            const uint64_t len = hi - lo;
-            const uint64_t step = (len + 32) / 33; // 32 interior probes split the range into <= 33 pieces
-            const uint64_t p = lo + (uint64_t)(tid + 1) * step - 1; // probe positions lo+step-1, lo+2step-1, ...
-            const bool le = (p < hi - 1) ? (cum[p] <= o0) : false;   // position hi-1 is known to be > o0
-            const uint32_t m = __ballot_sync(0xffffffffu, le);
-            const uint32_t k = __popc(m); // probes are monotone: the first k satisfy cum <= o0
-            const uint64_t nlo = (k == 0) ? lo : lo + (uint64_t)k * step;
-            const uint64_t nhi = (k == 32) ? hi : min(hi, lo + (uint64_t)(k + 1) * step);
-            lo = nlo; hi = nhi;
-        }
-        if (tid == 0) {
-            s_first = lo;
-            s_first_start = (lo == 0) ? 0 : cum[lo - 1];
-        }
-    }
-    __syncthreads();
-    const uint64_t g_lo = s_first;
-    for (int32_t r = (int32_t)tid; r <= kEmitSpan; r += kIsectThreads) {
-        const uint64_t g = g_lo + (uint64_t)r;
-        int64_t e = (g < n) ? cum[g] - o0 : (int64_t)kEmitSpan;
-        s_end[r] = (int32_t)min(e, (int64_t)kEmitSpan);
-    }
-    __syncthreads();
-
-    // Each thread walks its kEmitItems consecutive slots (one run lookup, then increments) into shared
-    // memory; the CTA then writes the span out with fully coalesced 256-byte warp stores -- per-thread
-    // 8-byte global stores would touch one 32-byte sector each and run at the L2's transaction rate.
-    auto phys = [](int32_t e) { return (e & ~7) | ((e & 7) ^ ((e >> 3) & 7)); }; // bank swizzle
-    int32_t o = (int32_t)tid * kEmitItems;
-    if (o < span) {
-        // run of this thread's first slot: first r with s_end[r] > o
-        int32_t lo = 0, hi = kEmitSpan;
-        while (lo < hi) {
-            const int32_t mid = (lo + hi) >> 1;
-            if (s_end[mid] > o) hi = mid; else lo = mid + 1;
-        }
-        int32_t r = lo;
-        const int32_t o_stop = min(o + kEmitItems, span);
-        while (o < o_stop) {
-            const uint64_t idx = perm[g_lo + (uint64_t)r];
-            const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
-            const uint32_t w = b.x1 - b.x0;
-            const int64_t run_start = (r == 0) ? s_first_start - o0 : (int64_t)s_end[r - 1];
-            const uint32_t j = (uint32_t)((int64_t)o - run_start);
-            uint32_t y = b.y0 + j / w, x = b.x0 + j % w;
-            const int64_t cid_enc = (int64_t)(idx / N) << (32 + tile_n_bits);
-            const int64_t depth_enc = (int64_t)__float_as_uint(depths[idx]);
-            const int32_t run_stop = min(s_end[r], o_stop);
-            for (; o < run_stop; ++o) {
-                const int64_t tile_id = (int64_t)y * tile_width + x;
-                s_keys[phys(o)] = cid_enc | (tile_id << 32) | depth_enc;
-                s_vals[phys(o)] = (int32_t)idx;
-                if (++x == b.x1) { x = b.x0; ++y; }
-            }
-            ++r;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < kEmitItems; ++k) {
-        const int32_t e = k * kIsectThreads + (int32_t)tid;
-        if (e < span) {
-            isect_ids[o0 + e] = s_keys[phys(e)];
-            flatten_ids[o0 + e] = s_vals[phys(e)];
-        }
-    }
-}
-
-// Count and depth key in one pass over the Gaussians (the plan phase of the two-phase sorted path).
-__global__ void __launch_bounds__(kIsectThreads) isect_plan_kernel(uint64_t n, uint32_t N,
-                                                                    const float *__restrict__ means2d,
+// ---- planned path, step 1: tile box, count and depth key of every Gaussian ---------------------------------
+// boxes[idx] = (x0 | y0 << 16, w | h << 16) in tiles.  Gaussians without tiles get the key 0xffffffff: they
+// end up behind every Gaussian that has tiles and never enter the run table.
+__global__ void __launch_bounds__(kIsectThreads) isect_plan_kernel(uint64_t n, const float *__restrict__ means2d,
                                                                     const int32_t *__restrict__ radii,
                                                                     const float *__restrict__ depths,
                                                                     uint32_t tile_size, uint32_t tile_width,
                                                                     uint32_t tile_height,
                                                                     int32_t *__restrict__ tiles_per_gauss,
-                                                                    uint64_t *__restrict__ keys64,
-                                                                    uint32_t *__restrict__ keys32,
-                                                                    uint32_t *__restrict__ vals) {
+                                                                    uint32_t *__restrict__ keys,
+                                                                    uint2 *__restrict__ boxes,
+                                                                    SortCtl *__restrict__ ctl) {
+    __shared__ uint32_t s_or[kIsectThreads / 32], s_nor[kIsectThreads / 32];
     const uint64_t idx = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
-    if (idx >= n) return;
-    const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
-    const int32_t cnt = b.active ? (int32_t)((b.y1 - b.y0) * (b.x1 - b.x0)) : 0;
-    tiles_per_gauss[idx] = cnt;
-    // Gaussians without tiles never emit: park them behind ALL others (camera field = C, one past the last)
-    const uint32_t d = cnt > 0 ? __float_as_uint(depths[idx]) : 0xffffffffu;
-    const uint64_t cam = cnt > 0 ? idx / N : n / N;
-    if (keys64) keys64[idx] = (cam << 32) | d;
-    else keys32[idx] = d;
-    vals[idx] = (uint32_t)idx;
+    uint32_t k_or = 0u, k_nor = 0u;
+    if (idx < n) {
+        const TileBox b = tile_box(means2d, radii, idx, tile_size, tile_width, tile_height);
+        const uint32_t w = b.x1 - b.x0, h = b.y1 - b.y0;
+        const int32_t cnt = b.active ? (int32_t)(w * h) : 0;
+        tiles_per_gauss[idx] = cnt;
+        uint32_t key = 0xffffffffu;
+        if (cnt > 0) {
+            key = __float_as_uint(depths[idx]);
+            k_or = key;
+            k_nor = ~key;
+        }
+        keys[idx] = key;
+        boxes[idx] = make_uint2(b.x0 | (b.y0 << 16), w | (h << 16));
+    }
+    k_or = __reduce_or_sync(0xffffffffu, k_or);
+    k_nor = __reduce_or_sync(0xffffffffu, k_nor);
+    if ((threadIdx.x & 31) == 0) { s_or[threadIdx.x >> 5] = k_or; s_nor[threadIdx.x >> 5] = k_nor; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kIsectThreads / 32; ++w) { k_or |= s_or[w]; k_nor |= s_nor[w]; }
+        if (k_or | k_nor) { // at least one Gaussian of this CTA touches a tile
+            atomicOr(&ctl->key_or, k_or);
+            atomicOr(&ctl->key_nor, k_nor);
+        }
+    }
+}
+
+// ---- step 3: run table ---------------------------------------------------------------------------------------
+// One scan over the Gaussians in depth order of the pair (has tiles ? 1 : 0, tile count).
+struct RunAcc {
+    unsigned long long cnt;
+    uint32_t runs;
+    __device__ __forceinline__ RunAcc &operator+=(const RunAcc &o) { cnt += o.cnt; runs += o.runs; return *this; }
+};
+__device__ __forceinline__ RunAcc operator+(RunAcc a, const RunAcc &b) { a += b; return a; }
+
+__device__ __forceinline__ RunAcc run_shfl_up(RunAcc v, int o) {
+    RunAcc r;
+    r.cnt = __shfl_up_sync(0xffffffffu, v.cnt, o);
+    r.runs = __shfl_up_sync(0xffffffffu, v.runs, o);
+    return r;
+}
+__device__ __forceinline__ RunAcc run_block_scan(RunAcc v, RunAcc *s_warp, RunAcc &total) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const RunAcc t = run_shfl_up(v, o);
+        if (lane >= (uint32_t)o) v += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = v;
+    __syncthreads();
+    RunAcc add = {0ull, 0u}, tot = {0ull, 0u};
+    for (int w = 0; w < kSortWarps; ++w) {
+        const RunAcc x = s_warp[w];
+        if ((uint32_t)w < warp) add += x;
+        tot += x;
+    }
+    total = tot;
+    return v + add;
+}
+
+struct RunTable {
+    uint32_t *end;  // cumulative number of intersections up to and including this run
+    uint32_t *idx;  // flattened Gaussian index (camera * N + gaussian)
+    uint2 *box;
+    uint32_t *key;  // depth bits
+};
+
+__device__ __forceinline__ const uint32_t *sorted_vals(const SortCtl *ctl, const uint32_t *v0, const uint32_t *v1) {
+    return (radix_passes_done(ctl, 4) & 1) ? v1 : v0;
+}
+
+__global__ void __launch_bounds__(kSortThreads) runs_blocksum_kernel(const SortCtl *__restrict__ ctl,
+                                                                     const uint32_t *__restrict__ v0,
+                                                                     const uint32_t *__restrict__ v1,
+                                                                     const int32_t *__restrict__ counts, uint64_t n,
+                                                                     uint32_t seg, RunAcc *__restrict__ bsum) {
+    __shared__ RunAcc s_warp[kSortWarps];
+    const uint32_t *perm = sorted_vals(ctl, v0, v1);
+    const SegRange r = cta_segment(n, seg);
+    RunAcc acc = {0ull, 0u};
+    for (uint64_t i = r.lo + threadIdx.x; i < r.hi; i += kSortThreads) {
+        const int32_t c = counts[perm[i]];
+        acc.cnt += (unsigned long long)c;
+        acc.runs += c > 0 ? 1u : 0u;
+    }
+    RunAcc tot;
+    run_block_scan(acc, s_warp, tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(kSortThreads) runs_build_kernel(SortCtl *__restrict__ ctl,
+                                                                  const uint32_t *__restrict__ v0,
+                                                                  const uint32_t *__restrict__ v1,
+                                                                  const uint32_t *__restrict__ k0,
+                                                                  const uint32_t *__restrict__ k1,
+                                                                  const int32_t *__restrict__ counts,
+                                                                  const uint2 *__restrict__ boxes, uint64_t n,
+                                                                  uint32_t seg, uint32_t nblocks,
+                                                                  const RunAcc *__restrict__ bsum, RunTable rt) {
+    __shared__ RunAcc s_warp[kSortWarps];
+    const bool odd = (radix_passes_done(ctl, 4) & 1) != 0;
+    const uint32_t *perm = odd ? v1 : v0;
+    const uint32_t *keys = odd ? k1 : k0;
+    RunAcc carry;
+    {
+        RunAcc part = {0ull, 0u};
+        for (uint32_t bb = threadIdx.x; bb < blockIdx.x; bb += kSortThreads) part += bsum[bb];
+        run_block_scan(part, s_warp, carry);
+    }
+    const SegRange r = cta_segment(n, seg);
+    for (uint64_t i0 = r.lo; i0 < r.hi; i0 += kSortThreads) {
+        const uint64_t i = i0 + threadIdx.x;
+        RunAcc v = {0ull, 0u};
+        uint32_t idx = 0;
+        if (i < r.hi) {
+            idx = perm[i];
+            const int32_t c = counts[idx];
+            v.cnt = (unsigned long long)c;
+            v.runs = c > 0 ? 1u : 0u;
+        }
+        RunAcc tot;
+        const RunAcc inc = run_block_scan(v, s_warp, tot);
+        if (v.runs) {
+            const uint32_t k = carry.runs + inc.runs - 1u;
+            rt.end[k] = (uint32_t)(carry.cnt + inc.cnt);
+            rt.idx[k] = idx;
+            rt.box[k] = boxes[idx];
+            rt.key[k] = keys[i];
+        }
+        carry += tot;
+    }
+    if (blockIdx.x == nblocks - 1 && threadIdx.x == 0) {
+        ctl->n_runs = carry.runs;
+        ctl->n_isects = carry.cnt;
+    }
+}
+
+// ---- steps 4 and 6: the chunk walk -----------------------------------------------------------------------------
+struct BinArgs {
+    RunTable rt;
+    const SortCtl *ctl;
+    uint32_t N;          // Gaussians per camera
+    uint32_t n_tiles;    // tiles per camera
+    uint32_t tile_width;
+    uint32_t tile_n_bits;
+    uint32_t multi_cam;
+    uint32_t t_lo, t_cnt; // window of global tile ids (camera * n_tiles + tile) counted by this launch
+    uint32_t T_total, P;
+    uint32_t *M;          // [P][T_total]
+    int32_t *flatten_ids;
+    int64_t *isect_ids;   // nullable
+};
+
+// first r in [0, n_runs) with end[r] > s (exists: s < end[n_runs - 1]); one probe per lane and round
+__device__ __forceinline__ uint32_t first_run_after(const uint32_t *__restrict__ end, uint32_t n_runs, uint32_t s) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lo = 0, hi = n_runs; // answer in [lo, hi)
+    while (hi - lo > 1) {
+        const uint32_t len = hi - lo;
+        const uint32_t step = (len + 32) / 33;
+        const uint32_t p = lo + (lane + 1) * step - 1;
+        const bool le = (p < hi - 1) ? (end[p] <= s) : false; // position hi-1 is known to be > s
+        const uint32_t k = __popc(__ballot_sync(0xffffffffu, le));
+        const uint32_t nlo = (k == 0) ? lo : lo + k * step;
+        const uint32_t nhi = (k == 32) ? hi : min(hi, lo + (k + 1) * step);
+        lo = nlo; hi = nhi;
+    }
+    return lo;
+}
+
+template <bool kScatter>
+__global__ void __launch_bounds__(32) tile_bin_kernel(const BinArgs a) {
+    extern __shared__ uint32_t s_cnt[]; // [t_cnt]
+    const uint32_t lane = threadIdx.x;
+    const uint32_t p = blockIdx.x;
+    uint32_t *row = a.M + (size_t)p * a.T_total + a.t_lo;
+    const unsigned long long I = a.ctl->n_isects;
+    const uint32_t n_runs = a.ctl->n_runs;
+    const uint32_t s_begin = (uint32_t)(((unsigned long long)p * I) / a.P);
+    const uint32_t s_end = (uint32_t)(((unsigned long long)(p + 1) * I) / a.P);
+    if (kScatter) {
+        if (s_begin >= s_end) return;
+        for (uint32_t t = lane; t < a.t_cnt; t += 32) s_cnt[t] = row[t];
+    } else {
+        for (uint32_t t = lane; t < a.t_cnt; t += 32) s_cnt[t] = 0;
+    }
+    __syncwarp();
+    if (s_begin < s_end) {
+        uint32_t r0 = first_run_after(a.rt.end, n_runs, s_begin);
+        uint32_t start0 = r0 ? a.rt.end[r0 - 1] : 0u; // first slot of run r0
+        for (uint32_t s0 = s_begin; s0 < s_end; s0 += 32) {
+            // window of 32 candidate runs; the run ends inside the step are strictly increasing (no empty runs)
+            const uint32_t r = r0 + lane;
+            const bool have = r < n_runs;
+            const uint32_t rel = have ? a.rt.end[r] - s0 : 0xffffffffu; // > 0 for lane 0
+            const uint32_t idx_l = have ? a.rt.idx[r] : 0u;
+            const uint2 box_l = have ? a.rt.box[r] : make_uint2(0u, 0u);
+            const uint32_t key_l = (kScatter && have) ? a.rt.key[r] : 0u;
+            const uint32_t endmask = __reduce_or_sync(0xffffffffu, rel <= 31u ? (1u << rel) : 0u);
+            // runs that end at or before this lane's slot = offset of this lane's run in the window (<= lane)
+            const uint32_t c = __popc(endmask & ((2u << lane) - 1u));
+            const uint32_t prev_rel = __shfl_sync(0xffffffffu, rel, c ? c - 1 : 0);
+            const uint32_t idx = __shfl_sync(0xffffffffu, idx_l, c);
+            const uint32_t bx = __shfl_sync(0xffffffffu, box_l.x, c), by = __shfl_sync(0xffffffffu, box_l.y, c);
+            const uint32_t key = __shfl_sync(0xffffffffu, key_l, c);
+            const uint32_t slot = s0 + lane;
+            const bool valid = slot < s_end;
+            const uint32_t run_start = c ? s0 + prev_rel : start0;
+            const uint32_t j = slot - run_start; // position inside the run's box, row-major
+            const uint32_t w = by & 0xffffu;
+            uint32_t tt = 0x80000000u | lane; // a value no tile id takes
+            uint32_t tile = 0, cam = 0;
+            bool in = false;
+            if (valid) {
+                const uint32_t dy = j / w, dx = j - dy * w;
+                tile = ((bx >> 16) + dy) * a.tile_width + (bx & 0xffffu) + dx;
+                cam = a.multi_cam ? idx / a.N : 0u;
+                const uint32_t g = cam * a.n_tiles + tile - a.t_lo;
+                in = g < a.t_cnt;
+                if (in) tt = g;
+            }
+            const uint32_t peers = __match_any_sync(0xffffffffu, tt);
+            uint32_t base = 0;
+            if (in) base = s_cnt[tt];
+            __syncwarp();
+            if (in) {
+                if (kScatter) {
+                    const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+                    a.flatten_ids[pos] = (int32_t)idx;
+                    if (a.isect_ids)
+                        a.isect_ids[pos] = ((int64_t)cam << (32 + a.tile_n_bits)) | ((int64_t)tile << 32) | (int64_t)key;
+                }
+                if ((peers >> lane) == 1u) s_cnt[tt] = base + __popc(peers);
+            }
+            __syncwarp();
+            // advance to the run that holds slot s0 + 32
+            const uint32_t adv = __popc(__ballot_sync(0xffffffffu, rel <= 32u));
+            if (adv) {
+                start0 = s0 + __shfl_sync(0xffffffffu, rel, adv - 1);
+                r0 += adv;
+            }
+        }
+    }
+    if (!kScatter) {
+        __syncwarp();
+        for (uint32_t t = lane; t < a.t_cnt; t += 32) row[t] = s_cnt[t];
+    }
+}
+
+// ---- step 5: exclusive scan of M over (tile, chunk) ----------------------------------------------------------
+// col_segsum: seg[s][t] = sum of M[p][t] over the chunks p of segment s.
+__global__ void __launch_bounds__(kIsectThreads) col_segsum_kernel(const uint32_t *__restrict__ M, uint32_t T,
+                                                                   uint32_t P, uint32_t seg_len,
+                                                                   uint32_t *__restrict__ seg) {
+    const uint32_t t = blockIdx.x * kIsectThreads + threadIdx.x;
+    if (t >= T) return;
+    const uint32_t s = blockIdx.y;
+    const uint32_t p0 = s * seg_len, p1 = min(P, p0 + seg_len);
+    uint32_t acc = 0;
+    for (uint32_t p = p0; p < p1; ++p) acc += M[(size_t)p * T + t];
+    seg[(size_t)s * T + t] = acc;
+}
+// col_tilescan (one CTA): seg[s][t] -> exclusive prefix over s plus the tile's first slot; tile offsets out.
+__global__ void __launch_bounds__(kSortThreads) col_tilescan_kernel(uint32_t *__restrict__ seg, uint32_t T, uint32_t S,
+                                                                    int32_t *__restrict__ tile_offsets /*nullable*/) {
+    __shared__ uint32_t s_warp[kSortWarps];
+    uint32_t carry = 0;
+    for (uint32_t t0 = 0; t0 < T; t0 += kSortThreads) {
+        const uint32_t t = t0 + threadIdx.x;
+        uint32_t tot = 0;
+        if (t < T)
+            for (uint32_t s = 0; s < S; ++s) tot += seg[(size_t)s * T + t];
+        uint32_t all;
+        const uint32_t inc = block_scan_inclusive<uint32_t>(tot, s_warp, all);
+        if (t < T) {
+            uint32_t run = carry + inc - tot; // first slot of tile t
+            if (tile_offsets) tile_offsets[t] = (int32_t)run;
+            for (uint32_t s = 0; s < S; ++s) {
+                const uint32_t v = seg[(size_t)s * T + t];
+                seg[(size_t)s * T + t] = run;
+                run += v;
+            }
+        }
+        carry += all;
+    }
+}
+// col_apply: M[p][t] = first output slot of chunk p in tile t.
+__global__ void __launch_bounds__(kIsectThreads) col_apply_kernel(uint32_t *__restrict__ M, uint32_t T, uint32_t P,
+                                                                  uint32_t seg_len, const uint32_t *__restrict__ seg) {
+    const uint32_t t = blockIdx.x * kIsectThreads + threadIdx.x;
+    if (t >= T) return;
+    const uint32_t s = blockIdx.y;
+    const uint32_t p0 = s * seg_len, p1 = min(P, p0 + seg_len);
+    uint32_t run = seg[(size_t)s * T + t];
+    for (uint32_t p = p0; p < p1; ++p) {
+        const uint32_t v = M[(size_t)p * T + t];
+        M[(size_t)p * T + t] = run;
+        run += v;
+    }
 }
 
 // IntersectTile.cu:206-252, restated as "first sorted position whose (cam, tile) >= id".
@@ -239,41 +440,149 @@ __global__ void __launch_bounds__(kIsectThreads) isect_offsets_kernel(uint64_t n
     }
 }
 
-struct CastI64 {
-    __host__ __device__ __forceinline__ int64_t operator()(const int32_t &v) const { return (int64_t)v; }
-};
-using CountIter = thrust::transform_iterator<CastI64, const int32_t *, int64_t>;
-using PermCountIter =
-    thrust::transform_iterator<CastI64, thrust::permutation_iterator<const int32_t *, const uint32_t *>, int64_t>;
-
+// ---- host-side geometry ------------------------------------------------------------------------------------------
 static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+struct DeviceShape {
+    int sms;
+    int smem_optin; // max dynamic shared memory per block
+    int smem_sm;    // shared memory per SM
+};
+static const DeviceShape &device_shape() {
+    // immutable after the first call (C++11 thread-safe initialisation); sm_100a: 148 SMs, 227 KB / 228 KB
+    static const DeviceShape s = [] {
+        DeviceShape d{148, 227 * 1024, 228 * 1024};
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) {
+            int v = 0;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) d.sms = v;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess && v > 0)
+                d.smem_optin = v;
+            if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev) == cudaSuccess && v > 0)
+                d.smem_sm = v;
+        }
+        return d;
+    }();
+    return s;
+}
+
+// segment length / CTA count of the 1024-thread sort and scan kernels
+struct SegPlan {
+    uint32_t nblocks, seg;
+};
+static SegPlan seg_plan(uint64_t n) {
+    const DeviceShape &d = device_shape();
+    uint64_t nb = (n + 4095) / 4096;
+    if (nb < 1) nb = 1;
+    if (nb > (uint64_t)d.sms) nb = (uint64_t)d.sms;
+    SegPlan s;
+    s.nblocks = (uint32_t)nb;
+    s.seg = (uint32_t)((n + nb - 1) / nb);
+    return s;
+}
+
+constexpr uint32_t kMaxWindowTiles = 48 * 1024; // 192 KB of shared-memory counters per warp at most
+
+struct BinPlan {
+    uint32_t T_total, t_win, n_win, P, S, seg_len;
+    size_t smem;
+};
+static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t tile_height) {
+    const DeviceShape &d = device_shape();
+    BinPlan b;
+    b.T_total = C * tile_width * tile_height;
+    b.t_win = b.T_total < kMaxWindowTiles ? b.T_total : kMaxWindowTiles;
+    if (b.t_win == 0) b.t_win = 1;
+    b.n_win = (b.T_total + b.t_win - 1) / b.t_win;
+    if (b.n_win == 0) b.n_win = 1;
+    b.smem = (size_t)b.t_win * 4;
+    uint32_t per_sm = (uint32_t)((size_t)d.smem_sm / (b.smem + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (per_sm > 16) per_sm = 16;
+    uint64_t P = (uint64_t)d.sms * per_sm;
+    const uint64_t n = (uint64_t)C * N;
+    const uint64_t cap = (n + 255) / 256; // no point in chunks of a handful of Gaussians
+    if (P > cap) P = cap;
+    if (P < 1) P = 1;
+    b.P = (uint32_t)P;
+    uint32_t S = b.T_total ? (65536u + b.T_total - 1) / b.T_total : 1u;
+    if (S > 64) S = 64;
+    if (S > b.P) S = b.P;
+    if (S < 1) S = 1;
+    b.seg_len = (b.P + S - 1) / S;
+    b.S = (b.P + b.seg_len - 1) / b.seg_len;
+    return b;
+}
+
+// Workspace of the plan; everything the emit needs afterwards lives here too.
+struct PlanWs {
+    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, M, seg, total;
+};
+static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp) {
+    PlanWs w;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { const size_t o = off; off += align256(bytes); return o; };
+    w.ctl = take(sizeof(SortCtl));
+    w.keys0 = take(n * 4); w.keys1 = take(n * 4);
+    w.vals0 = take(n * 4); w.vals1 = take(n * 4);
+    w.boxes = take(n * 8);
+    w.hist = take((size_t)sp.nblocks * kRadixBins * 4);
+    w.bsum = take((size_t)sp.nblocks * sizeof(RunAcc));
+    w.rt_end = take(n * 4); w.rt_idx = take(n * 4); w.rt_box = take(n * 8); w.rt_key = take(n * 4);
+    w.M = take((size_t)b.P * b.T_total * 4);
+    w.seg = take((size_t)b.S * b.T_total * 4);
+    w.total = off + 256;
+    return w;
+}
+
+template <typename KeyT>
+static int radix_sort_launch(KeyT *k0, KeyT *k1, uint32_t *v0, uint32_t *v1, uint64_t n, const SegPlan &sp, int passes,
+                             uint32_t begin_bit, uint32_t end_bit, const SortCtl *ctl, uint32_t *H, bool iota_first,
+                             cudaStream_t s) {
+    for (int pass = 0; pass < passes; ++pass) {
+        const uint32_t shift = begin_bit + 8u * (uint32_t)pass;
+        const uint32_t bits = end_bit - shift < 8u ? end_bit - shift : 8u;
+        const uint32_t mask = (1u << bits) - 1u;
+        // without a control block the host alternates the buffers itself
+        KeyT *ks = (!ctl && (pass & 1)) ? k1 : k0, *kd = (!ctl && (pass & 1)) ? k0 : k1;
+        uint32_t *vs = (!ctl && (pass & 1)) ? v1 : v0, *vd = (!ctl && (pass & 1)) ? v0 : v1;
+        radix_count_kernel<KeyT><<<sp.nblocks, kSortThreads, 0, s>>>(ks, kd, n, sp.seg, pass, shift, mask, ctl, H);
+        GSB_LAUNCH_CHECK();
+        radix_scatter_kernel<KeyT><<<sp.nblocks, kSortThreads, 0, s>>>(ks, kd, vs, vd, n, sp.seg, sp.nblocks, pass, shift,
+                                                                     mask, ctl, H, iota_first && pass == 0 ? 1 : 0);
+        GSB_LAUNCH_CHECK();
+    }
+    return GSB_OK;
+}
 
 } // namespace gsb
 
 extern "C" size_t gsb_isect_count_workspace(uint64_t n_elements) {
-    size_t bytes = 0;
-    gsb::CountIter it(nullptr, gsb::CastI64());
-    cub::DeviceScan::InclusiveSum(nullptr, bytes, it, (int64_t *)nullptr, (int64_t)n_elements);
-    return gsb::align256(bytes) + 256;
+    const gsb::SegPlan sp = gsb::seg_plan(n_elements);
+    return gsb::align256((size_t)sp.nblocks * sizeof(long long)) + 256;
 }
 
 extern "C" int gsb_isect_count(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
                                uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
                                int32_t *tiles_per_gauss, int64_t *cum_tiles, void *workspace,
                                size_t workspace_bytes, gsb_stream_t stream) {
+    using namespace gsb;
     const uint64_t n = (uint64_t)C * N;
     if (n == 0) return GSB_OK;
     if (!means2d || !radii || !tiles_per_gauss || !cum_tiles || tile_size == 0) return GSB_E_INVALID;
     if (!workspace || workspace_bytes < gsb_isect_count_workspace(n)) return GSB_E_WORKSPACE;
-    cudaStream_t s = gsb::as_stream(stream);
-    const uint32_t grid = (uint32_t)((n + gsb::kIsectThreads - 1) / gsb::kIsectThreads);
-    gsb::ProfScope ps("isect_count", s); // count kernel + scan
-    gsb::isect_count_kernel<<<grid, gsb::kIsectThreads, 0, s>>>(n, means2d, radii, tile_size, tile_width,
-                                                               tile_height, tiles_per_gauss);
+    cudaStream_t s = as_stream(stream);
+    const uint32_t grid = (uint32_t)((n + kIsectThreads - 1) / kIsectThreads);
+    ProfScope ps("isect_count", s); // count kernel + scan
+    isect_count_kernel<<<grid, kIsectThreads, 0, s>>>(n, means2d, radii, tile_size, tile_width, tile_height,
+                                                      tiles_per_gauss);
     GSB_LAUNCH_CHECK();
-    size_t bytes = workspace_bytes;
-    gsb::CountIter it(tiles_per_gauss, gsb::CastI64());
-    GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(workspace, bytes, it, cum_tiles, (int64_t)n, s));
+    const SegPlan sp = seg_plan(n);
+    long long *bsum = reinterpret_cast<long long *>(workspace);
+    scan_blocksum_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(tiles_per_gauss, n, sp.seg, bsum);
+    GSB_LAUNCH_CHECK();
+    scan_apply_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(tiles_per_gauss, n, sp.seg, bsum, cum_tiles);
+    GSB_LAUNCH_CHECK();
     return GSB_OK;
 }
 
@@ -290,178 +599,167 @@ extern "C" int gsb_isect_emit(uint32_t C, uint32_t N, const float *means2d, cons
     const uint32_t grid = (uint32_t)((n + gsb::kIsectThreads - 1) / gsb::kIsectThreads);
     gsb::ProfScope ps("isect_emit", gsb::as_stream(stream));
     gsb::isect_emit_kernel<<<grid, gsb::kIsectThreads, 0, gsb::as_stream(stream)>>>(
-        n, N, means2d, radii, depths, nullptr, cum_tiles, tile_size, tile_width, tile_height, tile_n_bits, isect_ids,
+        n, N, means2d, radii, depths, cum_tiles, tile_size, tile_width, tile_height, tile_n_bits, isect_ids,
         flatten_ids);
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }
 
+// Generic stable sort of unsorted (isect_id, flatten_id) pairs on the low 32+tile_bits+cam_bits key bits
+// (IntersectTile.cu:290-328): ceil(bits / 8) passes of the radix kernels of gsb_devsort.cuh.
 extern "C" size_t gsb_isect_sort_workspace(uint64_t n_isects) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const int64_t *)nullptr, (int64_t *)nullptr,
-                                    (const int32_t *)nullptr, (int32_t *)nullptr, (int64_t)n_isects, 0, 64);
-    return gsb::align256(bytes) + 256;
+    const gsb::SegPlan sp = gsb::seg_plan(n_isects);
+    return gsb::align256(n_isects * 8) + gsb::align256(n_isects * 4) +
+           gsb::align256((size_t)sp.nblocks * gsb::kRadixBins * 4) + 256;
 }
 
 extern "C" int gsb_isect_sort(uint64_t n_isects, uint32_t C, uint32_t tile_width, uint32_t tile_height,
                               const int64_t *isect_ids_in, const int32_t *flatten_ids_in,
                               int64_t *isect_ids_out, int32_t *flatten_ids_out, void *workspace,
                               size_t workspace_bytes, gsb_stream_t stream) {
+    using namespace gsb;
     if (n_isects == 0) return GSB_OK;
     if (!isect_ids_in || !flatten_ids_in || !isect_ids_out || !flatten_ids_out) return GSB_E_INVALID;
-    if (!workspace || workspace_bytes < gsb_isect_sort_workspace(n_isects)) return GSB_E_WORKSPACE;
-    const uint32_t tile_n_bits = gsb::bit_width_u32(tile_width * tile_height);
-    const uint32_t cam_n_bits = gsb::bit_width_u32(C);
-    size_t bytes = workspace_bytes;
-    gsb::ProfScope ps("isect_sort", gsb::as_stream(stream));
-    GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(workspace, bytes, isect_ids_in, isect_ids_out, flatten_ids_in,
-                                                 flatten_ids_out, (int64_t)n_isects, 0,
-                                                 (int)(32 + tile_n_bits + cam_n_bits), gsb::as_stream(stream)));
-    return GSB_OK;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < gsb_isect_sort_workspace(n_isects))
+        return GSB_E_WORKSPACE;
+    const uint32_t tile_n_bits = bit_width_u32(tile_width * tile_height);
+    const uint32_t cam_n_bits = bit_width_u32(C);
+    const uint32_t end_bit = 32 + tile_n_bits + cam_n_bits;
+    if (end_bit > 64) return GSB_E_INVALID;
+    const int passes = (int)((end_bit + 7) / 8);
+    cudaStream_t s = as_stream(stream);
+    ProfScope ps("isect_sort", s);
+    const SegPlan sp = seg_plan(n_isects);
+    char *base = reinterpret_cast<char *>(workspace);
+    unsigned long long *tmp_k = reinterpret_cast<unsigned long long *>(base);
+    uint32_t *tmp_v = reinterpret_cast<uint32_t *>(base + align256(n_isects * 8));
+    uint32_t *H = reinterpret_cast<uint32_t *>(base + align256(n_isects * 8) + align256(n_isects * 4));
+    unsigned long long *out_k = reinterpret_cast<unsigned long long *>(isect_ids_out);
+    uint32_t *out_v = reinterpret_cast<uint32_t *>(flatten_ids_out);
+    // The input is read-only: copy it into the buffer from which `passes` alternations end in the outputs.
+    unsigned long long *k0 = (passes & 1) ? tmp_k : out_k, *k1 = (passes & 1) ? out_k : tmp_k;
+    uint32_t *v0 = (passes & 1) ? tmp_v : out_v, *v1 = (passes & 1) ? out_v : tmp_v;
+    GSB_CUDA_TRY(cudaMemcpyAsync(k0, isect_ids_in, n_isects * 8, cudaMemcpyDeviceToDevice, s));
+    GSB_CUDA_TRY(cudaMemcpyAsync(v0, flatten_ids_in, n_isects * 4, cudaMemcpyDeviceToDevice, s));
+    return radix_sort_launch<unsigned long long>(k0, k1, v0, v1, n_isects, sp, passes, 0, end_bit, nullptr, H, false, s);
 }
 
-namespace gsb {
-// Workspace of the plan: [perm N u32][cum N i64] survive until the emit; the rest is scratch.
-struct PlanWs {
-    size_t perm, cum, keys_a, keys_b, vals_a, cub, cub_bytes, total;
-};
-static PlanWs plan_ws(uint64_t n, bool multi_cam) {
-    PlanWs w;
-    const size_t kb = multi_cam ? 8 : 4;
-    size_t off = 0;
-    w.perm = off; off += align256(n * 4);
-    w.cum = off; off += align256(n * 8);
-    w.keys_a = off; off += align256(n * kb);
-    w.keys_b = off; off += align256(n * kb);
-    w.vals_a = off; off += align256(n * 4);
-    size_t b1 = 0, b2 = 0;
-    if (multi_cam)
-        cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint64_t *)nullptr, (uint64_t *)nullptr,
-                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n, 0, 64);
-    else
-        cub::DeviceRadixSort::SortPairs(nullptr, b1, (const uint32_t *)nullptr, (uint32_t *)nullptr,
-                                        (const uint32_t *)nullptr, (uint32_t *)nullptr, (int64_t)n, 0, 32);
-    PermCountIter it(thrust::permutation_iterator<const int32_t *, const uint32_t *>(nullptr, nullptr), CastI64());
-    cub::DeviceScan::InclusiveSum(nullptr, b2, it, (int64_t *)nullptr, (int64_t)n);
-    w.cub_bytes = align256(b1 > b2 ? b1 : b2) + 256;
-    w.cub = off; off += w.cub_bytes;
-    w.total = off + 256;
-    return w;
-}
-struct PlannedWs {
-    size_t tmp_keys, tmp_vals, cub, cub_bytes, total;
-};
-static PlannedWs planned_ws(uint64_t n_isects) {
-    PlannedWs w;
-    size_t off = 0;
-    w.tmp_keys = off; off += align256(n_isects * 8);
-    w.tmp_vals = off; off += align256(n_isects * 4);
-    size_t b = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, b, (const int64_t *)nullptr, (int64_t *)nullptr, (const int32_t *)nullptr,
-                                    (int32_t *)nullptr, (int64_t)n_isects, 32, 64);
-    w.cub_bytes = align256(b) + 256;
-    w.cub = off; off += w.cub_bytes;
-    w.total = off + 256;
-    return w;
-}
-} // namespace gsb
-
-extern "C" size_t gsb_isect_plan_workspace(uint32_t C, uint32_t N) {
-    return gsb::plan_ws((uint64_t)C * N, C > 1).total;
+extern "C" size_t gsb_isect_plan_workspace(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t tile_height) {
+    const uint64_t n = (uint64_t)C * N;
+    return gsb::plan_ws(n, gsb::bin_plan(C, N, tile_width, tile_height), gsb::seg_plan(n)).total;
 }
 
 extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii, const float *depths,
                               uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-                              int32_t *tiles_per_gauss, int64_t *n_isects_out, void *plan_workspace,
-                              size_t plan_workspace_bytes, gsb_stream_t stream) {
+                              int32_t *tiles_per_gauss, int64_t *n_isects_out, int32_t *tile_offsets_out,
+                              void *plan_workspace, size_t plan_workspace_bytes, gsb_stream_t stream) {
     using namespace gsb;
     const uint64_t n = (uint64_t)C * N;
     if (!n_isects_out) return GSB_E_INVALID;
     cudaStream_t s = as_stream(stream);
-    if (n == 0) {
+    const uint64_t T64 = (uint64_t)C * tile_width * tile_height;
+    if (n == 0 || T64 == 0) {
         GSB_CUDA_TRY(cudaMemsetAsync(n_isects_out, 0, sizeof(int64_t), s));
+        if (tile_offsets_out && T64) GSB_CUDA_TRY(cudaMemsetAsync(tile_offsets_out, 0, T64 * 4, s));
+        if (n && tiles_per_gauss) GSB_CUDA_TRY(cudaMemsetAsync(tiles_per_gauss, 0, n * 4, s));
         return GSB_OK;
     }
     if (!means2d || !radii || !depths || !tiles_per_gauss || tile_size == 0) return GSB_E_INVALID;
     const uint32_t tile_n_bits = bit_width_u32(tile_width * tile_height);
     const uint32_t cam_n_bits = bit_width_u32(C);
     if (tile_n_bits + cam_n_bits > 32) return GSB_E_INVALID; // Intersect.cpp:50
-    const bool multi = C > 1;
-    const PlanWs w = plan_ws(n, multi);
+    if (tile_width > 0xffffu || tile_height > 0xffffu || n > 0x7fffffffull || T64 > 0x7fffffffull) return GSB_E_INVALID;
+    const BinPlan bp = bin_plan(C, N, tile_width, tile_height);
+    const SegPlan sp = seg_plan(n);
+    const PlanWs w = plan_ws(n, bp, sp);
     if (!plan_workspace || (reinterpret_cast<uintptr_t>(plan_workspace) & 255) || plan_workspace_bytes < w.total)
         return GSB_E_WORKSPACE;
     char *base = reinterpret_cast<char *>(plan_workspace);
-    uint32_t *perm = reinterpret_cast<uint32_t *>(base + w.perm);
-    int64_t *cum = reinterpret_cast<int64_t *>(base + w.cum);
-    uint32_t *vals_a = reinterpret_cast<uint32_t *>(base + w.vals_a);
-    void *cub_tmp = base + w.cub;
-    const uint32_t grid = (uint32_t)((n + kIsectThreads - 1) / kIsectThreads);
+    SortCtl *ctl = reinterpret_cast<SortCtl *>(base + w.ctl);
+    uint32_t *k0 = reinterpret_cast<uint32_t *>(base + w.keys0), *k1 = reinterpret_cast<uint32_t *>(base + w.keys1);
+    uint32_t *v0 = reinterpret_cast<uint32_t *>(base + w.vals0), *v1 = reinterpret_cast<uint32_t *>(base + w.vals1);
+    uint2 *boxes = reinterpret_cast<uint2 *>(base + w.boxes);
+    uint32_t *H = reinterpret_cast<uint32_t *>(base + w.hist);
+    RunAcc *bsum = reinterpret_cast<RunAcc *>(base + w.bsum);
+    RunTable rt{reinterpret_cast<uint32_t *>(base + w.rt_end), reinterpret_cast<uint32_t *>(base + w.rt_idx),
+                reinterpret_cast<uint2 *>(base + w.rt_box), reinterpret_cast<uint32_t *>(base + w.rt_key)};
+    uint32_t *M = reinterpret_cast<uint32_t *>(base + w.M);
+    uint32_t *seg = reinterpret_cast<uint32_t *>(base + w.seg);
     {
         ProfScope ps("isect_count", s);
-        uint64_t *k64 = multi ? reinterpret_cast<uint64_t *>(base + w.keys_a) : nullptr;
-        uint32_t *k32 = multi ? nullptr : reinterpret_cast<uint32_t *>(base + w.keys_a);
-        isect_plan_kernel<<<grid, kIsectThreads, 0, s>>>(n, N, means2d, radii, depths, tile_size, tile_width,
-                                                        tile_height, tiles_per_gauss, k64, k32, vals_a);
+        GSB_CUDA_TRY(cudaMemsetAsync(ctl, 0, sizeof(SortCtl), s));
+        const uint32_t grid = (uint32_t)((n + kIsectThreads - 1) / kIsectThreads);
+        isect_plan_kernel<<<grid, kIsectThreads, 0, s>>>(n, means2d, radii, depths, tile_size, tile_width, tile_height,
+                                                        tiles_per_gauss, k0, boxes, ctl);
         GSB_LAUNCH_CHECK();
     }
     {
         ProfScope ps("isect_depth_sort", s);
-        size_t bytes = w.cub_bytes;
-        if (multi) {
-            uint64_t *ka = reinterpret_cast<uint64_t *>(base + w.keys_a), *kb = reinterpret_cast<uint64_t *>(base + w.keys_b);
-            GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, ka, kb, vals_a, perm, (int64_t)n, 0,
-                                                         (int)(32 + cam_n_bits), s));
-        } else {
-            uint32_t *ka = reinterpret_cast<uint32_t *>(base + w.keys_a), *kb = reinterpret_cast<uint32_t *>(base + w.keys_b);
-            GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(cub_tmp, bytes, ka, kb, vals_a, perm, (int64_t)n, 0, 32, s));
-        }
-        bytes = w.cub_bytes;
-        PermCountIter it(thrust::permutation_iterator<const int32_t *, const uint32_t *>(tiles_per_gauss, perm), CastI64());
-        GSB_CUDA_TRY(cub::DeviceScan::InclusiveSum(cub_tmp, bytes, it, cum, (int64_t)n, s));
+        if (int rc = radix_sort_launch<uint32_t>(k0, k1, v0, v1, n, sp, 4, 0, 32, ctl, H, true, s)) return rc;
+        runs_blocksum_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(ctl, v0, v1, tiles_per_gauss, n, sp.seg, bsum);
+        GSB_LAUNCH_CHECK();
+        runs_build_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(ctl, v0, v1, k0, k1, tiles_per_gauss, boxes, n, sp.seg,
+                                                             sp.nblocks, bsum, rt);
+        GSB_LAUNCH_CHECK();
     }
     // device or pinned-host destination alike
-    GSB_CUDA_TRY(cudaMemcpyAsync(n_isects_out, cum + (n - 1), sizeof(int64_t), cudaMemcpyDefault, s));
+    GSB_CUDA_TRY(cudaMemcpyAsync(n_isects_out, &ctl->n_isects, sizeof(int64_t), cudaMemcpyDefault, s));
+    {
+        ProfScope ps("isect_tile_hist", s);
+        BinArgs a;
+        a.rt = rt; a.ctl = ctl; a.N = N; a.n_tiles = tile_width * tile_height; a.tile_width = tile_width;
+        a.tile_n_bits = tile_n_bits; a.multi_cam = C > 1 ? 1u : 0u;
+        a.T_total = bp.T_total; a.P = bp.P; a.M = M; a.flatten_ids = nullptr; a.isect_ids = nullptr;
+        if (bp.smem > 48 * 1024)
+            GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)bp.smem));
+        for (uint32_t wnd = 0; wnd < bp.n_win; ++wnd) {
+            a.t_lo = wnd * bp.t_win;
+            a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
+            tile_bin_kernel<false><<<bp.P, 32, bp.smem, s>>>(a);
+            GSB_LAUNCH_CHECK();
+        }
+        const dim3 cgrid((bp.T_total + kIsectThreads - 1) / kIsectThreads, bp.S);
+        col_segsum_kernel<<<cgrid, kIsectThreads, 0, s>>>(M, bp.T_total, bp.P, bp.seg_len, seg);
+        GSB_LAUNCH_CHECK();
+        col_tilescan_kernel<<<1, kSortThreads, 0, s>>>(seg, bp.T_total, bp.S, tile_offsets_out);
+        GSB_LAUNCH_CHECK();
+        col_apply_kernel<<<cgrid, kIsectThreads, 0, s>>>(M, bp.T_total, bp.P, bp.seg_len, seg);
+        GSB_LAUNCH_CHECK();
+    }
     return GSB_OK;
 }
 
-extern "C" size_t gsb_isect_emit_planned_workspace(uint64_t n_isects) { return gsb::planned_ws(n_isects).total; }
-
-extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
-                                      const float *depths, uint32_t tile_size, uint32_t tile_width,
-                                      uint32_t tile_height, uint64_t n_isects, const void *plan_workspace,
-                                      int64_t *isect_ids, int32_t *flatten_ids, void *workspace,
-                                      size_t workspace_bytes, gsb_stream_t stream) {
+extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t tile_height,
+                                      uint64_t n_isects, const void *plan_workspace, size_t plan_workspace_bytes,
+                                      int64_t *isect_ids /*nullable*/, int32_t *flatten_ids, gsb_stream_t stream) {
     using namespace gsb;
     const uint64_t n = (uint64_t)C * N;
     if (n == 0 || n_isects == 0) return GSB_OK;
-    if (!means2d || !radii || !depths || !plan_workspace || !isect_ids || !flatten_ids) return GSB_E_INVALID;
-    const uint32_t tile_n_bits = bit_width_u32(tile_width * tile_height);
-    const uint32_t cam_n_bits = bit_width_u32(C);
-    if (tile_n_bits + cam_n_bits > 32) return GSB_E_INVALID;
-    const PlanWs pw = plan_ws(n, C > 1);
-    const PlannedWs w = planned_ws(n_isects);
-    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < w.total)
-        return GSB_E_WORKSPACE;
+    if (!plan_workspace || !flatten_ids) return GSB_E_INVALID;
+    if (n_isects > 0x7fffffffull) return GSB_E_INVALID;
+    const BinPlan bp = bin_plan(C, N, tile_width, tile_height);
+    const SegPlan sp = seg_plan(n);
+    const PlanWs w = plan_ws(n, bp, sp);
+    if ((reinterpret_cast<uintptr_t>(plan_workspace) & 255) || plan_workspace_bytes < w.total) return GSB_E_WORKSPACE;
     cudaStream_t s = as_stream(stream);
-    const char *pbase = reinterpret_cast<const char *>(plan_workspace);
-    const uint32_t *perm = reinterpret_cast<const uint32_t *>(pbase + pw.perm);
-    const int64_t *cum = reinterpret_cast<const int64_t *>(pbase + pw.cum);
-    char *base = reinterpret_cast<char *>(workspace);
-    int64_t *tmp_keys = reinterpret_cast<int64_t *>(base + w.tmp_keys);
-    int32_t *tmp_vals = reinterpret_cast<int32_t *>(base + w.tmp_vals);
-    {
-        ProfScope ps("isect_emit", s);
-        const uint32_t egrid = (uint32_t)((n_isects + kEmitSpan - 1) / kEmitSpan);
-        isect_emit_balanced_kernel<<<egrid, kIsectThreads, 0, s>>>(n, N, n_isects, means2d, radii, depths, perm, cum,
-                                                                  tile_size, tile_width, tile_height, tile_n_bits,
-                                                                  tmp_keys, tmp_vals);
+    char *base = const_cast<char *>(reinterpret_cast<const char *>(plan_workspace));
+    BinArgs a;
+    a.rt = RunTable{reinterpret_cast<uint32_t *>(base + w.rt_end), reinterpret_cast<uint32_t *>(base + w.rt_idx),
+                    reinterpret_cast<uint2 *>(base + w.rt_box), reinterpret_cast<uint32_t *>(base + w.rt_key)};
+    a.ctl = reinterpret_cast<const SortCtl *>(base + w.ctl);
+    a.N = N; a.n_tiles = tile_width * tile_height; a.tile_width = tile_width;
+    a.tile_n_bits = bit_width_u32(tile_width * tile_height); a.multi_cam = C > 1 ? 1u : 0u;
+    a.T_total = bp.T_total; a.P = bp.P; a.M = reinterpret_cast<uint32_t *>(base + w.M);
+    a.flatten_ids = flatten_ids; a.isect_ids = isect_ids;
+    ProfScope ps("isect_emit", s);
+    if (bp.smem > 48 * 1024)
+        GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.smem));
+    for (uint32_t wnd = 0; wnd < bp.n_win; ++wnd) {
+        a.t_lo = wnd * bp.t_win;
+        a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
+        tile_bin_kernel<true><<<bp.P, 32, bp.smem, s>>>(a);
         GSB_LAUNCH_CHECK();
-    }
-    {
-        ProfScope ps("isect_sort", s);
-        size_t bytes = w.cub_bytes;
-        GSB_CUDA_TRY(cub::DeviceRadixSort::SortPairs(base + w.cub, bytes, tmp_keys, isect_ids, tmp_vals, flatten_ids,
-                                                     (int64_t)n_isects, 32, (int)(32 + tile_n_bits + cam_n_bits), s));
     }
     return GSB_OK;
 }

@@ -31,6 +31,7 @@ struct ProjParams {
     int32_t n_radial, n_tangential, n_thin_prism;
     int32_t *radii;
     float *means2d, *depths, *conics, *compensations;
+    uint32_t inputs_aligned16; // every input base pointer is 16-byte aligned: full slabs may use bulk copies
 };
 
 // GLM operator*(quat, vec3): v + 2 (w (u x v) + u x (u x v))   [glm/detail/type_quat.inl]
@@ -53,10 +54,14 @@ __global__ void __launch_bounds__(kProjThreads) projection_ut_kernel(const ProjP
     const uint32_t g0 = blockIdx.x * kProjThreads;
     const uint32_t cnt = min((uint32_t)kProjThreads, p.N - g0);
     const uint32_t tid = threadIdx.x;
-    const bool full = (cnt == kProjThreads); // full slabs are 16-byte aligned in every array
+    // cp.async.bulk needs 16-byte aligned global addresses: true for every full slab when the base pointers
+    // are (256 rows x 12 / 16 / 4 bytes), not for a contiguous view such as means[1:] -- the reference accepts
+    // those, so they take the plain staging loop instead of faulting
+    const bool full = (cnt == kProjThreads);
+    const bool bulk_in = full && p.inputs_aligned16;
 
     // ---- stage the slab ------------------------------------------------------------------
-    if (full) {
+    if (bulk_in) {
         if (tid == 0) {
             mbar_init(&s_bar, 1);
             mbar_fence_init();
@@ -258,6 +263,9 @@ extern "C" int gsb_projection_ut(
     p.radial = cam->radial_coeffs; p.tangential = cam->tangential_coeffs; p.thin_prism = cam->thin_prism_coeffs;
     p.n_radial = cam->radial_count; p.n_tangential = cam->tangential_count; p.n_thin_prism = cam->thin_prism_count;
     p.radii = radii; p.means2d = means2d; p.depths = depths; p.conics = conics; p.compensations = compensations;
+    const uintptr_t bits = reinterpret_cast<uintptr_t>(means) | reinterpret_cast<uintptr_t>(quats) |
+                           reinterpret_cast<uintptr_t>(scales) | reinterpret_cast<uintptr_t>(opacities);
+    p.inputs_aligned16 = (bits & 15) == 0 ? 1u : 0u;
     dim3 grid((N + gsb::kProjThreads - 1) / gsb::kProjThreads, C);
     {
         gsb::ProfScope ps("projection_ut", gsb::as_stream(stream));

@@ -18,11 +18,8 @@
 //             summed over the thread's two pixels, reduced across the warp with a 16-value
 //             butterfly (16 shuffles instead of 15 x 5) and added to a per-Gaussian 64-byte row
 //             with one 16-lane red.global.add.f32.
-//   finalize  one thread per Gaussian, float64 chain rule from the moments to
+//   finalize  one thread per Gaussian, float32 chain rule from the moments to
 //             (v_means, v_quats, v_scales, v_opacities, v_colors); writes every output element.
-#include <cstdlib>
-#include <cstring>
-
 #include "gsb_raster.cuh"
 
 namespace gsb {
@@ -429,180 +426,7 @@ __device__ __forceinline__ void event_registers(const BwdState &s, const EventWe
     R[7] = f2_sum(f2_mul(w.fac, s.vC)); R[15] = f2_sum(f2_mul(w.fac, s.vD));
 }
 
-// ---- tensor-core reduction of the ten geometric moments (perfect pinhole) -----------------------------
-// For one warp the moments of an event are a matrix product: [w1; w2] (2 x 64 pixels) times the monomial
-// table M (64 x 6: 1, x', y', x'^2, x'y', y'^2 in block-centred pixel offsets, which are multiples of 0.5
-// below 4 and therefore EXACT in tf32).  Eight events are stashed in shared memory and reduced together by
-// mma.sync.m16n8k8 (tf32 inputs, fp32 accumulate): rows 0-7 = w1 of events 0-7, rows 8-15 = w2.  The
-// weights are split w = hi + lo with hi = w truncated to tf32, lo = w - hi (exact in fp32), two MMAs per k-step, so
-// the products are exact to 2^-21 -- the sum is an fp32 sum, as with shuffles.  The raw moments about the
-// block centre are then shifted to the Gaussian's centre (x = x' - a) per event by its quad of lanes.
-constexpr int kMmaEvents = 8;
-constexpr int kMmaRowStride = 36; // float4 units: 32 lanes + 4 of padding (conflict-free 128-bit loads)
-
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
-                                                uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
-}
-// Reduces the first n_ev stashed events of this warp and adds their moments to global memory.
-__device__ __forceinline__ void mma_flush(const float4 *__restrict__ s_w, const float4 *__restrict__ s_ev,
-                                          const float2 *__restrict__ s_mono, int n_ev, float *__restrict__ moments) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t g = lane >> 2, t = lane & 3;
-    __syncwarp();
-    // four independent accumulator chains (hi/lo x even/odd k-step) keep the tensor pipe's latency off the
-    // critical path; hi = w with the 13 low mantissa bits cleared (what the tf32 datapath reads anyway),
-    // lo = w - hi exactly
-    float dh[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, dl[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-        const float4 a = s_w[g * kMmaRowStride + 4 * ks + t]; // (w1 pA, w2 pA, w1 pB, w2 pB) of lane 4ks+t, event g
-        const float2 b = s_mono[ks * 32 + lane];             // monomial g of that lane's two pixels
-        const uint32_t h0 = __float_as_uint(a.x) & 0xffffe000u, h1 = __float_as_uint(a.y) & 0xffffe000u;
-        const uint32_t h2 = __float_as_uint(a.z) & 0xffffe000u, h3 = __float_as_uint(a.w) & 0xffffe000u;
-        const uint32_t b0 = __float_as_uint(b.x), b1 = __float_as_uint(b.y);
-        mma_tf32_16x8x8(dh[ks & 1], h0, h1, h2, h3, b0, b1);
-        mma_tf32_16x8x8(dl[ks & 1], __float_as_uint(a.x - __uint_as_float(h0)), __float_as_uint(a.y - __uint_as_float(h1)),
-                        __float_as_uint(a.z - __uint_as_float(h2)), __float_as_uint(a.w - __uint_as_float(h3)), b0, b1);
-    }
-    float d[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d[i] = (dh[0][i] + dh[1][i]) + (dl[0][i] + dl[1][i]);
-    // lane (g, t) now holds, for event g: d[0], d[1] = raw w1 moments of monomials 2t, 2t+1; d[2], d[3] = w2's
-    const uint32_t base = lane & ~3u;
-    const float S1a = __shfl_sync(0xffffffffu, d[0], base), Sxa = __shfl_sync(0xffffffffu, d[1], base);
-    const float Sya = __shfl_sync(0xffffffffu, d[0], base + 1);
-    const float S1b = __shfl_sync(0xffffffffu, d[2], base), Sxb = __shfl_sync(0xffffffffu, d[3], base);
-    const float Syb = __shfl_sync(0xffffffffu, d[2], base + 1);
-    if ((int)g < n_ev && t < 3) {
-        const float4 ev = s_ev[g]; // (a, b) = Gaussian centre - block centre, bits of the Gaussian index
-        const float a = ev.x, b = ev.y;
-        float *row = moments + (size_t)__float_as_int(ev.z) * kMomFloats;
-        float f1, s1, f2_, s2; // first / second moment of this lane's column pair, for w1 and w2
-        if (t == 0) {          // columns (1, x')
-            f1 = 0.f;                         s1 = fmaf(-a, S1a, Sxa);
-            f2_ = S1b;                        s2 = fmaf(-a, S1b, Sxb);
-        } else if (t == 1) {   // columns (y', x'^2)
-            f1 = fmaf(-b, S1a, d[0]);         s1 = fmaf(a * a, S1a, fmaf(-2.f * a, Sxa, d[1]));
-            f2_ = fmaf(-b, S1b, d[2]);        s2 = fmaf(a * a, S1b, fmaf(-2.f * a, Sxb, d[3]));
-        } else {               // columns (x'y', y'^2)
-            f1 = fmaf(a * b, S1a, fmaf(-b, Sxa, fmaf(-a, Sya, d[0])));
-            s1 = fmaf(b * b, S1a, fmaf(-2.f * b, Sya, d[1]));
-            f2_ = fmaf(a * b, S1b, fmaf(-b, Sxb, fmaf(-a, Syb, d[2])));
-            s2 = fmaf(b * b, S1b, fmaf(-2.f * b, Syb, d[3]));
-        }
-        // slots: w1 -> (2t, 2t+1) = (-, W1X) (W1Y, W1XX) (W1XY, W1YY); w2 -> (8+2t, 9+2t) = (W2, W2X) ...
-        if (t != 0) red_add_f32(row + 2 * t, f1);
-        red_add_f32(row + 2 * t + 1, s1);
-        red_add_f32(row + kS_W2 + 2 * t, f2_);
-        red_add_f32(row + kS_W2 + 2 * t + 1, s2);
-    }
-    __syncwarp();
-}
-
-// The four remaining sums of an event (g and the colour gradient) by shuffles; lane 8*k holds slot k's
-// total afterwards (k = 0..3 -> kS_G, kS_CG, kS_CR, kS_CB ... see the caller).
-__device__ __forceinline__ float butterfly4(const BwdState &s, const EventWeights &w, bool hi16, bool hi8) {
-    // stage 1 (xor 16), pre-swapped: lanes 0-15 keep (cr, g) and send (cg, cb); lanes 16-31 the reverse
-    const float cA = f2_sum(f2_mul(w.fac, s.vA)), cB = f2_sum(f2_mul(w.fac, s.vB)); // (cr | cg), (cg | cr)
-    const float gs = f2_sum(w.g), cb = f2_sum(f2_mul(w.fac, s.vb));
-    float k0 = cA + __shfl_xor_sync(0xffffffffu, cB, 16);                         // lo16: cr, hi16: cg
-    float k1 = (hi16 ? cb : gs) + __shfl_xor_sync(0xffffffffu, hi16 ? gs : cb, 16); // lo16: g, hi16: cb
-    // stage 2 (xor 8)
-    const float send = hi8 ? k0 : k1, keep = hi8 ? k1 : k0;
-    float v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    v += __shfl_xor_sync(0xffffffffu, v, 4);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
-    v += __shfl_xor_sync(0xffffffffu, v, 1);
-    return v; // (hi16, hi8) = (0,0): cr  (0,1): g  (1,0): cg  (1,1): cb
-}
-
-// ---- transposed reduction (perfect pinhole): lanes own events --------------------------------------
-// Same idea as the tensor-core variant -- stash the per-pair weights of eight events, then reduce them with
-// the roles transposed -- but on the CUDA cores: in the flush a quad of lanes owns ONE event and walks the
-// block's 64 pixels (16 each) with loop-constant pixel offsets, accumulating the raw moments in registers
-// (packed (w1, w2) pairs: seven FFMA2/FADD2 per pixel for both weights, four scalar FMAs for the colour
-// gradient and g).  No shuffle is needed until the four partial sums of a quad are combined (two xor
-// stages), after which lane 0 of the quad shifts and adds the w1 moments, lane 1 the w2 moments, lane 2 the
-// colour gradient and g.  Stash layout per warp: row e (event) of kTrStride float4, slot p < 32 = first
-// pixel of lane p, slot p >= 32 = second pixel of lane p - 32, each (w1, w2, fac, g); s_v[p] = dL/d(colour)
-// of pixel slot p.  Flush lane (e, q) reads slots p = 4 i + q, i = 0..15: x' = q + 4 (i & 1) - 3.5,
-// y' = ((i & 7) >> 1) - 3.5 (+ 4 for i >= 8).
-// NOT the default: written at the end of round 1 without a GPU at hand; to be measured.
-constexpr int kTrEvents = 8;
-constexpr int kTrStride = 68; // float4 units: 64 pixel slots + 4 of padding (odd events land 16 banks away)
-
-__device__ __forceinline__ f2 f2_shfl_xor(f2 a, int m) {
-    return f2_make(__shfl_xor_sync(0xffffffffu, f2_lo(a), m), __shfl_xor_sync(0xffffffffu, f2_hi(a), m));
-}
-
-__device__ __forceinline__ void transpose_flush(const float4 *__restrict__ s_t, const float4 *__restrict__ s_ev,
-                                                const float4 *__restrict__ s_v, int n_ev,
-                                                float *__restrict__ moments) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t e = lane >> 2, q = lane & 3;
-    __syncwarp();
-    const float xq0 = (float)q - 3.5f, xq1 = (float)q + 0.5f;
-    f2 S1 = f2_bc(0.f), Sx = f2_bc(0.f), Sy = f2_bc(0.f), Sxx = f2_bc(0.f), Sxy = f2_bc(0.f), Syy = f2_bc(0.f);
-    float cr = 0.f, cg = 0.f, cb = 0.f, gs = 0.f;
-    const float4 *row = s_t + e * kTrStride + q;
-    const float4 *vrow = s_v + q;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const float4 w = row[4 * i];
-        const float4 v = vrow[4 * i];
-        const float x = (i & 1) ? xq1 : xq0;
-        const float yc = (float)((i & 7) >> 1) - 3.5f + ((i >= 8) ? 4.0f : 0.0f);
-        const f2 W = f2_make(w.x, w.y);
-        const f2 t = f2_mul(W, f2_bc(x));
-        S1 = f2_add(S1, W);
-        Sx = f2_add(Sx, t);
-        Sy = f2_fma(W, f2_bc(yc), Sy);
-        Sxx = f2_fma(t, f2_bc(x), Sxx);
-        Sxy = f2_fma(t, f2_bc(yc), Sxy);
-        Syy = f2_fma(W, f2_bc(yc * yc), Syy);
-        cr = fmaf(w.z, v.x, cr); cg = fmaf(w.z, v.y, cg); cb = fmaf(w.z, v.z, cb);
-        gs += w.w;
-    }
-#pragma unroll
-    for (int m = 1; m <= 2; m <<= 1) {
-        S1 = f2_add(S1, f2_shfl_xor(S1, m)); Sx = f2_add(Sx, f2_shfl_xor(Sx, m)); Sy = f2_add(Sy, f2_shfl_xor(Sy, m));
-        Sxx = f2_add(Sxx, f2_shfl_xor(Sxx, m)); Sxy = f2_add(Sxy, f2_shfl_xor(Sxy, m));
-        Syy = f2_add(Syy, f2_shfl_xor(Syy, m));
-        cr += __shfl_xor_sync(0xffffffffu, cr, m); cg += __shfl_xor_sync(0xffffffffu, cg, m);
-        cb += __shfl_xor_sync(0xffffffffu, cb, m); gs += __shfl_xor_sync(0xffffffffu, gs, m);
-    }
-    if ((int)e < n_ev && q < 3) {
-        const float4 ev = s_ev[e]; // (a, b) = Gaussian centre - block centre, bits of the Gaussian index
-        float *mrow = moments + (size_t)__float_as_int(ev.z) * kMomFloats;
-        if (q == 2) {
-            red_add_f32(mrow + kS_G, gs); red_add_f32(mrow + kS_CR, cr);
-            red_add_f32(mrow + kS_CG, cg); red_add_f32(mrow + kS_CB, cb);
-        } else {
-            const float a = ev.x, b = ev.y;
-            const bool hi = q == 1; // lane 0 of the quad finishes w1 (lo halves), lane 1 finishes w2 (hi halves)
-            const float s1 = hi ? f2_hi(S1) : f2_lo(S1), sx = hi ? f2_hi(Sx) : f2_lo(Sx), sy = hi ? f2_hi(Sy) : f2_lo(Sy);
-            const float sxx = hi ? f2_hi(Sxx) : f2_lo(Sxx), sxy = hi ? f2_hi(Sxy) : f2_lo(Sxy);
-            const float syy = hi ? f2_hi(Syy) : f2_lo(Syy);
-            // shift the raw moments about the block centre to the Gaussian's centre: x = x' - a, y = y' - b
-            const float mx = fmaf(-a, s1, sx), my = fmaf(-b, s1, sy);
-            const float mxx = fmaf(a * a, s1, fmaf(-2.f * a, sx, sxx));
-            const float mxy = fmaf(a * b, s1, fmaf(-b, sx, fmaf(-a, sy, sxy)));
-            const float myy = fmaf(b * b, s1, fmaf(-2.f * b, sy, syy));
-            float *dst = mrow + (hi ? kS_W2 : 0); // W1X..W1YY = 1..5, W2, W2X..W2YY = 8, 9..13
-            if (hi) red_add_f32(dst, s1);
-            red_add_f32(dst + 1, mx); red_add_f32(dst + 2, my); red_add_f32(dst + 3, mxx);
-            red_add_f32(dst + 4, mxy); red_add_f32(dst + 5, myy);
-        }
-    }
-    __syncwarp();
-}
-
-constexpr int kReduceShuffle = 0, kReduceMma = 1, kReduceTranspose = 2;
-
-template <bool kGeneral, int kReduce>
+template <bool kGeneral>
 __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TileParams p,
                                                                    const float *__restrict__ render_alphas,
                                                                    const int32_t *__restrict__ last_ids,
@@ -613,17 +437,6 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
     __shared__ __align__(8) uint64_t s_full[kStages];
     __shared__ int32_t s_warp_max[kTileThreads / 32];
     __shared__ CamModel s_cm;
-    // tensor-core reduction: per-warp stash of eight events' weights, their (centre offset, index), and
-    // the CTA-wide monomial fragments
-    constexpr bool kMma = kReduce == kReduceMma, kTr = kReduce == kReduceTranspose;
-    __shared__ __align__(16) float4 s_w[kMma ? (kTileThreads / 32) * kMmaEvents * kMmaRowStride : 1];
-    __shared__ __align__(16) float4 s_ev[(kMma || kTr) ? (kTileThreads / 32) * kMmaEvents : 1];
-    __shared__ __align__(8) float2 s_mono[kMma ? 8 * 32 : 1];
-    // transposed reduction: the weight stash is dynamic shared memory (with the ring it exceeds 48 KB)
-    extern __shared__ __align__(16) float4 s_dyn[]; // [warps][kTrEvents][kTrStride] then [warps][64]
-    static_assert(!(kGeneral && kReduce != kReduceShuffle), "the stash variants assume pixel-centre coordinates");
-    static_assert(kTrEvents == kMmaEvents, "s_ev is shared by the two stash variants");
-
     const uint32_t tile_id = blockIdx.x;
     if (p.masks != nullptr && !p.masks[tile_id]) return; // Bwd.cu:84-86
     const uint32_t tile_y = tile_id / p.tile_w, tile_x = tile_id % p.tile_w;
@@ -675,37 +488,6 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
         s.last0 = a.last; s.last1 = b.last;
     }
     const f2 PX = f2_make(pc.px0, pc.px1), PY = f2_make(pc.py0, pc.py1);
-    const bool hi8 = (tid & 8) != 0;
-    float4 *const my_w = s_w + (kMma ? (tid >> 5) * kMmaEvents * kMmaRowStride : 0);
-    float4 *const my_ev = s_ev + ((kMma || kTr) ? (tid >> 5) * kMmaEvents : 0);
-    float4 *const my_t = s_dyn + (kTr ? (tid >> 5) * kTrEvents * kTrStride : 0);
-    float4 *const my_v = s_dyn + (kTr ? (kTileThreads / 32) * kTrEvents * kTrStride + (tid >> 5) * 64 : 0);
-    if constexpr (kTr) {
-        my_v[tid & 31] = make_float4(f2_lo(s.vr), f2_lo(s.vg), f2_lo(s.vb), 0.f);
-        my_v[32 + (tid & 31)] = make_float4(f2_hi(s.vr), f2_hi(s.vg), f2_hi(s.vb), 0.f);
-    }
-    const float cxb = pc.bx0 + 3.5f, cyb = pc.by0 + 3.5f; // centre of the warp's 8x8 block
-    int n_ev = 0;
-    if constexpr (kMma) {
-        // s_mono[ks][lane] = monomial (lane >> 2) of the two pixels of lane 4*ks + (lane & 3), offsets from the
-        // block centre: x' = (l & 7) - 3.5, y' = (l >> 3) - 3.5 and + 0.5 (the thread's second row is 4 below)
-        for (uint32_t i = tid; i < 8 * 32; i += kTileThreads) {
-            const uint32_t ks = i >> 5, ln = i & 31, n = ln >> 2, l = 4 * ks + (ln & 3);
-            const float x = (float)(l & 7) - 3.5f, ya = (float)(l >> 3) - 3.5f, yb = ya + 4.0f;
-            float ma, mb;
-            switch (n) {
-                case 0: ma = 1.f; mb = 1.f; break;
-                case 1: ma = x; mb = x; break;
-                case 2: ma = ya; mb = yb; break;
-                case 3: ma = x * x; mb = x * x; break;
-                case 4: ma = x * ya; mb = x * yb; break;
-                case 5: ma = ya * ya; mb = yb * yb; break;
-                default: ma = 0.f; mb = 0.f; break;
-            }
-            s_mono[i] = make_float2(ma, mb);
-        }
-    }
-
     // CTA-wide newest contributor: nothing behind it can receive gradient
     int32_t wmax = __reduce_max_sync(0xffffffffu, max(s.last0, s.last1));
     if ((tid & 31) == 0) s_warp_max[tid >> 5] = wmax;
@@ -765,50 +547,22 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
             if (!__any_sync(0xffffffffu, p0 || p1)) continue;
             const float4 q3 = rec4[t * 4 + 3];
             const EventWeights w = bwd_weights(s, e, p0, p1, q2.z, q3.x, q3.y, q3.z);
-            if constexpr (kMma) {
-                my_w[n_ev * kMmaRowStride + (tid & 31)] = make_float4(f2_lo(w.w1), f2_lo(w.w2), f2_hi(w.w1), f2_hi(w.w2));
-                my_ev[n_ev] = make_float4(q0.x - cxb, q0.y - cyb, q3.w, 0.f); // same value from every lane
-                const float v = butterfly4(s, w, hi16, hi8);
-                if ((tid & 7) == 0) {
-                    const int slot = hi16 ? (hi8 ? kS_CB : kS_CG) : (hi8 ? kS_G : kS_CR);
-                    red_add_f32(moments + (size_t)__float_as_int(q3.w) * kMomFloats + slot, v);
-                }
-                if (++n_ev == kMmaEvents) {
-                    mma_flush(my_w, my_ev, s_mono, kMmaEvents, moments);
-                    n_ev = 0;
-                }
-            } else if constexpr (kTr) {
-                my_t[n_ev * kTrStride + (tid & 31)] = make_float4(f2_lo(w.w1), f2_lo(w.w2), f2_lo(w.fac), f2_lo(w.g));
-                my_t[n_ev * kTrStride + 32 + (tid & 31)] = make_float4(f2_hi(w.w1), f2_hi(w.w2), f2_hi(w.fac), f2_hi(w.g));
-                my_ev[n_ev] = make_float4(q0.x - cxb, q0.y - cyb, q3.w, 0.f); // same value from every lane
-                if (++n_ev == kTrEvents) {
-                    transpose_flush(my_t, my_ev, my_v, kTrEvents, moments);
-                    n_ev = 0;
-                }
-            } else {
-                float R[16];
-                event_registers(s, w, e, x, y, hi16, R);
-                butterfly16_preswapped(R);
-                if ((tid & 1) == 0) {
-                    const uint32_t slot = (tid & 31) >> 1;
-                    if (slot != (uint32_t)kS_PAD)
-                        red_add_f32(moments + (size_t)__float_as_int(q3.w) * kMomFloats + slot, R[0]);
-                }
+            float R[16];
+            event_registers(s, w, e, x, y, hi16, R);
+            butterfly16_preswapped(R);
+            if ((tid & 1) == 0) {
+                const uint32_t slot = (tid & 31) >> 1;
+                if (slot != (uint32_t)kS_PAD)
+                    red_add_f32(moments + (size_t)__float_as_int(q3.w) * kMomFloats + slot, R[0]);
             }
           }
         }
         __syncthreads(); // stage `st` may be refilled by batch b+2
     }
-    if constexpr (kMma) {
-        if (n_ev > 0) mma_flush(my_w, my_ev, s_mono, n_ev, moments);
-    }
-    if constexpr (kTr) {
-        if (n_ev > 0) transpose_flush(my_t, my_ev, my_v, n_ev, moments);
-    }
 }
 
 // ------------------------------------------------------------------------------------------
-// finalize: moments -> gradients (float64 chain rule, once per Gaussian)
+// finalize: moments -> gradients (chain rule once per Gaussian, float32: see FT below)
 // ------------------------------------------------------------------------------------------
 // chain-rule arithmetic type of finalize (float: validated against the f64 oracle, profiles/r1_parity.md)
 typedef float FT;
@@ -931,21 +685,6 @@ static int check_camera(const GsbCamera *cam) {
     return GSB_OK;
 }
 
-// GSB_BWD_REDUCE selects the reduction of the backward's moments for the perfect pinhole; read on every call
-// so a test can exercise the variants.
-//   (unset) / shuffle : 16-value butterfly per event -- the default, the fastest measured.
-//   mma       : tensor-core reduction of the geometric moments (mma_flush).  14 % fewer instructions per event,
-//               but 4 % SLOWER on the B200 (0.825 vs 0.790 ms, config B): the flush's LDS -> HMMA -> shuffle chain
-//               and the lower occupancy cost more than the saved issue slots.
-//   transpose : lane-per-event reduction on the CUDA cores (transpose_flush); not yet measured.
-static int bwd_reduce_mode() {
-    const char *e = getenv("GSB_BWD_REDUCE");
-    if (e && strcmp(e, "mma") == 0) return kReduceMma;
-    if (e && strcmp(e, "transpose") == 0) return kReduceTranspose;
-    return kReduceShuffle;
-}
-static constexpr size_t kTrDynSmem = (size_t)(kTileThreads / 32) * (kTrEvents * kTrStride + 64) * sizeof(float4);
-
 static bool general_camera(const GsbCamera *cam) {
     return cam->camera_model == GSB_CAMERA_FISHEYE || cam->radial_coeffs || cam->tangential_coeffs ||
            cam->thin_prism_coeffs;
@@ -1056,21 +795,12 @@ extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     {
         ProfScope ps("raster_bwd", s);
         fill_camera(p, cam);
-        const int mode = bwd_reduce_mode();
         if (general_camera(cam))
-            raster_bwd_kernel<true, kReduceShuffle><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(
-                p, render_alphas, last_ids, v_render_colors, v_render_alphas, moments);
-        else if (mode == kReduceMma)
-            raster_bwd_kernel<false, kReduceMma><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(
-                p, render_alphas, last_ids, v_render_colors, v_render_alphas, moments);
-        else if (mode == kReduceTranspose) {
-            GSB_CUDA_TRY(cudaFuncSetAttribute(raster_bwd_kernel<false, kReduceTranspose>,
-                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrDynSmem));
-            raster_bwd_kernel<false, kReduceTranspose><<<p.tile_w * p.tile_h, kTileThreads, kTrDynSmem, s>>>(
-                p, render_alphas, last_ids, v_render_colors, v_render_alphas, moments);
-        } else
-            raster_bwd_kernel<false, kReduceShuffle><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(
-                p, render_alphas, last_ids, v_render_colors, v_render_alphas, moments);
+            raster_bwd_kernel<true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids,
+                                                                                v_render_colors, v_render_alphas, moments);
+        else
+            raster_bwd_kernel<false><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids,
+                                                                                 v_render_colors, v_render_alphas, moments);
     }
     GSB_LAUNCH_CHECK();
     {

@@ -148,28 +148,23 @@ GSB_EXPORT std::tuple<at::Tensor, at::Tensor, at::Tensor> intersect_tile(
     at::Tensor tiles_per_gauss = at::empty_like(depths, depths.options().dtype(at::kInt));
     int64_t n_isects = 0;
     if (n_elements && sort) {
-        // Two-phase sorted path (gsb_intersect.cu): count, depth order and run offsets are enqueued before
-        // the one host read-back the API forces (Intersect.cpp:76); the number lands in pinned memory.
-        const size_t plan_bytes = gsb_isect_plan_workspace(C, N);
+        // Planned sorted path (gsb_intersect.cu): count, depth order, run table and the per-tile histogram are
+        // enqueued before the one host read-back the API forces (Intersect.cpp:76); the number lands in pinned memory.
+        const size_t plan_bytes = gsb_isect_plan_workspace(C, N, tile_width, tile_height);
         at::Tensor plan_ws = byte_workspace(plan_bytes, depths);
         at::Tensor n_host = at::empty({1}, at::TensorOptions().dtype(at::kLong).pinned_memory(true));
         gsb_check(gsb_isect_plan(C, N, means2d.data_ptr<float>(), radii.data_ptr<int32_t>(), depths.data_ptr<float>(),
                                  tile_size, tile_width, tile_height, tiles_per_gauss.data_ptr<int32_t>(),
-                                 n_host.data_ptr<int64_t>(), plan_ws.data_ptr(), plan_bytes, cur_stream()),
+                                 n_host.data_ptr<int64_t>(), nullptr, plan_ws.data_ptr(), plan_bytes, cur_stream()),
                   "intersect_tile/plan");
         c10::cuda::getCurrentCUDAStream().synchronize();
         n_isects = n_host.data_ptr<int64_t>()[0];
         at::Tensor isect_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kLong));
         at::Tensor flatten_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kInt));
         if (n_isects) {
-            const size_t ws_bytes = gsb_isect_emit_planned_workspace((uint64_t)n_isects);
-            at::Tensor ws = byte_workspace(ws_bytes, depths);
-            gsb_check(gsb_isect_emit_planned(C, N, means2d.data_ptr<float>(), radii.data_ptr<int32_t>(),
-                                             depths.data_ptr<float>(), tile_size, tile_width, tile_height,
-                                             (uint64_t)n_isects, plan_ws.data_ptr(),
-                                             isect_ids_sorted.data_ptr<int64_t>(),
-                                             flatten_ids_sorted.data_ptr<int32_t>(), ws.data_ptr(), ws_bytes,
-                                             cur_stream()),
+            gsb_check(gsb_isect_emit_planned(C, N, tile_width, tile_height, (uint64_t)n_isects, plan_ws.data_ptr(),
+                                             plan_bytes, isect_ids_sorted.data_ptr<int64_t>(),
+                                             flatten_ids_sorted.data_ptr<int32_t>(), cur_stream()),
                       "intersect_tile/emit_planned");
         }
         return std::make_tuple(tiles_per_gauss, isect_ids_sorted, flatten_ids_sorted);

@@ -106,7 +106,8 @@ GSB_API int gsb_profile_read(const char *kernel, double *total_ms);
  *      ProjectionUT3DGSFused.cu:17-203) ------------------------------------------
  * radii [C,N,2] int32 (0,0 = culled), means2d [C,N,2], depths [C,N], conics [C,N,3],
  * compensations [C,N] or NULL.  Culled rows of means2d/depths/conics are left
- * untouched, like the reference (Projection.cpp:70-73). */
+ * untouched, like the reference (Projection.cpp:70-73).  Inputs need only their natural 4-byte
+ * alignment (e.g. a contiguous view means[1:]); 16-byte aligned base pointers get the TMA staging path. */
 GSB_API int gsb_projection_ut(
     uint32_t C, uint32_t N,
     const float *means, const float *quats, const float *scales, const float *opacities /*nullable*/,
@@ -148,8 +149,8 @@ GSB_API int gsb_sh_bwd_views(uint32_t M, uint32_t K, uint32_t degrees_to_use, ui
  *   gsb_isect_count      tiles_per_gauss [C*N] int32 and its inclusive int64 scan
  *                        cum_tiles [C*N]; n_isects = cum_tiles[C*N-1].
  *   gsb_isect_emit       unsorted isect_ids [I] int64 / flatten_ids [I] int32.
- *   gsb_isect_sort       stable sort by the low 32+tile_bits+cam_bits key bits
- *                        (equal keys keep emission order, like CUB).
+ *   gsb_isect_sort       stable LSD radix sort (own kernels) by the low 32+tile_bits+cam_bits
+ *                        key bits; equal keys keep emission order, like the reference's CUB sort.
  * Non-packed ([C,N,...]) layout only; packed mode is rejected by the reference's
  * caller too (rasterizer.cpp:56). */
 GSB_API size_t gsb_isect_count_workspace(uint64_t n_elements);
@@ -167,29 +168,28 @@ GSB_API int gsb_isect_sort(uint64_t n_isects, uint32_t C, uint32_t tile_width, u
                            int64_t *isect_ids_out, int32_t *flatten_ids_out,
                            void *workspace, size_t workspace_bytes, gsb_stream_t stream);
 
-/* Two-phase sorted path for sort == true (same outputs as gsb_isect_emit + gsb_isect_sort, bit for
- * bit, with a third of the sort traffic): the Gaussians are first ordered by (camera, depth bits)
- * -- N elements instead of I -- the intersections are emitted in that order, and a stable radix
- * sort on the (camera, tile) key bits only finishes the job.  It is arranged around the host
- * read-back: everything that does not need the host to know n_isects (count, depth order, run
- * offsets) runs in the PLAN, so only the emit and the tile partition are left to enqueue once the
- * host has the number.
+/* Planned sorted path for sort == true: same outputs as gsb_isect_emit + gsb_isect_sort, bit for bit,
+ * without sorting any intersection.  The Gaussians are ordered by depth once (N elements, own radix
+ * sort), the I intersection slots in that order are cut into equal chunks, a per-(chunk, tile)
+ * histogram is scanned, and every intersection is then written DIRECTLY to its final (tile, depth,
+ * index) position (csrc/gsb_intersect.cu).  It is arranged around the one host read-back the
+ * operator API forces: everything that does not need the host to know n_isects runs in the PLAN.
  *   gsb_isect_plan          tiles_per_gauss [C*N]; *n_isects_out (device OR pinned host int64,
- *                           written asynchronously on `stream`); plan_workspace keeps the depth
- *                           permutation and the run offsets for the emit.
- *   gsb_isect_emit_planned  isect_ids / flatten_ids [n_isects], sorted; identical to
- *                           gsb_isect_emit + gsb_isect_sort bit for bit. */
-GSB_API size_t gsb_isect_plan_workspace(uint32_t C, uint32_t N);
+ *                           written asynchronously on `stream`); tile_offsets_out [C*th*tw] int32 or
+ *                           NULL -- the a6 result, a by-product of the plan's scan; plan_workspace
+ *                           keeps the run table and the per-chunk first slots for the emit.
+ *   gsb_isect_emit_planned  flatten_ids [n_isects] and, unless NULL, isect_ids [n_isects], sorted.
+ * Limits: C*N < 2^31, C*th*tw < 2^31, tile grid sides <= 65535, n_isects < 2^31. */
+GSB_API size_t gsb_isect_plan_workspace(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t tile_height);
 GSB_API int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
                            const float *depths, uint32_t tile_size, uint32_t tile_width,
                            uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *n_isects_out,
+                           int32_t *tile_offsets_out /*nullable*/,
                            void *plan_workspace, size_t plan_workspace_bytes, gsb_stream_t stream);
-GSB_API size_t gsb_isect_emit_planned_workspace(uint64_t n_isects);
-GSB_API int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
-                                   const float *depths, uint32_t tile_size, uint32_t tile_width,
-                                   uint32_t tile_height, uint64_t n_isects, const void *plan_workspace,
-                                   int64_t *isect_ids, int32_t *flatten_ids, void *workspace,
-                                   size_t workspace_bytes, gsb_stream_t stream);
+GSB_API int gsb_isect_emit_planned(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t tile_height,
+                                   uint64_t n_isects, const void *plan_workspace,
+                                   size_t plan_workspace_bytes, int64_t *isect_ids /*nullable*/,
+                                   int32_t *flatten_ids, gsb_stream_t stream);
 
 /* ---- a6: gsplat::intersect_offset (Ops.h:39-43, IntersectTile.cu:206-288) --------
  * offsets [C,tile_height,tile_width] int32; all zero when n_isects == 0. */

@@ -36,13 +36,13 @@ def lib(pkg):
     L = C.CDLL(path)
     L.gsb_error_string.restype = C.c_char_p
     for n in ("gsb_raster_fwd_workspace", "gsb_raster_bwd_workspace", "gsb_isect_count_workspace",
-              "gsb_isect_plan_workspace", "gsb_isect_emit_planned_workspace", "gsb_isect_sort_workspace"):
+              "gsb_isect_plan_workspace", "gsb_isect_sort_workspace"):
         getattr(L, n).restype = C.c_size_t
     return L
 
 
 # any non-null address will do: the calls below return before dereferencing it on the device
-_buf = np.zeros(4096, np.uint8)
+_buf = np.zeros(8192, np.uint8)
 PTR = C.c_void_p(_buf.ctypes.data)
 NULL = C.c_void_p(None)
 u32, u64, f32, i32, sz = C.c_uint32, C.c_uint64, C.c_float, C.c_int32, C.c_size_t
@@ -94,25 +94,28 @@ def test_intersect_argument_validation(lib):
                                NULL) == E_WORKSPACE
     assert lib.gsb_isect_count_workspace(u64(1000)) >= 256
     # plan: the host needs somewhere to read n_isects from; the key must fit 64 bits (Intersect.cpp:50)
-    need = lib.gsb_isect_plan_workspace(u32(1), u32(8))
+    need = lib.gsb_isect_plan_workspace(u32(1), u32(8), u32(4), u32(4))
     assert need >= 8 * (4 + 8)
-    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, NULL, PTR, sz(need),
+    aligned = C.c_void_p((PTR.value + 255) & ~255)
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, NULL, NULL, aligned, sz(need),
                               NULL) == E_INVALID
-    assert lib.gsb_isect_plan(u32(1), u32(8), NULL, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, PTR, sz(need),
+    assert lib.gsb_isect_plan(u32(1), u32(8), NULL, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, NULL, aligned, sz(need),
                               NULL) == E_INVALID
-    assert lib.gsb_isect_plan(u32(4), u32(8), PTR, PTR, PTR, u32(16), u32(1 << 16), u32(1 << 15), PTR, PTR, PTR,
+    assert lib.gsb_isect_plan(u32(4), u32(8), PTR, PTR, PTR, u32(16), u32(1 << 16), u32(1 << 15), PTR, PTR, NULL, aligned,
                               sz(1 << 20), NULL) == E_INVALID  # 32 tile bits + 3 camera bits > 32
-    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, PTR, sz(16),
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(1 << 16), u32(1), PTR, PTR, NULL, aligned,
+                              sz(1 << 20), NULL) == E_INVALID  # tile grid side > 65535 (box packing)
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, NULL, aligned, sz(16),
                               NULL) == E_WORKSPACE
-    misaligned = C.c_void_p(PTR.value + 8)
-    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, misaligned, sz(need),
+    misaligned = C.c_void_p(aligned.value + 8)
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, NULL, misaligned, sz(need),
                               NULL) == E_WORKSPACE
-    # emit: nothing to do without intersections; a short workspace is refused
-    assert lib.gsb_isect_emit_planned(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), u64(0), PTR, PTR, PTR,
-                                      PTR, sz(0), NULL) == OK
-    assert lib.gsb_isect_emit_planned(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), u64(100), PTR, PTR, PTR,
-                                      PTR, sz(64), NULL) == E_WORKSPACE
-    assert lib.gsb_isect_emit_planned_workspace(u64(100)) >= 100 * 12
+    # emit: nothing to do without intersections; a short or misaligned plan workspace is refused
+    assert lib.gsb_isect_emit_planned(u32(1), u32(8), u32(4), u32(4), u64(0), aligned, sz(need), PTR, PTR, NULL) == OK
+    assert lib.gsb_isect_emit_planned(u32(1), u32(8), u32(4), u32(4), u64(100), aligned, sz(64), PTR, PTR,
+                                      NULL) == E_WORKSPACE
+    assert lib.gsb_isect_emit_planned(u32(1), u32(8), u32(4), u32(4), u64(100), aligned, sz(need), PTR, NULL,
+                                      NULL) == E_INVALID
     assert lib.gsb_isect_sort(u64(0), u32(1), u32(4), u32(4), NULL, NULL, NULL, NULL, NULL, sz(0), NULL) == OK
     assert lib.gsb_isect_sort(u64(10), u32(1), u32(4), u32(4), PTR, PTR, PTR, PTR, PTR, sz(8), NULL) == E_WORKSPACE
 

@@ -1,23 +1,21 @@
-"""GPU: BASELINE.json configs[1] at FULL size (1 M Gaussians, 1920x1080, SH degree 3) -- checked through
-size-independent properties (the CPU oracle would need minutes here) and, when oracle/_ref is built,
-directly against the reference's own CUDA kernels on the same inputs."""
+"""GPU: BASELINE.json configs[1] (config B: 1 M Gaussians) and configs[3] (config D: 6 M Gaussians) at FULL size,
+1920x1080, SH degree 3 -- checked through size-independent properties (the CPU oracle would need minutes here)
+and directly against the reference's own CUDA kernels (oracle/_ref) on the same inputs: projection and SH
+element-wise, intersect bit-exact, blend forward 1e-4, blend backward 1e-3 with per-Gaussian bounds."""
 import numpy as np
 import pytest
 import torch
 
 import scenes
+from parity import assert_grad_close, rel
 
 pytestmark = pytest.mark.gpu
 
 
-def rel(a, b):
-    a, b = a.double(), b.double()
-    return float((a - b).norm() / b.norm().clamp_min(1e-30))
-
-
-@pytest.fixture(scope="module")
-def full(native, cuda_device):
-    sc = scenes.scene_b(N=1_000_000)
+@pytest.fixture(scope="module", params=[("B", 1_000_000), ("D", 6_000_000)], ids=["configB_1M", "configD_6M"])
+def full(request, native, cuda_device):
+    cfg, n_gauss = request.param
+    sc = scenes.scene_b(N=n_gauss)
     t = {k: torch.from_numpy(v).to(cuda_device) for k, v in sc.items() if isinstance(v, np.ndarray)}
     W, H = sc["width"], sc["height"]
     tw, th = (W + 15) // 16, (H + 15) // 16
@@ -33,7 +31,7 @@ def full(native, cuda_device):
     fa = (t["means"], t["quats"], t["scales"], colors.contiguous(), t["opacities"][None], t["background"], None, W, H, 16,
           t["viewmats"], t["Ks"], off, flat)
     r, a, li = native.rasterize_to_pixels_from_world_3dgs_fwd(*fa)
-    return dict(sc=sc, t=t, W=W, H=H, tw=tw, th=th, radii=radii, means2d=means2d, depths=depths, masks=masks, dirs=dirs,
+    return dict(cfg=cfg, N=n_gauss, sc=sc, t=t, W=W, H=H, tw=tw, th=th, radii=radii, means2d=means2d, depths=depths, masks=masks, dirs=dirs,
                 colors=colors, tpg=tpg, ids=ids, flat=flat, off=off, fa=fa, r=r, a=a, li=li)
 
 
@@ -49,6 +47,7 @@ def test_projection_and_intersect_properties(full):
     ids, flat, off, tpg = f["ids"], f["flat"], f["off"].reshape(-1).long(), f["tpg"]
     n = ids.shape[0]
     assert int(tpg.sum()) == n and n > 5_000_000
+    print(f"[config {f['cfg']}] visible {int(vis.sum())} / {f['N']}, intersections {n}")
     assert bool((ids[1:] >= ids[:-1]).all())                       # sorted by (tile, depth)
     assert int(flat.min()) >= 0 and int(flat.max()) < radii.shape[0]
     assert bool(vis[flat.long()].all())                            # only visible Gaussians are listed
@@ -106,27 +105,51 @@ def test_full_size_against_reference_kernels(native, full, cuda_device):
         pytest.skip("oracle/_ref/libgsplat_ref.so not built")
     ref = ref_ops.backend(native)
     f = full
+    tag = f"config {f['cfg']}"
     rr, ar, lr = ref.rasterize_to_pixels_from_world_3dgs_fwd(*f["fa"])
     e_img, e_a = rel(f["r"], rr), rel(f["a"], ar)
     lm = float((f["li"] != lr).float().mean())
-    print(f"[config B] image rel_l2 vs reference kernels {e_img:.2e}, alpha {e_a:.2e}, last_ids differ {lm:.2e}")
+    far = float(((f["r"] - rr).abs().amax(-1) > 1e-4).float().mean())
+    print(f"[{tag}] image rel_l2 vs reference kernels {e_img:.2e}, alpha {e_a:.2e}, last_ids differ {lm:.2e}, "
+          f"pixels off by > 1e-4: {far:.2e}, max abs {float((f['r'] - rr).abs().max()):.2e}")
     assert e_img < 1e-4 and e_a < 1e-4 and lm < 2e-3
+    assert far < 2e-3 and float((f["r"] - rr).abs().max()) < 2e-2
     g = torch.Generator(device=cuda_device).manual_seed(5)
     vr = torch.randn(rr.shape, device=cuda_device, generator=g)
     va = torch.randn(ar.shape, device=cuda_device, generator=g)
     g_ref = ref.rasterize_to_pixels_from_world_3dgs_bwd(*f["fa"], ar, lr, vr, va)
     g_new = native.rasterize_to_pixels_from_world_3dgs_bwd(*f["fa"], ar, lr, vr, va)
     for nm, a, b in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), g_new, g_ref):
-        e = rel(a, b)
-        print(f"[config B] {nm}: rel_l2 vs reference kernels {e:.2e}")
-        assert e < 1e-3, (nm, e)
+        assert_grad_close(a, b, nm, f["N"], tag=f"{tag} blend bwd vs reference kernels")
     # intersect: bit-exact on the reference's own projection outputs
-    radii, m2d, dep, _, _ = ref.projection_ut_3dgs_fused(f["t"]["means"], f["t"]["quats"], f["t"]["scales"],
-                                                         f["t"]["opacities"], f["t"]["viewmats"], f["t"]["Ks"], f["W"],
-                                                         f["H"], 0.3, 0.01, 1e4, 0.0)
+    t = f["t"]
+    radii, m2d, dep, con, _ = ref.projection_ut_3dgs_fused(t["means"], t["quats"], t["scales"], t["opacities"],
+                                                           t["viewmats"], t["Ks"], f["W"], f["H"], 0.3, 0.01, 1e4, 0.0)
     a = ref.intersect_tile(m2d, radii, dep, 1, 16, f["tw"], f["th"], True)
     b = native.intersect_tile(m2d, radii, dep, 1, 16, f["tw"], f["th"], True)
     assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert torch.equal(ref.intersect_offset(a[1], 1, f["tw"], f["th"]), native.intersect_offset(b[1], 1, f["tw"], f["th"]))
+    # projection, element-wise: radii flip only at ceil()/cull boundaries (fast-math vs IEEE), the rest to 1e-4 relative
     mism = int((radii != f["radii"]).any(-1).sum())
-    print(f"[config B] radii differing reference vs b200: {mism} / 1000000")
-    assert mism <= 1000
+    big = int((((radii - f["radii"]).abs() > 1) & (radii > 0) & (f["radii"] > 0)).any(-1).sum())
+    both = (radii > 0).all(-1) & (f["radii"] > 0).all(-1)
+    dm = (m2d - f["means2d"])[both].abs().max()
+    dd = ((dep - f["depths"])[both].abs() / dep[both].abs()).max()
+    print(f"[{tag}] projection vs reference: radii differ for {mism} / {f['N']} (steps > 1: {big}); max |means2d err| "
+          f"{float(dm):.2e} px; max rel depth err {float(dd):.2e}")
+    assert mism <= f["N"] // 1000 and big == 0
+    assert float(dm) < 5e-3 and float(dd) < 1e-5
+    # SH forward / backward, element-wise against the reference's kernels (recipe of tests/test_numerical_gradients.cpp:
+    # 1e-4), on this view's directions and masks
+    K = t["sh_coeffs"].shape[1]
+    dirs, masks = f["dirs"].reshape(-1, 3), f["masks"].reshape(-1)
+    c_ref = ref.spherical_harmonics_fwd(3, dirs, t["sh_coeffs"], masks)
+    c_new = native.spherical_harmonics_fwd(3, dirs, t["sh_coeffs"], masks)
+    assert torch.allclose(c_new[masks], c_ref[masks], rtol=1e-4, atol=1e-5)
+    vc = torch.randn(c_ref.shape, device=cuda_device, generator=g)
+    vco_ref, vd_ref = ref.spherical_harmonics_bwd(K, 3, dirs, t["sh_coeffs"], masks, vc, True)
+    vco_new, vd_new = native.spherical_harmonics_bwd(K, 3, dirs, t["sh_coeffs"], masks, vc, True)
+    assert torch.allclose(vco_new, vco_ref, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(vd_new, vd_ref, rtol=1e-4, atol=2e-5 * float(vd_ref.abs().max()))
+    print(f"[{tag}] SH fwd max abs err {float((c_new - c_ref)[masks].abs().max()):.2e}; bwd coeffs "
+          f"{float((vco_new - vco_ref).abs().max()):.2e}, dirs {float((vd_new - vd_ref).abs().max()):.2e}")

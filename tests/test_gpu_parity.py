@@ -15,18 +15,10 @@ import pytest
 import torch
 
 import scenes
+from parity import assert_grad_close, rel, to_dev
 
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
-
-
-def rel(a, b):
-    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
-    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
-
-
-def to_dev(sc, dev):
-    return {k: torch.from_numpy(v).to(dev) for k, v in sc.items() if isinstance(v, np.ndarray)}
 
 
 # ------------------------------------------------------------------------------------------
@@ -135,6 +127,24 @@ def test_projection_vs_oracle(native, orc, cuda_device, scene):
     assert int((r2.cpu().numpy() != r2_ref).any(-1).sum()) <= max(2, radii.shape[1] // 2000)
 
 
+def test_projection_accepts_offset_views(native, cuda_device):
+    """Contiguous views with a 4- / 12-byte storage offset (means[1:], opacities[1:] ...) are valid inputs of the
+    reference op (CHECK_INPUT only tests contiguity); the TMA staging path needs 16-byte aligned bases and must
+    not be taken for them."""
+    sc = scenes.scene_b(N=3001, width=640, height=360, view=1, scale_mul=3.0)
+    t = to_dev(sc, cuda_device)
+    args = lambda sl: (t["means"][sl], t["quats"][sl], t["scales"][sl], t["opacities"][sl], t["viewmats"], t["Ks"],
+                       sc["width"], sc["height"], 0.3, 0.01, 1e4, 0.0)
+    whole = native.projection_ut_3dgs_fused(*args(slice(None)))
+    view = native.projection_ut_3dgs_fused(*args(slice(1, None)))  # 3000 rows starting 12 / 16 / 4 bytes in
+    assert t["means"][1:].data_ptr() % 16 != 0 and t["means"][1:].is_contiguous()
+    torch.cuda.synchronize()
+    vis = (whole[0][:, 1:] > 0).all(-1)
+    assert torch.equal(view[0], whole[0][:, 1:])
+    assert torch.equal(view[1][vis], whole[1][:, 1:][vis]) and torch.equal(view[2][vis], whole[2][:, 1:][vis])
+    assert torch.equal(view[3][vis], whole[3][:, 1:][vis]) and int(vis.sum()) > 1000
+
+
 # ------------------------------------------------------------------------------------------
 # a7/a8: blend forward / backward, fed with the ORACLE's isect lists and colours
 # ------------------------------------------------------------------------------------------
@@ -181,14 +191,13 @@ def test_blend_fwd_bwd_vs_oracle(native, orc, cuda_device, name):
         off, flat, torch.from_numpy(ref["alphas"]).to(cuda_device), torch.from_numpy(ref["last_ids"]).to(cuda_device),
         torch.from_numpy(vrc).to(cuda_device), torch.from_numpy(vra).to(cuda_device))
     names = ("v_means", "v_quats", "v_scales", "v_colors", "v_opacities")
+    n_g = sc["means"].shape[0]
     for nm, gt in zip(names, g):
         got = gt.cpu().numpy().reshape(ref64[nm].shape)
-        e = rel(got, ref64[nm])
         n32 = rel(ref[nm], ref64[nm])
-        print(f"[{name}] {nm}: rel_l2 vs f64 oracle {e:.2e} (f32 oracle itself: {n32:.2e})")
-        assert e < 1e-3, (nm, e)
+        # whole-tensor 1e-3 AND per-Gaussian bounds (tests/parity.py)
+        assert_grad_close(got, ref64[nm], nm, n_g, tag=f"{name} vs f64 oracle; f32 oracle itself {n32:.1e}")
         # untouched Gaussians get exact zeros
-        n_g = sc["means"].shape[0]
         untouched = np.abs(ref64[nm]).reshape(n_g, -1).sum(-1) == 0
         assert np.all(got.reshape(n_g, -1)[untouched] == 0)
 
@@ -227,8 +236,8 @@ def test_blend_masks_no_background_and_ragged_image(native, orc, cuda_device):
         t["means"], t["quats"], t["scales"], colors, t["opacities"][None], None, torch.from_numpy(masks).to(cuda_device),
         W, H, 16, t["viewmats"], t["Ks"], off, flat, torch.from_numpy(am).to(cuda_device),
         torch.from_numpy(lm).to(cuda_device), torch.from_numpy(vrc).to(cuda_device), torch.from_numpy(vra).to(cuda_device))
-    for got, want in zip(g, gref):
-        assert rel(got.cpu().numpy().reshape(want.shape), want) < 1e-3
+    for nm, got, want in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), g, gref):
+        assert_grad_close(got.cpu().numpy().reshape(want.shape), want, nm, sc["means"].shape[0], tag="masked tiles")
 
 
 def test_blend_empty_inputs(native, cuda_device):
@@ -255,56 +264,41 @@ def test_blend_empty_inputs(native, cuda_device):
 # ------------------------------------------------------------------------------------------
 # whole path through the L3 mirror (autograd), against the oracle pipeline
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["small_rot", "a"])
+@pytest.mark.parametrize("name", ["small_rot", "a", "b30k"])
 def test_pipeline_autograd_vs_oracle(native, orc, cuda_device, name):
+    """Whole L3 path (SH -> intersect -> blend and the autograd chain back to every parameter) against the oracle
+    pipeline.  Both sides are given the SAME projection outputs (the oracle's): a radius that flips at a ceil()
+    boundary between two float implementations changes the intersection lists and makes an element-wise comparison
+    meaningless -- that effect is counted separately in test_projection_vs_oracle -- so the test asserts on every run."""
     sc = _blend_case(name)
     W, H = sc["width"], sc["height"]
     rng = np.random.default_rng(4)
     vrc = rng.standard_normal((1, H, W, 3)).astype(np.float32)
     vra = rng.standard_normal((1, H, W, 1)).astype(np.float32)
     ref = orc.render_pipeline(sc, "f32", True, vrc, vra)
+    ref64 = orc.render_pipeline(sc, "f64", False)
+    same64 = np.array_equal(ref64["flatten_ids"], ref["flatten_ids"])
+    if same64:
+        orc.backward_pipeline(sc, ref64, vrc, vra, "f64")
     t = to_dev(sc, cuda_device)
+    vis = (ref["radii"] > 0).all(-1)
+    proj = (torch.from_numpy(ref["radii"]).to(cuda_device),
+            torch.from_numpy(np.where(vis[..., None], ref["means2d"], 0).astype(np.float32)).to(cuda_device),
+            torch.from_numpy(np.where(vis, ref["depths"], 0).astype(np.float32)).to(cuda_device))
     leaves = {k: t[k].clone().requires_grad_(True) for k in ("means", "quats", "scales", "opacities", "sh_coeffs")}
     out = native.rasterize(leaves["means"], leaves["quats"], leaves["scales"], leaves["opacities"], leaves["sh_coeffs"],
-                           sc["sh_degree"], t["viewmats"], t["Ks"], W, H, bg_color=t.get("background"))
-    same_lists = out.n_isects == len(ref["flatten_ids"])
+                           sc["sh_degree"], t["viewmats"], t["Ks"], W, H, bg_color=t.get("background"), projection=proj)
+    assert out.n_isects == len(ref["flatten_ids"])
     loss = (out.render_colors * torch.from_numpy(vrc).to(cuda_device)).sum() + \
            (out.alpha.permute(1, 2, 0)[None] * torch.from_numpy(vra).to(cuda_device)).sum()
     loss.backward()
-    if not same_lists:
-        pytest.skip("a radius flipped at a ceil() boundary: isect lists differ by a few entries (counted in "
-                    "test_projection_vs_oracle); element-wise comparison is meaningless")
     assert rel(out.render_colors.detach().cpu().numpy(), ref["renders"]) < 1e-4
-    assert rel(leaves["means"].grad.cpu().numpy(), ref["v_means"] + ref["v_dirs"][0]) < 1e-3
-    assert rel(leaves["quats"].grad.cpu().numpy(), ref["v_quats"]) < 1e-3
-    assert rel(leaves["scales"].grad.cpu().numpy(), ref["v_scales"]) < 1e-3
-    assert rel(leaves["opacities"].grad.cpu().numpy(), ref["v_opacities"][0]) < 1e-3
-    assert rel(leaves["sh_coeffs"].grad.cpu().numpy(), ref["v_sh_coeffs"]) < 1e-3
-
-
-def test_blend_bwd_tensor_core_reduction_matches_shuffle_reduction(native, orc, cuda_device, monkeypatch):
-    """GSB_BWD_REDUCE=mma: the ten geometric moments of eight events at a time go through mma.sync (tf32 hi/lo
-    split, fp32 accumulate) instead of warp shuffles.  Same gradients to fp32 summation-order noise."""
-    sc = _blend_case("b30k")
-    W, H = sc["width"], sc["height"]
-    rng = np.random.default_rng(11)
-    vrc = torch.from_numpy(rng.standard_normal((1, H, W, 3)).astype(np.float32)).to(cuda_device)
-    vra = torch.from_numpy(rng.standard_normal((1, H, W, 1)).astype(np.float32)).to(cuda_device)
-    ref = orc.render_pipeline(sc, "f32", False)
-    t = to_dev(sc, cuda_device)
-    colors = torch.from_numpy(ref["colors"]).to(cuda_device)
-    off = torch.from_numpy(ref["tile_offsets"]).to(cuda_device)
-    flat = torch.from_numpy(ref["flatten_ids"]).to(cuda_device)
-    args = (t["means"], t["quats"], t["scales"], colors, t["opacities"][None], t.get("background"), None, W, H, 16,
-            t["viewmats"], t["Ks"], off, flat)
-    _, alphas, last_ids = native.rasterize_to_pixels_from_world_3dgs_fwd(*args)
-    out = {}
-    for mode in ("shuffle", "mma"):
-        monkeypatch.setenv("GSB_BWD_REDUCE", mode)
-        out[mode] = native.rasterize_to_pixels_from_world_3dgs_bwd(*args, alphas, last_ids, vrc, vra)
-        torch.cuda.synchronize()
-    for a, b, name in zip(out["shuffle"], out["mma"], ("v_means", "v_quats", "v_scales", "v_colors", "v_opacities")):
-        assert rel(b.cpu().numpy(), a.cpu().numpy()) < 2e-5, name
+    truth = ref64 if same64 else ref  # float64 arithmetic on the same lists when the f64 projection agrees
+    n_g = sc["means"].shape[0]
+    want = {"means": truth["v_means"] + truth["v_dirs"][0], "quats": truth["v_quats"], "scales": truth["v_scales"],
+            "opacities": truth["v_opacities"][0], "sh_coeffs": truth["v_sh_coeffs"]}
+    for k, w in want.items():
+        assert_grad_close(leaves[k].grad, w, k, n_g, tag=f"pipeline {name} vs {'f64' if same64 else 'f32'} oracle")
 
 
 def test_host_staged_steps_match_sequential_steps(native, cuda_device):
@@ -506,6 +500,5 @@ def test_distorted_camera_whole_path_vs_oracle(native, orc, cuda_device, model):
                                                        torch.from_numpy(vrc).to(cuda_device),
                                                        torch.from_numpy(vra).to(cuda_device), **nkw)
     for nm, got, want in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), g, g_ref):
-        eg = rel(got.cpu().numpy().reshape(want.shape), want)
-        print(f"[{model}] {nm}: rel_l2 vs f64 oracle {eg:.2e}")
-        assert eg < 1e-3, (nm, eg)
+        assert_grad_close(got.cpu().numpy().reshape(want.shape), want, nm, sc["means"].shape[0],
+                          tag=f"{model} vs f64 oracle")
