@@ -421,7 +421,10 @@ def main():
     ap.add_argument("--gaussians", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
     args = ap.parse_args()
+    if args.quick:
+        args.no_cpu_baseline = args.no_ref_cuda = True
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

@@ -335,3 +335,104 @@ def rasterize(means, quats, scales, opacities, sh_coeffs, sh_degree, viewmat, K,
         image=torch.clamp(renders[0].permute(2, 0, 1), 0.0, 1.0), alpha=alphas[0].permute(2, 0, 1),
         render_colors=renders, radii=radii[0].max(-1).values, depths=depths[0], means2d=means2d,
         n_isects=int(flatten_ids.shape[0]), visibility=masks[0])
+
+
+# ---------------------------------------------------------------------------------------------
+# the extended operator over the RAW SplatData tensors (include/gsplat/FusedOps.h).
+# ---------------------------------------------------------------------------------------------
+
+class _FusedGUTFunction(torch.autograd.Function):
+    """rasterize_from_world_fused_fwd / _bwd as one autograd node: raw parameters in, image out."""
+
+    @staticmethod
+    def forward(ctx, means, sh0, shN, scaling_raw, rotation_raw, opacity_raw, viewmat, K, bg, cfg):
+        sh_degree, scaling_modifier, width, height, eps2d, near, far, clip, camera, capacity = cfg
+        needs_bwd = any(t.requires_grad for t in (means, sh0, shN, scaling_raw, rotation_raw, opacity_raw))
+        args = (means.detach().contiguous(), sh0.detach().contiguous(), shN.detach().contiguous(),
+                scaling_raw.detach().contiguous(), rotation_raw.detach().contiguous(), opacity_raw.detach().contiguous())
+        cam = (camera.get("camera_model", PINHOLE), camera.get("radial_coeffs"), camera.get("tangential_coeffs"),
+               camera.get("thin_prism_coeffs"))
+        (renders, alphas, radii, means2d, depths, last_ids, tile_offsets, flatten_ids, workspace,
+         n_isects) = _product_ns().rasterize_from_world_fused_fwd(
+            *args, sh_degree, scaling_modifier, viewmat.contiguous(), K.contiguous(), width, height, eps2d, near, far,
+            clip, bg, cam[0], cam[1], cam[2], cam[3], capacity, needs_bwd)
+        ctx.save_for_backward(*args, viewmat, K, bg if bg is not None else torch.empty(0), radii, tile_offsets,
+                              flatten_ids, workspace, alphas, last_ids)
+        ctx.cfg = (sh_degree, scaling_modifier, width, height, cam, bg is not None)
+        ctx.mark_non_differentiable(radii, means2d, depths, n_isects)
+        return renders, alphas, radii, means2d, depths, n_isects
+
+    @staticmethod
+    def backward(ctx, v_renders, v_alphas, *_):
+        (means, sh0, shN, scaling_raw, rotation_raw, opacity_raw, viewmat, K, bg, radii, tile_offsets, flatten_ids,
+         workspace, alphas, last_ids) = ctx.saved_tensors
+        sh_degree, scaling_modifier, width, height, cam, has_bg = ctx.cfg
+        if v_alphas is None:
+            v_alphas = torch.zeros_like(alphas)
+        g = _product_ns().rasterize_from_world_fused_bwd(
+            means, sh0, shN, scaling_raw, rotation_raw, opacity_raw, sh_degree, scaling_modifier, viewmat, K, width,
+            height, bg if has_bg else None, cam[0], cam[1], cam[2], cam[3], radii, tile_offsets, flatten_ids, workspace,
+            alphas, last_ids, v_renders.contiguous(), v_alphas.contiguous())
+        v_bg = None
+        if has_bg and ctx.needs_input_grad[8]:
+            v_bg = (v_renders * (1.0 - alphas)).sum(dim=(-3, -2))
+        return g[0], g[1], (g[2] if g[2].numel() else None), g[3], g[4], g[5], None, None, v_bg, None
+
+
+@dataclass
+class FusedRenderOutput:
+    render_colors: torch.Tensor  # [1, H, W, 3]
+    alpha: torch.Tensor          # [1, H, W, 1]
+    radii: torch.Tensor          # [1, N, 2] int32
+    means2d: torch.Tensor        # [1, N, 2]
+    depths: torch.Tensor         # [1, N]
+    n_isects: torch.Tensor       # [1] int64 on the device
+    capacity: int                # 0: flatten_ids was sized exactly (one host read-back)
+
+    @property
+    def image(self):             # [3, H, W] clamped (rasterizer.cpp:401)
+        return torch.clamp(self.render_colors[0].permute(2, 0, 1), 0.0, 1.0)
+
+
+def rasterize_fused(means, sh0, shN, scaling_raw, rotation_raw, opacity_raw, sh_degree, viewmat, K, width, height,
+                    bg_color=None, scaling_modifier=1.0, eps2d=0.3, near_plane=0.01, far_plane=10000.0, radius_clip=0.0,
+                    camera_model=PINHOLE, radial_coeffs=None, tangential_coeffs=None, thin_prism_coeffs=None,
+                    isect_capacity: int = 0) -> FusedRenderOutput:
+    """gs::training::rasterize for RenderMode::RGB on the RAW SplatData tensors (what Trainer holds as parameters,
+    include/core/splat_data.hpp:104-109): means [N,3], sh0 [N,1,3], shN [N,K-1,3], log-scales [N,3], unnormalised
+    quaternions [N,4], logit opacities [N,1].  Same image and the same parameter gradients as
+
+        rasterize(means, normalize(rotation), exp(scaling), sigmoid(opacity), cat(sh0, shN), ...)
+
+    through autograd, in two kernels plus the intersect / blend kernels, with no torch glue.  isect_capacity > 0
+    removes the one host read-back (compare `n_isects` with the capacity afterwards)."""
+    load()
+    camera = dict(camera_model=camera_model, radial_coeffs=radial_coeffs, tangential_coeffs=tangential_coeffs,
+                  thin_prism_coeffs=thin_prism_coeffs)
+    cfg = (int(sh_degree), float(scaling_modifier), int(width), int(height), float(eps2d), float(near_plane),
+           float(far_plane), float(radius_clip), camera, int(isect_capacity))
+    renders, alphas, radii, means2d, depths, n_isects = _FusedGUTFunction.apply(
+        means, sh0, shN, scaling_raw, rotation_raw, opacity_raw, viewmat, K, bg_color, cfg)
+    return FusedRenderOutput(renders, alphas, radii, means2d, depths, n_isects, int(isect_capacity))
+
+
+def raw_from_activated(means, quats, scales, opacities, sh_coeffs):
+    """Test / bench helper: the raw SplatData tensors whose activations give the arguments (inverse of
+    splat_data.cpp:267-286): log-scales, the quaternion itself, logit opacities [N,1], sh split into sh0 / shN."""
+    op = opacities.clamp(1e-6, 1 - 1e-6)
+    return dict(means=means.clone(), sh0=sh_coeffs[:, :1, :].contiguous(), shN=sh_coeffs[:, 1:, :].contiguous(),
+                scaling_raw=torch.log(scales), rotation_raw=quats.clone(),
+                opacity_raw=torch.log(op / (1 - op)).unsqueeze(-1))
+
+
+def rasterize_from_raw(raw: dict, sh_degree, viewmat, K, width, height, bg_color=None, scaling_modifier=1.0,
+                       backend: OpsBackend | None = None, **kw) -> RenderOutput:
+    """The reference's own sequence on raw tensors: activations (splat_data.cpp:267-286) with torch, then rasterize().
+    The unfused counterpart of rasterize_fused(), used as its parity oracle and as the same-call-site baseline."""
+    means = raw["means"]
+    opac = torch.sigmoid(raw["opacity_raw"]).squeeze(-1)
+    quats = torch.nn.functional.normalize(raw["rotation_raw"], dim=-1)
+    scales = torch.exp(raw["scaling_raw"])
+    shs = torch.cat([raw["sh0"], raw["shN"]], dim=1)
+    return rasterize(means, quats, scales, opac, shs, sh_degree, viewmat, K, width, height, bg_color=bg_color,
+                     scaling_modifier=scaling_modifier, backend=backend, **kw)

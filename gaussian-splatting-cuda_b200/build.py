@@ -36,9 +36,10 @@ CUDA_SOURCES = [
     ("gsb_intersect.cu", ["-fmad=false"]),
     ("gsb_raster.cu", []),
     ("gsb_misc.cu", []),
+    ("gsb_fused.cu", ["-fmad=false"]),
 ]
-CUDA_HEADERS = ["gsb_common.cuh", "gsb_raster.cuh", "gsb_camera.cuh", "gsb_devsort.cuh"]
-SHIM_SOURCES = ["Ops.cpp", "torch_binding.cpp"]
+CUDA_HEADERS = ["gsb_common.cuh", "gsb_raster.cuh", "gsb_camera.cuh", "gsb_devsort.cuh", "gsb_sh.cuh", "gsb_projection.cuh"]
+SHIM_SOURCES = ["Ops.cpp", "FusedOps.cpp", "torch_binding.cpp"]
 
 
 def _run(cmd: list[str], verbose: bool) -> str:
@@ -112,7 +113,7 @@ def build_shim(verbose: bool = False, force: bool = False) -> str:
     incs = []
     for i in [os.path.join(INC, "gsplat"), INC] + tinc + [cuda_inc]:
         incs += ["-I", i]
-    hdrs = [os.path.join(INC, "gsb200.h")] + [os.path.join(INC, "gsplat", h) for h in ("Ops.h", "Common.h", "Cameras.h")]
+    hdrs = [os.path.join(INC, "gsb200.h")] + [os.path.join(INC, "gsplat", h) for h in ("Ops.h", "FusedOps.h", "Common.h", "Cameras.h")]
     objs = []
     for src in SHIM_SOURCES:
         sp = os.path.join(SHIM, src)

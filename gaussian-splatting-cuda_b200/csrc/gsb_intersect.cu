@@ -268,6 +268,7 @@ struct BinArgs {
     uint32_t *M;          // [P][T_total]
     int32_t *flatten_ids;
     int64_t *isect_ids;   // nullable
+    uint32_t cap;         // capacity of flatten_ids / isect_ids (>= n_isects unless the caller under-allocated)
 };
 
 // first r in [0, n_runs) with end[r] > s (exists: s < end[n_runs - 1]); one probe per lane and round
@@ -287,83 +288,159 @@ __device__ __forceinline__ uint32_t first_run_after(const uint32_t *__restrict__
     return lo;
 }
 
+// The walk of one chunk.  Per step the warp handles 32 consecutive slots: slot -> run -> tile (the MAP half) and
+// then rank / count / store (the COMMIT half).  The run table entries the next steps need sit in a per-warp ring in
+// shared memory, refilled 32 runs at a time from loads issued a refill earlier, so no global-memory latency is on the
+// serial chain (run pointer -> next step); the MAP of step k+1 is issued before the COMMIT of step k so their
+// shared-memory / shuffle latencies overlap.
+constexpr uint32_t kRing = 128; // run-table entries per warp in shared memory (>= 96 live at any time)
+
+struct RunEnt {
+    uint32_t end, idx, bx, by, key;
+};
+template <bool kScatter>
+__device__ __forceinline__ RunEnt load_run(const RunTable &rt, uint32_t r, uint32_t n_runs) {
+    RunEnt e;
+    e.end = 0xffffffffu; e.idx = 0; e.bx = 0; e.by = 0; e.key = 0;
+    if (r < n_runs) {
+        e.end = rt.end[r];
+        e.idx = rt.idx[r];
+        const uint2 b = rt.box[r];
+        e.bx = b.x; e.by = b.y;
+        if (kScatter) e.key = rt.key[r];
+    }
+    return e;
+}
+
+struct StepMap {
+    uint32_t tt;   // tile id relative to the window, or a per-lane dummy when the lane has nothing to place
+    uint32_t idx, key, tile, cam;
+    bool in;
+};
+
 template <bool kScatter>
 __global__ void __launch_bounds__(32) tile_bin_kernel(const BinArgs a) {
-    extern __shared__ uint32_t s_cnt[]; // [t_cnt]
+    extern __shared__ uint32_t s_mem[]; // [t_cnt counters][5 x kRing run entries]
+    uint32_t *s_cnt = s_mem;
+    uint32_t *s_end = s_mem + ((a.t_cnt + 31u) & ~31u);
+    uint32_t *s_idx = s_end + kRing, *s_bx = s_idx + kRing, *s_by = s_bx + kRing, *s_key = s_by + kRing;
     const uint32_t lane = threadIdx.x;
     const uint32_t p = blockIdx.x;
     uint32_t *row = a.M + (size_t)p * a.T_total + a.t_lo;
     const unsigned long long I = a.ctl->n_isects;
     const uint32_t n_runs = a.ctl->n_runs;
     const uint32_t s_begin = (uint32_t)(((unsigned long long)p * I) / a.P);
-    const uint32_t s_end = (uint32_t)(((unsigned long long)(p + 1) * I) / a.P);
+    const uint32_t s_stop = (uint32_t)(((unsigned long long)(p + 1) * I) / a.P);
     if (kScatter) {
-        if (s_begin >= s_end) return;
+        if (s_begin >= s_stop) return;
         for (uint32_t t = lane; t < a.t_cnt; t += 32) s_cnt[t] = row[t];
     } else {
         for (uint32_t t = lane; t < a.t_cnt; t += 32) s_cnt[t] = 0;
     }
-    __syncwarp();
-    if (s_begin < s_end) {
+    if (s_begin < s_stop) {
         uint32_t r0 = first_run_after(a.rt.end, n_runs, s_begin);
         uint32_t start0 = r0 ? a.rt.end[r0 - 1] : 0u; // first slot of run r0
-        for (uint32_t s0 = s_begin; s0 < s_end; s0 += 32) {
-            // window of 32 candidate runs; the run ends inside the step are strictly increasing (no empty runs)
-            const uint32_t r = r0 + lane;
-            const bool have = r < n_runs;
-            const uint32_t rel = have ? a.rt.end[r] - s0 : 0xffffffffu; // > 0 for lane 0
-            const uint32_t idx_l = have ? a.rt.idx[r] : 0u;
-            const uint2 box_l = have ? a.rt.box[r] : make_uint2(0u, 0u);
-            const uint32_t key_l = (kScatter && have) ? a.rt.key[r] : 0u;
+        // ring = runs [r0, r0 + 64); `pend` = the 32 runs after those, in flight
+        {
+            const RunEnt e0 = load_run<kScatter>(a.rt, r0 + lane, n_runs), e1 = load_run<kScatter>(a.rt, r0 + 32 + lane, n_runs);
+            const uint32_t w0 = (r0 + lane) & (kRing - 1), w1 = (r0 + 32 + lane) & (kRing - 1);
+            s_end[w0] = e0.end; s_idx[w0] = e0.idx; s_bx[w0] = e0.bx; s_by[w0] = e0.by; s_key[w0] = e0.key;
+            s_end[w1] = e1.end; s_idx[w1] = e1.idx; s_bx[w1] = e1.bx; s_by[w1] = e1.by; s_key[w1] = e1.key;
+        }
+        uint32_t ring_end = r0 + 64;
+        RunEnt pend = load_run<kScatter>(a.rt, ring_end + lane, n_runs);
+        __syncwarp();
+
+        // MAP: slots [s0, s0 + 32) -> (run, tile); advances (r0, start0) to the run that holds slot s0 + 32
+        auto map_step = [&](uint32_t s0) {
+            if (ring_end < r0 + 64) { // keep 64 runs ahead: a step consumes at most 32
+                const uint32_t w = (ring_end + lane) & (kRing - 1);
+                s_end[w] = pend.end; s_idx[w] = pend.idx; s_bx[w] = pend.bx; s_by[w] = pend.by; s_key[w] = pend.key;
+                ring_end += 32;
+                pend = load_run<kScatter>(a.rt, ring_end + lane, n_runs);
+                __syncwarp();
+            }
+            // the run ends inside the step are strictly increasing (no empty runs): bit e of endmask <=> a run ends
+            // after slot s0 + e - 1
+            const uint32_t rel = s_end[(r0 + lane) & (kRing - 1)] - s0; // > 0 for lane 0
             const uint32_t endmask = __reduce_or_sync(0xffffffffu, rel <= 31u ? (1u << rel) : 0u);
-            // runs that end at or before this lane's slot = offset of this lane's run in the window (<= lane)
-            const uint32_t c = __popc(endmask & ((2u << lane) - 1u));
-            const uint32_t prev_rel = __shfl_sync(0xffffffffu, rel, c ? c - 1 : 0);
-            const uint32_t idx = __shfl_sync(0xffffffffu, idx_l, c);
-            const uint32_t bx = __shfl_sync(0xffffffffu, box_l.x, c), by = __shfl_sync(0xffffffffu, box_l.y, c);
-            const uint32_t key = __shfl_sync(0xffffffffu, key_l, c);
+            const uint32_t c = __popc(endmask & ((2u << lane) - 1u)); // runs finished at or before this lane's slot
+            const uint32_t w = (r0 + c) & (kRing - 1);
+            const uint32_t prev_end = s_end[(r0 + c - 1u) & (kRing - 1)];
+            StepMap m;
+            m.idx = s_idx[w];
+            m.key = kScatter ? s_key[w] : 0u;
+            const uint32_t bx = s_bx[w], by = s_by[w];
             const uint32_t slot = s0 + lane;
-            const bool valid = slot < s_end;
-            const uint32_t run_start = c ? s0 + prev_rel : start0;
+            const uint32_t run_start = c ? prev_end : start0;
             const uint32_t j = slot - run_start; // position inside the run's box, row-major
-            const uint32_t w = by & 0xffffu;
-            uint32_t tt = 0x80000000u | lane; // a value no tile id takes
-            uint32_t tile = 0, cam = 0;
-            bool in = false;
-            if (valid) {
-                const uint32_t dy = j / w, dx = j - dy * w;
-                tile = ((bx >> 16) + dy) * a.tile_width + (bx & 0xffffu) + dx;
-                cam = a.multi_cam ? idx / a.N : 0u;
-                const uint32_t g = cam * a.n_tiles + tile - a.t_lo;
-                in = g < a.t_cnt;
-                if (in) tt = g;
+            const uint32_t bw = by & 0xffffu;
+            m.tt = 0x80000000u | lane;
+            m.tile = 0; m.cam = 0; m.in = false;
+            if (slot < s_stop) {
+                const uint32_t dy = j / bw, dx = j - dy * bw;
+                m.tile = ((bx >> 16) + dy) * a.tile_width + (bx & 0xffffu) + dx;
+                m.cam = a.multi_cam ? m.idx / a.N : 0u;
+                const uint32_t g = m.cam * a.n_tiles + m.tile - a.t_lo;
+                m.in = g < a.t_cnt;
+                if (m.in) m.tt = g;
             }
-            const uint32_t peers = __match_any_sync(0xffffffffu, tt);
-            uint32_t base = 0;
-            if (in) base = s_cnt[tt];
-            __syncwarp();
-            if (in) {
-                if (kScatter) {
-                    const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
-                    a.flatten_ids[pos] = (int32_t)idx;
-                    if (a.isect_ids)
-                        a.isect_ids[pos] = ((int64_t)cam << (32 + a.tile_n_bits)) | ((int64_t)tile << 32) | (int64_t)key;
-                }
-                if ((peers >> lane) == 1u) s_cnt[tt] = base + __popc(peers);
-            }
-            __syncwarp();
-            // advance to the run that holds slot s0 + 32
             const uint32_t adv = __popc(__ballot_sync(0xffffffffu, rel <= 32u));
             if (adv) {
-                start0 = s0 + __shfl_sync(0xffffffffu, rel, adv - 1);
+                start0 = s_end[(r0 + adv - 1u) & (kRing - 1)];
                 r0 += adv;
             }
+            return m;
+        };
+        // COMMIT: stable rank of equal tiles inside the step (lane order = depth order), counters, stores
+        auto commit_step = [&](const StepMap &m) {
+            const uint32_t peers = __match_any_sync(0xffffffffu, m.tt);
+            uint32_t base = 0;
+            if (m.in) base = s_cnt[m.tt];
+            __syncwarp();
+            if (m.in) {
+                if (kScatter) {
+                    const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
+                    if (pos < a.cap) a.flatten_ids[pos] = (int32_t)m.idx;
+                }
+                if ((peers >> lane) == 1u) s_cnt[m.tt] = base + __popc(peers);
+            }
+            __syncwarp();
+        };
+
+        StepMap cur = map_step(s_begin);
+        for (uint32_t s0 = s_begin; s0 < s_stop; s0 += 32) {
+            StepMap nxt = cur;
+            if (s0 + 32 < s_stop) nxt = map_step(s0 + 32);
+            commit_step(cur);
+            cur = nxt;
         }
     }
     if (!kScatter) {
         __syncwarp();
         for (uint32_t t = lane; t < a.t_cnt; t += 32) row[t] = s_cnt[t];
     }
+}
+
+// isect_ids of the sorted list, written in order (coalesced) instead of scattered with the values:
+//   key[pos] = cam << (32 + tile_bits) | tile << 32 | depth bits of flatten_ids[pos]
+// the tile of a position is found in the closed offsets table tile_off[0 .. T] (tile_off[T] = n_isects).
+__global__ void __launch_bounds__(kIsectThreads) isect_keys_kernel(uint32_t n, const uint32_t *__restrict__ tile_off,
+                                                                   uint32_t T, uint32_t n_tiles, uint32_t tile_n_bits,
+                                                                   const int32_t *__restrict__ flatten_ids,
+                                                                   const float *__restrict__ depths,
+                                                                   int64_t *__restrict__ isect_ids) {
+    const uint32_t pos = blockIdx.x * kIsectThreads + threadIdx.x;
+    if (pos >= n) return;
+    // last t in [0, T) with tile_off[t] <= pos  (offsets are non-decreasing; empty tiles repeat a value)
+    uint32_t lo = 0, hi = T;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(tile_off + mid) <= pos) lo = mid; else hi = mid;
+    }
+    const uint32_t cam = lo / n_tiles, tile = lo - cam * n_tiles;
+    const uint32_t idx = (uint32_t)flatten_ids[pos];
+    isect_ids[pos] = ((int64_t)cam << (32 + tile_n_bits)) | ((int64_t)tile << 32) | (int64_t)__float_as_uint(depths[idx]);
 }
 
 // ---- step 5: exclusive scan of M over (tile, chunk) ----------------------------------------------------------
@@ -381,7 +458,9 @@ __global__ void __launch_bounds__(kIsectThreads) col_segsum_kernel(const uint32_
 }
 // col_tilescan (one CTA): seg[s][t] -> exclusive prefix over s plus the tile's first slot; tile offsets out.
 __global__ void __launch_bounds__(kSortThreads) col_tilescan_kernel(uint32_t *__restrict__ seg, uint32_t T, uint32_t S,
-                                                                    int32_t *__restrict__ tile_offsets /*nullable*/) {
+                                                                    uint32_t *__restrict__ toff /* [T + 1] */,
+                                                                    int32_t *__restrict__ tile_offsets /*nullable*/,
+                                                                    int write_total) {
     __shared__ uint32_t s_warp[kSortWarps];
     uint32_t carry = 0;
     for (uint32_t t0 = 0; t0 < T; t0 += kSortThreads) {
@@ -393,6 +472,7 @@ __global__ void __launch_bounds__(kSortThreads) col_tilescan_kernel(uint32_t *__
         const uint32_t inc = block_scan_inclusive<uint32_t>(tot, s_warp, all);
         if (t < T) {
             uint32_t run = carry + inc - tot; // first slot of tile t
+            toff[t] = run;
             if (tile_offsets) tile_offsets[t] = (int32_t)run;
             for (uint32_t s = 0; s < S; ++s) {
                 const uint32_t v = seg[(size_t)s * T + t];
@@ -401,6 +481,10 @@ __global__ void __launch_bounds__(kSortThreads) col_tilescan_kernel(uint32_t *__
             }
         }
         carry += all;
+    }
+    if (threadIdx.x == 0) {
+        toff[T] = carry; // = n_isects
+        if (tile_offsets && write_total) tile_offsets[T] = (int32_t)carry;
     }
 }
 // col_apply: M[p][t] = first output slot of chunk p in tile t.
@@ -495,7 +579,7 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
     if (b.t_win == 0) b.t_win = 1;
     b.n_win = (b.T_total + b.t_win - 1) / b.t_win;
     if (b.n_win == 0) b.n_win = 1;
-    b.smem = (size_t)b.t_win * 4;
+    b.smem = (size_t)((b.t_win + 31u) & ~31u) * 4 + 5 * kRing * 4;
     uint32_t per_sm = (uint32_t)((size_t)d.smem_sm / (b.smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 16) per_sm = 16;
@@ -516,7 +600,7 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
 
 // Workspace of the plan; everything the emit needs afterwards lives here too.
 struct PlanWs {
-    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, M, seg, total;
+    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, M, seg, toff, total;
 };
 static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp) {
     PlanWs w;
@@ -531,6 +615,7 @@ static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp) {
     w.rt_end = take(n * 4); w.rt_idx = take(n * 4); w.rt_box = take(n * 8); w.rt_key = take(n * 4);
     w.M = take((size_t)b.P * b.T_total * 4);
     w.seg = take((size_t)b.S * b.T_total * 4);
+    w.toff = take(((size_t)b.T_total + 1) * 4);
     w.total = off + 256;
     return w;
 }
@@ -652,7 +737,8 @@ extern "C" size_t gsb_isect_plan_workspace(uint32_t C, uint32_t N, uint32_t tile
 extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii, const float *depths,
                               uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
                               int32_t *tiles_per_gauss, int64_t *n_isects_out, int32_t *tile_offsets_out,
-                              void *plan_workspace, size_t plan_workspace_bytes, gsb_stream_t stream) {
+                              int tile_offsets_total, void *plan_workspace, size_t plan_workspace_bytes,
+                              gsb_stream_t stream) {
     using namespace gsb;
     const uint64_t n = (uint64_t)C * N;
     if (!n_isects_out) return GSB_E_INVALID;
@@ -660,7 +746,8 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
     const uint64_t T64 = (uint64_t)C * tile_width * tile_height;
     if (n == 0 || T64 == 0) {
         GSB_CUDA_TRY(cudaMemsetAsync(n_isects_out, 0, sizeof(int64_t), s));
-        if (tile_offsets_out && T64) GSB_CUDA_TRY(cudaMemsetAsync(tile_offsets_out, 0, T64 * 4, s));
+        if (tile_offsets_out && T64)
+            GSB_CUDA_TRY(cudaMemsetAsync(tile_offsets_out, 0, (T64 + (tile_offsets_total ? 1 : 0)) * 4, s));
         if (n && tiles_per_gauss) GSB_CUDA_TRY(cudaMemsetAsync(tiles_per_gauss, 0, n * 4, s));
         return GSB_OK;
     }
@@ -709,7 +796,7 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
         BinArgs a;
         a.rt = rt; a.ctl = ctl; a.N = N; a.n_tiles = tile_width * tile_height; a.tile_width = tile_width;
         a.tile_n_bits = tile_n_bits; a.multi_cam = C > 1 ? 1u : 0u;
-        a.T_total = bp.T_total; a.P = bp.P; a.M = M; a.flatten_ids = nullptr; a.isect_ids = nullptr;
+        a.T_total = bp.T_total; a.P = bp.P; a.M = M; a.flatten_ids = nullptr; a.isect_ids = nullptr; a.cap = 0;
         if (bp.smem > 48 * 1024)
             GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)bp.smem));
@@ -722,7 +809,8 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
         const dim3 cgrid((bp.T_total + kIsectThreads - 1) / kIsectThreads, bp.S);
         col_segsum_kernel<<<cgrid, kIsectThreads, 0, s>>>(M, bp.T_total, bp.P, bp.seg_len, seg);
         GSB_LAUNCH_CHECK();
-        col_tilescan_kernel<<<1, kSortThreads, 0, s>>>(seg, bp.T_total, bp.S, tile_offsets_out);
+        col_tilescan_kernel<<<1, kSortThreads, 0, s>>>(seg, bp.T_total, bp.S, reinterpret_cast<uint32_t *>(base + w.toff),
+                                                    tile_offsets_out, tile_offsets_total);
         GSB_LAUNCH_CHECK();
         col_apply_kernel<<<cgrid, kIsectThreads, 0, s>>>(M, bp.T_total, bp.P, bp.seg_len, seg);
         GSB_LAUNCH_CHECK();
@@ -730,13 +818,14 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
     return GSB_OK;
 }
 
-extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t tile_height,
-                                      uint64_t n_isects, const void *plan_workspace, size_t plan_workspace_bytes,
-                                      int64_t *isect_ids /*nullable*/, int32_t *flatten_ids, gsb_stream_t stream) {
+extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depths, uint32_t tile_width,
+                                      uint32_t tile_height, uint64_t n_isects, const void *plan_workspace,
+                                      size_t plan_workspace_bytes, int64_t *isect_ids /*nullable*/, int32_t *flatten_ids,
+                                      gsb_stream_t stream) {
     using namespace gsb;
     const uint64_t n = (uint64_t)C * N;
     if (n == 0 || n_isects == 0) return GSB_OK;
-    if (!plan_workspace || !flatten_ids) return GSB_E_INVALID;
+    if (!plan_workspace || !flatten_ids || (isect_ids && !depths)) return GSB_E_INVALID;
     if (n_isects > 0x7fffffffull) return GSB_E_INVALID;
     const BinPlan bp = bin_plan(C, N, tile_width, tile_height);
     const SegPlan sp = seg_plan(n);
@@ -751,7 +840,7 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, uint32_t tile_widt
     a.N = N; a.n_tiles = tile_width * tile_height; a.tile_width = tile_width;
     a.tile_n_bits = bit_width_u32(tile_width * tile_height); a.multi_cam = C > 1 ? 1u : 0u;
     a.T_total = bp.T_total; a.P = bp.P; a.M = reinterpret_cast<uint32_t *>(base + w.M);
-    a.flatten_ids = flatten_ids; a.isect_ids = isect_ids;
+    a.flatten_ids = flatten_ids; a.isect_ids = nullptr; a.cap = (uint32_t)n_isects;
     ProfScope ps("isect_emit", s);
     if (bp.smem > 48 * 1024)
         GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.smem));
@@ -759,6 +848,12 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, uint32_t tile_widt
         a.t_lo = wnd * bp.t_win;
         a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
         tile_bin_kernel<true><<<bp.P, 32, bp.smem, s>>>(a);
+        GSB_LAUNCH_CHECK();
+    }
+    if (isect_ids) { // only the operator API wants the 64-bit keys back (intersect_offset consumes them)
+        const uint32_t grid = (uint32_t)((n_isects + kIsectThreads - 1) / kIsectThreads);
+        isect_keys_kernel<<<grid, kIsectThreads, 0, s>>>((uint32_t)n_isects, reinterpret_cast<const uint32_t *>(base + w.toff),
+                                                        bp.T_total, a.n_tiles, a.tile_n_bits, flatten_ids, depths, isect_ids);
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

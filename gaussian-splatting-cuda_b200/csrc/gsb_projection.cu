@@ -13,7 +13,7 @@
 // This file is compiled with -fmad=false: radii come out of ceilf() and feed the bit-exact tile
 // intersection, so the arithmetic deliberately follows the reference's operation order without
 // FMA contraction (the CPU oracle is built with -ffp-contract=off for the same reason).
-#include "gsb_camera.cuh"
+#include "gsb_projection.cuh"
 
 namespace gsb {
 
@@ -33,14 +33,6 @@ struct ProjParams {
     float *means2d, *depths, *conics, *compensations;
     uint32_t inputs_aligned16; // every input base pointer is 16-byte aligned: full slabs may use bulk copies
 };
-
-// GLM operator*(quat, vec3): v + 2 (w (u x v) + u x (u x v))   [glm/detail/type_quat.inl]
-__device__ __forceinline__ V3<float> quat_rotate(float qw, float qx, float qy, float qz, V3<float> v) {
-    const V3<float> u = {qx, qy, qz};
-    const V3<float> uv = cross(u, v);
-    const V3<float> uuv = cross(u, uv);
-    return v + ((uv * qw) + uuv) * 2.0f;
-}
 
 __global__ void __launch_bounds__(kProjThreads) projection_ut_kernel(const ProjParams p) {
     __shared__ __align__(128) float s_means[kProjThreads * 3];
@@ -95,120 +87,24 @@ __global__ void __launch_bounds__(kProjThreads) projection_ut_kernel(const ProjP
                         p.tangential ? p.tangential + (size_t)cid * p.n_tangential : nullptr, p.n_tangential,
                         p.thin_prism ? p.thin_prism + (size_t)cid * p.n_thin_prism : nullptr, p.n_thin_prism);
     __syncthreads();
-    const CamPose pose = cam_pose_from_viewmat(p.viewmats0 + cid * 16);
-    // centre-of-shutter pose = slerp(q, q, 0.5), 0.5 t + 0.5 t (global shutter: start == end)
-    float mw, mx, my, mz;
-    {
-        const float cosT = pose.qw * pose.qw + pose.qx * pose.qx + pose.qy * pose.qy + pose.qz * pose.qz;
-        if (cosT > 1.0f - 1.1920929e-07f) {
-            mw = pose.qw * 0.5f + pose.qw * 0.5f; mx = pose.qx * 0.5f + pose.qx * 0.5f;
-            my = pose.qy * 0.5f + pose.qy * 0.5f; mz = pose.qz * 0.5f + pose.qz * 0.5f;
-        } else {
-            const float ang = acosf(cosT);
-            const float s0 = sinf(0.5f * ang), sd = sinf(ang);
-            mw = (s0 * pose.qw + s0 * pose.qw) / sd; mx = (s0 * pose.qx + s0 * pose.qx) / sd;
-            my = (s0 * pose.qy + s0 * pose.qy) / sd; mz = (s0 * pose.qz + s0 * pose.qz) / sd;
-        }
-    }
-    const V3<float> t_mid = {0.5f * pose.tx + 0.5f * pose.tx, 0.5f * pose.ty + 0.5f * pose.ty,
-                             0.5f * pose.tz + 0.5f * pose.tz};
-    const V3<float> t0 = {pose.tx, pose.ty, pose.tz};
+    const ProjPose pp = proj_pose_from_viewmat(p.viewmats0 + cid * 16);
+    ProjConsts pk;
+    pk.W = p.W; pk.H = p.H; pk.eps2d = p.eps2d; pk.near_plane = p.near_plane; pk.far_plane = p.far_plane;
+    pk.radius_clip = p.radius_clip; pk.ut = p.ut;
 
     // ---- per-Gaussian work -----------------------------------------------------------------
     int32_t rx_i = 0, ry_i = 0;
     float o_mx = 0.f, o_my = 0.f, o_depth = 0.f, o_c0 = 0.f, o_c1 = 0.f, o_c2 = 0.f, o_comp = 0.f;
     bool keep = false;
     if (tid < cnt) {
-        do {
-            const V3<float> mean = {s_means[tid * 3], s_means[tid * 3 + 1], s_means[tid * 3 + 2]};
-            const float sc[3] = {s_scales[tid * 3], s_scales[tid * 3 + 1], s_scales[tid * 3 + 2]};
-            float qw = s_quats[tid * 4], qx = s_quats[tid * 4 + 1], qy = s_quats[tid * 4 + 2], qz = s_quats[tid * 4 + 3];
-            { // glm::normalize(quat)
-                const float len = sqrtf(qw * qw + qx * qx + qy * qy + qz * qz);
-                if (len <= 0.f) { qw = 1.f; qx = qy = qz = 0.f; }
-                else { const float ool = 1.0f / len; qw *= ool; qx *= ool; qy *= ool; qz *= ool; }
-            }
-            const V3<float> mean_c = quat_rotate(mw, mx, my, mz, mean) + t_mid;
-            if (mean_c.z < p.near_plane || mean_c.z > p.far_plane) break;
-
-            // sigma points (Cameras.cuh:1034-1083)
-            const float alpha = p.ut.alpha, beta = p.ut.beta, kappa = p.ut.kappa;
-            const float D = 3.0f;
-            const float lambda = alpha * alpha * (D + kappa) - D;
-            const M3<float> R = rotmat_raw(qw, qx, qy, qz);
-            const float sq = sqrtf(D + lambda);
-            const float w0m = lambda / (D + lambda);
-            const float w0c = lambda / (D + lambda) + (1.0f - alpha * alpha + beta);
-            const float wi = 1.0f / (2.0f * (D + lambda));
-
-            float ipx[7], ipy[7];
-            float mx2 = 0.f, my2 = 0.f;
-            bool valid = p.ut.require_all_sigma_points_valid != 0;
-            bool early = false;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                V3<float> pt = mean;
-                if (i > 0) {
-                    const int a = (i - 1) % 3;
-                    const V3<float> delta = col(R, a) * (sq * sc[a]);
-                    pt = (i <= 3) ? (mean + delta) : (mean - delta);
-                }
-                const V3<float> cam = quat_rotate(pose.qw, pose.qx, pose.qy, pose.qz, pt) + t0;
-                float px, py;
-                const bool pv = cam_project(s_cm, cam, p.ut.in_image_margin_factor, px, py);
-                if (p.ut.require_all_sigma_points_valid) {
-                    valid = valid && pv;
-                    if (!pv) { early = true; break; }
-                } else {
-                    valid = valid || pv;
-                }
-                ipx[i] = px; ipy[i] = py;
-                const float w = (i == 0) ? w0m : wi;
-                mx2 += w * px;
-                my2 += w * py;
-            }
-            if (early || !valid) break;
-            float cxx = 0.f, cxy = 0.f, cyy = 0.f;
-#pragma unroll
-            for (int i = 0; i < 7; ++i) {
-                const float w = (i == 0) ? w0c : wi;
-                const float dx = ipx[i] - mx2, dy = ipy[i] - my2;
-                cxx += w * (dx * dx);
-                cxy += w * (dx * dy);
-                cyy += w * (dy * dy);
-            }
-            // add_blur (Utils.cuh:171-179)
-            const float det_orig = cxx * cyy - cxy * cxy;
-            cxx += p.eps2d;
-            cyy += p.eps2d;
-            const float det = cxx * cyy - cxy * cxy;
-            const float compensation = sqrtf(fmaxf(0.f, det_orig / det));
-            if (det <= 0.f) break;
-            const float ood = 1.0f / (cxx * cyy - cxy * cxy); // glm::inverse(mat2)
-
-            float extend = 3.33f;
-            if (p.opacities) {
-                float opacity = s_opac[tid];
-                opacity *= compensation; // multiplied even when compensations are not returned (:156-157)
-                if (opacity < kAlphaThreshold) break;
-                extend = fminf(extend, sqrtf(2.0f * logf(opacity / kAlphaThreshold)));
-            }
-            const float b = 0.5f * (cxx + cyy);
-            const float tmp = sqrtf(fmaxf(0.01f, b * b - det));
-            const float v1 = b + tmp;
-            const float r1 = extend * sqrtf(v1);
-            const float radius_x = ceilf(fminf(extend * sqrtf(cxx), r1));
-            const float radius_y = ceilf(fminf(extend * sqrtf(cyy), r1));
-            if (radius_x <= p.radius_clip && radius_y <= p.radius_clip) break;
-            if (mx2 + radius_x <= 0 || mx2 - radius_x >= (float)p.W || my2 + radius_y <= 0 ||
-                my2 - radius_y >= (float)p.H)
-                break;
-            keep = true;
-            rx_i = (int32_t)radius_x; ry_i = (int32_t)radius_y;
-            o_mx = mx2; o_my = my2; o_depth = mean_c.z;
-            o_c0 = cyy * ood; o_c1 = -cxy * ood; o_c2 = cxx * ood;
-            o_comp = compensation;
-        } while (false);
+        const V3<float> mean = {s_means[tid * 3], s_means[tid * 3 + 1], s_means[tid * 3 + 2]};
+        const float sc[3] = {s_scales[tid * 3], s_scales[tid * 3 + 1], s_scales[tid * 3 + 2]};
+        const ProjResult r = project_gaussian(pk, s_cm, pp, mean, sc, s_quats[tid * 4], s_quats[tid * 4 + 1],
+                                              s_quats[tid * 4 + 2], s_quats[tid * 4 + 3], p.opacities != nullptr,
+                                              p.opacities ? s_opac[tid] : 0.f);
+        keep = r.keep;
+        rx_i = r.rx; ry_i = r.ry;
+        o_mx = r.mx; o_my = r.my; o_depth = r.depth; o_c0 = r.c0; o_c1 = r.c1; o_c2 = r.c2; o_comp = r.comp;
     }
 
     // ---- outputs ---------------------------------------------------------------------------

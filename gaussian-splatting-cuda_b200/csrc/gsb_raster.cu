@@ -56,28 +56,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_records_kernel(uint32_t N, 
                            quats[(size_t)g * 4 + 3]};
     const float scale[3] = {scales[(size_t)g * 3], scales[(size_t)g * 3 + 1], scales[(size_t)g * 3 + 2]};
     const float opac = opacities[g];
-    GaussGeom<double> gg;
-    gauss_geom<double>(cam, mean, quat, scale, gg);
     float4 v0, v1, v2, v3;
-    v3 = make_float4(colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2], __int_as_float((int)g));
-    const bool dead = gg.degenerate || !(opac > 0.f);
-    if (dead) {
-        // never passes the rejection test: Ns (== 0) >= +inf * Ds is false
-        v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-        v1 = make_float4(0.f, 0.f, 0.f, 0.f);
-        v2 = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
-    } else {
-        const double ax = 1.0 / cam.fx, ay = 1.0 / cam.fy;
-        const double id0 = 1.0 / gg.d0;
-        const double kk = -0.5 * 1.4426950408889634 * id0;
-        const float lop = (float)log2((double)opac);
-        v0 = make_float4((float)(cam.fx * gg.uc + cam.cx), (float)(cam.fy * gg.vc + cam.cy),
-                         (float)(kk * gg.n[0] * ax * ax), (float)(kk * gg.n[1] * ax * ay));
-        v1 = make_float4((float)(kk * gg.n[2] * ay * ay), (float)(gg.d[0] * id0 * ax), (float)(gg.d[1] * id0 * ay),
-                         (float)(gg.d[2] * id0 * ax * ax));
-        v2 = make_float4((float)(gg.d[3] * id0 * ax * ay), (float)(gg.d[4] * id0 * ay * ay), lop,
-                         kLog2AlphaThr - kTauMargin - lop);
-    }
+    const float col[3] = {colors[(size_t)g * 3], colors[(size_t)g * 3 + 1], colors[(size_t)g * 3 + 2]};
+    make_record(cam, mean, quat, scale, opac, col, (int32_t)g, v0, v1, v2, v3);
     float4 *dst = reinterpret_cast<float4 *>(recs + g);
     dst[0] = v0; dst[1] = v1; dst[2] = v2; dst[3] = v3;
 }
@@ -86,7 +67,9 @@ __global__ void __launch_bounds__(kPrepThreads) prep_records_kernel(uint32_t N, 
 // tile geometry shared by fwd and bwd
 // ------------------------------------------------------------------------------------------
 struct TileParams {
-    uint32_t n_isects;
+    uint32_t n_isects;  // end of the last tile's range when the offsets have no closing entry
+    uint32_t cap;       // capacity of flatten_ids: every range is clipped to it (== n_isects on the operator path)
+    uint32_t closed;    // tile_offsets has tile_w*tile_h + 1 entries, the last one = n_isects (fused path)
     uint32_t W, H, tile_w, tile_h;
     const GaussRec *recs;
     const float *backgrounds; // [3] or null
@@ -201,8 +184,10 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
         return;
     }
 
-    const int32_t range_start = p.tile_offsets[tile_id];
-    const int32_t range_end = (tile_id == p.tile_w * p.tile_h - 1) ? (int32_t)p.n_isects : p.tile_offsets[tile_id + 1];
+    const int32_t range_start = min(p.tile_offsets[tile_id], (int32_t)p.cap);
+    const int32_t range_end = min((!p.closed && tile_id == p.tile_w * p.tile_h - 1) ? (int32_t)p.n_isects
+                                                                                     : p.tile_offsets[tile_id + 1],
+                                  (int32_t)p.cap);
     const int32_t total = max(range_end - range_start, 0);
     const int32_t n_batches = (total + kBatch - 1) / kBatch;
 
@@ -318,15 +303,6 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
 // ------------------------------------------------------------------------------------------
 // backward
 // ------------------------------------------------------------------------------------------
-
-// Moment row of a Gaussian (16 floats, kMomFloats), x / y in pixels relative to (pcx, pcy):
-//   w1 = dL/dNs, w2 = dL/dDs, g = dL/d(power) summed, c = dL/d(colour).
-// Slot s and slot s ^ 8 are partners in the first stage of the warp reduction: they differ only in the
-// weight (w1 <-> w2) or in a per-pixel constant, which is what makes that stage select-free.
-enum MomentSlot : int {
-    kS_G = 0, kS_W1X = 1, kS_W1Y = 2, kS_W1XX = 3, kS_W1XY = 4, kS_W1YY = 5, kS_CR = 6, kS_CB = 7,
-    kS_W2 = 8, kS_W2X = 9, kS_W2Y = 10, kS_W2XX = 11, kS_W2XY = 12, kS_W2YY = 13, kS_CG = 14, kS_PAD = 15
-};
 
 // Sum 16 per-lane values across the warp: after the call lane L holds in v[0] the warp-wide total of
 // slot (L >> 1).  16 shuffles (8+4+2+1+1) instead of 16 x 5.  On entry lanes 16..31 hold slot (i ^ 8) in
@@ -444,8 +420,10 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
     const uint32_t tid = threadIdx.x;
     const bool hi16 = (tid & 16) != 0;
 
-    const int32_t range_start = p.tile_offsets[tile_id];
-    const int32_t range_end = (tile_id == p.tile_w * p.tile_h - 1) ? (int32_t)p.n_isects : p.tile_offsets[tile_id + 1];
+    const int32_t range_start = min(p.tile_offsets[tile_id], (int32_t)p.cap);
+    const int32_t range_end = min((!p.closed && tile_id == p.tile_w * p.tile_h - 1) ? (int32_t)p.n_isects
+                                                                                     : p.tile_offsets[tile_id + 1],
+                                  (int32_t)p.cap);
 
     float bg[3] = {0.f, 0.f, 0.f};
     if (p.backgrounds) { bg[0] = p.backgrounds[0]; bg[1] = p.backgrounds[1]; bg[2] = p.backgrounds[2]; }
@@ -564,9 +542,6 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
 // ------------------------------------------------------------------------------------------
 // finalize: moments -> gradients (chain rule once per Gaussian, float32: see FT below)
 // ------------------------------------------------------------------------------------------
-// chain-rule arithmetic type of finalize (float: validated against the f64 oracle, profiles/r1_parity.md)
-typedef float FT;
-
 __global__ void __launch_bounds__(kPrepThreads) finalize_grads_kernel(
     uint32_t N, const float *__restrict__ means, const float *__restrict__ quats, const float *__restrict__ scales,
     const float *__restrict__ opacities, const float *__restrict__ viewmat, const float *__restrict__ K,
@@ -589,85 +564,14 @@ __global__ void __launch_bounds__(kPrepThreads) finalize_grads_kernel(
         }
     }
     v_colors[(size_t)g * 3] = m[kS_CR]; v_colors[(size_t)g * 3 + 1] = m[kS_CG]; v_colors[(size_t)g * 3 + 2] = m[kS_CB];
-    const float opac = opacities[g];
-    bool any = false;
-#pragma unroll
-    for (int i = 0; i < 16; ++i)
-        if (i != kS_CR && i != kS_CG && i != kS_CB && i != kS_PAD) any = any || (m[i] != 0.f);
-    float om[3] = {0.f, 0.f, 0.f}, oq[4] = {0.f, 0.f, 0.f, 0.f}, os[3] = {0.f, 0.f, 0.f}, oo = 0.f;
-    if (any) {
+    float om[3], oq[4], os[3], oo;
+    {
         const float mean[3] = {means[(size_t)g * 3], means[(size_t)g * 3 + 1], means[(size_t)g * 3 + 2]};
         const float quat[4] = {quats[(size_t)g * 4], quats[(size_t)g * 4 + 1], quats[(size_t)g * 4 + 2],
                                quats[(size_t)g * 4 + 3]};
         const float scale[3] = {scales[(size_t)g * 3], scales[(size_t)g * 3 + 1], scales[(size_t)g * 3 + 2]};
-        GaussGeom<FT> gg;
-        gauss_geom<FT>(cam, mean, quat, scale, gg);
-        if (!gg.degenerate) {
-            const float4 *r4 = reinterpret_cast<const float4 *>(recs + g);
-            const float4 q0 = r4[0], q1 = r4[1], q2 = r4[2];
-            const FT cn0 = q0.z, cn1 = q0.w, cn2 = q1.x;
-            const FT cd1 = q1.y, cd2 = q1.z, cd3 = q1.w, cd4 = q2.x, cd5 = q2.y;
-            const FT M0 = m[kS_W1X], M1 = m[kS_W1Y], M2 = m[kS_W1XX], M3_ = m[kS_W1XY], M4 = m[kS_W1YY], M5 = m[kS_W2],
-                     M6 = m[kS_W2X], M7 = m[kS_W2Y], M8 = m[kS_W2XX], M9 = m[kS_W2XY], M10 = m[kS_W2YY];
-            const FT ax = FT(1) / (FT)cam.fx, ay = FT(1) / (FT)cam.fy;
-            const FT id0 = FT(1) / gg.d0;
-            const FT kk = FT(-0.5 * 1.4426950408889634);
-            // gradients w.r.t. the projected centre (pixels -> normalised image coordinates)
-            const FT vpcx = -(FT(2) * cn0 * M0 + cn1 * M1 + cd1 * M5 + FT(2) * cd3 * M6 + cd4 * M7);
-            const FT vpcy = -(cn1 * M0 + FT(2) * cn2 * M1 + cd2 * M5 + cd4 * M6 + FT(2) * cd5 * M7);
-            FT vuc = (FT)cam.fx * vpcx, vvc = (FT)cam.fy * vpcy;
-            // gradients w.r.t. the un-normalised quadratic-form coefficients
-            const FT vn0 = M2 * kk * ax * ax * id0, vn1 = M3_ * kk * ax * ay * id0, vn2 = M4 * kk * ay * ay * id0;
-            const FT vd1 = M6 * ax * id0, vd2 = M7 * ay * id0, vd3 = M8 * ax * ax * id0, vd4 = M9 * ax * ay * id0,
-                         vd5 = M10 * ay * ay * id0;
-            const FT vd0 = -(cn0 * M2 + cn1 * M3_ + cn2 * M4 + cd1 * M6 + cd2 * M7 + cd3 * M8 + cd4 * M9 + cd5 * M10) * id0;
-            // n = (E0.E0, 2 E0.E1, E1.E1), d = (G.G, 2 G.A0, 2 G.A1, A0.A0, 2 A0.A1, A1.A1)
-            const V3<FT> vE0 = gg.E0 * (FT(2) * vn0) + gg.E1 * (FT(2) * vn1);
-            const V3<FT> vE1 = gg.E1 * (FT(2) * vn2) + gg.E0 * (FT(2) * vn1);
-            V3<FT> vG = gg.G * (FT(2) * vd0) + gg.A0 * (FT(2) * vd1) + gg.A1 * (FT(2) * vd2);
-            V3<FT> vA0 = gg.G * (FT(2) * vd1) + gg.A0 * (FT(2) * vd3) + gg.A1 * (FT(2) * vd4) + cross(gg.gro, vE0);
-            V3<FT> vA1 = gg.G * (FT(2) * vd2) + gg.A1 * (FT(2) * vd5) + gg.A0 * (FT(2) * vd4) + cross(gg.gro, vE1);
-            const V3<FT> vgro = cross(vE0, gg.A0) + cross(vE1, gg.A1);
-            vG = vG - vgro * gg.zc;
-            FT vzc = -dot(gg.G, vgro);
-            vA0 = vA0 + vG * gg.uc;
-            vA1 = vA1 + vG * gg.vc;
-            const V3<FT> vA2 = vG;
-            vuc += dot(gg.A0, vG);
-            vvc += dot(gg.A1, vG);
-            const FT iz = FT(1) / gg.zc;
-            const FT vxc = vuc * iz, vyc = vvc * iz;
-            vzc += -(gg.uc * vuc + gg.vc * vvc) * iz;
-            // mu_c = Binv mu + t
-            om[0] = (float)((FT)cam.Binv[0][0] * vxc + (FT)cam.Binv[1][0] * vyc + (FT)cam.Binv[2][0] * vzc);
-            om[1] = (float)((FT)cam.Binv[0][1] * vxc + (FT)cam.Binv[1][1] * vyc + (FT)cam.Binv[2][1] * vzc);
-            om[2] = (float)((FT)cam.Binv[0][2] * vxc + (FT)cam.Binv[1][2] * vyc + (FT)cam.Binv[2][2] * vzc);
-            // A = M B  ->  vM = vA B^T ;  M[i][k] = Rg[k][i] / s_i
-            const FT vA[3][3] = {{vA0.x, vA1.x, vA2.x}, {vA0.y, vA1.y, vA2.y}, {vA0.z, vA1.z, vA2.z}};
-            FT vRg[3][3];
-            for (int i = 0; i < 3; ++i) {
-                FT vsi = FT(0);
-                for (int k = 0; k < 3; ++k) {
-                    const FT vM = vA[i][0] * (FT)cam.B[k][0] + vA[i][1] * (FT)cam.B[k][1] + vA[i][2] * (FT)cam.B[k][2];
-                    vsi += vM * gg.Rg.m[k][i];
-                    vRg[k][i] = vM * gg.inv_s[i];
-                }
-                os[i] = (float)(-vsi * gg.inv_s[i] * gg.inv_s[i]);
-            }
-            // quaternion VJP including the normalisation (Utils.cuh:104-126)
-            const FT w = gg.qn[0], x = gg.qn[1], y = gg.qn[2], z = gg.qn[3];
-            FT vq[4];
-            vq[0] = FT(2) * (x * (vRg[2][1] - vRg[1][2]) + y * (vRg[0][2] - vRg[2][0]) + z * (vRg[1][0] - vRg[0][1]));
-            vq[1] = FT(2) * (-FT(2) * x * (vRg[1][1] + vRg[2][2]) + y * (vRg[1][0] + vRg[0][1]) + z * (vRg[2][0] + vRg[0][2]) +
-                           w * (vRg[2][1] - vRg[1][2]));
-            vq[2] = FT(2) * (x * (vRg[1][0] + vRg[0][1]) - FT(2) * y * (vRg[0][0] + vRg[2][2]) + z * (vRg[2][1] + vRg[1][2]) +
-                           w * (vRg[0][2] - vRg[2][0]));
-            vq[3] = FT(2) * (x * (vRg[2][0] + vRg[0][2]) + y * (vRg[2][1] + vRg[1][2]) - FT(2) * z * (vRg[0][0] + vRg[1][1]) +
-                           w * (vRg[1][0] - vRg[0][1]));
-            const FT dq = vq[0] * w + vq[1] * x + vq[2] * y + vq[3] * z;
-            for (int k = 0; k < 4; ++k) oq[k] = (float)((vq[k] - dq * gg.qn[k]) * gg.inv_qnorm);
-            oo = (opac > 0.f) ? m[kS_G] / opac : 0.f; // sum vis * v_alpha
-        }
+        const float4 *r4 = reinterpret_cast<const float4 *>(recs + g);
+        finalize_gaussian(cam, mean, quat, scale, opacities[g], r4[0], r4[1], r4[2], m, om, oq, os, oo);
     }
     v_means[(size_t)g * 3] = om[0]; v_means[(size_t)g * 3 + 1] = om[1]; v_means[(size_t)g * 3 + 2] = om[2];
     v_scales[(size_t)g * 3] = os[0]; v_scales[(size_t)g * 3 + 1] = os[1]; v_scales[(size_t)g * 3 + 2] = os[2];
@@ -705,6 +609,45 @@ extern "C" size_t gsb_raster_bwd_workspace(uint32_t N) {
     return gsb::align256((size_t)N * sizeof(gsb::GaussRec)) + gsb::align256((size_t)N * gsb::kMomFloats * 4) + 256;
 }
 
+namespace gsb {
+static void fill_tiles(TileParams &p, uint64_t n_isects, uint32_t cap, int closed, uint32_t image_width,
+                       uint32_t image_height, const GaussRec *recs, const float *backgrounds, const uint8_t *masks,
+                       const int32_t *tile_offsets, const int32_t *flatten_ids, const GsbCamera *cam) {
+    p.n_isects = (uint32_t)n_isects; p.cap = cap; p.closed = closed ? 1u : 0u;
+    p.W = image_width; p.H = image_height;
+    p.tile_w = (image_width + 15) / 16; p.tile_h = (image_height + 15) / 16;
+    p.recs = recs; p.backgrounds = backgrounds; p.masks = masks;
+    p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
+    fill_camera(p, cam);
+}
+static int launch_fwd(const TileParams &p, const GsbCamera *cam, float *renders, float *alphas, int32_t *last_ids,
+                      cudaStream_t s) {
+    {
+        ProfScope ps("raster_fwd", s);
+        if (general_camera(cam))
+            raster_fwd_kernel<true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
+        else
+            raster_fwd_kernel<false><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
+    }
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+static int launch_bwd(const TileParams &p, const GsbCamera *cam, const float *render_alphas, const int32_t *last_ids,
+                      const float *v_render_colors, const float *v_render_alphas, float *moments, cudaStream_t s) {
+    {
+        ProfScope ps("raster_bwd", s);
+        if (general_camera(cam))
+            raster_bwd_kernel<true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids,
+                                                                                v_render_colors, v_render_alphas, moments);
+        else
+            raster_bwd_kernel<false><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids,
+                                                                                 v_render_colors, v_render_alphas, moments);
+    }
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+} // namespace gsb
+
 extern "C" int gsb_raster_fwd(uint32_t C, uint32_t N, uint64_t n_isects, const float *means, const float *quats,
                               const float *scales, const float *colors, const float *opacities,
                               const float *backgrounds, const uint8_t *masks, uint32_t image_width,
@@ -732,21 +675,9 @@ extern "C" int gsb_raster_fwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
         GSB_LAUNCH_CHECK();
     }
     TileParams p;
-    p.n_isects = (uint32_t)n_isects;
-    p.W = image_width; p.H = image_height;
-    p.tile_w = (image_width + 15) / 16; p.tile_h = (image_height + 15) / 16;
-    p.recs = recs; p.backgrounds = backgrounds; p.masks = masks;
-    p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
-    {
-        ProfScope ps("raster_fwd", s);
-        fill_camera(p, cam);
-        if (general_camera(cam))
-            raster_fwd_kernel<true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
-        else
-            raster_fwd_kernel<false><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, renders, alphas, last_ids);
-    }
-    GSB_LAUNCH_CHECK();
-    return GSB_OK;
+    fill_tiles(p, n_isects, (uint32_t)n_isects, 0, image_width, image_height, recs, backgrounds, masks, tile_offsets,
+               flatten_ids, cam);
+    return launch_fwd(p, cam, renders, alphas, last_ids, s);
 }
 
 extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const float *means, const float *quats,
@@ -787,22 +718,9 @@ extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     }
     GSB_LAUNCH_CHECK();
     TileParams p;
-    p.n_isects = (uint32_t)n_isects;
-    p.W = image_width; p.H = image_height;
-    p.tile_w = (image_width + 15) / 16; p.tile_h = (image_height + 15) / 16;
-    p.recs = recs; p.backgrounds = backgrounds; p.masks = masks;
-    p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
-    {
-        ProfScope ps("raster_bwd", s);
-        fill_camera(p, cam);
-        if (general_camera(cam))
-            raster_bwd_kernel<true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids,
-                                                                                v_render_colors, v_render_alphas, moments);
-        else
-            raster_bwd_kernel<false><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids,
-                                                                                 v_render_colors, v_render_alphas, moments);
-    }
-    GSB_LAUNCH_CHECK();
+    fill_tiles(p, n_isects, (uint32_t)n_isects, 0, image_width, image_height, recs, backgrounds, masks, tile_offsets,
+               flatten_ids, cam);
+    if (int rc = launch_bwd(p, cam, render_alphas, last_ids, v_render_colors, v_render_alphas, moments, s)) return rc;
     {
         ProfScope ps("raster_finalize", s);
         finalize_grads_kernel<<<(N + kPrepThreads - 1) / kPrepThreads, kPrepThreads, 0, s>>>(
@@ -811,4 +729,47 @@ extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     }
     GSB_LAUNCH_CHECK();
     return GSB_OK;
+}
+
+// ---- fused path: blend forward / backward on records made by gsb_fused_front ---------------------------
+// `workspace` is the fused workspace ([records][moments], gsb_fused_workspace); tile_offsets has th*tw + 1 entries
+// (gsb_isect_plan with tile_offsets_total), so no host-side intersection count is needed: `capacity` is only the size
+// of flatten_ids.
+extern "C" int gsb_raster_fwd_recs(uint32_t N, uint32_t capacity, const void *workspace, size_t workspace_bytes,
+                                   const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                                   uint32_t image_height, const GsbCamera *cam, const int32_t *tile_offsets,
+                                   const int32_t *flatten_ids, float *renders, float *alphas, int32_t *last_ids,
+                                   gsb_stream_t stream) {
+    using namespace gsb;
+    if (int rc = check_camera(cam)) return rc;
+    if (image_width == 0 || image_height == 0) return GSB_OK;
+    if (!renders || !alphas || !last_ids || !tile_offsets) return GSB_E_INVALID;
+    if (capacity > 0 && !flatten_ids) return GSB_E_INVALID;
+    if (capacity > 0x7fffffffu) return GSB_E_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < gsb_raster_bwd_workspace(N))
+        return GSB_E_WORKSPACE;
+    TileParams p;
+    fill_tiles(p, 0, capacity, 1, image_width, image_height, reinterpret_cast<const GaussRec *>(workspace), backgrounds,
+               masks, tile_offsets, flatten_ids, cam);
+    return launch_fwd(p, cam, renders, alphas, last_ids, as_stream(stream));
+}
+
+extern "C" int gsb_raster_bwd_recs(uint32_t N, uint32_t capacity, void *workspace, size_t workspace_bytes,
+                                   const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                                   uint32_t image_height, const GsbCamera *cam, const int32_t *tile_offsets,
+                                   const int32_t *flatten_ids, const float *render_alphas, const int32_t *last_ids,
+                                   const float *v_render_colors, const float *v_render_alphas, gsb_stream_t stream) {
+    using namespace gsb;
+    if (int rc = check_camera(cam)) return rc;
+    if (N == 0 || image_width == 0 || image_height == 0) return GSB_OK;
+    if (!tile_offsets || !render_alphas || !last_ids || !v_render_colors || !v_render_alphas) return GSB_E_INVALID;
+    if (capacity > 0 && !flatten_ids) return GSB_E_INVALID;
+    if (capacity > 0x7fffffffu) return GSB_E_INVALID;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < gsb_raster_bwd_workspace(N))
+        return GSB_E_WORKSPACE;
+    float *moments = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align256((size_t)N * sizeof(GaussRec)));
+    TileParams p;
+    fill_tiles(p, 0, capacity, 1, image_width, image_height, reinterpret_cast<const GaussRec *>(workspace), backgrounds,
+               masks, tile_offsets, flatten_ids, cam);
+    return launch_bwd(p, cam, render_alphas, last_ids, v_render_colors, v_render_alphas, moments, as_stream(stream));
 }

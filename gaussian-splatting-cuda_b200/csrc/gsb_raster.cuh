@@ -124,6 +124,129 @@ __device__ inline void gauss_geom(const CamConst &c, const float *mean, const fl
     if (!(g.d0 > T(0)) || !isfinite((double)g.d0)) g.degenerate = true;
 }
 
+
+// The 64-byte record of one Gaussian (activated parameters in, float64 set-up): see GaussRec.
+__device__ __forceinline__ void make_record(const CamConst &cam, const float (&mean)[3], const float (&quat)[4],
+                                            const float (&scale)[3], float opac, const float (&col)[3], int32_t gid,
+                                            float4 &v0, float4 &v1, float4 &v2, float4 &v3) {
+    GaussGeom<double> gg;
+    gauss_geom<double>(cam, mean, quat, scale, gg);
+    v3 = make_float4(col[0], col[1], col[2], __int_as_float(gid));
+    const bool dead = gg.degenerate || !(opac > 0.f);
+    if (dead) {
+        // never passes the rejection test: Ns (== 0) >= +inf * Ds is false
+        v0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        v1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        v2 = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7f800000));
+    } else {
+        const double ax = 1.0 / cam.fx, ay = 1.0 / cam.fy;
+        const double id0 = 1.0 / gg.d0;
+        const double kk = -0.5 * 1.4426950408889634 * id0;
+        const float lop = (float)log2((double)opac);
+        v0 = make_float4((float)(cam.fx * gg.uc + cam.cx), (float)(cam.fy * gg.vc + cam.cy),
+                         (float)(kk * gg.n[0] * ax * ax), (float)(kk * gg.n[1] * ax * ay));
+        v1 = make_float4((float)(kk * gg.n[2] * ay * ay), (float)(gg.d[0] * id0 * ax), (float)(gg.d[1] * id0 * ay),
+                         (float)(gg.d[2] * id0 * ax * ax));
+        v2 = make_float4((float)(gg.d[3] * id0 * ax * ay), (float)(gg.d[4] * id0 * ay * ay), lop,
+                         kLog2AlphaThr - kTauMargin - lop);
+    }
+}
+
+// Moment row of a Gaussian (16 floats, kMomFloats), x / y in pixels relative to (pcx, pcy):
+//   w1 = dL/dNs, w2 = dL/dDs, g = dL/d(power) summed, c = dL/d(colour).
+// Slot s and slot s ^ 8 are partners in the first stage of the warp reduction: they differ only in the
+// weight (w1 <-> w2) or in a per-pixel constant, which is what makes that stage select-free.
+enum MomentSlot : int {
+    kS_G = 0, kS_W1X = 1, kS_W1Y = 2, kS_W1XX = 3, kS_W1XY = 4, kS_W1YY = 5, kS_CR = 6, kS_CB = 7,
+    kS_W2 = 8, kS_W2X = 9, kS_W2Y = 10, kS_W2XX = 11, kS_W2XY = 12, kS_W2YY = 13, kS_CG = 14, kS_PAD = 15
+};
+
+// chain-rule arithmetic type of the finalize step (float: validated against the f64 oracle, profiles/r1_parity.md)
+typedef float FT;
+
+// Chain rule from the 15 moments of one Gaussian to the gradients of its ACTIVATED parameters
+// (RasterizeToPixelsFromWorld3DGSBwd.cu:318-370 summed over the pixels): om = v_mean, oq = v_quat w.r.t. the
+// quaternion as passed (normalisation included, Utils.cuh:104-126), os = v_scale, oo = v_opacity.
+// q0..q2 = the Gaussian's record (normalised coefficients).  The colour gradient is m[kS_CR/CG/CB] itself.
+__device__ __forceinline__ void finalize_gaussian(const CamConst &cam, const float (&mean)[3], const float (&quat)[4],
+                                                  const float (&scale)[3], float opac, const float4 q0,
+                                                  const float4 q1, const float4 q2, const float (&m)[16],
+                                                  float (&om)[3], float (&oq)[4], float (&os)[3], float &oo) {
+    bool any = false;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+        if (i != kS_CR && i != kS_CG && i != kS_CB && i != kS_PAD) any = any || (m[i] != 0.f);
+    om[0] = om[1] = om[2] = 0.f; oq[0] = oq[1] = oq[2] = oq[3] = 0.f; os[0] = os[1] = os[2] = 0.f; oo = 0.f;
+    if (any) {
+        GaussGeom<FT> gg;
+        gauss_geom<FT>(cam, mean, quat, scale, gg);
+        if (!gg.degenerate) {
+            const FT cn0 = q0.z, cn1 = q0.w, cn2 = q1.x;
+            const FT cd1 = q1.y, cd2 = q1.z, cd3 = q1.w, cd4 = q2.x, cd5 = q2.y;
+            const FT M0 = m[kS_W1X], M1 = m[kS_W1Y], M2 = m[kS_W1XX], M3_ = m[kS_W1XY], M4 = m[kS_W1YY], M5 = m[kS_W2],
+                     M6 = m[kS_W2X], M7 = m[kS_W2Y], M8 = m[kS_W2XX], M9 = m[kS_W2XY], M10 = m[kS_W2YY];
+            const FT ax = FT(1) / (FT)cam.fx, ay = FT(1) / (FT)cam.fy;
+            const FT id0 = FT(1) / gg.d0;
+            const FT kk = FT(-0.5 * 1.4426950408889634);
+            // gradients w.r.t. the projected centre (pixels -> normalised image coordinates)
+            const FT vpcx = -(FT(2) * cn0 * M0 + cn1 * M1 + cd1 * M5 + FT(2) * cd3 * M6 + cd4 * M7);
+            const FT vpcy = -(cn1 * M0 + FT(2) * cn2 * M1 + cd2 * M5 + cd4 * M6 + FT(2) * cd5 * M7);
+            FT vuc = (FT)cam.fx * vpcx, vvc = (FT)cam.fy * vpcy;
+            // gradients w.r.t. the un-normalised quadratic-form coefficients
+            const FT vn0 = M2 * kk * ax * ax * id0, vn1 = M3_ * kk * ax * ay * id0, vn2 = M4 * kk * ay * ay * id0;
+            const FT vd1 = M6 * ax * id0, vd2 = M7 * ay * id0, vd3 = M8 * ax * ax * id0, vd4 = M9 * ax * ay * id0,
+                         vd5 = M10 * ay * ay * id0;
+            const FT vd0 = -(cn0 * M2 + cn1 * M3_ + cn2 * M4 + cd1 * M6 + cd2 * M7 + cd3 * M8 + cd4 * M9 + cd5 * M10) * id0;
+            // n = (E0.E0, 2 E0.E1, E1.E1), d = (G.G, 2 G.A0, 2 G.A1, A0.A0, 2 A0.A1, A1.A1)
+            const V3<FT> vE0 = gg.E0 * (FT(2) * vn0) + gg.E1 * (FT(2) * vn1);
+            const V3<FT> vE1 = gg.E1 * (FT(2) * vn2) + gg.E0 * (FT(2) * vn1);
+            V3<FT> vG = gg.G * (FT(2) * vd0) + gg.A0 * (FT(2) * vd1) + gg.A1 * (FT(2) * vd2);
+            V3<FT> vA0 = gg.G * (FT(2) * vd1) + gg.A0 * (FT(2) * vd3) + gg.A1 * (FT(2) * vd4) + cross(gg.gro, vE0);
+            V3<FT> vA1 = gg.G * (FT(2) * vd2) + gg.A1 * (FT(2) * vd5) + gg.A0 * (FT(2) * vd4) + cross(gg.gro, vE1);
+            const V3<FT> vgro = cross(vE0, gg.A0) + cross(vE1, gg.A1);
+            vG = vG - vgro * gg.zc;
+            FT vzc = -dot(gg.G, vgro);
+            vA0 = vA0 + vG * gg.uc;
+            vA1 = vA1 + vG * gg.vc;
+            const V3<FT> vA2 = vG;
+            vuc += dot(gg.A0, vG);
+            vvc += dot(gg.A1, vG);
+            const FT iz = FT(1) / gg.zc;
+            const FT vxc = vuc * iz, vyc = vvc * iz;
+            vzc += -(gg.uc * vuc + gg.vc * vvc) * iz;
+            // mu_c = Binv mu + t
+            om[0] = (float)((FT)cam.Binv[0][0] * vxc + (FT)cam.Binv[1][0] * vyc + (FT)cam.Binv[2][0] * vzc);
+            om[1] = (float)((FT)cam.Binv[0][1] * vxc + (FT)cam.Binv[1][1] * vyc + (FT)cam.Binv[2][1] * vzc);
+            om[2] = (float)((FT)cam.Binv[0][2] * vxc + (FT)cam.Binv[1][2] * vyc + (FT)cam.Binv[2][2] * vzc);
+            // A = M B  ->  vM = vA B^T ;  M[i][k] = Rg[k][i] / s_i
+            const FT vA[3][3] = {{vA0.x, vA1.x, vA2.x}, {vA0.y, vA1.y, vA2.y}, {vA0.z, vA1.z, vA2.z}};
+            FT vRg[3][3];
+            for (int i = 0; i < 3; ++i) {
+                FT vsi = FT(0);
+                for (int k = 0; k < 3; ++k) {
+                    const FT vM = vA[i][0] * (FT)cam.B[k][0] + vA[i][1] * (FT)cam.B[k][1] + vA[i][2] * (FT)cam.B[k][2];
+                    vsi += vM * gg.Rg.m[k][i];
+                    vRg[k][i] = vM * gg.inv_s[i];
+                }
+                os[i] = (float)(-vsi * gg.inv_s[i] * gg.inv_s[i]);
+            }
+            // quaternion VJP including the normalisation (Utils.cuh:104-126)
+            const FT w = gg.qn[0], x = gg.qn[1], y = gg.qn[2], z = gg.qn[3];
+            FT vq[4];
+            vq[0] = FT(2) * (x * (vRg[2][1] - vRg[1][2]) + y * (vRg[0][2] - vRg[2][0]) + z * (vRg[1][0] - vRg[0][1]));
+            vq[1] = FT(2) * (-FT(2) * x * (vRg[1][1] + vRg[2][2]) + y * (vRg[1][0] + vRg[0][1]) + z * (vRg[2][0] + vRg[0][2]) +
+                           w * (vRg[2][1] - vRg[1][2]));
+            vq[2] = FT(2) * (x * (vRg[1][0] + vRg[0][1]) - FT(2) * y * (vRg[0][0] + vRg[2][2]) + z * (vRg[2][1] + vRg[1][2]) +
+                           w * (vRg[0][2] - vRg[2][0]));
+            vq[3] = FT(2) * (x * (vRg[2][0] + vRg[0][2]) + y * (vRg[2][1] + vRg[1][2]) - FT(2) * z * (vRg[0][0] + vRg[1][1]) +
+                           w * (vRg[1][0] - vRg[0][1]));
+            const FT dq = vq[0] * w + vq[1] * x + vq[2] * y + vq[3] * z;
+            for (int k = 0; k < 4; ++k) oq[k] = (float)((vq[k] - dq * gg.qn[k]) * gg.inv_qnorm);
+            oo = (opac > 0.f) ? m[kS_G] / opac : 0.f; // sum vis * v_alpha
+        }
+    }
+}
+
 // Per-pair evaluation, shared VERBATIM by the forward and backward kernels (explicitly rounded
 // operations: the two kernels must agree bit-for-bit on which pairs pass the alpha test), for a
 // thread's two pixels at once on packed fp32 pairs (lo = pixel 0, hi = pixel 1):

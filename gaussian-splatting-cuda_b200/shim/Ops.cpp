@@ -155,14 +155,14 @@ GSB_EXPORT std::tuple<at::Tensor, at::Tensor, at::Tensor> intersect_tile(
         at::Tensor n_host = at::empty({1}, at::TensorOptions().dtype(at::kLong).pinned_memory(true));
         gsb_check(gsb_isect_plan(C, N, means2d.data_ptr<float>(), radii.data_ptr<int32_t>(), depths.data_ptr<float>(),
                                  tile_size, tile_width, tile_height, tiles_per_gauss.data_ptr<int32_t>(),
-                                 n_host.data_ptr<int64_t>(), nullptr, plan_ws.data_ptr(), plan_bytes, cur_stream()),
+                                 n_host.data_ptr<int64_t>(), nullptr, 0, plan_ws.data_ptr(), plan_bytes, cur_stream()),
                   "intersect_tile/plan");
         c10::cuda::getCurrentCUDAStream().synchronize();
         n_isects = n_host.data_ptr<int64_t>()[0];
         at::Tensor isect_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kLong));
         at::Tensor flatten_ids_sorted = at::empty({n_isects}, depths.options().dtype(at::kInt));
         if (n_isects) {
-            gsb_check(gsb_isect_emit_planned(C, N, tile_width, tile_height, (uint64_t)n_isects, plan_ws.data_ptr(),
+            gsb_check(gsb_isect_emit_planned(C, N, depths.data_ptr<float>(), tile_width, tile_height, (uint64_t)n_isects, plan_ws.data_ptr(),
                                              plan_bytes, isect_ids_sorted.data_ptr<int64_t>(),
                                              flatten_ids_sorted.data_ptr<int32_t>(), cur_stream()),
                       "intersect_tile/emit_planned");

@@ -7,6 +7,7 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 
+#include "FusedOps.h"
 #include "Ops.h"
 #include "gsb200.h"
 
@@ -117,6 +118,38 @@ Tensor sh_bwd_views(int64_t degree, const Tensor &means, const Tensor &campos, c
     return v_coeffs;
 }
 
+// Extended operators (include/gsplat/FusedOps.h).  Flattened like the rest: the result struct becomes a tuple.
+std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fused_fwd(
+    const Tensor &means, const Tensor &sh0, const Tensor &shN, const Tensor &scaling_raw, const Tensor &rotation_raw,
+    const Tensor &opacity_raw, int64_t sh_degree, double scaling_modifier, const Tensor &viewmat, const Tensor &K,
+    int64_t width, int64_t height, double eps2d, double near_plane, double far_plane, double radius_clip,
+    const OT &backgrounds, int64_t camera_model, const OT &radial, const OT &tangential, const OT &thin_prism,
+    int64_t isect_capacity, bool prepare_backward) {
+    auto r = gsplat::rasterize_from_world_fused_fwd(
+        means, sh0, shN, scaling_raw, rotation_raw, opacity_raw, (uint32_t)sh_degree, (float)scaling_modifier, viewmat, K,
+        (uint32_t)width, (uint32_t)height, (float)eps2d, (float)near_plane, (float)far_plane, (float)radius_clip,
+        backgrounds, static_cast<gsplat::CameraModelType>(camera_model), UnscentedTransformParameters{}, radial, tangential,
+        thin_prism, isect_capacity, prepare_backward);
+    return std::make_tuple(r.renders, r.alphas, r.radii, r.means2d, r.depths, r.last_ids, r.tile_offsets, r.flatten_ids,
+                           r.workspace, r.n_isects);
+}
+
+std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fused_bwd(
+    const Tensor &means, const Tensor &sh0, const Tensor &shN, const Tensor &scaling_raw, const Tensor &rotation_raw,
+    const Tensor &opacity_raw, int64_t sh_degree, double scaling_modifier, const Tensor &viewmat, const Tensor &K,
+    int64_t width, int64_t height, const OT &backgrounds, int64_t camera_model, const OT &radial, const OT &tangential,
+    const OT &thin_prism, const Tensor &radii, const Tensor &tile_offsets, const Tensor &flatten_ids, Tensor workspace,
+    const Tensor &render_alphas, const Tensor &last_ids, const Tensor &v_render_colors, const Tensor &v_render_alphas) {
+    auto r = gsplat::rasterize_from_world_fused_bwd(
+        means, sh0, shN, scaling_raw, rotation_raw, opacity_raw, (uint32_t)sh_degree, (float)scaling_modifier, viewmat, K,
+        (uint32_t)width, (uint32_t)height, backgrounds, static_cast<gsplat::CameraModelType>(camera_model),
+        UnscentedTransformParameters{}, radial, tangential, thin_prism, radii, tile_offsets, flatten_ids, workspace,
+        render_alphas, last_ids, v_render_colors, v_render_alphas);
+    Tensor v_shN = std::get<2>(r);
+    if (!v_shN.defined()) v_shN = at::empty({0}, means.options());
+    return std::make_tuple(std::get<0>(r), std::get<1>(r), v_shN, std::get<3>(r), std::get<4>(r), std::get<5>(r));
+}
+
 Tensor quats_to_rotmats(const Tensor &quats) { return gsplat::quats_to_rotmats(quats); }
 
 std::tuple<Tensor, Tensor> relocation(const Tensor &opacities, const Tensor &scales, const Tensor &ratios,
@@ -142,6 +175,13 @@ TORCH_LIBRARY(gsplat_b200, m) {
     m.def("spherical_harmonics_bwd_views(int degree, Tensor means, Tensor campos, Tensor coeffs, Tensor v_colors, "
           "Tensor(a!) v_means) -> Tensor",
           &sh_bwd_views);
+    m.def("rasterize_from_world_fused_fwd", &fused_fwd);
+    m.def("rasterize_from_world_fused_bwd(Tensor means, Tensor sh0, Tensor shN, Tensor scaling_raw, Tensor rotation_raw, "
+          "Tensor opacity_raw, int sh_degree, float scaling_modifier, Tensor viewmat, Tensor K, int width, int height, "
+          "Tensor? backgrounds, int camera_model, Tensor? radial, Tensor? tangential, Tensor? thin_prism, Tensor radii, "
+          "Tensor tile_offsets, Tensor flatten_ids, Tensor(a!) workspace, Tensor render_alphas, Tensor last_ids, "
+          "Tensor v_render_colors, Tensor v_render_alphas) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)",
+          &fused_bwd);
     m.def("quats_to_rotmats", &quats_to_rotmats);
     m.def("relocation", &relocation);
     m.def("add_noise(Tensor raw_opacities, Tensor raw_scales, Tensor raw_quats, Tensor noise, Tensor(a!) means, float current_lr) -> ()",

@@ -176,17 +176,23 @@ GSB_API int gsb_isect_sort(uint64_t n_isects, uint32_t C, uint32_t tile_width, u
  * operator API forces: everything that does not need the host to know n_isects runs in the PLAN.
  *   gsb_isect_plan          tiles_per_gauss [C*N]; *n_isects_out (device OR pinned host int64,
  *                           written asynchronously on `stream`); tile_offsets_out [C*th*tw] int32 or
- *                           NULL -- the a6 result, a by-product of the plan's scan; plan_workspace
- *                           keeps the run table and the per-chunk first slots for the emit.
- *   gsb_isect_emit_planned  flatten_ids [n_isects] and, unless NULL, isect_ids [n_isects], sorted.
+ *                           NULL -- the a6 result, a by-product of the plan's scan (with
+ *                           tile_offsets_total != 0 one more entry, [C*th*tw] = n_isects, so a
+ *                           consumer needs no host-side count); plan_workspace keeps the run table
+ *                           and the per-chunk first slots for the emit.
+ *   gsb_isect_emit_planned  flatten_ids and, unless NULL, isect_ids, sorted.  `n_isects` is the CAPACITY
+ *                           of those arrays: the true count is read on the device, slots beyond the
+ *                           capacity are dropped (a caller that allocates from a guess checks the
+ *                           count afterwards) -- with the exact count it is the reference's behaviour.
  * Limits: C*N < 2^31, C*th*tw < 2^31, tile grid sides <= 65535, n_isects < 2^31. */
 GSB_API size_t gsb_isect_plan_workspace(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t tile_height);
 GSB_API int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii,
                            const float *depths, uint32_t tile_size, uint32_t tile_width,
                            uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *n_isects_out,
-                           int32_t *tile_offsets_out /*nullable*/,
+                           int32_t *tile_offsets_out /*nullable*/, int tile_offsets_total,
                            void *plan_workspace, size_t plan_workspace_bytes, gsb_stream_t stream);
-GSB_API int gsb_isect_emit_planned(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t tile_height,
+GSB_API int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depths /*for isect_ids*/,
+                                   uint32_t tile_width, uint32_t tile_height,
                                    uint64_t n_isects, const void *plan_workspace,
                                    size_t plan_workspace_bytes, int64_t *isect_ids /*nullable*/,
                                    int32_t *flatten_ids, gsb_stream_t stream);
@@ -230,6 +236,60 @@ GSB_API int gsb_raster_bwd(
     const float *v_render_colors, const float *v_render_alphas,
     float *v_means, float *v_quats, float *v_scales, float *v_colors, float *v_opacities,
     void *workspace, size_t workspace_bytes, gsb_stream_t stream);
+
+/* ---- the L3 glue folded into the path -- an EXTENDED operator set over the raw SplatData --------
+ * The reference's caller activates the parameters and builds SH inputs with ~10 torch kernels around the
+ * operators every step (src/core/splat_data.cpp:267-286: exp / sigmoid / normalize / cat(sh0, shN);
+ * src/training/rasterization/rasterizer.cpp:250-266: inverse(viewmat), dirs, masks, clamp_min(SH + 0.5)) and
+ * their autograd backward.  These entry points take the RAW tensors instead (fastgs already does,
+ * fastgs/rasterization/include/rasterization_api.h:25-75) and keep the unfused operators above untouched:
+ *
+ *   gsb_fused_front   activations -> UT projection (bit-identical radii / means2d / depths to a1) -> SH colour of
+ *                     the view direction (+0.5, clamp) -> blend record; zeroes the backward's moment rows.
+ *   gsb_isect_plan / gsb_isect_emit_planned          (above; tile_offsets_total = 1, isect_ids = NULL)
+ *   gsb_raster_fwd_recs / gsb_raster_bwd_recs        a7 / a8 on the records of gsb_fused_front
+ *   gsb_fused_back    moments -> gradients of the RAW parameters: finalize chain rule, exp / sigmoid /
+ *                     normalise backward, clamp mask, SH backward straight into the sh0 / shN layouts,
+ *                     direction gradient added to the position gradient.  Every output element is written.
+ *
+ * No step of this sequence needs a host-side value: flatten_ids may be allocated from a capacity guess
+ * (intersections beyond it are dropped; compare *n_isects_out with the capacity afterwards), so a whole
+ * training step can be enqueued -- or captured in a CUDA graph -- without a synchronisation. */
+typedef struct GsbSplatRaw {
+    uint32_t N;
+    uint32_t sh_coeffs;       /* K: coefficients per Gaussian, sh0 included (shN holds K - 1) */
+    uint32_t sh_degree;       /* active degree, (degree + 1)^2 <= K */
+    float scaling_modifier;
+    const float *means;        /* [N,3] */
+    const float *sh0;          /* [N,1,3] */
+    const float *shN;          /* [N,K-1,3], may be NULL when K == 1 */
+    const float *scaling_raw;  /* [N,3] log-scales */
+    const float *rotation_raw; /* [N,4] (w,x,y,z), not normalised; 16-byte aligned */
+    const float *opacity_raw;  /* [N] logits */
+} GsbSplatRaw;
+
+GSB_API size_t gsb_fused_workspace(uint32_t N); /* [records][moments]; == gsb_raster_bwd_workspace(N) */
+GSB_API int gsb_fused_front(const GsbSplatRaw *splats, const GsbCamera *cam, uint32_t image_width,
+                            uint32_t image_height, float eps2d, float near_plane, float far_plane,
+                            float radius_clip, int zero_moments,
+                            int32_t *radii /*[N,2]*/, float *means2d /*[N,2]*/, float *depths /*[N]*/,
+                            void *workspace, size_t workspace_bytes, gsb_stream_t stream);
+GSB_API int gsb_raster_fwd_recs(uint32_t N, uint32_t capacity, const void *workspace, size_t workspace_bytes,
+                                const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                                uint32_t image_height, const GsbCamera *cam,
+                                const int32_t *tile_offsets /*[th*tw + 1]*/, const int32_t *flatten_ids,
+                                float *renders, float *alphas, int32_t *last_ids, gsb_stream_t stream);
+GSB_API int gsb_raster_bwd_recs(uint32_t N, uint32_t capacity, void *workspace, size_t workspace_bytes,
+                                const float *backgrounds, const uint8_t *masks, uint32_t image_width,
+                                uint32_t image_height, const GsbCamera *cam,
+                                const int32_t *tile_offsets /*[th*tw + 1]*/, const int32_t *flatten_ids,
+                                const float *render_alphas, const int32_t *last_ids,
+                                const float *v_render_colors, const float *v_render_alphas, gsb_stream_t stream);
+GSB_API int gsb_fused_back(const GsbSplatRaw *splats, const GsbCamera *cam, uint32_t image_width,
+                           uint32_t image_height, const int32_t *radii, const void *workspace,
+                           size_t workspace_bytes, float *v_means, float *v_sh0, float *v_shN /*NULL iff K == 1*/,
+                           float *v_scaling, float *v_rotation /*16-byte aligned*/, float *v_opacity,
+                           gsb_stream_t stream);
 
 /* ---- link-surface ops used by the densification strategies -------------------------
  * gsplat::quats_to_rotmats (Ops.h:46-48, QuatToRotmatCUDA.cu:14-39): [N,4] -> [N,3,3] */

@@ -97,24 +97,24 @@ def test_intersect_argument_validation(lib):
     need = lib.gsb_isect_plan_workspace(u32(1), u32(8), u32(4), u32(4))
     assert need >= 8 * (4 + 8)
     aligned = C.c_void_p((PTR.value + 255) & ~255)
-    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, NULL, NULL, aligned, sz(need),
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, NULL, NULL, i32(0), aligned, sz(need),
                               NULL) == E_INVALID
-    assert lib.gsb_isect_plan(u32(1), u32(8), NULL, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, NULL, aligned, sz(need),
+    assert lib.gsb_isect_plan(u32(1), u32(8), NULL, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, NULL, i32(0), aligned, sz(need),
                               NULL) == E_INVALID
-    assert lib.gsb_isect_plan(u32(4), u32(8), PTR, PTR, PTR, u32(16), u32(1 << 16), u32(1 << 15), PTR, PTR, NULL, aligned,
+    assert lib.gsb_isect_plan(u32(4), u32(8), PTR, PTR, PTR, u32(16), u32(1 << 16), u32(1 << 15), PTR, PTR, NULL, i32(0), aligned,
                               sz(1 << 20), NULL) == E_INVALID  # 32 tile bits + 3 camera bits > 32
-    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(1 << 16), u32(1), PTR, PTR, NULL, aligned,
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(1 << 16), u32(1), PTR, PTR, NULL, i32(0), aligned,
                               sz(1 << 20), NULL) == E_INVALID  # tile grid side > 65535 (box packing)
-    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, NULL, aligned, sz(16),
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, NULL, i32(0), aligned, sz(16),
                               NULL) == E_WORKSPACE
     misaligned = C.c_void_p(aligned.value + 8)
-    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, NULL, misaligned, sz(need),
+    assert lib.gsb_isect_plan(u32(1), u32(8), PTR, PTR, PTR, u32(16), u32(4), u32(4), PTR, PTR, NULL, i32(0), misaligned, sz(need),
                               NULL) == E_WORKSPACE
     # emit: nothing to do without intersections; a short or misaligned plan workspace is refused
-    assert lib.gsb_isect_emit_planned(u32(1), u32(8), u32(4), u32(4), u64(0), aligned, sz(need), PTR, PTR, NULL) == OK
-    assert lib.gsb_isect_emit_planned(u32(1), u32(8), u32(4), u32(4), u64(100), aligned, sz(64), PTR, PTR,
+    assert lib.gsb_isect_emit_planned(u32(1), u32(8), PTR, u32(4), u32(4), u64(0), aligned, sz(need), PTR, PTR, NULL) == OK
+    assert lib.gsb_isect_emit_planned(u32(1), u32(8), PTR, u32(4), u32(4), u64(100), aligned, sz(64), PTR, PTR,
                                       NULL) == E_WORKSPACE
-    assert lib.gsb_isect_emit_planned(u32(1), u32(8), u32(4), u32(4), u64(100), aligned, sz(need), PTR, NULL,
+    assert lib.gsb_isect_emit_planned(u32(1), u32(8), PTR, u32(4), u32(4), u64(100), aligned, sz(need), PTR, NULL,
                                       NULL) == E_INVALID
     assert lib.gsb_isect_sort(u64(0), u32(1), u32(4), u32(4), NULL, NULL, NULL, NULL, NULL, sz(0), NULL) == OK
     assert lib.gsb_isect_sort(u64(10), u32(1), u32(4), u32(4), PTR, PTR, PTR, PTR, PTR, sz(8), NULL) == E_WORKSPACE

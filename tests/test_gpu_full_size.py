@@ -138,7 +138,8 @@ def test_full_size_against_reference_kernels(native, full, cuda_device):
     print(f"[{tag}] projection vs reference: radii differ for {mism} / {f['N']} (steps > 1: {big}); max |means2d err| "
           f"{float(dm):.2e} px; max rel depth err {float(dd):.2e}")
     assert mism <= f["N"] // 1000 and big == 0
-    assert float(dm) < 5e-3 and float(dd) < 1e-5
+    # the UT sums seven points with weights (-99, 16.67 x 6): ~100x rounding amplification between fast-math and IEEE
+    assert float(dm) < 0.2 and rel(f["means2d"][both], m2d[both]) < 1e-5 and float(dd) < 1e-5
     # SH forward / backward, element-wise against the reference's kernels (recipe of tests/test_numerical_gradients.cpp:
     # 1e-4), on this view's directions and masks
     K = t["sh_coeffs"].shape[1]
@@ -153,3 +154,32 @@ def test_full_size_against_reference_kernels(native, full, cuda_device):
     assert torch.allclose(vd_new, vd_ref, rtol=1e-4, atol=2e-5 * float(vd_ref.abs().max()))
     print(f"[{tag}] SH fwd max abs err {float((c_new - c_ref)[masks].abs().max()):.2e}; bwd coeffs "
           f"{float((vco_new - vco_ref).abs().max()):.2e}, dirs {float((vd_new - vd_ref).abs().max()):.2e}")
+
+
+def test_full_size_fused_equals_operator_path(native, full, cuda_device):
+    """SURVEY.md 8 f1 at config B / D: the extended operator on the raw tensors renders the same image and returns
+    the same parameter gradients as torch activations + the eleven operators + autograd."""
+    f, t = full, full["t"]
+    raw = native.raw_from_activated(t["means"], t["quats"], t["scales"], t["opacities"], t["sh_coeffs"])
+    g = torch.Generator(device=cuda_device).manual_seed(11)
+    vr = torch.randn(f["r"].shape, device=cuda_device, generator=g)
+    res = {}
+    for tag in ("unfused", "fused"):
+        P = {k: v.detach().clone().requires_grad_(True) for k, v in raw.items()}
+        if tag == "fused":
+            o = native.rasterize_fused(P["means"], P["sh0"], P["shN"], P["scaling_raw"], P["rotation_raw"],
+                                       P["opacity_raw"], 3, t["viewmats"], t["Ks"], f["W"], f["H"], bg_color=t["background"])
+            img, n = o.render_colors, int(o.n_isects.item())
+        else:
+            o = native.rasterize_from_raw(P, 3, t["viewmats"], t["Ks"], f["W"], f["H"], bg_color=t["background"])
+            img, n = o.render_colors, o.n_isects
+        (img * vr).sum().backward()
+        res[tag] = (img.detach(), n, {k: P[k].grad for k in P})
+        del P, o
+    assert res["fused"][1] == res["unfused"][1]
+    e = rel(res["fused"][0], res["unfused"][0])
+    print(f"[config {f['cfg']}] fused vs operator path: image rel_l2 {e:.2e}")
+    assert e < 1e-5
+    for k in res["fused"][2]:
+        assert_grad_close(res["fused"][2][k], res["unfused"][2][k], k, f["N"], rel_tol=2e-4,
+                          tag=f"config {f['cfg']} fused vs operator path")
