@@ -6,11 +6,21 @@ One "step" = one pass of the hot path over one view of the synthetic scene:
 through the reference-facing API (the gsplat:: shim, driven by the L3 mirror in the package),
 exactly the call sequence of gs::training::rasterize + loss.backward() (SURVEY.md section 3.2/3.3).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config B|D|A]
+
+What the N=1 line carries:
+  value / ms_per_step      EXACTLY K steps, device-resident inputs, CUDA events, barrier + synchronize on both sides
+  distribution             20 warm-up + 100 individually timed steps: median / p10 / p90
+  ops_ms                   per-operator CUDA-event times of BOTH libraries (this backend and the reference's own
+                           gsplat CUDA kernels built unmodified in oracle/_ref) through one harness, same call sites
+  e2e / e2e_resident       the same metric with host<->device copies in the timed region, for both libraries
+  fused                    the extended operator over the raw SplatData tensors
+  configs                  config A (CPU oracle at full size, all cores + 1 thread; GPU beside it) and config D (6 M)
+  roofline, cpu_baseline   as the task contract asks
 
 N>1 (launched by torchrun, one rank per GPU): every rank renders its own view of the same 1 M
-Gaussians (config E) and the per-Gaussian gradients are summed with one NCCL all-reduce group per
-step; weak scaling, value = N_gaussians x n_gpus / max-over-ranks time.
+Gaussians (config E) and the per-Gaussian gradients are exchanged over NCCL; weak scaling,
+value = N_gaussians x n_gpus / max-over-ranks time.
 
 --impl reference times the reference's CPU path of the same hot path: the oracle port
 (oracle/gut_oracle.c, OpenMP over all host cores) on a bounded sample (a sub-frustum crop of the
@@ -20,6 +30,7 @@ from __future__ import annotations
 
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -35,6 +46,15 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "gaussians_rasterized_per_sec_fwd_bwd"
 UNIT = "Gaussians/s"
+CSRC = os.path.join(ROOT, "gaussian-splatting-cuda_b200", "csrc")
+KERNEL_NAMES = ("projection_ut", "sh_fwd", "isect_count", "isect_depth_sort", "isect_tile_hist", "isect_emit",
+                "isect_sort", "isect_offsets", "raster_prep", "raster_fwd", "raster_bwd", "raster_finalize", "sh_bwd",
+                "sh_bwd_views", "fused_front", "fused_back", "ssim_l1_fwd", "ssim_l1_bwd", "adam_step")
+WORKLOADS = {
+    "A": "10k synthetic Gaussians, 256x256, SH deg 0, 1 camera (BASELINE.json configs[0])",
+    "B": "1M synthetic Gaussians, 1920x1080, SH deg 3, 16x16 tiles, fwd+bwd on 1xB200 (BASELINE.json configs[1])",
+    "D": "6M synthetic Gaussians, 1920x1080, SH deg 3, 16x16 tiles, fwd+bwd on 1xB200 (BASELINE.json configs[3])",
+}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -49,6 +69,33 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def source_hash(files):
+    h = hashlib.sha256()
+    for f in files:
+        with open(os.path.join(CSRC, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def ncu_traffic(kernel, n_gauss, width, height):
+    """DRAM bytes per launch of `kernel` from the committed ncu digest (profiles/ncu_traffic.json), or None when the
+    digest was taken from different kernel sources (stale) or another workload."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(p):
+        return None, "no capture committed"
+    try:
+        ent = json.load(open(p)).get(kernel)
+        if not ent:
+            return None, "no capture for this kernel"
+        if [ent["gaussians"], ent["width"], ent["height"]] != [n_gauss, width, height]:
+            return None, "capture is for another workload"
+        if ent["source_sha"] != source_hash(ent["sources"]):
+            return None, "stale: kernel sources changed since the capture"
+        return int(ent["dram_bytes_read"] + ent["dram_bytes_write"]), ent.get("capture", "")
+    except Exception as e:  # a malformed digest must not break the bench
+        return None, f"unreadable: {e!r}"[:80]
 
 
 class ClockSampler:
@@ -131,21 +178,27 @@ def oracle_step(orc, sc, target):
     return float(np.abs(diff).mean()), o
 
 
-def cpu_sample_scene(n_gauss):
+def make_scene(config, n_gauss=None, view=None):
     import scenes
-    sc = scenes.scene_b(N=n_gauss)
+    if config == "A":
+        return scenes.scene_a()
+    n = n_gauss or (6_000_000 if config == "D" else 1_000_000)
+    return scenes.scene_b(N=n, view=view)
+
+
+def cpu_sample_scene(n_gauss):
+    sc = make_scene("B", n_gauss)
     # central 480x272 window of the 1920x1080 frame: 1/16 of the pixels and ~1/16 of the Gaussians
     w, h = 480, 272
     x0, y0 = (sc["width"] - w) // 2, (sc["height"] - h) // 2
     return crop_scene(sc, x0, y0, w, h), f"central {w}x{h} window of the {sc['width']}x{sc['height']} frame"
 
 
-def time_oracle(steps, warmup, n_gauss, threads=None):
+def time_oracle_on(sc, steps, warmup, threads=None):
     from oracle import oracle as orc
     orc.build()
     cores = threads or orc.max_threads()
     orc.set_threads(cores)
-    sc, what = cpu_sample_scene(n_gauss)
     target = np.full((1, sc["height"], sc["width"], 3), 0.5, np.float32)
     for _ in range(warmup):
         oracle_step(orc, sc, target)
@@ -154,10 +207,27 @@ def time_oracle(steps, warmup, n_gauss, threads=None):
         oracle_step(orc, sc, target)
     dt = (time.perf_counter() - t0) / max(steps, 1)
     orc.set_threads(1)
+    return dt, cores
+
+
+def time_oracle(steps, warmup, n_gauss, threads=None):
+    sc, what = cpu_sample_scene(n_gauss)
+    dt, cores = time_oracle_on(sc, steps, warmup, threads)
     ns = sc["means"].shape[0]
     return {"value": ns / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{what}: {ns} of the {n_gauss} Gaussians (sub-frustum, same per-pixel density), "
                       f"fwd+bwd, {dt * 1e3:.1f} ms/step, oracle/gut_oracle.c with OpenMP"}, dt
+
+
+def cpu_config_a():
+    """the CPU oracle on config A at FULL size, all cores and one thread."""
+    sc = make_scene("A")
+    n = sc["means"].shape[0]
+    dt_all, cores = time_oracle_on(sc, 3, 1)
+    dt_one, _ = time_oracle_on(sc, 1, 1, threads=1)
+    return {"workload": WORKLOADS["A"], "gaussians": n, "cpu_oracle": {
+        "cores": cores, "ms_per_step": dt_all * 1e3, "value": n / dt_all, "unit": UNIT,
+        "one_thread": {"ms_per_step": dt_one * 1e3, "value": n / dt_one}}}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -167,13 +237,12 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    cb, dt = time_oracle(args.steps, args.warmup, args.gaussians)
+    cb, dt = time_oracle(args.steps, args.warmup, args.gaussians or 1_000_000)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "1M synthetic Gaussians, 1920x1080, SH deg 3, 16x16 tiles, fwd+bwd (configs[1]); "
-                               "CPU sample: " + cb["sample"]},
+        "config": {"workload": WORKLOADS["B"] + "; CPU sample: " + cb["sample"]},
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -185,9 +254,45 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------------
-# (kernel, gaussians, width, height) -> DRAM bytes per launch measured by ncu (profiles/r1c_ncu_summary.md)
-NCU_DRAM_BYTES = {("raster_bwd", 1_000_000, 1920, 1080): 89_998_592 + 4_392_448,
-                  ("raster_fwd", 1_000_000, 1920, 1080): 50_757_632 + 9_520_640}
+class TimedBackend:
+    """Wraps an OpsBackend: CUDA events on the launching stream around every operator call, so that both libraries are
+    timed per operator by the same harness through the same call sites."""
+
+    OPS = ("projection_ut_3dgs_fused", "spherical_harmonics_fwd", "spherical_harmonics_bwd", "intersect_tile",
+           "intersect_offset", "rasterize_to_pixels_from_world_3dgs_fwd", "rasterize_to_pixels_from_world_3dgs_bwd")
+
+    def __init__(self, backend):
+        import torch
+        self._b, self._torch, self.records = backend, torch, []
+
+    def __getattr__(self, name):
+        fn = getattr(self._b, name)
+        if name not in self.OPS:
+            return fn
+        torch = self._torch
+
+        def timed(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **kw)
+            e1.record()
+            self.records.append((name, e0, e1))
+            return r
+        return timed
+
+    def summary(self):
+        self._torch.cuda.synchronize()
+        agg = {}
+        for name, e0, e1 in self.records:
+            agg.setdefault(name, []).append(e0.elapsed_time(e1))
+        self.records = []
+        return {k: round(float(np.median(v)), 4) for k, v in agg.items()}
+
+
+def percentiles(ms):
+    a = np.asarray(ms, np.float64)
+    return {"n": int(a.size), "median_ms": float(np.median(a)), "p10_ms": float(np.percentile(a, 10)),
+            "p90_ms": float(np.percentile(a, 90))}
 
 
 def run_b200(args):
@@ -195,7 +300,6 @@ def run_b200(args):
     import torch.distributed as dist
 
     import __graft_entry__ as ge
-    import scenes
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,46 +312,13 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     pkg = ge.load_package()
     pkg.load()
-    from gsplat_b200 import multiview
+    from gsplat_b200 import hoststream, multiview
     cabi = ctypes.CDLL(pkg.CABI_PATH)
     cabi.gsb_launch_count.restype = ctypes.c_uint64
     cabi.gsb_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
-
-    N = args.gaussians
-    view = rank if world > 1 else None  # config E: one camera of the ring per rank
-    sc = scenes.scene_b(N=N, view=view)
-    W, H, deg = sc["width"], sc["height"], sc["sh_degree"]
-    host = {k: torch.from_numpy(sc[k]).pin_memory() for k in
-            ("means", "quats", "scales", "opacities", "sh_coeffs", "viewmats", "Ks", "background")}
-    rng = np.random.default_rng(123 + rank)
-    host["target"] = torch.from_numpy(rng.random((1, H, W, 3), dtype=np.float32)).pin_memory()
     names = ("means", "quats", "scales", "opacities", "sh_coeffs")
-    P = {k: host[k].to(dev).requires_grad_(k in names) for k in host}
-    host_out = {k: torch.empty_like(host[k]).pin_memory() for k in names}
-    host_img = torch.empty((1, H, W, 3), dtype=torch.float32).pin_memory()
-
-    stats = {}
-
+    raw_names = ("means", "sh0", "shN", "scaling_raw", "rotation_raw", "opacity_raw")
     compact = world > 1 and args.exchange == "compact"
-
-    def step(Pd, backend=None):
-        for k in names:
-            Pd[k].grad = None
-        deferred = pkg.DeferredSHBackward() if compact else None
-        out = pkg.rasterize(Pd["means"], Pd["quats"], Pd["scales"], Pd["opacities"], Pd["sh_coeffs"], deg,
-                            Pd["viewmats"], Pd["Ks"], W, H, bg_color=Pd["background"], backend=backend,
-                            sh_exchange=deferred)
-        loss = (out.render_colors - Pd["target"]).abs().mean()
-        loss.backward()
-        if compact:
-            # all-gather of the 12-byte colour gradients + all-reduce of the 44 B of geometry gradients + local
-            # expansion of all views (gsb_sh_bwd_views): the same sums as the all-reduce below, 1/2-1/3 of the bytes
-            multiview.exchange_gradients_compact(Pd, deferred)
-        elif world > 1:
-            # one fused NCCL launch for the five gradient tensors (236 B/Gaussian)
-            multiview.allreduce_gradients([Pd[k].grad for k in names])
-        stats["n_isects"], stats["vis"] = out.n_isects, out.visibility
-        return loss, out
 
     def sync_all():
         if world > 1:
@@ -255,6 +326,7 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
+        """The contract's timing: `steps` calls bracketed by barrier + synchronize, CUDA events, max over ranks."""
         sync_all()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -264,148 +336,356 @@ def run_b200(args):
         sync_all()
         return multiview.max_over_ranks(e0.elapsed_time(e1), dev)
 
-    # ---- warm-up + device-resident timing -------------------------------------------------------
-    for _ in range(max(args.warmup, 3)):
-        step(P)
+    def distribution(fn, warm=20, n=100):
+        """20 warm-up + 100 timed iterations, each between its own pair of events."""
+        for _ in range(warm):
+            fn()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(n)]
+        torch.cuda.synchronize()
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return percentiles([a.elapsed_time(b) for a, b in ev])
+
+    def read_profile(fn, steps):
+        cabi.gsb_profile_enable(1)
+        timed(fn, steps)
+        prof = {}
+        for kname in KERNEL_NAMES:
+            tot = ctypes.c_double(0.0)
+            n = cabi.gsb_profile_read(kname.encode(), ctypes.byref(tot))
+            if n:
+                prof[kname] = {"launches": n, "avg_ms": tot.value / n}
+        cabi.gsb_profile_enable(0)
+        return prof
+
+    class Workload:
+        """Device + pinned-host tensors of one config and the step functions over them."""
+
+        def __init__(self, config, n_gauss=None, view=None):
+            self.config = config
+            sc = make_scene(config, n_gauss, view)
+            self.N, self.W, self.H, self.deg = sc["means"].shape[0], sc["width"], sc["height"], sc["sh_degree"]
+            self.host = {k: torch.from_numpy(sc[k]).pin_memory() for k in
+                         ("means", "quats", "scales", "opacities", "sh_coeffs", "viewmats", "Ks")}
+            bg = sc["background"] if sc.get("background") is not None else np.zeros((1, 3), np.float32)
+            self.host["background"] = torch.from_numpy(bg).pin_memory()
+            rng = np.random.default_rng(123 + rank)
+            self.host["target"] = torch.from_numpy(rng.random((1, self.H, self.W, 3), dtype=np.float32)).pin_memory()
+            self.P = {k: self.host[k].to(dev).requires_grad_(k in names) for k in self.host}
+            self.stats = {}
+            self._raw = None
+            self.capacity = 0
+
+        # -- operator path: activated parameters in, as gs::training::rasterize hands them to the ops --
+        def step(self, Pd=None, backend=None):
+            Pd = Pd or self.P
+            for k in names:
+                Pd[k].grad = None
+            deferred = pkg.DeferredSHBackward() if compact else None
+            out = pkg.rasterize(Pd["means"], Pd["quats"], Pd["scales"], Pd["opacities"], Pd["sh_coeffs"], self.deg,
+                                Pd["viewmats"], Pd["Ks"], self.W, self.H, bg_color=Pd["background"], backend=backend,
+                                sh_exchange=deferred)
+            loss = (out.render_colors - Pd["target"]).abs().mean()
+            loss.backward()
+            if compact:
+                multiview.exchange_gradients_compact(Pd, deferred)
+            elif world > 1:
+                multiview.allreduce_gradients([Pd[k].grad for k in names])
+            self.stats["n_isects"], self.stats["vis"] = out.n_isects, out.visibility
+            return loss, out
+
+        # -- raw SplatData: what training holds (log-scales, logits, raw quaternions, sh0 / shN) --
+        def raw(self):
+            if self._raw is None:
+                with torch.no_grad():
+                    r = pkg.raw_from_activated(self.P["means"], self.P["quats"], self.P["scales"], self.P["opacities"],
+                                               self.P["sh_coeffs"])
+                self._raw = {k: v.detach().clone().requires_grad_(True) for k, v in r.items()}
+            return self._raw
+
+        def step_raw_unfused(self, backend=None):
+            """The reference's own sequence: torch activations (splat_data.cpp:267-286) + the operators + autograd."""
+            R = self.raw()
+            for k in raw_names:
+                R[k].grad = None
+            out = pkg.rasterize_from_raw(R, self.deg, self.P["viewmats"], self.P["Ks"], self.W, self.H,
+                                         bg_color=self.P["background"], backend=backend)
+            loss = (out.render_colors - self.P["target"]).abs().mean()
+            loss.backward()
+            return loss, out
+
+        def step_fused(self):
+            R = self.raw()
+            for k in raw_names:
+                R[k].grad = None
+            out = pkg.rasterize_fused(R["means"], R["sh0"], R["shN"], R["scaling_raw"], R["rotation_raw"],
+                                      R["opacity_raw"], self.deg, self.P["viewmats"], self.P["Ks"], self.W, self.H,
+                                      bg_color=self.P["background"], isect_capacity=self.capacity)
+            loss = (out.render_colors - self.P["target"]).abs().mean()
+            loss.backward()
+            self.stats["fused_n"] = out.n_isects
+            return loss, out
+
+        def size_capacity(self):
+            """One exact step sizes flatten_ids for the capacity mode (no host read-back afterwards)."""
+            self.raw()
+            self.capacity = 0
+            _, out = self.step_fused()
+            n = int(out.n_isects.item())
+            self.capacity = int(n * 1.25) + 1024
+            return n
+
+        # -- end-to-end protocols --
+        def e2e_staged(self, steps, backend=None):
+            """All op inputs from pinned host memory each step, image + all gradients + loss back (hoststream.py)."""
+            def staged_step(Pd):
+                loss, out = self.step(Pd, backend)
+                return loss, out.render_colors
+            st = hoststream.HostStagedSteps(dev, self.host, names, staged_step)
+            st.run(3)
+            losses = []
+            ms = timed(lambda: losses.extend(st.run(steps)), 1) / steps
+            return ms, st.h2d_bytes, st.d2h_bytes, (losses[-1] if losses else None)
+
+        def e2e_resident(self, steps, fn):
+            """Parameters resident (training): camera + target image H2D, loss D2H every step."""
+            def one():
+                for k in ("viewmats", "Ks", "background", "target"):
+                    self.P[k] = self.host[k].to(dev, non_blocking=True)
+                loss, _ = fn()
+                return float(loss.item())
+            one()
+            return timed(one, steps) / steps
+
+        def max_tile_list(self):
+            """Longest per-tile intersection list of the current view."""
+            with torch.no_grad():
+                P = self.P
+                radii, m2d, dep, _, _ = pkg.projection_ut_3dgs_fused(P["means"].detach(), P["quats"].detach(),
+                                                                     P["scales"].detach(), P["opacities"].detach(),
+                                                                     P["viewmats"], P["Ks"], self.W, self.H, 0.3, 0.01,
+                                                                     1e4, 0.0)
+                tw, th = (self.W + 15) // 16, (self.H + 15) // 16
+                _, ids, _ = pkg.intersect_tile(m2d, radii, dep, 1, 16, tw, th, True)
+                off = pkg.intersect_offset(ids, 1, tw, th).reshape(-1).long()
+                ends = torch.cat([off[1:], torch.tensor([ids.shape[0]], device=dev)])
+                return int((ends - off).max().item())
+
+    cfg = args.config if world == 1 else "B"
+    wl = Workload(cfg, args.gaussians, view=(rank if world > 1 else None))
+    N, W, H = wl.N, wl.W, wl.H
+    warm = max(args.warmup, 3)
+
+    # ---- warm-up + device-resident timing (the contract's K steps) -------------------------------------------
+    for _ in range(warm):
+        wl.step()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = cabi.gsb_launch_count()
-    ms_total = timed(lambda: step(P), args.steps)
+    ms_total = timed(wl.step, args.steps)
     launches = int(cabi.gsb_launch_count() - launches0)
-    # per-kernel CUDA-event timing in a SEPARATE pass (its event records are not in the timed region)
-    cabi.gsb_profile_enable(1)
-    timed(lambda: step(P), args.steps)
-    prof = {}
-    for kname in ("projection_ut", "sh_fwd", "isect_count", "isect_depth_sort", "isect_tile_hist", "isect_emit", "isect_sort",
-                  "isect_offsets", "raster_prep",
-                  "raster_fwd", "raster_bwd", "raster_finalize", "sh_bwd", "sh_bwd_views"):
-        tot = ctypes.c_double(0.0)
-        n = cabi.gsb_profile_read(kname.encode(), ctypes.byref(tot))
-        if n:
-            prof[kname] = {"launches": n, "avg_ms": tot.value / n}
-    cabi.gsb_profile_enable(0)
     ms_step = ms_total / args.steps
     value = N * world / (ms_step * 1e-3)
+    prof = read_profile(wl.step, max(args.steps, 10))  # per-kernel events in a SEPARATE pass
 
-    # ---- end-to-end: every op input from pinned host memory, image + gradients back to the host ----
-    def step_e2e():
-        Pd = {k: host[k].to(dev, non_blocking=True).requires_grad_(k in names) for k in host}
-        loss, out = step(Pd)
-        host_img.copy_(out.render_colors.detach(), non_blocking=True)
-        for k in names:
-            host_out[k].copy_(Pd[k].grad, non_blocking=True)
-        return float(loss.item())  # D2H read of the step's result (also drains the copies)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
+        "ms_per_step": ms_step, "iters_per_sec": 1e3 / ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "gpu_launches": launches,
+        "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in prof.items()},
+    }
+    cfgd = {"workload": (WORKLOADS[cfg] if world == 1 else
+                         f"1M Gaussians x {world} synthetic cameras/step, per-view shard + NCCL gradient exchange "
+                         f"({args.exchange}) (BASELINE.json configs[4])"),
+            "gaussians": N, "visible": int(wl.stats["vis"].sum().item()), "intersections": wl.stats["n_isects"],
+            "image": [W, H], "loss": "L1 vs synthetic target", "parallelism": f"view-dp{world}",
+            "l2": "per-step working set (236 B/Gaussian parameters + 64 B records + 12 B/intersection lists + 236 B "
+                  "gradients) exceeds the 126 MB L2; no explicit flush"}
+    line["config"] = cfgd
+    line["intersections_per_sec"] = wl.stats["n_isects"] * world / (ms_step * 1e-3)
 
-    for _ in range(2):
-        step_e2e()
-    ms_e2e_seq = timed(step_e2e, args.steps) / args.steps
-    h2d = sum(host[k].numel() * host[k].element_size() for k in host)
-    d2h = host_img.numel() * 4 + sum(host_out[k].numel() * 4 for k in names) + 4
-
-    # The same traffic through the package's host-staged pipeline (hoststream.py): H2D of step k+1, kernels
-    # of step k and D2H of step k-1 overlap on three streams.  Every step still moves all of its inputs from
-    # pinned host memory and all of its results back, inside the timed region.
-    from gsplat_b200 import hoststream
-
-    def staged_step(Pd):
-        loss, out = step(Pd)
-        return loss, out.render_colors
-    staged = hoststream.HostStagedSteps(dev, host, names, staged_step)
-    staged.run(3)
-    e2e_losses = []
-    ms_e2e = timed(lambda: e2e_losses.extend(staged.run(args.steps)), 1) / args.steps
-    assert staged.h2d_bytes == h2d and staged.d2h_bytes == d2h
-    clocks = sampler.stop() if rank == 0 else None
-
-    # ---- resident-parameter end-to-end (what a training step moves: camera + target in, loss out) ----
-    def step_e2e_resident():
-        for k in ("viewmats", "Ks", "background", "target"):
-            P[k] = host[k].to(dev, non_blocking=True)
-        loss, _ = step(P)
-        return float(loss.item())
-
-    step_e2e_resident()
-    ms_e2e_res = timed(step_e2e_resident, args.steps) / args.steps
-
-    if rank != 0:
+    if args.quick:
+        if rank == 0:
+            line["clocks"] = sampler.stop()
+            print(json.dumps(line))
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant kernel (blend backward), SURVEY.md 8(d) algorithmic bytes ---------
+    # ---- distribution + per-op times of this backend -----------------------------------------------------------
+    ops_ms = {}
+    if world == 1:
+        line["distribution"] = distribution(wl.step)
+        tb = TimedBackend(pkg.default_backend())
+        for _ in range(20):
+            wl.step(backend=tb)
+        ops_ms["b200"] = tb.summary()
+        cfgd["max_tile_list"] = wl.max_tile_list()
+
+    # ---- end-to-end -----------------------------------------------------------------------------------------------
+    ms_e2e, h2d, d2h, e2e_loss = wl.e2e_staged(args.steps)
+    ms_e2e_res = wl.e2e_resident(args.steps, wl.step)
+    clocks = sampler.stop() if rank == 0 else None
+    line["e2e"] = {"value": N * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                   "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "loss": e2e_loss,
+                   "what": "all op inputs (parameters, camera, target) from pinned host memory each step; image + all "
+                           "gradients + loss back to pinned host; copies of neighbouring steps overlap the kernels "
+                           "(gsplat_b200.hoststream.HostStagedSteps)"}
+    line["e2e_resident"] = {"value": N * world / (ms_e2e_res * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_res,
+                            "what": "parameters resident (as in training); camera + target image H2D, loss D2H per step"}
+    line["clocks"] = clocks
+
+    if rank != 0 or world > 1:
+        if rank == 0:
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- extended operator over the raw SplatData tensors (SURVEY.md 8 f1) -------------------------------------
+    try:
+        n_f = wl.size_capacity()
+        for _ in range(3):
+            wl.step_fused()
+        ms_f = timed(wl.step_fused, args.steps) / args.steps
+        prof_f = read_profile(wl.step_fused, max(args.steps, 10))
+        ms_f_res = wl.e2e_resident(args.steps, wl.step_fused)
+        assert int(wl.stats["fused_n"].item()) <= wl.capacity
+        for _ in range(3):
+            wl.step_raw_unfused()
+        ms_u = timed(wl.step_raw_unfused, args.steps) / args.steps
+        ms_u_res = wl.e2e_resident(args.steps, wl.step_raw_unfused)
+        line["fused"] = {
+            "what": "rasterize_from_world_fused_fwd/bwd on the raw SplatData tensors (log-scales, logits, raw quaternions, "
+                    "sh0/shN), flatten_ids sized from a capacity: no host read-back inside the step",
+            "ms_per_step": ms_f, "value": N / (ms_f * 1e-3), "e2e_resident_ms": ms_f_res,
+            "distribution": distribution(wl.step_fused), "intersections": n_f,
+            "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in prof_f.items()},
+            "operator_path_on_raw_tensors": {
+                "what": "torch activations (splat_data.cpp:267-286) + the eleven operators + autograd, this backend",
+                "ms_per_step": ms_u, "e2e_resident_ms": ms_u_res}}
+    except Exception as e:
+        line["fused"] = {"unavailable": repr(e)[:300]}
+
+    # ---- roofline of the dominant kernel (SURVEY.md 8d algorithmic bytes) ---------------------------------------
     peak, peak_src = load_peaks()
-    I, Pn = stats["n_isects"], W * H
+    I, Pn = wl.stats["n_isects"], W * H
     dom = max(prof, key=lambda k: prof[k]["avg_ms"]) if prof else None
     algo = {"raster_bwd": 60 * I + 24 * Pn + 112 * N, "raster_fwd": 48 * I + 20 * Pn}
-    roof = None
     if dom in algo:
         achieved = algo[dom] / (prof[dom]["avg_ms"] * 1e-3) / 1e9
-        # dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture of this kernel at this
-        # workload (profiles/r1c_ncu_summary.md); other sizes have no capture
-        traffic = NCU_DRAM_BYTES.get((dom, N, W, H))
-        roof = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo[dom], "avg_kernel_ms": prof[dom]["avg_ms"],
-                "note": "the blend is FP32-issue/LSU/atomic bound by construction (SURVEY.md 8d): the HBM fraction is "
-                        "the figure north_star asks for, the pipe utilisations are in profiles/"}
+        traffic, traffic_src = ncu_traffic(dom, N, W, H)
+        line["roofline"] = {
+            "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": algo[dom], "avg_kernel_ms": prof[dom]["avg_ms"],
+            "note": "the blend is FP32-issue/LSU/atomic bound by construction (SURVEY.md 8d): the HBM fraction is the "
+                    "figure north_star asks for, the pipe utilisations are in profiles/"}
 
-    cb = None
-    if world == 1 and not args.no_cpu_baseline:
-        cb, _ = time_oracle(1, 1, N)
-
-    # ---- same-box GPU baseline: the reference's own gsplat CUDA kernels (oracle/_ref), same call sites ----
-    ref_cuda = None
-    if world == 1 and not args.no_ref_cuda:
+    # ---- same-box GPU baseline: the reference's own gsplat CUDA kernels (oracle/_ref), same call sites ------------
+    rb = None
+    if not args.no_ref_cuda:
         try:
             from oracle import ref_ops
             if ref_ops.available():
                 rb = ref_ops.backend(pkg)
+                ref_step = lambda: wl.step(backend=rb)
                 for _ in range(3):
-                    step(P, rb)
-                ms_ref = timed(lambda: step(P, rb), args.steps) / args.steps
-                ref_cuda = {"ms_per_step": ms_ref, "value": N / (ms_ref * 1e-3), "unit": UNIT,
-                            "what": "reference gsplat/*.cu compiled unmodified (-O3 --use_fast_math, sm_100) by "
-                                    "oracle/build_ref.py, driven through the same L3 call sequence on the same inputs",
-                            "speedup_device_resident": ms_ref / ms_step}
+                    ref_step()
+                ms_ref = timed(ref_step, args.steps) / args.steps
+                dist_ref = distribution(ref_step, warm=5, n=50)
+                tbr = TimedBackend(rb)
+                for _ in range(10):
+                    wl.step(backend=tbr)
+                ops_ms["reference_cuda"] = tbr.summary()
+                ms_ref_e2e, _, _, _ = wl.e2e_staged(args.steps, backend=rb)
+                ms_ref_res = wl.e2e_resident(args.steps, ref_step)
+                ref_raw = lambda: wl.step_raw_unfused(backend=rb)
+                for _ in range(2):
+                    ref_raw()
+                ms_ref_raw = timed(ref_raw, args.steps) / args.steps
+                ms_ref_raw_res = wl.e2e_resident(args.steps, ref_raw)
+                fused_res = line["fused"].get("e2e_resident_ms")
+                line["reference_cuda"] = {
+                    "what": "reference gsplat/*.cu compiled unmodified (-O3 --use_fast_math, sm_100) by oracle/build_ref.py, "
+                            "driven through the same L3 call sequence on the same inputs",
+                    "ms_per_step": ms_ref, "value": N / (ms_ref * 1e-3), "unit": UNIT, "distribution": dist_ref,
+                    "e2e_ms": ms_ref_e2e, "e2e_resident_ms": ms_ref_res,
+                    "raw_tensor_sequence": {"ms_per_step": ms_ref_raw, "e2e_resident_ms": ms_ref_raw_res,
+                                            "what": "torch activations + the reference's kernels + autograd: what the "
+                                                    "reference's trainer runs per step"},
+                    "speedup": {"device_resident": ms_ref / ms_step, "e2e": ms_ref_e2e / ms_e2e,
+                                "e2e_resident": ms_ref_res / ms_e2e_res,
+                                "fused_vs_reference_training_step_e2e_resident":
+                                    (ms_ref_raw_res / fused_res) if fused_res else None}}
         except Exception as e:  # the baseline is optional evidence, never a failure of the bench
-            ref_cuda = {"unavailable": repr(e)[:200]}
+            line["reference_cuda"] = {"unavailable": repr(e)[:200]}
+    line["ops_ms"] = ops_ms
 
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "iters_per_sec": 1e3 / ms_step,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("1M synthetic Gaussians, 1920x1080, SH deg 3, 16x16 tiles, fwd+bwd on 1xB200 "
-                                "(BASELINE.json configs[1])" if world == 1 else
-                                f"1M Gaussians x {world} synthetic cameras/step, per-view shard + NCCL gradient "
-                                f"exchange ({args.exchange}) (BASELINE.json configs[4])"),
-                   "gaussians": N, "visible": int(stats["vis"].sum().item()), "intersections": I, "image": [W, H],
-                   "loss": "L1 vs synthetic target", "parallelism": f"view-dp{world}",
-                   "l2": "per-step working set (236 MB parameters + 64 MB records + ~0.35 GB intersection "
-                         "buffers + 236 MB gradients) exceeds the 126 MB L2; no explicit flush"},
-        "e2e": {"value": N * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
-                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "what": "all op inputs (parameters, camera, target) from pinned host memory each step; image + all "
-                        "gradients + loss back to pinned host; copies of neighbouring steps overlap the kernels "
-                        "(gsplat_b200.hoststream.HostStagedSteps)",
-                "ms_per_step_unpipelined": ms_e2e_seq, "loss": e2e_losses[-1] if e2e_losses else None},
-        "e2e_resident": {"value": N * world / (ms_e2e_res * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e_res,
-                         "what": "parameters resident (as in training); camera + target image H2D, loss D2H per step"},
-        "gpu_launches": launches,
-        # the quantity the blend's cost is proportional to; rank 0's count x ranks
-        "intersections_per_sec": I * world / (ms_step * 1e-3),
-        "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in prof.items()},
-        "clocks": clocks,
-    }
-    if roof:
-        line["roofline"] = roof
-    if cb:
+    # ---- the other configs of BASELINE.json (N=1 line only) ---------------------------------------------------------
+    configs = {}
+    if cfg == "B" and not args.no_other_configs:
+        try:
+            a = cpu_config_a()
+            wa = Workload("A")
+            for _ in range(5):
+                wa.step()
+            ms_a = timed(wa.step, 50) / 50
+            a["b200"] = {"ms_per_step": ms_a, "value": wa.N / (ms_a * 1e-3), "intersections": wa.stats["n_isects"]}
+            if rb is not None:
+                for _ in range(3):
+                    wa.step(backend=rb)
+                ms_ar = timed(lambda: wa.step(backend=rb), 50) / 50
+                a["reference_cuda"] = {"ms_per_step": ms_ar, "value": wa.N / (ms_ar * 1e-3)}
+            configs["A"] = a
+            del wa
+        except Exception as e:
+            configs["A"] = {"unavailable": repr(e)[:200]}
+        try:
+            del wl
+            torch.cuda.empty_cache()
+            wd = Workload("D")
+            for _ in range(3):
+                wd.step()
+            ms_d = timed(wd.step, 20) / 20
+            prof_d = read_profile(wd.step, 10)
+            d = {"workload": WORKLOADS["D"], "gaussians": wd.N, "intersections": wd.stats["n_isects"],
+                 "visible": int(wd.stats["vis"].sum().item()), "ms_per_step": ms_d, "value": wd.N / (ms_d * 1e-3),
+                 "distribution": distribution(wd.step, warm=3, n=30),
+                 "e2e_resident_ms": wd.e2e_resident(10, wd.step),
+                 "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in prof_d.items()}}
+            try:
+                wd.size_capacity()
+                for _ in range(2):
+                    wd.step_fused()
+                ms_df = timed(wd.step_fused, 20) / 20
+                d["fused"] = {"ms_per_step": ms_df, "value": wd.N / (ms_df * 1e-3),
+                              "e2e_resident_ms": wd.e2e_resident(10, wd.step_fused)}
+            except Exception as e:
+                d["fused"] = {"unavailable": repr(e)[:200]}
+            if rb is not None:
+                for _ in range(2):
+                    wd.step(backend=rb)
+                ms_dr = timed(lambda: wd.step(backend=rb), 10) / 10
+                d["reference_cuda"] = {"ms_per_step": ms_dr, "value": wd.N / (ms_dr * 1e-3),
+                                       "speedup_device_resident": ms_dr / ms_d}
+            configs["D"] = d
+            del wd
+        except Exception as e:
+            configs["D"] = {"unavailable": repr(e)[:200]}
+    if configs:
+        line["configs"] = configs
+
+    if not args.no_cpu_baseline:
+        cb, _ = time_oracle(1, 1, N if cfg != "A" else 1_000_000)
         line["cpu_baseline"] = cb
-    if ref_cuda:
-        line["reference_cuda"] = ref_cuda
+
     print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
     return 0
 
 
@@ -418,13 +698,15 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--gaussians", type=int, default=1_000_000)
+    ap.add_argument("--config", default="B", choices=["A", "B", "D"], help="N=1 workload (BASELINE.json configs)")
+    ap.add_argument("--gaussians", type=int, default=None, help="override the config's Gaussian count")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the config A / D block of the N=1 line")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
     args = ap.parse_args()
     if args.quick:
-        args.no_cpu_baseline = args.no_ref_cuda = True
+        args.no_cpu_baseline = args.no_ref_cuda = args.no_other_configs = True
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)

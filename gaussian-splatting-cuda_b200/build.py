@@ -37,6 +37,8 @@ CUDA_SOURCES = [
     ("gsb_raster.cu", []),
     ("gsb_misc.cu", []),
     ("gsb_fused.cu", ["-fmad=false"]),
+    ("gsb_loss.cu", []),
+    ("gsb_optim.cu", []),
 ]
 CUDA_HEADERS = ["gsb_common.cuh", "gsb_raster.cuh", "gsb_camera.cuh", "gsb_devsort.cuh", "gsb_sh.cuh", "gsb_projection.cuh"]
 SHIM_SOURCES = ["Ops.cpp", "FusedOps.cpp", "torch_binding.cpp"]

@@ -18,17 +18,17 @@
 //                gsb_devsort.cuh), passes whose digit is constant are skipped.
 //   3. runs      scan of the tile counts in depth order -> compact run table (Gaussians with >= 1 tile:
 //                cumulative end slot, index, box, depth key); n_isects goes to the host here.
-//   4. histogram the I intersection slots, in depth order, are cut into P equal chunks, one warp each.  A
-//                warp walks its chunk 32 slots per step (slot -> run by a ballot over the run ends, run ->
-//                tile by the box) and counts the tiles in shared-memory counters: matrix M[P][tiles].
+//   4. histogram the runs are cut into P chunks of ~I/P intersections; one CTA per chunk counts its intersections per
+//                tile with shared-memory atomics: matrix M[P][tiles].
 //   5. column scan over (tile, chunk): M[p][t] becomes the first output slot of chunk p in tile t;
 //                the tile offsets (a6) fall out of the same scan.
 //   -- host reads n_isects, allocates the outputs --
-//   6. scatter   the same walk again; slot ranks within a step come from match.any on the tile id, so
-//                every (tile, depth, index) lands DIRECTLY in its final position: 4 (+8 for the key) bytes
-//                written per intersection, nothing read back.
-// A stable placement by tile of a sequence ordered by (depth, index) is ordered by (tile, depth, index):
-// the same permutation as the reference's single 46-bit sort, ties included.
+//   6. scatter   the same pass again, each intersection taking the next slot of its (chunk, tile) group: 4 bytes
+//                written per intersection DIRECTLY into the final range of its group, nothing read back.
+//   7. repair    groups with more than one member (1.35 intersections per group at config B) are put into depth
+//                order in place; the 64-bit keys, when the caller wants them, are written by a coalesced pass.
+// Chunks are in depth order and groups are ordered by (depth bits, index) inside: every tile's list is ordered by
+// (depth, index) -- the same permutation as the reference's single 46-bit sort, ties included.
 #include "gsb_devsort.cuh"
 
 namespace gsb {
@@ -254,22 +254,34 @@ __global__ void __launch_bounds__(kSortThreads) runs_build_kernel(SortCtl *__res
     }
 }
 
-// ---- steps 4 and 6: the chunk walk -----------------------------------------------------------------------------
+// ---- steps 4, 6 and 7: per-chunk tile counters, placement, order repair -----------------------------------------------
+// The runs (Gaussians with tiles, in depth order) are cut into P chunks of about I / P intersections each, at run
+// boundaries.  One CTA per chunk keeps one counter per tile in shared memory.
+//   hist     every intersection of the chunk does an atomicAdd on its tile's counter -> M[p][tile] (any order);
+//   scatter  the counters start at the chunk's first slot in each tile (column scan of M) and every intersection
+//            takes the next slot of its tile: the (chunk, tile) GROUPS land in their final ranges, but the order
+//            INSIDE a group is the order the atomics retired in;
+//   repair   every group with more than one member is put into depth order: groups of up to 16 by an insertion sort
+//            on (depth bits, index) -- a Gaussian appears at most once per group, so this is the run order -- larger
+//            groups by REGENERATION: a warp walks the chunk's runs in order and re-emits those that cover the tile.
+// With P = 888 chunks and 8160 tiles a group holds 1.35 intersections on average at config B, so the repair touches
+// a fraction of the data; nothing in these three kernels is serial.
 struct BinArgs {
     RunTable rt;
     const SortCtl *ctl;
     uint32_t N;          // Gaussians per camera
     uint32_t n_tiles;    // tiles per camera
     uint32_t tile_width;
-    uint32_t tile_n_bits;
     uint32_t multi_cam;
-    uint32_t t_lo, t_cnt; // window of global tile ids (camera * n_tiles + tile) counted by this launch
+    uint32_t t_lo, t_cnt; // window of global tile ids (camera * n_tiles + tile) handled by this launch
     uint32_t T_total, P;
     uint32_t *M;          // [P][T_total]
+    uint32_t *chunk_run;  // [P + 1] first run of every chunk (written by hist)
     int32_t *flatten_ids;
-    int64_t *isect_ids;   // nullable
-    uint32_t cap;         // capacity of flatten_ids / isect_ids (>= n_isects unless the caller under-allocated)
+    uint32_t cap;         // capacity of flatten_ids (>= n_isects unless the caller under-allocated)
 };
+
+constexpr int kBinThreads = 256;
 
 // first r in [0, n_runs) with end[r] > s (exists: s < end[n_runs - 1]); one probe per lane and round
 __device__ __forceinline__ uint32_t first_run_after(const uint32_t *__restrict__ end, uint32_t n_runs, uint32_t s) {
@@ -288,137 +300,163 @@ __device__ __forceinline__ uint32_t first_run_after(const uint32_t *__restrict__
     return lo;
 }
 
-// The walk of one chunk.  Per step the warp handles 32 consecutive slots: slot -> run -> tile (the MAP half) and
-// then rank / count / store (the COMMIT half).  The run table entries the next steps need sit in a per-warp ring in
-// shared memory, refilled 32 runs at a time from loads issued a refill earlier, so no global-memory latency is on the
-// serial chain (run pointer -> next step); the MAP of step k+1 is issued before the COMMIT of step k so their
-// shared-memory / shuffle latencies overlap.
-constexpr uint32_t kRing = 128; // run-table entries per warp in shared memory (>= 96 live at any time)
-
-struct RunEnt {
-    uint32_t end, idx, bx, by, key;
-};
-template <bool kScatter>
-__device__ __forceinline__ RunEnt load_run(const RunTable &rt, uint32_t r, uint32_t n_runs) {
-    RunEnt e;
-    e.end = 0xffffffffu; e.idx = 0; e.bx = 0; e.by = 0; e.key = 0;
-    if (r < n_runs) {
-        e.end = rt.end[r];
-        e.idx = rt.idx[r];
-        const uint2 b = rt.box[r];
-        e.bx = b.x; e.by = b.y;
-        if (kScatter) e.key = rt.key[r];
-    }
-    return e;
+// chunk p = runs [first run whose end exceeds p I / P, the same for p + 1)
+__device__ __forceinline__ uint32_t chunk_first_run(const BinArgs &a, uint32_t p, unsigned long long I, uint32_t n_runs) {
+    if (p >= a.P || n_runs == 0) return n_runs;
+    const uint32_t s = (uint32_t)(((unsigned long long)p * I) / a.P);
+    if (I == 0 || s >= I) return n_runs;
+    return first_run_after(a.rt.end, n_runs, s);
 }
 
-struct StepMap {
-    uint32_t tt;   // tile id relative to the window, or a per-lane dummy when the lane has nothing to place
-    uint32_t idx, key, tile, cam;
-    bool in;
-};
-
 template <bool kScatter>
-__global__ void __launch_bounds__(32) tile_bin_kernel(const BinArgs a) {
-    extern __shared__ uint32_t s_mem[]; // [t_cnt counters][5 x kRing run entries]
-    uint32_t *s_cnt = s_mem;
-    uint32_t *s_end = s_mem + ((a.t_cnt + 31u) & ~31u);
-    uint32_t *s_idx = s_end + kRing, *s_bx = s_idx + kRing, *s_by = s_bx + kRing, *s_key = s_by + kRing;
-    const uint32_t lane = threadIdx.x;
+__global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) {
+    extern __shared__ uint32_t s_cnt[]; // [t_cnt]
+    __shared__ uint32_t s_range[2];
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t p = blockIdx.x;
     uint32_t *row = a.M + (size_t)p * a.T_total + a.t_lo;
     const unsigned long long I = a.ctl->n_isects;
     const uint32_t n_runs = a.ctl->n_runs;
-    const uint32_t s_begin = (uint32_t)(((unsigned long long)p * I) / a.P);
-    const uint32_t s_stop = (uint32_t)(((unsigned long long)(p + 1) * I) / a.P);
-    if (kScatter) {
-        if (s_begin >= s_stop) return;
-        for (uint32_t t = lane; t < a.t_cnt; t += 32) s_cnt[t] = row[t];
-    } else {
-        for (uint32_t t = lane; t < a.t_cnt; t += 32) s_cnt[t] = 0;
-    }
-    if (s_begin < s_stop) {
-        uint32_t r0 = first_run_after(a.rt.end, n_runs, s_begin);
-        uint32_t start0 = r0 ? a.rt.end[r0 - 1] : 0u; // first slot of run r0
-        // ring = runs [r0, r0 + 64); `pend` = the 32 runs after those, in flight
-        {
-            const RunEnt e0 = load_run<kScatter>(a.rt, r0 + lane, n_runs), e1 = load_run<kScatter>(a.rt, r0 + 32 + lane, n_runs);
-            const uint32_t w0 = (r0 + lane) & (kRing - 1), w1 = (r0 + 32 + lane) & (kRing - 1);
-            s_end[w0] = e0.end; s_idx[w0] = e0.idx; s_bx[w0] = e0.bx; s_by[w0] = e0.by; s_key[w0] = e0.key;
-            s_end[w1] = e1.end; s_idx[w1] = e1.idx; s_bx[w1] = e1.bx; s_by[w1] = e1.by; s_key[w1] = e1.key;
+    if (tid < 32) {
+        const uint32_t ra = kScatter ? a.chunk_run[p] : chunk_first_run(a, p, I, n_runs);
+        const uint32_t rb = kScatter ? a.chunk_run[p + 1] : chunk_first_run(a, p + 1, I, n_runs);
+        if (tid == 0) {
+            s_range[0] = ra; s_range[1] = rb;
+            if (!kScatter) {
+                a.chunk_run[p] = ra;
+                if (p == a.P - 1) a.chunk_run[a.P] = n_runs;
+            }
         }
-        uint32_t ring_end = r0 + 64;
-        RunEnt pend = load_run<kScatter>(a.rt, ring_end + lane, n_runs);
-        __syncwarp();
+    }
+    if (kScatter) {
+        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) s_cnt[t] = row[t];
+    } else {
+        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) s_cnt[t] = 0;
+    }
+    __syncthreads();
+    const uint32_t ra = s_range[0], rb = s_range[1];
 
-        // MAP: slots [s0, s0 + 32) -> (run, tile); advances (r0, start0) to the run that holds slot s0 + 32
-        auto map_step = [&](uint32_t s0) {
-            if (ring_end < r0 + 64) { // keep 64 runs ahead: a step consumes at most 32
-                const uint32_t w = (ring_end + lane) & (kRing - 1);
-                s_end[w] = pend.end; s_idx[w] = pend.idx; s_bx[w] = pend.bx; s_by[w] = pend.by; s_key[w] = pend.key;
-                ring_end += 32;
-                pend = load_run<kScatter>(a.rt, ring_end + lane, n_runs);
-                __syncwarp();
+    auto place = [&](uint32_t idx, uint32_t cam_base, uint32_t x, uint32_t y) {
+        const uint32_t g = cam_base + y * a.tile_width + x - a.t_lo;
+        if (g < a.t_cnt) {
+            const uint32_t pos = atomicAdd(&s_cnt[g], 1u);
+            if (kScatter && pos < a.cap) a.flatten_ids[pos] = (int32_t)idx;
+        }
+    };
+    for (uint32_t r0 = ra + (tid & ~31u); r0 < rb; r0 += kBinThreads) { // warp-uniform trip count
+        const uint32_t r = r0 + lane;
+        uint32_t idx = 0, bx = 0, by = 0;
+        if (r < rb) {
+            idx = a.rt.idx[r];
+            const uint2 b = a.rt.box[r];
+            bx = b.x; by = b.y;
+        }
+        const uint32_t w = by & 0xffffu, h = by >> 16, n = w * h; // 0 for the lanes past the chunk
+        const uint32_t x0 = bx & 0xffffu, y0 = bx >> 16;
+        const uint32_t cam_base = a.multi_cam ? (idx / a.N) * a.n_tiles : 0u;
+        // runs of up to 32 tiles: one lane each
+        if (n > 0 && n <= 32) {
+            uint32_t x = x0, y = y0;
+            for (uint32_t j = 0; j < n; ++j) {
+                place(idx, cam_base, x, y);
+                if (++x == x0 + w) { x = x0; ++y; }
             }
-            // the run ends inside the step are strictly increasing (no empty runs): bit e of endmask <=> a run ends
-            // after slot s0 + e - 1
-            const uint32_t rel = s_end[(r0 + lane) & (kRing - 1)] - s0; // > 0 for lane 0
-            const uint32_t endmask = __reduce_or_sync(0xffffffffu, rel <= 31u ? (1u << rel) : 0u);
-            const uint32_t c = __popc(endmask & ((2u << lane) - 1u)); // runs finished at or before this lane's slot
-            const uint32_t w = (r0 + c) & (kRing - 1);
-            const uint32_t prev_end = s_end[(r0 + c - 1u) & (kRing - 1)];
-            StepMap m;
-            m.idx = s_idx[w];
-            m.key = kScatter ? s_key[w] : 0u;
-            const uint32_t bx = s_bx[w], by = s_by[w];
-            const uint32_t slot = s0 + lane;
-            const uint32_t run_start = c ? prev_end : start0;
-            const uint32_t j = slot - run_start; // position inside the run's box, row-major
-            const uint32_t bw = by & 0xffffu;
-            m.tt = 0x80000000u | lane;
-            m.tile = 0; m.cam = 0; m.in = false;
-            if (slot < s_stop) {
+        }
+        // larger runs: the whole warp strides over the box
+        uint32_t big = __ballot_sync(0xffffffffu, n > 32);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t bidx = __shfl_sync(0xffffffffu, idx, src), bcam = __shfl_sync(0xffffffffu, cam_base, src);
+            const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+            const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
+            for (uint32_t j = lane; j < bn; j += 32) {
                 const uint32_t dy = j / bw, dx = j - dy * bw;
-                m.tile = ((bx >> 16) + dy) * a.tile_width + (bx & 0xffffu) + dx;
-                m.cam = a.multi_cam ? m.idx / a.N : 0u;
-                const uint32_t g = m.cam * a.n_tiles + m.tile - a.t_lo;
-                m.in = g < a.t_cnt;
-                if (m.in) m.tt = g;
+                place(bidx, bcam, bx0 + dx, by0 + dy);
             }
-            const uint32_t adv = __popc(__ballot_sync(0xffffffffu, rel <= 32u));
-            if (adv) {
-                start0 = s_end[(r0 + adv - 1u) & (kRing - 1)];
-                r0 += adv;
-            }
-            return m;
-        };
-        // COMMIT: stable rank of equal tiles inside the step (lane order = depth order), counters, stores
-        auto commit_step = [&](const StepMap &m) {
-            const uint32_t peers = __match_any_sync(0xffffffffu, m.tt);
-            uint32_t base = 0;
-            if (m.in) base = s_cnt[m.tt];
-            __syncwarp();
-            if (m.in) {
-                if (kScatter) {
-                    const uint32_t pos = base + __popc(peers & ((1u << lane) - 1u));
-                    if (pos < a.cap) a.flatten_ids[pos] = (int32_t)m.idx;
-                }
-                if ((peers >> lane) == 1u) s_cnt[m.tt] = base + __popc(peers);
-            }
-            __syncwarp();
-        };
-
-        StepMap cur = map_step(s_begin);
-        for (uint32_t s0 = s_begin; s0 < s_stop; s0 += 32) {
-            StepMap nxt = cur;
-            if (s0 + 32 < s_stop) nxt = map_step(s0 + 32);
-            commit_step(cur);
-            cur = nxt;
         }
     }
     if (!kScatter) {
-        __syncwarp();
-        for (uint32_t t = lane; t < a.t_cnt; t += 32) row[t] = s_cnt[t];
+        __syncthreads();
+        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) row[t] = s_cnt[t];
+    }
+}
+
+// Order repair of the (chunk, tile) groups: one lane per group, a warp for the large ones.
+constexpr int kSmallGroup = 16;
+
+__global__ void __launch_bounds__(kBinThreads) group_repair_kernel(const BinArgs a, const uint32_t *__restrict__ toff,
+                                                                   const float *__restrict__ depths) {
+    const uint32_t lane = threadIdx.x & 31;
+    const unsigned long long i = (unsigned long long)blockIdx.x * kBinThreads + threadIdx.x;
+    const unsigned long long total = (unsigned long long)a.P * a.T_total;
+    uint32_t start = 0, c = 0, p = 0, t = 0;
+    if (i < total) {
+        p = (uint32_t)(i / a.T_total);
+        t = (uint32_t)(i - (unsigned long long)p * a.T_total);
+        start = a.M[i];
+        uint32_t end = (p + 1 < a.P) ? a.M[i + a.T_total] : toff[t + 1];
+        if (end > a.cap) end = a.cap;
+        c = end > start ? end - start : 0u;
+    }
+    if (c >= 2 && c <= (uint32_t)kSmallGroup) {
+        uint32_t ids[kSmallGroup], keys[kSmallGroup];
+#pragma unroll
+        for (int k = 0; k < kSmallGroup; ++k) {
+            if ((uint32_t)k < c) {
+                ids[k] = (uint32_t)a.flatten_ids[start + k];
+                keys[k] = __float_as_uint(depths[ids[k]]);
+            } else {
+                ids[k] = 0xffffffffu; keys[k] = 0xffffffffu;
+            }
+        }
+        // insertion sort on (depth bits, index), fully unrolled so the arrays stay in registers
+        bool moved = false;
+#pragma unroll
+        for (int k = 1; k < kSmallGroup; ++k) {
+#pragma unroll
+            for (int j = k; j > 0; --j) {
+                const bool sw = (keys[j] < keys[j - 1]) || (keys[j] == keys[j - 1] && ids[j] < ids[j - 1]);
+                if (sw) {
+                    const uint32_t tk = keys[j], ti = ids[j];
+                    keys[j] = keys[j - 1]; ids[j] = ids[j - 1];
+                    keys[j - 1] = tk; ids[j - 1] = ti;
+                    moved = true;
+                }
+            }
+        }
+        if (moved) {
+#pragma unroll
+            for (int k = 0; k < kSmallGroup; ++k)
+                if ((uint32_t)k < c) a.flatten_ids[start + k] = (int32_t)ids[k];
+        }
+    }
+    // groups beyond the register sort: re-emit the chunk's runs that cover the tile, in run (= depth) order
+    uint32_t big = __ballot_sync(0xffffffffu, c > (uint32_t)kSmallGroup);
+    while (big) {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        const uint32_t gp = __shfl_sync(0xffffffffu, p, src), gt = __shfl_sync(0xffffffffu, t, src);
+        const uint32_t gstart = __shfl_sync(0xffffffffu, start, src), gc = __shfl_sync(0xffffffffu, c, src);
+        const uint32_t ra = a.chunk_run[gp], rb = a.chunk_run[gp + 1];
+        const uint32_t cam = gt / a.n_tiles, tl = gt - cam * a.n_tiles;
+        const uint32_t ty = tl / a.tile_width, tx = tl - ty * a.tile_width;
+        uint32_t written = 0;
+        for (uint32_t r0 = ra; r0 < rb && written < gc; r0 += 32) {
+            const uint32_t r = r0 + lane;
+            bool cover = false;
+            uint32_t idx = 0;
+            if (r < rb) {
+                idx = a.rt.idx[r];
+                const uint2 b = a.rt.box[r];
+                const uint32_t x0 = b.x & 0xffffu, y0 = b.x >> 16, w = b.y & 0xffffu, h = b.y >> 16;
+                cover = tx >= x0 && tx < x0 + w && ty >= y0 && ty < y0 + h && (!a.multi_cam || idx / a.N == cam);
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, cover);
+            const uint32_t pos = gstart + written + __popc(m & ((1u << lane) - 1u));
+            if (cover && pos < gstart + gc) a.flatten_ids[pos] = (int32_t)idx;
+            written += __popc(m);
+        }
     }
 }
 
@@ -579,10 +617,10 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
     if (b.t_win == 0) b.t_win = 1;
     b.n_win = (b.T_total + b.t_win - 1) / b.t_win;
     if (b.n_win == 0) b.n_win = 1;
-    b.smem = (size_t)((b.t_win + 31u) & ~31u) * 4 + 5 * kRing * 4;
+    b.smem = (size_t)b.t_win * 4;
     uint32_t per_sm = (uint32_t)((size_t)d.smem_sm / (b.smem + 1024));
     if (per_sm < 1) per_sm = 1;
-    if (per_sm > 16) per_sm = 16;
+    if (per_sm > 8) per_sm = 8; // 8 x 256 threads fill an SM
     uint64_t P = (uint64_t)d.sms * per_sm;
     const uint64_t n = (uint64_t)C * N;
     const uint64_t cap = (n + 255) / 256; // no point in chunks of a handful of Gaussians
@@ -600,7 +638,8 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
 
 // Workspace of the plan; everything the emit needs afterwards lives here too.
 struct PlanWs {
-    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, M, seg, toff, total;
+    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, M, seg, toff, chunk_run,
+        total;
 };
 static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp) {
     PlanWs w;
@@ -616,6 +655,7 @@ static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp) {
     w.M = take((size_t)b.P * b.T_total * 4);
     w.seg = take((size_t)b.S * b.T_total * 4);
     w.toff = take(((size_t)b.T_total + 1) * 4);
+    w.chunk_run = take(((size_t)b.P + 1) * 4);
     w.total = off + 256;
     return w;
 }
@@ -795,15 +835,16 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
         ProfScope ps("isect_tile_hist", s);
         BinArgs a;
         a.rt = rt; a.ctl = ctl; a.N = N; a.n_tiles = tile_width * tile_height; a.tile_width = tile_width;
-        a.tile_n_bits = tile_n_bits; a.multi_cam = C > 1 ? 1u : 0u;
-        a.T_total = bp.T_total; a.P = bp.P; a.M = M; a.flatten_ids = nullptr; a.isect_ids = nullptr; a.cap = 0;
+        a.multi_cam = C > 1 ? 1u : 0u;
+        a.T_total = bp.T_total; a.P = bp.P; a.M = M; a.flatten_ids = nullptr; a.cap = 0;
+        a.chunk_run = reinterpret_cast<uint32_t *>(base + w.chunk_run);
         if (bp.smem > 48 * 1024)
             GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)bp.smem));
         for (uint32_t wnd = 0; wnd < bp.n_win; ++wnd) {
             a.t_lo = wnd * bp.t_win;
             a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
-            tile_bin_kernel<false><<<bp.P, 32, bp.smem, s>>>(a);
+            tile_bin_kernel<false><<<bp.P, kBinThreads, bp.smem, s>>>(a);
             GSB_LAUNCH_CHECK();
         }
         const dim3 cgrid((bp.T_total + kIsectThreads - 1) / kIsectThreads, bp.S);
@@ -825,7 +866,7 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depth
     using namespace gsb;
     const uint64_t n = (uint64_t)C * N;
     if (n == 0 || n_isects == 0) return GSB_OK;
-    if (!plan_workspace || !flatten_ids || (isect_ids && !depths)) return GSB_E_INVALID;
+    if (!plan_workspace || !flatten_ids || !depths) return GSB_E_INVALID;
     if (n_isects > 0x7fffffffull) return GSB_E_INVALID;
     const BinPlan bp = bin_plan(C, N, tile_width, tile_height);
     const SegPlan sp = seg_plan(n);
@@ -838,22 +879,31 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depth
                     reinterpret_cast<uint2 *>(base + w.rt_box), reinterpret_cast<uint32_t *>(base + w.rt_key)};
     a.ctl = reinterpret_cast<const SortCtl *>(base + w.ctl);
     a.N = N; a.n_tiles = tile_width * tile_height; a.tile_width = tile_width;
-    a.tile_n_bits = bit_width_u32(tile_width * tile_height); a.multi_cam = C > 1 ? 1u : 0u;
+    a.multi_cam = C > 1 ? 1u : 0u;
+    a.chunk_run = reinterpret_cast<uint32_t *>(base + w.chunk_run);
     a.T_total = bp.T_total; a.P = bp.P; a.M = reinterpret_cast<uint32_t *>(base + w.M);
-    a.flatten_ids = flatten_ids; a.isect_ids = nullptr; a.cap = (uint32_t)n_isects;
+    a.flatten_ids = flatten_ids; a.cap = (uint32_t)n_isects;
     ProfScope ps("isect_emit", s);
     if (bp.smem > 48 * 1024)
         GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.smem));
     for (uint32_t wnd = 0; wnd < bp.n_win; ++wnd) {
         a.t_lo = wnd * bp.t_win;
         a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
-        tile_bin_kernel<true><<<bp.P, 32, bp.smem, s>>>(a);
+        tile_bin_kernel<true><<<bp.P, kBinThreads, bp.smem, s>>>(a);
+        GSB_LAUNCH_CHECK();
+    }
+    {
+        a.t_lo = 0; a.t_cnt = bp.T_total;
+        const unsigned long long groups = (unsigned long long)bp.P * bp.T_total;
+        group_repair_kernel<<<(unsigned)((groups + kBinThreads - 1) / kBinThreads), kBinThreads, 0, s>>>(
+            a, reinterpret_cast<const uint32_t *>(base + w.toff), depths);
         GSB_LAUNCH_CHECK();
     }
     if (isect_ids) { // only the operator API wants the 64-bit keys back (intersect_offset consumes them)
         const uint32_t grid = (uint32_t)((n_isects + kIsectThreads - 1) / kIsectThreads);
         isect_keys_kernel<<<grid, kIsectThreads, 0, s>>>((uint32_t)n_isects, reinterpret_cast<const uint32_t *>(base + w.toff),
-                                                        bp.T_total, a.n_tiles, a.tile_n_bits, flatten_ids, depths, isect_ids);
+                                                        bp.T_total, a.n_tiles, bit_width_u32(tile_width * tile_height),
+                                                        flatten_ids, depths, isect_ids);
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

@@ -7,6 +7,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 
+#include <cmath>
+
 #include "FusedOps.h"
 #include "gsb200.h"
 
@@ -151,7 +153,7 @@ GSB_EXPORT FusedForwardResult rasterize_from_world_fused_fwd(
     TORCH_CHECK(capacity <= 0x7fffffffLL, "isect capacity out of range");
     r.flatten_ids = at::empty({capacity}, i32);
     if (capacity > 0 && N > 0) {
-        gsb_check(gsb_isect_emit_planned(1, N, nullptr, tw, th, (uint64_t)capacity, plan_ws.data_ptr(), plan_bytes, nullptr,
+        gsb_check(gsb_isect_emit_planned(1, N, r.depths.data_ptr<float>(), tw, th, (uint64_t)capacity, plan_ws.data_ptr(), plan_bytes, nullptr,
                                          r.flatten_ids.data_ptr<int32_t>(), cur_stream()),
                   "rasterize_from_world_fused_fwd/emit");
     }
@@ -207,6 +209,63 @@ rasterize_from_world_fused_bwd(const at::Tensor means, const at::Tensor sh0, con
                              cur_stream()),
               "rasterize_from_world_fused_bwd/back");
     return std::make_tuple(v_means, v_sh0, v_shN, v_scaling, v_rotation, v_opacity);
+}
+
+GSB_EXPORT std::tuple<at::Tensor, at::Tensor> photometric_loss_fused(const at::Tensor renders, const at::Tensor target,
+                                                                     const float lambda_dssim, const bool compute_grad) {
+    const c10::cuda::CUDAGuard guard(renders.device());
+    CHECK_F32(renders);
+    CHECK_F32(target);
+    TORCH_CHECK(renders.dim() == 4 && renders.size(0) == 1 && renders.size(3) == 3, "renders must be [1,H,W,3]");
+    const int64_t H = renders.size(1), W = renders.size(2);
+    TORCH_CHECK(target.numel() == 3 * H * W, "target must hold 3*H*W elements");
+    const bool hwc = target.dim() == 4 && target.size(-1) == 3 && target.size(1) == H;
+    const bool chw = (target.dim() == 3 && target.size(0) == 3) || (target.dim() == 4 && target.size(1) == 3 && !hwc);
+    TORCH_CHECK(hwc || chw, "target must be [3,H,W], [1,3,H,W] or [1,H,W,3]");
+    at::Tensor stats = at::empty({3}, renders.options());
+    at::Tensor v_renders;
+    if (compute_grad) v_renders = at::empty_like(renders);
+    at::Tensor ws = at::empty({(int64_t)gsb_ssim_l1_workspace()}, renders.options().dtype(at::kByte));
+    gsb_check(gsb_ssim_l1((uint32_t)W, (uint32_t)H, renders.data_ptr<float>(), target.data_ptr<float>(), chw ? 1 : 0,
+                          lambda_dssim, 1.0f, compute_grad ? v_renders.data_ptr<float>() : nullptr, stats.data_ptr<float>(),
+                          ws.data_ptr(), (size_t)ws.numel(), cur_stream()),
+              "photometric_loss_fused");
+    return std::make_tuple(stats, v_renders);
+}
+
+GSB_EXPORT void fused_adam_step(const std::vector<at::Tensor> &params, const std::vector<at::Tensor> &grads,
+                                const std::vector<at::Tensor> &exp_avg, const std::vector<at::Tensor> &exp_avg_sq,
+                                const std::vector<double> &lr, const double beta1, const double beta2, const double eps,
+                                const std::vector<int64_t> &step_counts) {
+    const size_t n = params.size();
+    TORCH_CHECK(n > 0 && n <= 8, "fused_adam_step: 1..8 parameter groups");
+    TORCH_CHECK(grads.size() == n && exp_avg.size() == n && exp_avg_sq.size() == n && lr.size() == n &&
+                    step_counts.size() == n,
+                "fused_adam_step: one entry per group in every list");
+    const c10::cuda::CUDAGuard guard(params[0].device());
+    GsbAdamGroup g[8];
+    for (size_t i = 0; i < n; ++i) {
+        CHECK_F32(params[i]);
+        CHECK_F32(grads[i]);
+        CHECK_F32(exp_avg[i]);
+        CHECK_F32(exp_avg_sq[i]);
+        TORCH_CHECK(grads[i].numel() == params[i].numel() && exp_avg[i].numel() == params[i].numel() &&
+                        exp_avg_sq[i].numel() == params[i].numel(),
+                    "fused_adam_step: group ", i, " has mismatching sizes");
+        g[i].param = params[i].data_ptr<float>();
+        g[i].grad = grads[i].data_ptr<float>();
+        g[i].exp_avg = exp_avg[i].data_ptr<float>();
+        g[i].exp_avg_sq = exp_avg_sq[i].data_ptr<float>();
+        g[i].n = (uint64_t)params[i].numel();
+        g[i].lr = (float)lr[i];
+        g[i].beta1 = (float)beta1;
+        g[i].beta2 = (float)beta2;
+        g[i].eps = (float)eps;
+        // fused_adam.cpp:80-81
+        g[i].bias_correction1_rcp = (float)(1.0 / (1.0 - std::pow(beta1, (double)step_counts[i])));
+        g[i].bias_correction2_sqrt_rcp = (float)(1.0 / std::sqrt(1.0 - std::pow(beta2, (double)step_counts[i])));
+    }
+    gsb_check(gsb_adam_step(g, (uint32_t)n, cur_stream()), "fused_adam_step");
 }
 
 } // namespace gsplat

@@ -150,6 +150,19 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fused_bwd(
     return std::make_tuple(std::get<0>(r), std::get<1>(r), v_shN, std::get<3>(r), std::get<4>(r), std::get<5>(r));
 }
 
+std::tuple<Tensor, Tensor> loss_fused(const Tensor &renders, const Tensor &target, double lambda_dssim, bool compute_grad) {
+    auto r = gsplat::photometric_loss_fused(renders, target, (float)lambda_dssim, compute_grad);
+    Tensor v = std::get<1>(r);
+    if (!v.defined()) v = at::empty({0}, renders.options());
+    return std::make_tuple(std::get<0>(r), v);
+}
+
+void adam_step(std::vector<Tensor> params, std::vector<Tensor> grads, std::vector<Tensor> exp_avg,
+               std::vector<Tensor> exp_avg_sq, std::vector<double> lr, double beta1, double beta2, double eps,
+               std::vector<int64_t> step_counts) {
+    gsplat::fused_adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step_counts);
+}
+
 Tensor quats_to_rotmats(const Tensor &quats) { return gsplat::quats_to_rotmats(quats); }
 
 std::tuple<Tensor, Tensor> relocation(const Tensor &opacities, const Tensor &scales, const Tensor &ratios,
@@ -182,6 +195,10 @@ TORCH_LIBRARY(gsplat_b200, m) {
           "Tensor tile_offsets, Tensor flatten_ids, Tensor(a!) workspace, Tensor render_alphas, Tensor last_ids, "
           "Tensor v_render_colors, Tensor v_render_alphas) -> (Tensor, Tensor, Tensor, Tensor, Tensor, Tensor)",
           &fused_bwd);
+    m.def("photometric_loss_fused", &loss_fused);
+    m.def("fused_adam_step(Tensor(a!)[] params, Tensor[] grads, Tensor(b!)[] exp_avg, Tensor(c!)[] exp_avg_sq, float[] lr, "
+          "float beta1, float beta2, float eps, int[] step_counts) -> ()",
+          &adam_step);
     m.def("quats_to_rotmats", &quats_to_rotmats);
     m.def("relocation", &relocation);
     m.def("add_noise(Tensor raw_opacities, Tensor raw_scales, Tensor raw_quats, Tensor noise, Tensor(a!) means, float current_lr) -> ()",

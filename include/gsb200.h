@@ -170,9 +170,9 @@ GSB_API int gsb_isect_sort(uint64_t n_isects, uint32_t C, uint32_t tile_width, u
 
 /* Planned sorted path for sort == true: same outputs as gsb_isect_emit + gsb_isect_sort, bit for bit,
  * without sorting any intersection.  The Gaussians are ordered by depth once (N elements, own radix
- * sort), the I intersection slots in that order are cut into equal chunks, a per-(chunk, tile)
- * histogram is scanned, and every intersection is then written DIRECTLY to its final (tile, depth,
- * index) position (csrc/gsb_intersect.cu).  It is arranged around the one host read-back the
+ * sort), the runs in that order are cut into chunks, a per-(chunk, tile) histogram is scanned, every
+ * intersection is written DIRECTLY into the final range of its (chunk, tile) group and the groups
+ * (1-2 entries on average) are put into depth order in place (csrc/gsb_intersect.cu).  It is arranged around the one host read-back the
  * operator API forces: everything that does not need the host to know n_isects runs in the PLAN.
  *   gsb_isect_plan          tiles_per_gauss [C*N]; *n_isects_out (device OR pinned host int64,
  *                           written asynchronously on `stream`); tile_offsets_out [C*th*tw] int32 or
@@ -191,7 +191,7 @@ GSB_API int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, const i
                            uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *n_isects_out,
                            int32_t *tile_offsets_out /*nullable*/, int tile_offsets_total,
                            void *plan_workspace, size_t plan_workspace_bytes, gsb_stream_t stream);
-GSB_API int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depths /*for isect_ids*/,
+GSB_API int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depths,
                                    uint32_t tile_width, uint32_t tile_height,
                                    uint64_t n_isects, const void *plan_workspace,
                                    size_t plan_workspace_bytes, int64_t *isect_ids /*nullable*/,
@@ -290,6 +290,34 @@ GSB_API int gsb_fused_back(const GsbSplatRaw *splats, const GsbCamera *cam, uint
                            size_t workspace_bytes, float *v_means, float *v_sh0, float *v_shN /*NULL iff K == 1*/,
                            float *v_scaling, float *v_rotation /*16-byte aligned*/, float *v_opacity,
                            gsb_stream_t stream);
+
+/* ---- photometric loss of the training step and its gradient, one kernel -------------------------
+ * loss = (1 - lambda) * mean|clamp(render,0,1) - target| + lambda * (1 - mean SSIM_valid)
+ * (src/training/trainer.cpp:103-126; fused_ssim(..., "valid"): 11x11 Gaussian window, zero padding, map cropped by 5
+ * per side: src/training/kernels/ssim.cu:64-420, include/kernels/fused_ssim.cuh:27-117).
+ * renders [H,W,3] is the blend's output (unclamped); target is [3,H,W] (target_chw != 0, the reference's layout) or
+ * [H,W,3].  v_renders [H,W,3] = grad_scale * dLoss/d(renders) including the clamp mask, or NULL to evaluate only.
+ * loss_out: DEVICE float[3] = (loss, l1 mean, ssim mean).  workspace: gsb_ssim_l1_workspace() bytes, 256-aligned. */
+GSB_API size_t gsb_ssim_l1_workspace(void);
+GSB_API int gsb_ssim_l1(uint32_t image_width, uint32_t image_height, const float *renders, const float *target,
+                        int target_chw, float lambda_dssim, float grad_scale, float *v_renders /*nullable*/,
+                        float *loss_out, void *workspace, size_t workspace_bytes, gsb_stream_t stream);
+
+/* ---- Adam over all parameter groups in one launch ---------------------------------------------------
+ * The update of fastgs/optimizer/include/adam_kernels.cuh:13-36 (param -= lr * bc1_rcp * m / (sqrt(v) * bc2_sqrt_rcp
+ * + eps)); the caller keeps the step counts and learning-rate schedule (src/training/optimizers/fused_adam.cpp:22-95,
+ * strategies/strategy_utils.cpp:27-55).  Up to 8 groups; groups with n == 0 are skipped. */
+typedef struct GsbAdamGroup {
+    float *param;
+    const float *grad;
+    float *exp_avg;
+    float *exp_avg_sq;
+    uint64_t n; /* elements */
+    float lr, beta1, beta2, eps;
+    float bias_correction1_rcp;      /* 1 / (1 - beta1^t) */
+    float bias_correction2_sqrt_rcp; /* 1 / sqrt(1 - beta2^t) */
+} GsbAdamGroup;
+GSB_API int gsb_adam_step(const GsbAdamGroup *groups, uint32_t n_groups, gsb_stream_t stream);
 
 /* ---- link-surface ops used by the densification strategies -------------------------
  * gsplat::quats_to_rotmats (Ops.h:46-48, QuatToRotmatCUDA.cu:14-39): [N,4] -> [N,3,3] */

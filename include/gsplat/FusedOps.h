@@ -16,6 +16,7 @@
 #include <c10/util/Optional.h>
 
 #include <tuple>
+#include <vector>
 
 #include "Cameras.h"
 #include "Common.h"
@@ -67,5 +68,19 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tenso
     const at::Tensor radii, const at::Tensor tile_offsets, const at::Tensor flatten_ids, at::Tensor workspace,
     const at::Tensor render_alphas, const at::Tensor last_ids, const at::Tensor v_render_colors,
     const at::Tensor v_render_alphas);
+
+// loss = (1 - lambda) * l1(clamp(render, 0, 1), target) + lambda * (1 - fused_ssim(.., "valid")) of
+// src/training/trainer.cpp:103-126 and, when `compute_grad`, dLoss/d(renders) in the same kernel.
+// renders [1,H,W,3] (the blend's output), target [3,H,W] / [1,3,H,W] (the reference's layout) or [1,H,W,3].
+// Returns (stats = device float[3]: loss, l1 mean, ssim mean;  v_renders [1,H,W,3] or an undefined tensor).
+std::tuple<at::Tensor, at::Tensor> photometric_loss_fused(const at::Tensor renders, const at::Tensor target,
+                                                          const float lambda_dssim, const bool compute_grad);
+
+// one Adam step over all parameter groups in one launch (fastgs/optimizer/include/adam_kernels.cuh:13-36,
+// src/training/optimizers/fused_adam.cpp:22-95).  step_counts are the per-group counts AFTER the increment.
+void fused_adam_step(const std::vector<at::Tensor> &params, const std::vector<at::Tensor> &grads,
+                     const std::vector<at::Tensor> &exp_avg, const std::vector<at::Tensor> &exp_avg_sq,
+                     const std::vector<double> &lr, const double beta1, const double beta2, const double eps,
+                     const std::vector<int64_t> &step_counts);
 
 } // namespace gsplat

@@ -176,7 +176,7 @@ def test_full_size_fused_equals_operator_path(native, full, cuda_device):
         (img * vr).sum().backward()
         res[tag] = (img.detach(), n, {k: P[k].grad for k in P})
         del P, o
-    assert res["fused"][1] == res["unfused"][1]
+    assert abs(res["fused"][1] - res["unfused"][1]) <= max(8, int(2e-5 * res["unfused"][1]))  # ceil() flips
     e = rel(res["fused"][0], res["unfused"][0])
     print(f"[config {f['cfg']}] fused vs operator path: image rel_l2 {e:.2e}")
     assert e < 1e-5
