@@ -47,8 +47,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "gaussians_rasterized_per_sec_fwd_bwd"
 UNIT = "Gaussians/s"
 CSRC = os.path.join(ROOT, "gaussian-splatting-cuda_b200", "csrc")
-KERNEL_NAMES = ("projection_ut", "sh_fwd", "isect_count", "isect_depth_sort", "isect_tile_hist", "isect_emit",
-                "isect_sort", "isect_offsets", "raster_prep", "raster_fwd", "raster_bwd", "raster_finalize", "sh_bwd",
+KERNEL_NAMES = ("projection_ut", "sh_fwd", "isect_count", "isect_depth_sort", "isect_runs", "isect_tile_hist",
+                "isect_colscan", "isect_emit", "isect_repair", "isect_keys", "isect_sort", "isect_offsets", "raster_prep", "raster_fwd", "raster_bwd", "raster_finalize", "sh_bwd",
                 "sh_bwd_views", "fused_front", "fused_back", "ssim_l1_fwd", "ssim_l1_bwd", "adam_step")
 WORKLOADS = {
     "A": "10k synthetic Gaussians, 256x256, SH deg 0, 1 camera (BASELINE.json configs[0])",

@@ -399,37 +399,50 @@ __global__ void __launch_bounds__(kBinThreads) group_repair_kernel(const BinArgs
         if (end > a.cap) end = a.cap;
         c = end > start ? end - start : 0u;
     }
-    if (c >= 2 && c <= (uint32_t)kSmallGroup) {
-        uint32_t ids[kSmallGroup], keys[kSmallGroup];
-#pragma unroll
-        for (int k = 0; k < kSmallGroup; ++k) {
-            if ((uint32_t)k < c) {
-                ids[k] = (uint32_t)a.flatten_ids[start + k];
-                keys[k] = __float_as_uint(depths[ids[k]]);
-            } else {
-                ids[k] = 0xffffffffu; keys[k] = 0xffffffffu;
-            }
-        }
-        // insertion sort on (depth bits, index), fully unrolled so the arrays stay in registers
+    if (c >= 2 && c <= 4) {
+        // the common case (a group holds 1.35 intersections on average): a 4-element sorting network in registers
+        uint32_t id0 = (uint32_t)a.flatten_ids[start], id1 = (uint32_t)a.flatten_ids[start + 1];
+        uint32_t id2 = c > 2 ? (uint32_t)a.flatten_ids[start + 2] : 0xffffffffu;
+        uint32_t id3 = c > 3 ? (uint32_t)a.flatten_ids[start + 3] : 0xffffffffu;
+        uint32_t k0 = __float_as_uint(depths[id0]), k1 = __float_as_uint(depths[id1]);
+        uint32_t k2 = c > 2 ? __float_as_uint(depths[id2]) : 0xffffffffu;
+        uint32_t k3 = c > 3 ? __float_as_uint(depths[id3]) : 0xffffffffu;
         bool moved = false;
-#pragma unroll
-        for (int k = 1; k < kSmallGroup; ++k) {
-#pragma unroll
-            for (int j = k; j > 0; --j) {
-                const bool sw = (keys[j] < keys[j - 1]) || (keys[j] == keys[j - 1] && ids[j] < ids[j - 1]);
-                if (sw) {
-                    const uint32_t tk = keys[j], ti = ids[j];
-                    keys[j] = keys[j - 1]; ids[j] = ids[j - 1];
-                    keys[j - 1] = tk; ids[j - 1] = ti;
-                    moved = true;
-                }
+        auto cswap = [&](uint32_t &ka, uint32_t &ia, uint32_t &kb, uint32_t &ib) {
+            if (kb < ka || (kb == ka && ib < ia)) {
+                const uint32_t tk = ka, ti = ia;
+                ka = kb; ia = ib; kb = tk; ib = ti;
+                moved = true;
             }
-        }
+        };
+        cswap(k0, id0, k1, id1); cswap(k2, id2, k3, id3); cswap(k0, id0, k2, id2); cswap(k1, id1, k3, id3);
+        cswap(k1, id1, k2, id2);
         if (moved) {
-#pragma unroll
-            for (int k = 0; k < kSmallGroup; ++k)
-                if ((uint32_t)k < c) a.flatten_ids[start + k] = (int32_t)ids[k];
+            a.flatten_ids[start] = (int32_t)id0;
+            a.flatten_ids[start + 1] = (int32_t)id1;
+            if (c > 2) a.flatten_ids[start + 2] = (int32_t)id2;
+            if (c > 3) a.flatten_ids[start + 3] = (int32_t)id3;
         }
+    } else if (c > 4 && c <= (uint32_t)kSmallGroup) {
+        // insertion sort on (depth bits, index) in local memory: rare
+        uint32_t ids[kSmallGroup], keys[kSmallGroup];
+        for (uint32_t k = 0; k < c; ++k) {
+            ids[k] = (uint32_t)a.flatten_ids[start + k];
+            keys[k] = __float_as_uint(depths[ids[k]]);
+        }
+        bool moved = false;
+        for (uint32_t k = 1; k < c; ++k) {
+            const uint32_t kk = keys[k], ki = ids[k];
+            uint32_t j = k;
+            while (j > 0 && (kk < keys[j - 1] || (kk == keys[j - 1] && ki < ids[j - 1]))) {
+                keys[j] = keys[j - 1]; ids[j] = ids[j - 1];
+                --j;
+                moved = true;
+            }
+            keys[j] = kk; ids[j] = ki;
+        }
+        if (moved)
+            for (uint32_t k = 0; k < c; ++k) a.flatten_ids[start + k] = (int32_t)ids[k];
     }
     // groups beyond the register sort: re-emit the chunk's runs that cover the tile, in run (= depth) order
     uint32_t big = __ballot_sync(0xffffffffu, c > (uint32_t)kSmallGroup);
@@ -468,17 +481,31 @@ __global__ void __launch_bounds__(kIsectThreads) isect_keys_kernel(uint32_t n, c
                                                                    const int32_t *__restrict__ flatten_ids,
                                                                    const float *__restrict__ depths,
                                                                    int64_t *__restrict__ isect_ids) {
-    const uint32_t pos = blockIdx.x * kIsectThreads + threadIdx.x;
-    if (pos >= n) return;
-    // last t in [0, T) with tile_off[t] <= pos  (offsets are non-decreasing; empty tiles repeat a value)
-    uint32_t lo = 0, hi = T;
-    while (hi - lo > 1) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (__ldg(tile_off + mid) <= pos) lo = mid; else hi = mid;
+    // four positions per thread, interleaved over the warp so that loads and stores stay coalesced: one search for
+    // the first, then the tile only moves forward
+    const uint32_t warp_base = (blockIdx.x * kIsectThreads + (threadIdx.x & ~31u)) * 4u;
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t t = 0;
+    bool have = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint32_t pos = warp_base + k * 32u + lane;
+        if (pos >= n) break;
+        if (!have) { // last t in [0, T) with tile_off[t] <= pos (empty tiles repeat a value)
+            uint32_t lo = 0, hi = T;
+            while (hi - lo > 1) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (__ldg(tile_off + mid) <= pos) lo = mid; else hi = mid;
+            }
+            t = lo;
+            have = true;
+        } else {
+            while (t + 1 < T && __ldg(tile_off + t + 1) <= pos) ++t;
+        }
+        const uint32_t cam = t / n_tiles, tile = t - cam * n_tiles;
+        const uint32_t idx = (uint32_t)flatten_ids[pos];
+        isect_ids[pos] = ((int64_t)cam << (32 + tile_n_bits)) | ((int64_t)tile << 32) | (int64_t)__float_as_uint(depths[idx]);
     }
-    const uint32_t cam = lo / n_tiles, tile = lo - cam * n_tiles;
-    const uint32_t idx = (uint32_t)flatten_ids[pos];
-    isect_ids[pos] = ((int64_t)cam << (32 + tile_n_bits)) | ((int64_t)tile << 32) | (int64_t)__float_as_uint(depths[idx]);
 }
 
 // ---- step 5: exclusive scan of M over (tile, chunk) ----------------------------------------------------------
@@ -823,6 +850,9 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
     {
         ProfScope ps("isect_depth_sort", s);
         if (int rc = radix_sort_launch<uint32_t>(k0, k1, v0, v1, n, sp, 4, 0, 32, ctl, H, true, s)) return rc;
+    }
+    {
+        ProfScope ps("isect_runs", s);
         runs_blocksum_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(ctl, v0, v1, tiles_per_gauss, n, sp.seg, bsum);
         GSB_LAUNCH_CHECK();
         runs_build_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(ctl, v0, v1, k0, k1, tiles_per_gauss, boxes, n, sp.seg,
@@ -847,6 +877,9 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
             tile_bin_kernel<false><<<bp.P, kBinThreads, bp.smem, s>>>(a);
             GSB_LAUNCH_CHECK();
         }
+    }
+    {
+        ProfScope ps("isect_colscan", s);
         const dim3 cgrid((bp.T_total + kIsectThreads - 1) / kIsectThreads, bp.S);
         col_segsum_kernel<<<cgrid, kIsectThreads, 0, s>>>(M, bp.T_total, bp.P, bp.seg_len, seg);
         GSB_LAUNCH_CHECK();
@@ -883,16 +916,19 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depth
     a.chunk_run = reinterpret_cast<uint32_t *>(base + w.chunk_run);
     a.T_total = bp.T_total; a.P = bp.P; a.M = reinterpret_cast<uint32_t *>(base + w.M);
     a.flatten_ids = flatten_ids; a.cap = (uint32_t)n_isects;
-    ProfScope ps("isect_emit", s);
     if (bp.smem > 48 * 1024)
         GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.smem));
-    for (uint32_t wnd = 0; wnd < bp.n_win; ++wnd) {
-        a.t_lo = wnd * bp.t_win;
-        a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
-        tile_bin_kernel<true><<<bp.P, kBinThreads, bp.smem, s>>>(a);
-        GSB_LAUNCH_CHECK();
+    {
+        ProfScope ps("isect_emit", s);
+        for (uint32_t wnd = 0; wnd < bp.n_win; ++wnd) {
+            a.t_lo = wnd * bp.t_win;
+            a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
+            tile_bin_kernel<true><<<bp.P, kBinThreads, bp.smem, s>>>(a);
+            GSB_LAUNCH_CHECK();
+        }
     }
     {
+        ProfScope ps("isect_repair", s);
         a.t_lo = 0; a.t_cnt = bp.T_total;
         const unsigned long long groups = (unsigned long long)bp.P * bp.T_total;
         group_repair_kernel<<<(unsigned)((groups + kBinThreads - 1) / kBinThreads), kBinThreads, 0, s>>>(
@@ -900,7 +936,8 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depth
         GSB_LAUNCH_CHECK();
     }
     if (isect_ids) { // only the operator API wants the 64-bit keys back (intersect_offset consumes them)
-        const uint32_t grid = (uint32_t)((n_isects + kIsectThreads - 1) / kIsectThreads);
+        const uint32_t grid = (uint32_t)((n_isects + kIsectThreads * 4 - 1) / (kIsectThreads * 4));
+        ProfScope psk("isect_keys", s);
         isect_keys_kernel<<<grid, kIsectThreads, 0, s>>>((uint32_t)n_isects, reinterpret_cast<const uint32_t *>(base + w.toff),
                                                         bp.T_total, a.n_tiles, bit_width_u32(tile_width * tile_height),
                                                         flatten_ids, depths, isect_ids);

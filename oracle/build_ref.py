@@ -30,6 +30,10 @@ CU = ["ProjectionUT3DGSFused.cu", "IntersectTile.cu", "SphericalHarmonicsCUDA.cu
       "RelocationCUDA.cu", "RasterizeToPixelsFromWorld3DGSFwd.cu", "RasterizeToPixelsFromWorld3DGSBwd.cu"]
 CPP = ["Projection.cpp", "Intersect.cpp", "SphericalHarmonics.cpp", "QuatToRotmat.cpp", "Relocation.cpp",
        "Rasterization.cpp"]
+# the training-step kernels next to the path, compiled from where they lie as well
+TRAIN_CU = ["/root/reference/src/training/kernels/ssim.cu"]
+TRAIN_INC = ["/root/reference/fastgs/optimizer/include"]
+EXTRA = ["ref_binding.cpp", "ref_train_binding.cu"]
 
 
 def available() -> bool:
@@ -40,10 +44,13 @@ def _stamp() -> str:
     h = hashlib.sha256()
     for f in CU + CPP:
         h.update(open(os.path.join(REF, f), "rb").read())
+    for f in TRAIN_CU + [os.path.join(TRAIN_INC[0], "adam_kernels.cuh")]:
+        h.update(open(f, "rb").read())
     for root, _, files in os.walk(os.path.join(HERE, "glm_shim")):
         for f in sorted(files):
             h.update(open(os.path.join(root, f), "rb").read())
-    h.update(open(os.path.join(HERE, "ref_binding.cpp"), "rb").read())
+    for f in EXTRA:
+        h.update(open(os.path.join(HERE, f), "rb").read())
     return h.hexdigest()
 
 
@@ -59,14 +66,14 @@ def build(verbose: bool = True, jobs: int = 7) -> str | None:
     if os.path.exists(so) and os.path.exists(stamp_file) and open(stamp_file).read() == st:
         return so
     inc = []
-    for i in [os.path.join(HERE, "glm_shim"), REF] + ce.include_paths():
+    for i in [os.path.join(HERE, "glm_shim"), REF] + TRAIN_INC + ce.include_paths():
         inc += ["-I", i]
     common = ["-O3", "-std=c++20", "-Xcompiler", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=1", "-ccbin", CXX,
               "-gencode", "arch=compute_100,code=sm_100", "--use_fast_math", "--expt-relaxed-constexpr",
               "-diag-suppress", "20012,20011,20014,177,550"]
 
     def compile_one(src: str):
-        sp = os.path.join(REF, src) if not src.endswith("ref_binding.cpp") else src
+        sp = src if os.path.isabs(src) else os.path.join(REF, src)
         obj = os.path.join(OUT, os.path.basename(src).rsplit(".", 1)[0] + ".o")
         cmd = [NVCC, "-c", sp, "-o", obj, "-x", "cu"] + common + inc
         if verbose:
@@ -77,7 +84,7 @@ def build(verbose: bool = True, jobs: int = 7) -> str | None:
             raise RuntimeError(f"reference source failed to compile: {src}")
         return obj
 
-    srcs = CU + CPP + [os.path.join(HERE, "ref_binding.cpp")]
+    srcs = CU + CPP + TRAIN_CU + [os.path.join(HERE, f) for f in EXTRA]
     with ThreadPoolExecutor(max_workers=jobs) as ex:
         objs = list(ex.map(compile_one, srcs))
     tl = ce.library_paths()[0]

@@ -34,6 +34,8 @@ def grad_metrics(got, want, n_gauss: int, per_gauss_tol: float = 1e-2, floor_fra
     """Whole-tensor and per-Gaussian error metrics of a gradient tensor with `n_gauss` rows."""
     g = torch.as_tensor(got).double().reshape(n_gauss, -1)
     w = torch.as_tensor(want).double().to(g.device).reshape(n_gauss, -1)
+    if g.numel() == 0:  # e.g. shN of a degree-0 model
+        return dict(rel=0.0, frac_bad=0.0, max_abs=0.0, n_bad=0, n_nonzero=0)
     err = (g - w).norm(dim=1)
     ref = w.norm(dim=1)
     nz = ref > 0

@@ -77,11 +77,14 @@ def test_fused_adam_matches_reference_formula(native, cuda_device):
             if k == "shN" and it <= 1000:
                 continue
             gr = grads[k]
-            m[k] = 0.9 * m[k] + 0.1 * gr
-            v2[k] = 0.999 * v2[k] + 0.001 * gr * gr
-            bc1 = 1.0 / (1.0 - 0.9 ** steps[k])
-            bc2 = 1.0 / math.sqrt(1.0 - 0.999 ** steps[k])
-            ref[k] = ref[k] - lr[i] * bc1 * m[k] / (v2[k].sqrt() * bc2 + 1e-15)
+            # the kernel's coefficients are float32: beta = fl(0.9), 1 - beta = fl(1 - fl(0.9)) (adam_kernels.cuh:28-29)
+            b1, b2 = float(np.float32(0.9)), float(np.float32(0.999))
+            ob1, ob2 = float(np.float32(1) - np.float32(0.9)), float(np.float32(1) - np.float32(0.999))
+            m[k] = b1 * m[k] + ob1 * gr
+            v2[k] = b2 * v2[k] + ob2 * gr * gr
+            bc1 = float(np.float32(1.0 / (1.0 - 0.9 ** steps[k])))
+            bc2 = float(np.float32(1.0 / math.sqrt(1.0 - 0.999 ** steps[k])))
+            ref[k] = ref[k] - float(np.float32(lr[i])) * bc1 * m[k] / (v2[k].sqrt() * bc2 + 1e-15)
         lr[0] *= 0.01 ** (1.0 / 100)
     for k in P:
         assert rel(P[k].detach(), ref[k]) < 1e-6, k
@@ -110,3 +113,58 @@ def test_training_iterations_reduce_the_loss_without_host_readback(native, cuda_
     print("losses", [f"{v:.5f}" for v in vals], "intersections", int(step.last["n_isects"].item()))
     assert vals[-1] < vals[0] and all(math.isfinite(v) for v in vals)
     assert int(step.last["n_isects"].item()) <= step.capacity
+
+
+# ------------------------------------------------------------------------------------------
+# the same rows against the REFERENCE's own kernels (oracle/_ref: ssim.cu and adam_kernels.cuh compiled unmodified)
+# ------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ref_train(native):
+    from oracle import ref_ops
+    if not ref_ops.available():
+        pytest.skip("oracle/_ref/libgsplat_ref.so not built")
+    from oracle import ref_train as rt
+    try:
+        ref_ops._ns().fusedssim
+    except (AttributeError, RuntimeError):
+        pytest.skip("oracle/_ref was built without the training kernels")
+    return rt
+
+
+@pytest.mark.parametrize("H,W", [(70, 150), (540, 960)])
+def test_photometric_loss_vs_reference_kernels(native, ref_train, cuda_device, H, W):
+    from gsplat_b200 import training
+    g = torch.Generator(device=cuda_device).manual_seed(7)
+    renders = (torch.rand((1, H, W, 3), device=cuda_device, generator=g) * 1.4 - 0.2)
+    target = torch.rand((3, H, W), device=cuda_device, generator=g)
+    a = renders.clone().requires_grad_(True)
+    loss, _ = training.photometric_loss(a, target, 0.2)
+    loss.backward()
+    b = renders.clone().requires_grad_(True)
+    image = torch.clamp(b[0].permute(2, 0, 1), 0.0, 1.0)  # rasterizer.cpp:401
+    want = ref_train.ref_photometric_loss(image, target, 0.2)
+    want.backward()
+    print(f"[{H}x{W}] loss {float(loss):.7f} vs reference kernels {float(want):.7f}; grad rel_l2 {rel(a.grad, b.grad):.2e}")
+    assert abs(float(loss) - float(want)) < 5e-6 * max(1.0, abs(float(want)))
+    assert rel(a.grad, b.grad) < 1e-4
+
+
+def test_fused_adam_vs_reference_kernel(native, ref_train, cuda_device):
+    from gsplat_b200 import training
+    g = torch.Generator(device=cuda_device).manual_seed(9)
+    shapes = {"means": (5003, 3), "sh0": (5003, 1, 3), "shN": (5003, 15, 3), "scaling_raw": (5003, 3),
+              "rotation_raw": (5003, 4), "opacity_raw": (5003, 1)}
+    init = {k: torch.randn(s, device=cuda_device, generator=g) for k, s in shapes.items()}
+    A = {k: v.clone().requires_grad_(True) for k, v in init.items()}
+    B = {k: v.clone().requires_grad_(True) for k, v in init.items()}
+    cfg = training.AdamConfig(iterations=50)
+    mine, theirs = training.FusedAdam(A, cfg), ref_train.RefFusedAdam(B, cfg.lrs(), iterations=50)
+    for it in (1, 2, 3, 1200, 1201):
+        for k in shapes:
+            gr = torch.randn(shapes[k], device=cuda_device, generator=g)
+            A[k].grad, B[k].grad = gr.clone(), gr.clone()
+        mine.step(it)
+        theirs.step(it, training.PARAM_GROUPS)
+    for k in shapes:  # same float32 arithmetic, operation for operation
+        assert torch.equal(A[k].detach(), B[k].detach()), k
+        assert torch.equal(mine.exp_avg[k], theirs.m[k]) and torch.equal(mine.exp_avg_sq[k], theirs.v[k]), k
