@@ -316,6 +316,8 @@ def run_b200(args):
     cabi = ctypes.CDLL(pkg.CABI_PATH)
     cabi.gsb_launch_count.restype = ctypes.c_uint64
     cabi.gsb_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
+    if args.bwd_variant:
+        cabi.gsb_debug_set_bwd_variant(ctypes.c_int(args.bwd_variant))
     names = ("means", "quats", "scales", "opacities", "sh_coeffs")
     raw_names = ("means", "sh0", "shN", "scaling_raw", "rotation_raw", "opacity_raw")
     compact = world > 1 and args.exchange == "compact"
@@ -627,6 +629,65 @@ def run_b200(args):
             line["reference_cuda"] = {"unavailable": repr(e)[:200]}
     line["ops_ms"] = ops_ms
 
+    # ---- training iteration: render -> L1 + SSIM loss -> backward -> Adam (BASELINE.json "iters/sec") ----
+    def train_block(w, steps):
+        from gsplat_b200 import training
+        tgt_chw = w.P["target"][0].permute(2, 0, 1).contiguous()
+        host_tgt = tgt_chw.cpu().pin_memory()
+        out = {}
+        P1 = {k: v.detach().clone().requires_grad_(True) for k, v in w.raw().items()}
+        ts = training.TrainStep(P1, w.deg, w.W, w.H, optimizer=training.FusedAdam(P1))
+        ts.size_capacity(w.P["viewmats"], w.P["Ks"], tgt_chw, w.P["background"])
+
+        def it_b200():
+            for k in ("viewmats", "Ks", "background"):
+                w.P[k] = w.host[k].to(dev, non_blocking=True)
+            tg = host_tgt.to(dev, non_blocking=True)
+            return float(ts(w.P["viewmats"], w.P["Ks"], tg, w.P["background"]).item())
+        for _ in range(3):
+            it_b200()
+        ms = timed(it_b200, steps) / steps
+        prof_t = read_profile(it_b200, max(steps, 10))
+        assert int(ts.last["n_isects"].item()) <= ts.capacity
+        out["b200"] = {"ms_per_iter": ms, "iters_per_sec": 1e3 / ms,
+                       "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in prof_t.items()},
+                       "what": "extended operator on raw tensors + fused SSIM/L1 loss-and-gradient kernel + one-launch Adam; "
+                               "camera + target H2D and loss D2H every iteration"}
+        if rb is not None:
+            try:
+                from oracle import ref_train
+                P2 = {k: v.detach().clone().requires_grad_(True) for k, v in w.raw().items()}
+                ropt = ref_train.RefFusedAdam(P2, training.AdamConfig().lrs())
+                state = {"it": 0}
+
+                def it_ref():
+                    for k in ("viewmats", "Ks", "background"):
+                        w.P[k] = w.host[k].to(dev, non_blocking=True)
+                    tg = host_tgt.to(dev, non_blocking=True)
+                    o = pkg.rasterize_from_raw(P2, w.deg, w.P["viewmats"], w.P["Ks"], w.W, w.H,
+                                               bg_color=w.P["background"], backend=rb)
+                    loss = ref_train.ref_photometric_loss(o.image, tg, 0.2)
+                    loss.backward()
+                    state["it"] += 1
+                    ropt.step(state["it"], training.PARAM_GROUPS)
+                    ropt.zero_grad()
+                    return float(loss.item())
+                for _ in range(2):
+                    it_ref()
+                ms_r = timed(it_ref, steps) / steps
+                out["reference_cuda"] = {"ms_per_iter": ms_r, "iters_per_sec": 1e3 / ms_r,
+                                         "what": "the reference's own kernels for every stage (gsplat operators, ssim.cu, "
+                                                 "adam_kernels.cuh) glued by torch exactly as its trainer does"}
+                out["speedup"] = ms_r / ms
+            except Exception as e:
+                out["reference_cuda"] = {"unavailable": repr(e)[:200]}
+        return out
+
+    try:
+        line["train"] = train_block(wl, args.steps)
+    except Exception as e:
+        line["train"] = {"unavailable": repr(e)[:300]}
+
     # ---- the other configs of BASELINE.json (N=1 line only) ---------------------------------------------------------
     configs = {}
     if cfg == "B" and not args.no_other_configs:
@@ -674,6 +735,10 @@ def run_b200(args):
                 ms_dr = timed(lambda: wd.step(backend=rb), 10) / 10
                 d["reference_cuda"] = {"ms_per_step": ms_dr, "value": wd.N / (ms_dr * 1e-3),
                                        "speedup_device_resident": ms_dr / ms_d}
+            try:
+                d["train"] = train_block(wd, 10)
+            except Exception as e:
+                d["train"] = {"unavailable": repr(e)[:200]}
             configs["D"] = d
             del wd
         except Exception as e:
@@ -704,6 +769,7 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the config A / D block of the N=1 line")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
+    ap.add_argument("--bwd-variant", type=int, default=0, help="diagnostics: 1 = narrow blend-backward kernel")
     args = ap.parse_args()
     if args.quick:
         args.no_cpu_baseline = args.no_ref_cuda = args.no_other_configs = True

@@ -99,6 +99,9 @@ GSB_API int gsb_version(void);
  * "isect_emit", "isect_sort", "isect_offsets", "raster_prep", "raster_fwd", "raster_bwd",
  * "raster_finalize") and returns how many launches were found. */
 GSB_API uint64_t gsb_launch_count(void);
+/* Which blend-backward kernel the perfect-pinhole path launches: 0 = default (wide: a warp owns 16 x 8 pixels),
+ * 1 = narrow (8 x 8 pixels per warp).  Same results up to fp32 summation order; for profiling and tests. */
+GSB_API void gsb_debug_set_bwd_variant(int variant);
 GSB_API void gsb_profile_enable(int on);
 GSB_API int gsb_profile_read(const char *kernel, double *total_ms);
 
