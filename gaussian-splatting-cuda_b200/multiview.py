@@ -22,12 +22,14 @@ def allreduce_gradients(grads: Sequence[torch.Tensor], average_over: int | None 
     """Sum the gradient tensors over all ranks IN PLACE with one coalesced collective launch
     (ncclGroupStart/End around five all-reduces: 236 B per Gaussian), optionally dividing by the number
     of views so the result is the gradient of the mean loss."""
+    grads = [g for g in grads if g is not None]
+    if not grads:
+        return
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         if average_over and average_over != 1:
             for g in grads:
                 g.div_(average_over)
         return
-    grads = [g for g in grads if g is not None]
     dev = grads[0].device
     if dev.type == "cuda":
         with dist._coalescing_manager(group=group, device=dev, async_ops=False):
@@ -41,8 +43,18 @@ def allreduce_gradients(grads: Sequence[torch.Tensor], average_over: int | None 
             g.div_(average_over)
 
 
+_side_streams: dict = {}
+
+
+def _side_stream(device):
+    key = (device.type, device.index)
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device)
+    return _side_streams[key]
+
+
 def exchange_gradients_compact(params: dict, deferred, sh_views_fn=None, average_over: int | None = None,
-                               group=None) -> None:
+                               group=None, overlap_group=None) -> None:
     """The exchange step with 1/2 to 1/3 of the all-reduce's traffic.
 
     `params` maps 'means', 'quats', 'scales', 'opacities', 'sh_coeffs' to the leaf tensors; after
@@ -55,24 +67,52 @@ def exchange_gradients_compact(params: dict, deferred, sh_views_fn=None, average
          position gradient is added to the (already reduced) means.grad.
     Result: every rank holds the same sums as allreduce_gradients() would give after per-rank SH backward.
     `sh_views_fn(degree, means, campos, coeffs, v_colors, v_means) -> v_coeffs` defaults to the product op;
-    the gloo tests pass the oracle's."""
+    the gloo tests pass the oracle's.
+
+    `overlap_group`: a second process group over the same ranks (dist.new_group()).  The geometry all-reduce does not
+    depend on the colour all-gather or on the SH expansion, so with its own communicator it runs on a side stream
+    UNDER them (NVSwitch has the bandwidth for both); the expansion then writes the SH part of the position gradient
+    into a scratch tensor that is added once the all-reduce has landed.  `deferred` may be a list (several views per
+    rank): their colour gradients are stacked before the gather."""
     if sh_views_fn is None:
         from . import default_backend
         sh_views_fn = default_backend().spherical_harmonics_bwd_views
     means, coeffs = params["means"], params["sh_coeffs"]
-    vc, cp = deferred.v_colors, deferred.campos.reshape(1, 3).contiguous()
+    sinks = list(deferred) if isinstance(deferred, (list, tuple)) else [deferred]
+    sh_degree = sinks[0].sh_degree
+    vc = torch.stack([d.v_colors for d in sinks]).contiguous()                      # [v_local, N, 3]
+    cp = torch.stack([d.campos.reshape(3) for d in sinks]).contiguous()             # [v_local, 3]
+    geo = [params[k].grad for k in ("means", "quats", "scales", "opacities")]
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    pending, scratch = None, None
     if world > 1:
-        vc_all = torch.empty((world,) + tuple(vc.shape), dtype=vc.dtype, device=vc.device)
-        cp_all = torch.empty((world, 3), dtype=cp.dtype, device=cp.device)
-        dist.all_gather_into_tensor(vc_all.view(-1, vc.shape[-1]), vc, group=group)  # concatenation along dim 0
+        overlap = overlap_group is not None and vc.device.type == "cuda"
+        if overlap:
+            comp, side = torch.cuda.current_stream(vc.device), _side_stream(vc.device)
+            side.wait_stream(comp)  # the blend gradients are complete
+            with torch.cuda.stream(side):
+                allreduce_gradients(geo, group=overlap_group)
+            pending = side
+            for g in geo:
+                g.record_stream(side)
+        vc_all = torch.empty((world * vc.shape[0],) + tuple(vc.shape[1:]), dtype=vc.dtype, device=vc.device)
+        cp_all = torch.empty((world * cp.shape[0], 3), dtype=cp.dtype, device=cp.device)
+        dist.all_gather_into_tensor(vc_all.view(-1, vc.shape[-1]), vc.view(-1, vc.shape[-1]), group=group)
         dist.all_gather_into_tensor(cp_all, cp, group=group)
-        allreduce_gradients([params[k].grad for k in ("means", "quats", "scales", "opacities")], group=group)
+        if not overlap:
+            allreduce_gradients(geo, group=group)
     else:
-        vc_all, cp_all = vc.unsqueeze(0), cp
+        vc_all, cp_all = vc, cp
     with torch.no_grad():
-        coeffs.grad = sh_views_fn(deferred.sh_degree, means.detach().contiguous(), cp_all.contiguous(),
-                                  coeffs.detach().contiguous(), vc_all.contiguous(), means.grad)
+        v_means = means.grad
+        if pending is not None:  # means.grad is still being reduced: expand into a scratch tensor
+            scratch = torch.zeros_like(means.grad)
+            v_means = scratch
+        coeffs.grad = sh_views_fn(sh_degree, means.detach().contiguous(), cp_all.contiguous(),
+                                  coeffs.detach().contiguous(), vc_all.contiguous(), v_means)
+        if pending is not None:
+            torch.cuda.current_stream(vc.device).wait_stream(pending)
+            means.grad.add_(scratch)
     if average_over and average_over != 1:
         for k in ("means", "quats", "scales", "opacities", "sh_coeffs"):
             params[k].grad.div_(average_over)

@@ -102,5 +102,59 @@ def build(verbose: bool = True, jobs: int = 7) -> str | None:
     return so
 
 
+L3_SRC = "/root/reference/src/training/rasterization/rasterizer_autograd.cpp"
+
+
+def build_l3_harness(verbose: bool = True) -> str | None:
+    """The reference's rasterizer_autograd.cpp (unmodified) + oracle/ref_l3_harness.cpp linked against THIS repo's drop-in
+    library: oracle/_ref/libref_l3_b200.so (tests/test_gpu_reference_l3.py executes it on the GPU)."""
+    if not os.path.exists(L3_SRC):
+        return None
+    from torch.utils import cpp_extension as ce
+
+    root = os.path.dirname(HERE)
+    lib_dir = os.path.join(root, "gaussian-splatting-cuda_b200", "lib")
+    shim = os.path.join(lib_dir, "libgsplat_b200.so")
+    if not os.path.exists(shim):
+        return None
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, "libref_l3_b200.so")
+    h = hashlib.sha256()
+    for f in (L3_SRC, os.path.join(HERE, "ref_l3_harness.cpp"), os.path.join(root, "include", "gsplat", "Ops.h")):
+        h.update(open(f, "rb").read())
+    st = h.hexdigest()
+    if os.path.exists(so) and os.path.exists(so + ".stamp") and open(so + ".stamp").read() == st:
+        return so
+    inc = []
+    for i in [os.path.join(root, "tests", "link_stubs"), os.path.join(root, "include", "gsplat"), os.path.join(root, "include"),
+              "/root/reference/src/training"] + ce.include_paths() + ["/usr/local/cuda/include"]:
+        inc += ["-I", i]
+    objs = []
+    for src in (L3_SRC, os.path.join(HERE, "ref_l3_harness.cpp")):
+        obj = os.path.join(OUT, "l3_" + os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        if verbose:
+            print("[build_ref] L3", os.path.basename(src), flush=True)
+        p = subprocess.run([CXX, "-std=c++20", "-O2", "-fPIC", "-DGSB_NO_GLM", "-D_GLIBCXX_USE_CXX11_ABI=1", "-c", src, "-o",
+                            obj] + inc, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout[-6000:])
+            raise RuntimeError(f"L3 harness source failed to compile: {src}")
+        objs.append(obj)
+    tl = ce.library_paths()[0]
+    p = subprocess.run([CXX, "-shared", "-o", so] + objs + ["-L", lib_dir, "-lgsplat_b200", "-lgsb200", "-L", tl, "-ltorch",
+                        "-ltorch_cpu", "-lc10", "-ltorch_cuda", "-lc10_cuda", "-Wl,--no-undefined",
+                        "-Wl,-rpath,$ORIGIN/../../gaussian-splatting-cuda_b200/lib", "-Wl,-rpath," + tl],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout[-6000:])
+        raise RuntimeError("linking oracle/_ref/libref_l3_b200.so failed")
+    for o in objs:
+        os.remove(o)
+    with open(so + ".stamp", "w") as f:
+        f.write(st)
+    return so
+
+
 if __name__ == "__main__":
     print(build())
+    print(build_l3_harness())
