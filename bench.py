@@ -318,8 +318,6 @@ def run_b200(args):
     cabi = ctypes.CDLL(pkg.CABI_PATH)
     cabi.gsb_launch_count.restype = ctypes.c_uint64
     cabi.gsb_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
-    if args.bwd_variant:
-        cabi.gsb_debug_set_bwd_variant(ctypes.c_int(args.bwd_variant))
     names = ("means", "quats", "scales", "opacities", "sh_coeffs")
     raw_names = ("means", "sh0", "shN", "scaling_raw", "rotation_raw", "opacity_raw")
     compact = world > 1 and args.exchange == "compact"
@@ -784,7 +782,6 @@ def main():
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the config A / D block of the N=1 line")
     ap.add_argument("--quick", action="store_true", help="device-resident timing only (profiling runs)")
-    ap.add_argument("--bwd-variant", type=int, default=0, help="diagnostics: 1 = narrow blend-backward kernel")
     args = ap.parse_args()
     if args.quick:
         args.no_cpu_baseline = args.no_ref_cuda = args.no_other_configs = True

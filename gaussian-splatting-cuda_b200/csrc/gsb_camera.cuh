@@ -32,41 +32,45 @@ __device__ __forceinline__ float poly_horner5(const float *c, float x) {
     return y;
 }
 
-// Cameras.cuh:759-815: smallest positive root of 1 + a x + b x^2 + c x^3
-__device__ inline float fisheye_max_angle_cubic(float a, float b, float c) {
+// Smallest positive real root of 1 + a x + b x^2 + c x^3 (+inf when there is none): where the derivative of the
+// fisheye polynomial first vanishes, i.e. the largest angle up to which the model is monotonic (what
+// Cameras.cuh:759-815 computes).  Linear / quadratic cases directly; the cubic through its depressed form
+// t^3 + P t + Q (x = t - B/3 for the monic x^3 + B x^2 + A x + C0), Cardano for one real root, the
+// trigonometric form for three.
+__device__ inline float smallest_positive_root_cubic(float a, float b, float c) {
     const float INF = 3.402823466e+38f;
     if (c == 0.0f) {
-        if (b == 0.0f) return a >= 0.0f ? INF : -1.0f / a;
-        float delta = a * a - 4.0f * b;
-        if (delta >= 0.0f) {
-            delta = sqrtf(delta) - a;
-            if (delta > 0.0f) return 2.0f / delta;
-        }
-    } else {
-        const float boc = b / c, boc2 = boc * boc;
-        const float t1 = (9.0f * a * boc - 2.0f * b * boc2 - 27.0f) / c;
-        const float t2 = 3.0f * a / c - boc2;
-        const float delta = t1 * t1 + 4.0f * t2 * t2 * t2;
-        if (delta >= 0.0f) {
-            const float d2 = sqrtf(delta);
-            const float cube_root = cbrtf((d2 + t1) / 2.0f);
-            if (cube_root != 0.0f) {
-                const float soln = (cube_root - (t2 / cube_root) - boc) / 3.0f;
-                if (soln > 0.0f) return soln;
-            }
-        } else {
-            const float theta = atan2f(sqrtf(-delta), t1) / 3.0f;
-            const float two_third_pi = 2.0f * 3.14159265358979323846f / 3.0f;
-            const float t3 = 2.0f * sqrtf(-t2);
-            float soln = INF;
-            for (int i = -1; i <= 1; ++i) {
-                const float sv = (t3 * cosf(theta + (float)i * two_third_pi) - boc) / 3.0f;
-                if (sv > 0.0f) soln = fminf(soln, sv);
-            }
-            return soln;
-        }
+        if (b == 0.0f) return a < 0.0f ? -1.0f / a : INF;                 // 1 + a x
+        const float disc = a * a - 4.0f * b;                              // 1 + a x + b x^2
+        if (disc < 0.0f) return INF;
+        // the root with the smaller magnitude in its cancellation-free form: 2 / (-a + sqrt(disc)); the other root is
+        // either negative or larger
+        const float q = sqrtf(disc) - a;
+        return q > 0.0f ? 2.0f / q : INF;
     }
-    return INF;
+    const float B = b / c, A = a / c, C0 = 1.0f / c;                      // monic coefficients
+    const float P = A - B * B / 3.0f;
+    const float Q = 2.0f * B * B * B / 27.0f - A * B / 3.0f + C0;
+    const float shift = -B / 3.0f;
+    const float D = 0.25f * Q * Q + P * P * P / 27.0f;
+    if (D >= 0.0f) {                                                      // one real root
+        const float sD = sqrtf(D);
+        const float u = cbrtf(-0.5f * Q + sD);
+        // v = cbrt(-Q/2 - sqrt(D)) = -P / (3 u): avoids the second cube root and its cancellation
+        if (u == 0.0f) return INF;
+        const float x = u - P / (3.0f * u) + shift;
+        return x > 0.0f ? x : INF;
+    }
+    const float m = 2.0f * sqrtf(-P / 3.0f);                              // three real roots
+    const float phi = atan2f(sqrtf(-D), -0.5f * Q) / 3.0f;
+    const float third = 2.0943951023931953f;                              // 2 pi / 3
+    float best = INF;
+#pragma unroll
+    for (int k = -1; k <= 1; ++k) {
+        const float x = m * cosf(phi + (float)k * third) + shift;
+        if (x > 0.0f) best = fminf(best, x);
+    }
+    return best;
 }
 
 // Built once per CTA from the DEVICE camera arrays (the reference rebuilds it in every thread).
@@ -90,7 +94,7 @@ __device__ inline void cam_model_build(CamModel &m, int camera_model, uint32_t W
         const float mdx = fmaxf(m.W - m.cx, m.cx), mdy = fmaxf(m.H - m.cy, m.cy);
         const float max_radius_pixels = sqrtf(mdx * mdx + mdy * mdy);
         if (fk[3] == 0.f) {
-            m.max_angle = sqrtf(fisheye_max_angle_cubic(3.f * fk[0], 5.f * fk[1], 7.f * fk[2]));
+            m.max_angle = sqrtf(smallest_positive_root_cubic(3.f * fk[0], 5.f * fk[1], 7.f * fk[2]));
         } else {
             const float dd[4] = {6.f * fk[0], 20.f * fk[1], 42.f * fk[2], 72.f * fk[3]};
             float x = 1.57f;
@@ -118,6 +122,39 @@ __device__ inline void cam_model_build(CamModel &m, int camera_model, uint32_t W
     }
 }
 
+// OpenCV pinhole distortion (rational radial g = N(r)/D(r), r = x^2 + y^2; tangential p1, p2; thin prism s1..s4):
+//   u = g x + 2 p1 x y + p2 (r + 2 x^2) + s1 r + s2 r^2,   v = g y + p1 (r + 2 y^2) + 2 p2 x y + s3 r + s4 r^2
+// and, when asked, the Jacobian d(u, v)/d(x, y) (with dr/dx = 2x, dr/dy = 2y and g' = (N' D - N D') / D^2).
+struct OpenCVDistortion {
+    float u, v, radial;
+    float ux, uy, vx, vy;
+};
+template <bool kJacobian>
+__device__ __forceinline__ OpenCVDistortion opencv_distort(const CamModel &m, float x, float y) {
+    OpenCVDistortion o;
+    const float r = x * x + y * y;
+    const float N = 1.0f + r * (m.k[0] + r * (m.k[1] + r * m.k[2]));
+    const float D = 1.0f + r * (m.k[3] + r * (m.k[4] + r * m.k[5]));
+    const float g = N / D;
+    o.radial = g;
+    const float xy2 = 2.0f * x * y;
+    o.u = g * x + m.p[0] * xy2 + m.p[1] * (r + 2.0f * x * x) + r * (m.s[0] + r * m.s[1]);
+    o.v = g * y + m.p[0] * (r + 2.0f * y * y) + m.p[1] * xy2 + r * (m.s[2] + r * m.s[3]);
+    o.ux = o.uy = o.vx = o.vy = 0.f;
+    if (kJacobian) {
+        const float Nr = m.k[0] + r * (2.0f * m.k[1] + r * (3.0f * m.k[2]));
+        const float Dr = m.k[3] + r * (2.0f * m.k[4] + r * (3.0f * m.k[5]));
+        const float gr = (Nr * D - N * Dr) / (D * D);
+        const float tu = m.s[0] + 2.0f * m.s[1] * r, tv = m.s[2] + 2.0f * m.s[3] * r; // d(thin prism)/dr
+        const float rx = 2.0f * x, ry = 2.0f * y;
+        o.ux = g + x * gr * rx + 2.0f * m.p[0] * y + 6.0f * m.p[1] * x + tu * rx;
+        o.uy = x * gr * ry + 2.0f * m.p[0] * x + 2.0f * m.p[1] * y + tu * ry;
+        o.vx = y * gr * rx + 2.0f * m.p[0] * x + 2.0f * m.p[1] * y + tv * rx;
+        o.vy = g + y * gr * ry + 6.0f * m.p[0] * y + 2.0f * m.p[1] * x + tv * ry;
+    }
+    return o;
+}
+
 // Cameras.cuh:228-240
 __device__ __forceinline__ bool in_bounds_margin(float px, float py, float W, float H, float margin) {
     const float MX = W * margin, MY = H * margin;
@@ -134,17 +171,10 @@ __device__ inline bool cam_project(const CamModel &m, V3<float> cam, float margi
         return in_bounds_margin(ox, oy, m.W, m.H, margin);
     }
     if (m.kind == kCamOpenCVPinhole) {
-        const float u = cam.x / cam.z, v = cam.y / cam.z;
-        const float u2 = u * u, v2 = v * v, r2 = u2 + v2;
-        const float a1 = 2.f * u * v, a2 = r2 + 2.f * u2, a3 = r2 + 2.f * v2;
-        const float num = 1.f + r2 * (m.k[0] + r2 * (m.k[1] + r2 * m.k[2]));
-        const float den = 1.f + r2 * (m.k[3] + r2 * (m.k[4] + r2 * m.k[5]));
-        const float icD = num / den;
-        const float dx = m.p[0] * a1 + m.p[1] * a2 + r2 * (m.s[0] + r2 * m.s[1]);
-        const float dy = m.p[0] * a3 + m.p[1] * a1 + r2 * (m.s[2] + r2 * m.s[3]);
-        ox = (icD * u + dx) * m.fx + m.cx;
-        oy = (icD * v + dy) * m.fy + m.cy;
-        return (icD > 0.8f) && in_bounds_margin(ox, oy, m.W, m.H, margin);
+        const OpenCVDistortion d = opencv_distort<false>(m, cam.x / cam.z, cam.y / cam.z);
+        ox = d.u * m.fx + m.cx;
+        oy = d.v * m.fy + m.cy;
+        return (d.radial > 0.8f) && in_bounds_margin(ox, oy, m.W, m.H, margin); // Cameras.cuh:590-596
     }
     // fisheye
     const float ax = fabsf(cam.x), ay = fabsf(cam.y);
@@ -169,36 +199,22 @@ __device__ inline bool cam_unproject_normalized(const CamModel &m, float px, flo
     const float u0 = (px - m.cx) / m.fx, v0 = (py - m.cy) / m.fy;
     xn = u0; yn = v0;
     if (m.kind == kCamPerfectPinhole) return true;
-    if (m.kind == kCamOpenCVPinhole) { // Newton, at most 5 iterations
+    if (m.kind == kCamOpenCVPinhole) {
+        // Newton on distort(x, y) = (u0, v0) from the distorted point itself; the reference's iteration budget and
+        // stopping rules (Cameras.cuh:698-740): at most 5 steps, stop on a non-positive radial factor, a Jacobian
+        // determinant below 1e-6, or steps below 1e-6
         float x = u0, y = v0;
         bool converged = false;
         for (int iter = 0; iter < 5; ++iter) {
-            const float r = x * x + y * y, r2 = r * r;
-            const float alpha = 1.0f + r * (m.k[0] + r * (m.k[1] + r * m.k[2]));
-            const float beta = 1.0f + r * (m.k[3] + r * (m.k[4] + r * m.k[5]));
-            const float d = alpha / beta;
-            if (d <= 0.f) break;
-            const float p1 = m.p[0], p2 = m.p[1], s1 = m.s[0], s2 = m.s[1], s3 = m.s[2], s4 = m.s[3];
-            const float fx_ = d * x + 2.f * p1 * x * y + p2 * (r + 2.f * x * x) + s1 * r + s2 * r2 - u0;
-            const float fy_ = d * y + 2.f * p2 * x * y + p1 * (r + 2.f * y * y) + s3 * r + s4 * r2 - v0;
-            const float alpha_r = m.k[0] + r * (2.0f * m.k[1] + r * (3.0f * m.k[2]));
-            const float beta_r = m.k[3] + r * (2.0f * m.k[4] + r * (3.0f * m.k[5]));
-            const float d_r = (alpha_r * beta - alpha * beta_r) / (beta * beta);
-            const float d_x = 2.0f * x * d_r, d_y = 2.0f * y * d_r;
-            float fx_x = d + d_x * x + 2.0f * p1 * y + 6.0f * p2 * x;
-            fx_x += 2.0f * x * (s1 + 2.0f * s2 * r);
-            float fx_y = d_y * x + 2.0f * p1 * x + 2.0f * p2 * y;
-            fx_y += 2.0f * y * (s1 + 2.0f * s2 * r);
-            float fy_x = d_x * y + 2.0f * p2 * y + 2.0f * p1 * x;
-            fy_x += 2.0f * x * (s3 + 2.0f * s4 * r);
-            float fy_y = d + d_y * y + 2.0f * p2 * x + 6.0f * p1 * y;
-            fy_y += 2.0f * y * (s3 + 2.0f * s4 * r);
-            const float det = fx_y * fy_x - fx_x * fy_y;
+            const OpenCVDistortion d = opencv_distort<true>(m, x, y);
+            if (d.radial <= 0.f) break;
+            const float ru = u0 - d.u, rv = v0 - d.v;          // residual of the target
+            const float det = d.ux * d.vy - d.uy * d.vx;
             if (fabsf(det) < 1e-6f) break;
-            const float dx = (fx_ * fy_y - fy_ * fx_y) / det;
-            const float dy = (fy_ * fx_x - fx_ * fy_x) / det;
-            x += dx; y += dy;
-            if (fabsf(dx) < 1e-6f && fabsf(dy) < 1e-6f) { converged = true; break; }
+            const float sx = (ru * d.vy - d.uy * rv) / det;     // Cramer: J (sx, sy) = (ru, rv)
+            const float sy = (d.ux * rv - ru * d.vx) / det;
+            x += sx; y += sy;
+            if (fabsf(sx) < 1e-6f && fabsf(sy) < 1e-6f) { converged = true; break; }
         }
         xn = x; yn = y;
         return converged;

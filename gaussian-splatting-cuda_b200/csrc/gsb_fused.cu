@@ -16,8 +16,8 @@
 //                        layouts, the direction gradient added to the position gradient.
 //
 // Per Gaussian the front reads 236 B and writes 84 (+64) B, the back reads ~364 B and writes 236 B: both are
-// HBM streaming kernels.  The shN rows (180 B at K = 16, 4-byte aligned only) are moved per 256-Gaussian slab with
-// one TMA bulk copy each way (46 KB, 16-byte aligned as a whole) and read from shared memory at an odd word stride.
+// HBM streaming kernels.  The shN rows (180 B at K = 16, 4-byte aligned only) are moved per 128-Gaussian slab with
+// one TMA bulk copy each way (23 KB per 128-Gaussian slab, 16-byte aligned as a whole) and read from shared memory at an odd word stride.
 // Compiled with -fmad=false like gsb_projection.cu: the radii must be the a1 operator's, bit for bit.
 #include "gsb_projection.cuh"
 #include "gsb_raster.cuh"
@@ -25,7 +25,7 @@
 
 namespace gsb {
 
-constexpr int kFusedThreads = 256;
+constexpr int kFusedThreads = 128; // 96-122 registers per thread: 128-thread CTAs keep 4-5 of them on an SM
 
 struct FusedParams {
     uint32_t N, K; // K = SH coefficients per Gaussian including sh0
@@ -93,9 +93,9 @@ __device__ __forceinline__ void stage_rows_in(float *s_rows, const float *g_rows
 }
 
 template <int DEG>
-__global__ void __launch_bounds__(kFusedThreads) fused_front_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, 5) fused_front_kernel(const FusedParams p) {
     constexpr int NB = (DEG + 1) * (DEG + 1);
-    extern __shared__ __align__(128) float s_rows[]; // [256][(K-1)*3]
+    extern __shared__ __align__(128) float s_rows[]; // [kFusedThreads][(K-1)*3]
     __shared__ FusedCam s_cam;
     __shared__ __align__(8) uint64_t s_bar;
     const uint32_t tid = threadIdx.x;
@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kFusedThreads) fused_front_kernel(const FusedP
 }
 
 template <int DEG>
-__global__ void __launch_bounds__(kFusedThreads) fused_back_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, 4) fused_back_kernel(const FusedParams p) {
     constexpr int NB = (DEG + 1) * (DEG + 1);
     extern __shared__ __align__(128) float s_rows[]; // shN rows in, v_shN rows out (each thread owns its row)
     __shared__ FusedCam s_cam;

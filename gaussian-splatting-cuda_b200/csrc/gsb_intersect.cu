@@ -356,10 +356,23 @@ __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) 
         const uint32_t cam_base = a.multi_cam ? (idx / a.N) * a.n_tiles : 0u;
         // runs of up to 32 tiles: one lane each
         if (n > 0 && n <= 32) {
+            // four tiles per trip: the four shared-memory atomics are in flight together (their return value, the
+            // slot, is what the store waits for)
             uint32_t x = x0, y = y0;
-            for (uint32_t j = 0; j < n; ++j) {
-                place(idx, cam_base, x, y);
-                if (++x == x0 + w) { x = x0; ++y; }
+            for (uint32_t j = 0; j < n; j += 4) {
+                uint32_t g[4], pos[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    g[u] = (j + u < n) ? cam_base + y * a.tile_width + x - a.t_lo : 0xffffffffu;
+                    if (++x == x0 + w) { x = x0; ++y; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pos[u] = (g[u] < a.t_cnt) ? atomicAdd(&s_cnt[g[u]], 1u) : 0xffffffffu;
+                if (kScatter) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (pos[u] < a.cap) a.flatten_ids[pos[u]] = (int32_t)idx;
+                }
             }
         }
         // larger runs: the whole warp strides over the box
@@ -423,7 +436,34 @@ __global__ void __launch_bounds__(kBinThreads) group_repair_kernel(const BinArgs
             if (c > 2) a.flatten_ids[start + 2] = (int32_t)id2;
             if (c > 3) a.flatten_ids[start + 3] = (int32_t)id3;
         }
-    } else if (c > 4 && c <= (uint32_t)kSmallGroup) {
+    } else if (c > 4 && c <= 8) {
+        // up to eight: Batcher's odd-even merge network (19 comparators) in registers, padding with +inf keys
+        uint32_t id[8], k[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            id[e] = (uint32_t)e < c ? (uint32_t)a.flatten_ids[start + e] : 0xffffffffu;
+            k[e] = (uint32_t)e < c ? __float_as_uint(depths[id[e]]) : 0xffffffffu;
+        }
+        bool moved = false;
+        auto cs = [&](int i, int j) {
+            if (k[j] < k[i] || (k[j] == k[i] && id[j] < id[i])) {
+                const uint32_t tk = k[i], ti = id[i];
+                k[i] = k[j]; id[i] = id[j]; k[j] = tk; id[j] = ti;
+                moved = true;
+            }
+        };
+        cs(0, 1); cs(2, 3); cs(4, 5); cs(6, 7);
+        cs(0, 2); cs(1, 3); cs(4, 6); cs(5, 7);
+        cs(1, 2); cs(5, 6);
+        cs(0, 4); cs(1, 5); cs(2, 6); cs(3, 7);
+        cs(2, 4); cs(3, 5);
+        cs(1, 2); cs(3, 4); cs(5, 6);
+        if (moved) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if ((uint32_t)e < c) a.flatten_ids[start + e] = (int32_t)id[e];
+        }
+    } else if (c > 8 && c <= (uint32_t)kSmallGroup) {
         // insertion sort on (depth bits, index) in local memory: rare
         uint32_t ids[kSmallGroup], keys[kSmallGroup];
         for (uint32_t k = 0; k < c; ++k) {
@@ -650,6 +690,13 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
     if (per_sm > 8) per_sm = 8; // 8 x 256 threads fill an SM
     uint64_t P = (uint64_t)d.sms * per_sm;
     const uint64_t n = (uint64_t)C * N;
+    // a (chunk, tile) group should hold one or two intersections: more Gaussians -> more waves of chunks, as long as
+    // the P x tiles matrix stays below 128 MB
+    uint64_t waves = (n + 2500000 - 1) / 2500000;
+    if (waves < 1) waves = 1;
+    if (waves > 4) waves = 4;
+    while (waves > 1 && P * waves * b.T_total * 4 > (128ull << 20)) --waves;
+    P *= waves;
     const uint64_t cap = (n + 255) / 256; // no point in chunks of a handful of Gaussians
     if (P > cap) P = cap;
     if (P < 1) P = 1;

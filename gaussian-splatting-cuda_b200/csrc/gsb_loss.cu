@@ -68,21 +68,32 @@ __global__ void __launch_bounds__(kLossThreads) ssim_l1_kernel(const LossParams 
             sY[r][q] = Y;
         }
         __syncthreads();
-        // (1) horizontal window on 36 rows x 26 columns, a strip of 13 outputs per work item
+        // (1) horizontal window on 36 rows x 26 columns, a strip of 13 outputs per work item.  The five windowed
+        //     quantities ride on packed fp32 pairs: (X, Y), (X^2, Y^2) and a scalar XY -- three FMA issues per tap
         for (int it = tid; it < kR2 * 2; it += kLossThreads) {
             const int r = it >> 1, q0 = (it & 1) * 13;
-            float x[23], y[23];
+            f2 xy[23], sq[23];
+            float pr[23];
 #pragma unroll
-            for (int k = 0; k < 23; ++k) { x[k] = sX[r][q0 + k]; y[k] = sY[r][q0 + k]; }
+            for (int k = 0; k < 23; ++k) {
+                const float xv = sX[r][q0 + k], yv = sY[r][q0 + k];
+                xy[k] = f2_make(xv, yv);
+                sq[k] = f2_mul(xy[k], xy[k]);
+                pr[k] = xv * yv;
+            }
 #pragma unroll
             for (int o = 0; o < 13; ++o) {
-                float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+                f2 a02 = f2_bc(0.f), a13 = f2_bc(0.f);
+                float a4 = 0.f;
 #pragma unroll
                 for (int k = 0; k < 11; ++k) {
-                    const float w = c_win[k], xv = x[o + k], yv = y[o + k];
-                    a0 += w * xv; a1 += w * (xv * xv); a2 += w * yv; a3 += w * (yv * yv); a4 += w * (xv * yv);
+                    const float w = c_win[k];
+                    a02 = f2_fma(f2_bc(w), xy[o + k], a02);
+                    a13 = f2_fma(f2_bc(w), sq[o + k], a13);
+                    a4 += w * pr[o + k];
                 }
-                sH[0][r][q0 + o] = a0; sH[1][r][q0 + o] = a1; sH[2][r][q0 + o] = a2; sH[3][r][q0 + o] = a3;
+                sH[0][r][q0 + o] = f2_lo(a02); sH[2][r][q0 + o] = f2_hi(a02);
+                sH[1][r][q0 + o] = f2_lo(a13); sH[3][r][q0 + o] = f2_hi(a13);
                 sH[4][r][q0 + o] = a4;
             }
         }
@@ -91,17 +102,29 @@ __global__ void __launch_bounds__(kLossThreads) ssim_l1_kernel(const LossParams 
         for (int it = tid; it < kR1 * 2; it += kLossThreads) {
             const int q = it >> 1, r0 = (it & 1) * 13;
             float acc5[5][13];
+            {
+                f2 v02[23], v13[23];
+                float v4[23];
 #pragma unroll
-            for (int s = 0; s < 5; ++s) {
-                float v[23];
-#pragma unroll
-                for (int k = 0; k < 23; ++k) v[k] = sH[s][r0 + k][q];
+                for (int k = 0; k < 23; ++k) {
+                    v02[k] = f2_make(sH[0][r0 + k][q], sH[2][r0 + k][q]);
+                    v13[k] = f2_make(sH[1][r0 + k][q], sH[3][r0 + k][q]);
+                    v4[k] = sH[4][r0 + k][q];
+                }
 #pragma unroll
                 for (int o = 0; o < 13; ++o) {
-                    float a = 0.f;
+                    f2 a02 = f2_bc(0.f), a13 = f2_bc(0.f);
+                    float a4 = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 11; ++k) a += c_win[k] * v[o + k];
-                    acc5[s][o] = a;
+                    for (int k = 0; k < 11; ++k) {
+                        const float w = c_win[k];
+                        a02 = f2_fma(f2_bc(w), v02[o + k], a02);
+                        a13 = f2_fma(f2_bc(w), v13[o + k], a13);
+                        a4 += w * v4[o + k];
+                    }
+                    acc5[0][o] = f2_lo(a02); acc5[2][o] = f2_hi(a02);
+                    acc5[1][o] = f2_lo(a13); acc5[3][o] = f2_hi(a13);
+                    acc5[4][o] = a4;
                 }
             }
 #pragma unroll
@@ -131,21 +154,26 @@ __global__ void __launch_bounds__(kLossThreads) ssim_l1_kernel(const LossParams 
             }
         }
         __syncthreads();
-        // (3) horizontal window of the derivative maps: 26 rows x 16 columns, strips of 8
+        // (3) horizontal window of the derivative maps: 26 rows x 16 columns, strips of 8; maps 0 and 1 packed
         for (int it = tid; it < kR1 * 2; it += kLossThreads) {
             const int r = it >> 1, q0 = (it & 1) * 8;
+            f2 v01[18];
+            float v2[18];
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                float v[18];
+            for (int k = 0; k < 18; ++k) {
+                v01[k] = f2_make(sM[0][r][q0 + k], sM[1][r][q0 + k]);
+                v2[k] = sM[2][r][q0 + k];
+            }
 #pragma unroll
-                for (int k = 0; k < 18; ++k) v[k] = sM[s][r][q0 + k];
+            for (int o = 0; o < 8; ++o) {
+                f2 a01 = f2_bc(0.f);
+                float a2 = 0.f;
 #pragma unroll
-                for (int o = 0; o < 8; ++o) {
-                    float a = 0.f;
-#pragma unroll
-                    for (int k = 0; k < 11; ++k) a += c_win[k] * v[o + k];
-                    sG[s][r][q0 + o] = a;
+                for (int k = 0; k < 11; ++k) {
+                    a01 = f2_fma(f2_bc(c_win[k]), v01[o + k], a01);
+                    a2 += c_win[k] * v2[o + k];
                 }
+                sG[0][r][q0 + o] = f2_lo(a01); sG[1][r][q0 + o] = f2_hi(a01); sG[2][r][q0 + o] = a2;
             }
         }
         __syncthreads();
@@ -153,17 +181,24 @@ __global__ void __launch_bounds__(kLossThreads) ssim_l1_kernel(const LossParams 
         for (int it = tid; it < kT * 2; it += kLossThreads) {
             const int q = it >> 1, r0 = (it & 1) * 8;
             float s3[3][8];
+            {
+                f2 v01[18];
+                float v2[18];
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-                float v[18];
-#pragma unroll
-                for (int k = 0; k < 18; ++k) v[k] = sG[s][r0 + k][q];
+                for (int k = 0; k < 18; ++k) {
+                    v01[k] = f2_make(sG[0][r0 + k][q], sG[1][r0 + k][q]);
+                    v2[k] = sG[2][r0 + k][q];
+                }
 #pragma unroll
                 for (int o = 0; o < 8; ++o) {
-                    float a = 0.f;
+                    f2 a01 = f2_bc(0.f);
+                    float a2 = 0.f;
 #pragma unroll
-                    for (int k = 0; k < 11; ++k) a += c_win[k] * v[o + k];
-                    s3[s][o] = a;
+                    for (int k = 0; k < 11; ++k) {
+                        a01 = f2_fma(f2_bc(c_win[k]), v01[o + k], a01);
+                        a2 += c_win[k] * v2[o + k];
+                    }
+                    s3[0][o] = f2_lo(a01); s3[1][o] = f2_hi(a01); s3[2][o] = a2;
                 }
             }
 #pragma unroll

@@ -63,31 +63,35 @@ __global__ void __launch_bounds__(kMiscThreads) quat_to_rotmat_kernel(uint32_t N
         for (int c = 0; c < 3; ++c) o[r * 3 + c] = R.m[r][c];
 }
 
-// Eq. (9) of "3D Gaussian Splatting as Markov Chain Monte Carlo"
+// gsplat::relocation (RelocationCUDA.cu:12-43): Eq. (9) of "3D Gaussian Splatting as Markov Chain Monte Carlo".
+// A Gaussian split into n copies keeps its appearance with opacity o' = 1 - (1 - o)^(1/n) and scales multiplied by
+//     o / sum_{i=1..n} sum_{k=0..i-1} C(i-1, k) (-1)^k o'^(k+1) / sqrt(k+1).
+// The double sum is evaluated k-major here: the power of o' and 1/sqrt(k+1) are built once per k (no powf in the
+// loop) and multiplied by the column sum of the caller's binomial table, sum_{i=k+1..n} binoms[i-1][k].
 __global__ void __launch_bounds__(kMiscThreads) relocation_kernel(uint32_t N, const float *__restrict__ opacities,
                                                                    const float *__restrict__ scales,
                                                                    const int32_t *__restrict__ ratios,
                                                                    const float *__restrict__ binoms, int32_t n_max,
                                                                    float *__restrict__ new_opacities,
                                                                    float *__restrict__ new_scales) {
-    const uint32_t idx = blockIdx.x * kMiscThreads + threadIdx.x;
-    if (idx >= N) return;
-    const int n_idx = ratios[idx];
-    const float op = opacities[idx];
-    const float new_op = 1.0f - powf(1.0f - op, 1.0f / (float)n_idx);
-    new_opacities[idx] = new_op;
-    float denom_sum = 0.0f;
-    for (int i = 1; i <= n_idx; ++i) {
-        for (int k = 0; k <= i - 1; ++k) {
-            const float bin_coeff = binoms[(i - 1) * n_max + k];
-            const float sign = (k & 1) ? -1.0f : 1.0f; // pow(-1, k)
-            const float term = (sign / sqrtf((float)(k + 1))) * powf(new_op, (float)(k + 1));
-            denom_sum += bin_coeff * term;
-        }
+    const uint32_t g = blockIdx.x * kMiscThreads + threadIdx.x;
+    if (g >= N) return;
+    const int copies = ratios[g];
+    const float o = opacities[g];
+    const float o_new = 1.0f - powf(1.0f - o, 1.0f / (float)copies);
+    new_opacities[g] = o_new;
+    float series = 0.0f;
+    float pw = o_new; // (-1)^k o'^(k+1), k = 0
+    for (int k = 0; k < copies; ++k) {
+        float column = 0.0f;
+        for (int i = k + 1; i <= copies; ++i) column += binoms[(i - 1) * n_max + k];
+        series += column * pw * rsqrtf((float)(k + 1));
+        pw *= -o_new;
     }
-    const float coeff = op / denom_sum;
-#pragma unroll
-    for (int i = 0; i < 3; ++i) new_scales[(size_t)idx * 3 + i] = coeff * scales[(size_t)idx * 3 + i];
+    const float grow = o / series;
+    new_scales[(size_t)g * 3] = grow * scales[(size_t)g * 3];
+    new_scales[(size_t)g * 3 + 1] = grow * scales[(size_t)g * 3 + 1];
+    new_scales[(size_t)g * 3 + 2] = grow * scales[(size_t)g * 3 + 2];
 }
 
 __global__ void __launch_bounds__(kMiscThreads) add_noise_kernel(uint32_t N, const float *__restrict__ raw_opacities,

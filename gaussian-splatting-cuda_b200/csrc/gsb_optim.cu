@@ -23,6 +23,7 @@ struct AdamGroupDev {
 struct AdamArgs {
     AdamGroupDev g[kAdamMaxGroups];
     int n_groups;
+    const float *dyn; // optional DEVICE array [n_groups][4] = (lr, bias_correction1_rcp, bias_correction2_sqrt_rcp, enabled)
 };
 
 __device__ __forceinline__ void adam_one(float &p, float &m, float &v, float grad, const AdamGroupDev &g) {
@@ -41,7 +42,12 @@ __global__ void __launch_bounds__(kAdamThreads) adam_multi_kernel(const AdamArgs
     unsigned long long base = 0;
     while (gi < a.n_groups && c >= a.g[gi].chunk_end) { base = a.g[gi].chunk_end; ++gi; }
     if (gi >= a.n_groups) return;
-    const AdamGroupDev &g = a.g[gi];
+    AdamGroupDev g = a.g[gi];
+    if (a.dyn) { // step-dependent scalars come from device memory: the launch can be replayed from a CUDA graph
+        const float4 d = reinterpret_cast<const float4 *>(a.dyn)[gi];
+        if (d.w == 0.0f) return;
+        g.lr = d.x; g.bc1_rcp = d.y; g.bc2_sqrt_rcp = d.z;
+    }
     const unsigned long long e0 = (c - base) * 4ull;
     if (e0 + 4 <= g.n && g.vec) {
         float4 p = reinterpret_cast<float4 *>(g.param)[c - base];
@@ -64,16 +70,26 @@ __global__ void __launch_bounds__(kAdamThreads) adam_multi_kernel(const AdamArgs
 
 } // namespace gsb
 
+extern "C" int gsb_adam_step_dynamic(const GsbAdamGroup *groups, uint32_t n_groups, const float *dynamic_scalars,
+                                     gsb_stream_t stream);
+
 extern "C" int gsb_adam_step(const GsbAdamGroup *groups, uint32_t n_groups, gsb_stream_t stream) {
+    return gsb_adam_step_dynamic(groups, n_groups, nullptr, stream);
+}
+
+extern "C" int gsb_adam_step_dynamic(const GsbAdamGroup *groups, uint32_t n_groups, const float *dynamic_scalars,
+                                     gsb_stream_t stream) {
     using namespace gsb;
     if (n_groups == 0) return GSB_OK;
     if (!groups || n_groups > (uint32_t)kAdamMaxGroups) return GSB_E_INVALID;
+    if (reinterpret_cast<uintptr_t>(dynamic_scalars) & 15) return GSB_E_INVALID;
     AdamArgs a;
+    a.dyn = dynamic_scalars;
     a.n_groups = 0;
     unsigned long long chunks = 0;
     for (uint32_t i = 0; i < n_groups; ++i) {
         const GsbAdamGroup &g = groups[i];
-        if (g.n == 0) continue;
+        if (g.n == 0 && !dynamic_scalars) continue; // (with dynamic scalars the group index must stay aligned)
         if (!g.param || !g.grad || !g.exp_avg || !g.exp_avg_sq) return GSB_E_INVALID;
         AdamGroupDev &d = a.g[a.n_groups++];
         d.param = g.param; d.grad = g.grad; d.exp_avg = g.exp_avg; d.exp_avg_sq = g.exp_avg_sq;

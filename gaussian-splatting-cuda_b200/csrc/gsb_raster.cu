@@ -20,8 +20,6 @@
 //             with one 16-lane red.global.add.f32.
 //   finalize  one thread per Gaussian, float32 chain rule from the moments to
 //             (v_means, v_quats, v_scales, v_opacities, v_colors); writes every output element.
-#include <atomic>
-
 #include "gsb_raster.cuh"
 
 namespace gsb {
@@ -542,176 +540,6 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
 }
 
 // ------------------------------------------------------------------------------------------
-// backward, wide variant (perfect pinhole): a warp owns a 16 x 8 pixel block, a thread four pixels
-// ------------------------------------------------------------------------------------------
-// Per (warp, record) event the reduction (16-value butterfly + RED), the record loads and the loop overhead are
-// about 40 % of the instructions and do not depend on how many pixels the warp covers.  Footprints at 1080p are
-// mostly wider than 8 pixels, so when one 8 x 8 block of a tile row survives the cull its neighbour usually does
-// too: giving a warp BOTH blocks (two packed pixel pairs per thread: columns x and x + 8, rows y and y + 4) halves
-// the number of events for such records while the per-pixel arithmetic stays the same.  CTA = 2 warps per tile.
-constexpr int kWideThreads = 64;
-
-__device__ __forceinline__ void event_registers_wide(const BwdState &sa, const EventWeights &wa, const PairEval2 &ea, f2 xa,
-                                                     const BwdState &sb, const EventWeights &wb, const PairEval2 &eb, f2 xb,
-                                                     f2 y, bool hi16, float (&R)[16]) {
-    const f2 ua1 = hi16 ? wa.w2 : wa.w1, ua2 = hi16 ? wa.w1 : wa.w2;
-    const f2 ub1 = hi16 ? wb.w2 : wb.w1, ub2 = hi16 ? wb.w1 : wb.w2;
-    const float gs = f2_sum(f2_add(wa.g, wb.g)), w2s = f2_sum(f2_add(wa.w2, wb.w2));
-    R[0] = hi16 ? w2s : gs;
-    R[8] = hi16 ? gs : w2s;
-    R[1] = f2_sum(f2_fma(ub1, xb, f2_mul(ua1, xa)));       R[2] = f2_sum(f2_mul(f2_add(ua1, ub1), y));
-    R[3] = f2_sum(f2_fma(ub1, eb.xx, f2_mul(ua1, ea.xx))); R[4] = f2_sum(f2_fma(ub1, eb.xy, f2_mul(ua1, ea.xy)));
-    R[5] = f2_sum(f2_mul(f2_add(ua1, ub1), ea.yy));        // yy is the same for both column blocks
-    R[9] = f2_sum(f2_fma(ub2, xb, f2_mul(ua2, xa)));       R[10] = f2_sum(f2_mul(f2_add(ua2, ub2), y));
-    R[11] = f2_sum(f2_fma(ub2, eb.xx, f2_mul(ua2, ea.xx))); R[12] = f2_sum(f2_fma(ub2, eb.xy, f2_mul(ua2, ea.xy)));
-    R[13] = f2_sum(f2_mul(f2_add(ua2, ub2), ea.yy));
-    R[6] = f2_sum(f2_fma(wb.fac, sb.vA, f2_mul(wa.fac, sa.vA))); R[14] = f2_sum(f2_fma(wb.fac, sb.vB, f2_mul(wa.fac, sa.vB)));
-    R[7] = f2_sum(f2_fma(wb.fac, sb.vC, f2_mul(wa.fac, sa.vC))); R[15] = f2_sum(f2_fma(wb.fac, sb.vD, f2_mul(wa.fac, sa.vD)));
-}
-
-__global__ void __launch_bounds__(kWideThreads, 10) raster_bwd_wide_kernel(const TileParams p,
-                                                                       const float *__restrict__ render_alphas,
-                                                                       const int32_t *__restrict__ last_ids,
-                                                                       const float *__restrict__ v_render_colors,
-                                                                       const float *__restrict__ v_render_alphas,
-                                                                       float *__restrict__ moments) {
-    __shared__ __align__(128) GaussRec s_rec[kStages][kBatch];
-    __shared__ __align__(8) uint64_t s_full[kStages];
-    __shared__ int32_t s_warp_max[kWideThreads / 32];
-    const uint32_t tile_id = blockIdx.x;
-    if (p.masks != nullptr && !p.masks[tile_id]) return; // Bwd.cu:84-86
-    const uint32_t tile_y = tile_id / p.tile_w, tile_x = tile_id % p.tile_w;
-    const uint32_t tid = threadIdx.x, w = tid >> 5, l = tid & 31;
-    const bool hi16 = (tid & 16) != 0;
-    // pixels: columns xa = x, xb = x + 8; rows y0, y0 + 4 (the pairs are packed over the rows)
-    const uint32_t xa = tile_x * 16 + (l & 7), xb = xa + 8;
-    const uint32_t y0 = tile_y * 16 + w * 8 + (l >> 3), y1 = y0 + 4;
-
-    const int32_t range_start = min(p.tile_offsets[tile_id], (int32_t)p.cap);
-    const int32_t range_end = min((!p.closed && tile_id == p.tile_w * p.tile_h - 1) ? (int32_t)p.n_isects
-                                                                                     : p.tile_offsets[tile_id + 1],
-                                  (int32_t)p.cap);
-    float bg[3] = {0.f, 0.f, 0.f};
-    if (p.backgrounds) { bg[0] = p.backgrounds[0]; bg[1] = p.backgrounds[1]; bg[2] = p.backgrounds[2]; }
-
-    struct PixelIn { float T, vr, vg, vb, tfva; int32_t last; };
-    auto load_pixel = [&](bool in, uint32_t x, uint32_t y) {
-        PixelIn r;
-        if (in) {
-            const size_t pix = (size_t)y * p.W + x;
-            const float Tf = 1.0f - render_alphas[pix];
-            r.T = Tf;
-            r.last = last_ids[pix];
-            r.vr = v_render_colors[pix * 3]; r.vg = v_render_colors[pix * 3 + 1]; r.vb = v_render_colors[pix * 3 + 2];
-            const float va = v_render_alphas[pix];
-            const float bgd = bg[0] * r.vr + bg[1] * r.vg + bg[2] * r.vb;
-            r.tfva = Tf * va - Tf * bgd; // Bwd.cu:307-316
-        } else {
-            r.T = 1.f; r.last = -1; r.vr = r.vg = r.vb = 0.f; r.tfva = 0.f;
-        }
-        return r;
-    };
-    auto make_state = [&](uint32_t x, BwdState &s) {
-        s.in0 = (x < p.W) && (y0 < p.H);
-        s.in1 = (x < p.W) && (y1 < p.H);
-        const PixelIn a = load_pixel(s.in0, x, y0), b = load_pixel(s.in1, x, y1);
-        s.T = f2_make(a.T, b.T);
-        s.bdot = f2_bc(0.0f);
-        s.tfva = f2_make(a.tfva, b.tfva);
-        s.vr = f2_make(a.vr, b.vr); s.vg = f2_make(a.vg, b.vg); s.vb = f2_make(a.vb, b.vb);
-        s.vA = hi16 ? s.vg : s.vr;
-        s.vB = hi16 ? s.vr : s.vg;
-        s.vC = hi16 ? f2_bc(0.0f) : s.vb;
-        s.vD = hi16 ? s.vb : f2_bc(0.0f);
-        s.last0 = a.last; s.last1 = b.last;
-    };
-    BwdState sa, sb;
-    make_state(xa, sa);
-    make_state(xb, sb);
-    const f2 PXA = f2_bc((float)xa + 0.5f), PXB = f2_bc((float)xb + 0.5f);
-    const f2 PY = f2_make((float)y0 + 0.5f, (float)y1 + 0.5f);
-    // cull box of the warp: 16 x 8 pixel centres
-    const float bx0 = (float)(tile_x * 16) + 0.5f, bx1 = bx0 + 15.0f;
-    const float by0 = (float)(tile_y * 16 + w * 8) + 0.5f, by1 = by0 + 7.0f;
-
-    int32_t wmax = __reduce_max_sync(0xffffffffu, max(max(sa.last0, sa.last1), max(sb.last0, sb.last1)));
-    if (l == 0) s_warp_max[w] = wmax;
-    if (tid == 0) {
-        for (int st = 0; st < kStages; ++st) mbar_init(&s_full[st], 1);
-        mbar_fence_init();
-    }
-    __syncthreads();
-    int32_t hi = max(s_warp_max[0], s_warp_max[1]);
-    hi = min(hi, range_end - 1);
-    const int32_t total = hi - range_start + 1;
-    if (total <= 0) return;
-    const int32_t n_batches = (total + kBatch - 1) / kBatch;
-    wmax = min(wmax, hi);
-
-    // a batch is 128 records, two per thread
-    auto issue = [&](int st, int32_t gid_lo, int32_t gid_hi, uint32_t cnt) {
-        if (tid == 0) mbar_arrive_expect_tx(&s_full[st], cnt * (uint32_t)sizeof(GaussRec));
-        if (tid < cnt) bulk_g2s(s_rec[st] + tid, p.recs + gid_lo, (uint32_t)sizeof(GaussRec), &s_full[st]);
-        if (tid + kWideThreads < cnt)
-            bulk_g2s(s_rec[st] + tid + kWideThreads, p.recs + gid_hi, (uint32_t)sizeof(GaussRec), &s_full[st]);
-    };
-    auto ids_of = [&](int32_t b, int32_t &lo, int32_t &hi2) {
-        const int32_t i0 = hi - b * kBatch - (int32_t)tid, i1 = i0 - kWideThreads;
-        lo = (i0 >= range_start) ? p.flatten_ids[i0] : 0;
-        hi2 = (i1 >= range_start) ? p.flatten_ids[i1] : 0;
-    };
-    int32_t nlo = 0, nhi = 0;
-    {
-        int32_t g0, g1;
-        ids_of(0, g0, g1);
-        issue(0, g0, g1, (uint32_t)min(total, kBatch));
-        ids_of(1, nlo, nhi);
-    }
-    for (int32_t b = 0; b < n_batches; ++b) {
-        const int st = b & 1;
-        if (b + 1 < n_batches) {
-            issue(st ^ 1, nlo, nhi, (uint32_t)min(total - (b + 1) * kBatch, kBatch));
-            ids_of(b + 2, nlo, nhi);
-        }
-        mbar_wait(&s_full[st], (uint32_t)((b >> 1) & 1));
-        const int32_t cnt = min(total - b * kBatch, kBatch);
-        const int32_t top = hi - b * kBatch; // sorted index of slot 0
-        const float4 *rec4 = reinterpret_cast<const float4 *>(s_rec[st]);
-        const int32_t t_first = max(0, top - wmax);
-        for (int32_t c0 = t_first & ~31; c0 < cnt; c0 += 32) {
-            const int32_t rl = c0 + (int32_t)l;
-            bool cand = false;
-            if (rl >= t_first && rl < cnt)
-                cand = block_may_pass(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], bx0, bx1, by0, by1);
-            uint32_t cmask = __ballot_sync(0xffffffffu, cand);
-            while (cmask) {
-                const int32_t t = c0 + __ffs(cmask) - 1;
-                cmask &= cmask - 1;
-                const int32_t idx = top - t;
-                const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
-                const f2 xA = f2_add(PXA, f2_bc(-q0.x)), xB = f2_add(PXB, f2_bc(-q0.x)), y = f2_add(PY, f2_bc(-q0.y));
-                const PairEval2 ea = pair_eval2(q0, q1, q2, xA, y), eb = pair_eval2(q0, q1, q2, xB, y);
-                const bool a0 = ea.pass0 && sa.in0 && idx <= sa.last0, a1 = ea.pass1 && sa.in1 && idx <= sa.last1;
-                const bool b0 = eb.pass0 && sb.in0 && idx <= sb.last0, b1 = eb.pass1 && sb.in1 && idx <= sb.last1;
-                if (!__any_sync(0xffffffffu, a0 || a1 || b0 || b1)) continue;
-                const float4 q3 = rec4[t * 4 + 3];
-                const EventWeights wa = bwd_weights(sa, ea, a0, a1, q2.z, q3.x, q3.y, q3.z);
-                const EventWeights wb = bwd_weights(sb, eb, b0, b1, q2.z, q3.x, q3.y, q3.z);
-                float R[16];
-                event_registers_wide(sa, wa, ea, xA, sb, wb, eb, xB, y, hi16, R);
-                butterfly16_preswapped(R);
-                if ((tid & 1) == 0) {
-                    const uint32_t slot = l >> 1;
-                    if (slot != (uint32_t)kS_PAD)
-                        red_add_f32(moments + (size_t)__float_as_int(q3.w) * kMomFloats + slot, R[0]);
-                }
-            }
-        }
-        __syncthreads(); // stage `st` may be refilled by batch b+2
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // finalize: moments -> gradients (chain rule once per Gaussian, float32: see FT below)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kPrepThreads) finalize_grads_kernel(
@@ -804,17 +632,11 @@ static int launch_fwd(const TileParams &p, const GsbCamera *cam, float *renders,
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }
-// variant: 0 = default, 1 = 8 x 8 blocks / two pixels per thread, 2 = 16 x 8 blocks / four pixels per thread
-static std::atomic<int> g_bwd_variant{0};
 static int launch_bwd(const TileParams &p, const GsbCamera *cam, const float *render_alphas, const int32_t *last_ids,
                       const float *v_render_colors, const float *v_render_alphas, float *moments, cudaStream_t s) {
     {
         ProfScope ps("raster_bwd", s);
-        const int variant = g_bwd_variant.load(std::memory_order_relaxed);
-        if (!general_camera(cam) && variant != 1)
-            raster_bwd_wide_kernel<<<p.tile_w * p.tile_h, kWideThreads, 0, s>>>(p, render_alphas, last_ids, v_render_colors,
-                                                                              v_render_alphas, moments);
-        else if (general_camera(cam))
+        if (general_camera(cam))
             raster_bwd_kernel<true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, render_alphas, last_ids,
                                                                                 v_render_colors, v_render_alphas, moments);
         else
@@ -952,7 +774,3 @@ extern "C" int gsb_raster_bwd_recs(uint32_t N, uint32_t capacity, void *workspac
     return launch_bwd(p, cam, render_alphas, last_ids, v_render_colors, v_render_alphas, moments, as_stream(stream));
 }
 
-// Diagnostics only (profiles/, tests of both kernels): which blend-backward kernel the perfect-pinhole path launches.
-// 0 / 2 = wide (16 x 8 pixels per warp, the default), 1 = narrow (8 x 8 pixels per warp).  Results agree to fp32
-// summation order; distorted cameras always use the narrow kernel.
-extern "C" void gsb_debug_set_bwd_variant(int variant) { gsb::g_bwd_variant.store(variant, std::memory_order_relaxed); }

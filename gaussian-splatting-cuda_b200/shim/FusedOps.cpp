@@ -268,4 +268,38 @@ GSB_EXPORT void fused_adam_step(const std::vector<at::Tensor> &params, const std
     gsb_check(gsb_adam_step(g, (uint32_t)n, cur_stream()), "fused_adam_step");
 }
 
+GSB_EXPORT void fused_adam_step_dynamic(const std::vector<at::Tensor> &params, const std::vector<at::Tensor> &grads,
+                                        const std::vector<at::Tensor> &exp_avg, const std::vector<at::Tensor> &exp_avg_sq,
+                                        const at::Tensor dynamic_scalars, const double beta1, const double beta2,
+                                        const double eps) {
+    const size_t n = params.size();
+    TORCH_CHECK(n > 0 && n <= 8, "fused_adam_step_dynamic: 1..8 parameter groups");
+    TORCH_CHECK(grads.size() == n && exp_avg.size() == n && exp_avg_sq.size() == n, "one entry per group in every list");
+    CHECK_F32(dynamic_scalars);
+    TORCH_CHECK(dynamic_scalars.numel() == (int64_t)n * 4, "dynamic_scalars must be [n_groups, 4]");
+    const c10::cuda::CUDAGuard guard(params[0].device());
+    GsbAdamGroup g[8];
+    for (size_t i = 0; i < n; ++i) {
+        CHECK_F32(params[i]);
+        CHECK_F32(grads[i]);
+        CHECK_F32(exp_avg[i]);
+        CHECK_F32(exp_avg_sq[i]);
+        TORCH_CHECK(grads[i].numel() == params[i].numel() && exp_avg[i].numel() == params[i].numel() &&
+                        exp_avg_sq[i].numel() == params[i].numel(),
+                    "fused_adam_step_dynamic: group ", i, " has mismatching sizes");
+        g[i].param = params[i].data_ptr<float>();
+        g[i].grad = grads[i].data_ptr<float>();
+        g[i].exp_avg = exp_avg[i].data_ptr<float>();
+        g[i].exp_avg_sq = exp_avg_sq[i].data_ptr<float>();
+        g[i].n = (uint64_t)params[i].numel();
+        g[i].lr = 0.f;
+        g[i].beta1 = (float)beta1;
+        g[i].beta2 = (float)beta2;
+        g[i].eps = (float)eps;
+        g[i].bias_correction1_rcp = g[i].bias_correction2_sqrt_rcp = 1.f;
+    }
+    gsb_check(gsb_adam_step_dynamic(g, (uint32_t)n, dynamic_scalars.data_ptr<float>(), cur_stream()),
+              "fused_adam_step_dynamic");
+}
+
 } // namespace gsplat

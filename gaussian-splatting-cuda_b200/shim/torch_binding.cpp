@@ -163,6 +163,12 @@ void adam_step(std::vector<Tensor> params, std::vector<Tensor> grads, std::vecto
     gsplat::fused_adam_step(params, grads, exp_avg, exp_avg_sq, lr, beta1, beta2, eps, step_counts);
 }
 
+void adam_step_dynamic(std::vector<Tensor> params, std::vector<Tensor> grads, std::vector<Tensor> exp_avg,
+                       std::vector<Tensor> exp_avg_sq, const Tensor &dynamic_scalars, double beta1, double beta2,
+                       double eps) {
+    gsplat::fused_adam_step_dynamic(params, grads, exp_avg, exp_avg_sq, dynamic_scalars, beta1, beta2, eps);
+}
+
 Tensor quats_to_rotmats(const Tensor &quats) { return gsplat::quats_to_rotmats(quats); }
 
 std::tuple<Tensor, Tensor> relocation(const Tensor &opacities, const Tensor &scales, const Tensor &ratios,
@@ -199,6 +205,9 @@ TORCH_LIBRARY(gsplat_b200, m) {
     m.def("fused_adam_step(Tensor(a!)[] params, Tensor[] grads, Tensor(b!)[] exp_avg, Tensor(c!)[] exp_avg_sq, float[] lr, "
           "float beta1, float beta2, float eps, int[] step_counts) -> ()",
           &adam_step);
+    m.def("fused_adam_step_dynamic(Tensor(a!)[] params, Tensor[] grads, Tensor(b!)[] exp_avg, Tensor(c!)[] exp_avg_sq, "
+          "Tensor dynamic_scalars, float beta1, float beta2, float eps) -> ()",
+          &adam_step_dynamic);
     m.def("quats_to_rotmats", &quats_to_rotmats);
     m.def("relocation", &relocation);
     m.def("add_noise(Tensor raw_opacities, Tensor raw_scales, Tensor raw_quats, Tensor noise, Tensor(a!) means, float current_lr) -> ()",

@@ -141,3 +141,113 @@ class TrainStep:
             n = int(out.n_isects.item())
         self.capacity = int(n * slack) + 1024
         return n
+
+
+class GraphedTrainStep:
+    """The whole iteration -- extended render operator, loss-and-gradient kernel, blend backward, fused back kernel, Adam --
+    captured ONCE in a CUDA graph and replayed: one graph launch per iteration instead of ~25 kernel launches and their
+    torch bookkeeping.  Possible because nothing inside the iteration needs a host-side value: the intersection buffers
+    are sized from a capacity (the count stays on the device, `overflowed()` checks it afterwards) and Adam's
+    step-dependent scalars (learning rates, bias corrections, the shN freeze of the first 1000 iterations) are read from a
+    small device tensor that is refreshed before every replay.
+
+    Per iteration the host copies the camera (viewmat, K), the background and the target image into static device buffers
+    (pinned -> device, on the replay stream) and reads the loss back when it wants to."""
+
+    def __init__(self, params: dict, sh_degree: int, width: int, height: int, cfg: AdamConfig | None = None,
+                 lambda_dssim: float = 0.2, capacity_slack: float = 1.25):
+        load()
+        self.params, self.sh_degree, self.W, self.H = params, int(sh_degree), int(width), int(height)
+        self.lambda_dssim = float(lambda_dssim)
+        self.opt = FusedAdam(params, cfg)
+        self.slack = capacity_slack
+        dev = params["means"].device
+        self.dev = dev
+        self.static = {"viewmat": torch.zeros((1, 4, 4), device=dev), "K": torch.zeros((1, 3, 3), device=dev),
+                       "background": torch.zeros((1, 3), device=dev),
+                       "target": torch.zeros((3, self.H, self.W), device=dev)}
+        self.dyn = torch.zeros((len(PARAM_GROUPS), 4), device=dev)
+        self.dyn_host = torch.zeros((len(PARAM_GROUPS), 4)).pin_memory()
+        self.graph = None
+        self.loss = None
+        self.stats = None
+        self.n_isects = None
+        self.capacity = 0
+        self.iteration = 0
+
+    def _body(self):
+        P, S = self.params, self.static
+        out = rasterize_fused(P["means"], P["sh0"], P["shN"], P["scaling_raw"], P["rotation_raw"], P["opacity_raw"],
+                              self.sh_degree, S["viewmat"], S["K"], self.W, self.H, bg_color=S["background"],
+                              isect_capacity=self.capacity)
+        loss, stats = photometric_loss(out.render_colors, S["target"], self.lambda_dssim)
+        loss.backward()
+        names = [k for k in PARAM_GROUPS if P[k].numel() > 0]
+        with torch.no_grad():
+            _product_ns().fused_adam_step_dynamic([P[k] for k in names], [P[k].grad for k in names],
+                                                  [self.opt.exp_avg[k] for k in names],
+                                                  [self.opt.exp_avg_sq[k] for k in names],
+                                                  self.dyn[[PARAM_GROUPS.index(k) for k in names]].contiguous()
+                                                  if len(names) != len(PARAM_GROUPS) else self.dyn,
+                                                  self.opt.cfg.beta1, self.opt.cfg.beta2, self.opt.cfg.eps)
+        return loss, stats, out.n_isects
+
+    def _set_inputs(self, viewmat, K, target, background):
+        S = self.static
+        S["viewmat"].copy_(viewmat.reshape(1, 4, 4), non_blocking=True)
+        S["K"].copy_(K.reshape(1, 3, 3), non_blocking=True)
+        S["target"].copy_(target.reshape(3, self.H, self.W), non_blocking=True)
+        if background is not None:
+            S["background"].copy_(background.reshape(1, 3), non_blocking=True)
+
+    def _set_scalars(self):
+        """fused_adam.cpp:61-81 on the host: step counts, bias corrections, the shN freeze; strategy_utils.cpp:52-55 lr."""
+        o = self.opt
+        for i, k in enumerate(PARAM_GROUPS):
+            o.steps[k] += 1
+            t = o.steps[k]
+            enabled = 0.0 if (k == "shN" and self.iteration <= 1000) else 1.0
+            self.dyn_host[i, 0] = o.lr[i]
+            self.dyn_host[i, 1] = 1.0 / (1.0 - o.cfg.beta1 ** t)
+            self.dyn_host[i, 2] = 1.0 / math.sqrt(1.0 - o.cfg.beta2 ** t)
+            self.dyn_host[i, 3] = enabled
+        self.dyn.copy_(self.dyn_host, non_blocking=True)
+        o.lr[0] *= o.gamma
+
+    def capture(self, viewmat, K, target, background=None):
+        """Sizes the intersection capacity with one exact render, warms up and captures the graph."""
+        self._set_inputs(viewmat, K, target, background)
+        with torch.no_grad():
+            P, S = self.params, self.static
+            out = rasterize_fused(P["means"], P["sh0"], P["shN"], P["scaling_raw"], P["rotation_raw"], P["opacity_raw"],
+                                  self.sh_degree, S["viewmat"], S["K"], self.W, self.H, bg_color=S["background"])
+            n = int(out.n_isects.item())
+        self.capacity = int(n * self.slack) + 1024
+        self.dyn.zero_()  # warm-up iterations must not move the parameters: every group disabled
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                for p in self.params.values():
+                    p.grad = None
+                self._body()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        for p in self.params.values():
+            p.grad = None
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.stats, self.n_isects = self._body()
+        return n
+
+    def __call__(self, viewmat, K, target, background=None):
+        if self.graph is None:
+            self.capture(viewmat, K, target, background)
+        self.iteration += 1
+        self._set_inputs(viewmat, K, target, background)
+        self._set_scalars()
+        self.graph.replay()
+        return self.loss
+
+    def overflowed(self) -> bool:
+        """True when the last iteration had more intersections than the captured buffers hold (re-capture then)."""
+        return int(self.n_isects.item()) > self.capacity

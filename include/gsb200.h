@@ -99,9 +99,6 @@ GSB_API int gsb_version(void);
  * "isect_emit", "isect_sort", "isect_offsets", "raster_prep", "raster_fwd", "raster_bwd",
  * "raster_finalize") and returns how many launches were found. */
 GSB_API uint64_t gsb_launch_count(void);
-/* Which blend-backward kernel the perfect-pinhole path launches: 0 = default (wide: a warp owns 16 x 8 pixels),
- * 1 = narrow (8 x 8 pixels per warp).  Same results up to fp32 summation order; for profiling and tests. */
-GSB_API void gsb_debug_set_bwd_variant(int variant);
 GSB_API void gsb_profile_enable(int on);
 GSB_API int gsb_profile_read(const char *kernel, double *total_ms);
 
@@ -321,6 +318,11 @@ typedef struct GsbAdamGroup {
     float bias_correction2_sqrt_rcp; /* 1 / sqrt(1 - beta2^t) */
 } GsbAdamGroup;
 GSB_API int gsb_adam_step(const GsbAdamGroup *groups, uint32_t n_groups, gsb_stream_t stream);
+/* Same, with the step-dependent scalars read from DEVICE memory at run time: dynamic_scalars [n_groups][4] floats =
+ * (lr, bias_correction1_rcp, bias_correction2_sqrt_rcp, enabled != 0), 16-byte aligned; the lr / bias fields of
+ * `groups` are ignored.  Lets a whole training iteration be captured once in a CUDA graph and replayed. */
+GSB_API int gsb_adam_step_dynamic(const GsbAdamGroup *groups, uint32_t n_groups, const float *dynamic_scalars,
+                                  gsb_stream_t stream);
 
 /* ---- link-surface ops used by the densification strategies -------------------------
  * gsplat::quats_to_rotmats (Ops.h:46-48, QuatToRotmatCUDA.cu:14-39): [N,4] -> [N,3,3] */

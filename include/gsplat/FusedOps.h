@@ -83,4 +83,10 @@ void fused_adam_step(const std::vector<at::Tensor> &params, const std::vector<at
                      const std::vector<double> &lr, const double beta1, const double beta2, const double eps,
                      const std::vector<int64_t> &step_counts);
 
+// The same step with (lr, 1/(1-beta1^t), 1/sqrt(1-beta2^t), enabled) per group in a DEVICE tensor [n_groups,4]: nothing
+// step-dependent is baked into the launch, so the iteration can be replayed from a CUDA graph.
+void fused_adam_step_dynamic(const std::vector<at::Tensor> &params, const std::vector<at::Tensor> &grads,
+                             const std::vector<at::Tensor> &exp_avg, const std::vector<at::Tensor> &exp_avg_sq,
+                             const at::Tensor dynamic_scalars, const double beta1, const double beta2, const double eps);
+
 } // namespace gsplat

@@ -301,36 +301,6 @@ def test_pipeline_autograd_vs_oracle(native, orc, cuda_device, name):
         assert_grad_close(leaves[k].grad, w, k, n_g, tag=f"pipeline {name} vs {'f64' if same64 else 'f32'} oracle")
 
 
-def test_blend_bwd_wide_and_narrow_kernels_agree(native, orc, cuda_device):
-    """The perfect-pinhole backward has two kernels: 16 x 8 pixels per warp (default) and 8 x 8.  Same moments up to
-    fp32 summation order; each is also compared with the oracle / the reference in the tests above through the default."""
-    import ctypes
-    lib = ctypes.CDLL(native.CABI_PATH)
-    sc = _blend_case("b30k")
-    W, H = sc["width"], sc["height"]
-    rng = np.random.default_rng(11)
-    vrc = torch.from_numpy(rng.standard_normal((1, H, W, 3)).astype(np.float32)).to(cuda_device)
-    vra = torch.from_numpy(rng.standard_normal((1, H, W, 1)).astype(np.float32)).to(cuda_device)
-    ref = orc.render_pipeline(sc, "f32", False)
-    t = to_dev(sc, cuda_device)
-    colors = torch.from_numpy(ref["colors"]).to(cuda_device)
-    off = torch.from_numpy(ref["tile_offsets"]).to(cuda_device)
-    flat = torch.from_numpy(ref["flatten_ids"]).to(cuda_device)
-    args = (t["means"], t["quats"], t["scales"], colors, t["opacities"][None], t.get("background"), None, W, H, 16,
-            t["viewmats"], t["Ks"], off, flat)
-    _, alphas, last_ids = native.rasterize_to_pixels_from_world_3dgs_fwd(*args)
-    out = {}
-    try:
-        for name, v in (("narrow", 1), ("wide", 2)):
-            lib.gsb_debug_set_bwd_variant(v)
-            out[name] = native.rasterize_to_pixels_from_world_3dgs_bwd(*args, alphas, last_ids, vrc, vra)
-            torch.cuda.synchronize()
-    finally:
-        lib.gsb_debug_set_bwd_variant(0)
-    for a, b, name in zip(out["narrow"], out["wide"], ("v_means", "v_quats", "v_scales", "v_colors", "v_opacities")):
-        assert rel(b.cpu().numpy(), a.cpu().numpy()) < 2e-5, name
-
-
 def test_host_staged_steps_match_sequential_steps(native, cuda_device):
     """The three-stream host pipeline (hoststream.py) returns, for every step, exactly what a blocking
     copy-in / step / copy-out sequence returns: same loss, same image, same gradients (bit for bit -- the

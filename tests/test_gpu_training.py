@@ -115,6 +115,34 @@ def test_training_iterations_reduce_the_loss_without_host_readback(native, cuda_
     assert int(step.last["n_isects"].item()) <= step.capacity
 
 
+def test_graphed_iteration_equals_eager_iteration(native, cuda_device):
+    """GraphedTrainStep (one CUDA-graph launch per iteration) moves the parameters exactly like the eager TrainStep."""
+    from gsplat_b200 import training
+    sc = scenes.scene_b(N=20000, width=640, height=360, view=2, scale_mul=2.0)
+    t = to_dev(sc, cuda_device)
+    raw = native.raw_from_activated(t["means"], t["quats"], t["scales"], t["opacities"], t["sh_coeffs"])
+    g = torch.Generator(device=cuda_device).manual_seed(3)
+    tgt = torch.rand((3, 360, 640), device=cuda_device, generator=g)
+    cfg = training.AdamConfig(means_lr=1.6e-3)
+    A = {k: v.detach().clone().requires_grad_(True) for k, v in raw.items()}
+    B = {k: v.detach().clone().requires_grad_(True) for k, v in raw.items()}
+    eager = training.TrainStep(A, 3, 640, 360, optimizer=training.FusedAdam(A, cfg))
+    eager.size_capacity(t["viewmats"], t["Ks"], tgt, t["background"])
+    graphed = training.GraphedTrainStep(B, 3, 640, 360, cfg)
+    la, lb = [], []
+    for it in range(4):
+        la.append(float(eager(t["viewmats"], t["Ks"], tgt, t["background"])))
+        lb.append(float(graphed(t["viewmats"], t["Ks"], tgt, t["background"])))
+    assert not graphed.overflowed()
+    print("eager ", [f"{v:.6f}" for v in la])
+    print("graph ", [f"{v:.6f}" for v in lb])
+    for a, b in zip(la, lb):
+        assert abs(a - b) < 2e-5 * max(1.0, abs(a))
+    for k in A:  # blend gradients are accumulated with float atomics: equal up to summation order, then through Adam
+        if A[k].numel():
+            assert rel(B[k].detach(), A[k].detach()) < 1e-4, k
+
+
 # ------------------------------------------------------------------------------------------
 # the same rows against the REFERENCE's own kernels (oracle/_ref: ssim.cu and adam_kernels.cuh compiled unmodified)
 # ------------------------------------------------------------------------------------------
@@ -165,6 +193,6 @@ def test_fused_adam_vs_reference_kernel(native, ref_train, cuda_device):
             A[k].grad, B[k].grad = gr.clone(), gr.clone()
         mine.step(it)
         theirs.step(it, training.PARAM_GROUPS)
-    for k in shapes:  # same float32 arithmetic, operation for operation
-        assert torch.equal(A[k].detach(), B[k].detach()), k
-        assert torch.equal(mine.exp_avg[k], theirs.m[k]) and torch.equal(mine.exp_avg_sq[k], theirs.v[k]), k
+    for k in shapes:  # same float32 formula; the reference build is --use_fast_math (approximate sqrt / division)
+        assert rel(A[k].detach(), B[k].detach()) < 2e-6, k
+        assert rel(mine.exp_avg[k], theirs.m[k]) < 2e-6 and rel(mine.exp_avg_sq[k], theirs.v[k]) < 2e-6, k
