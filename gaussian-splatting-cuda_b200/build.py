@@ -35,6 +35,7 @@ CUDA_SOURCES = [
     ("gsb_sh.cu", []),
     ("gsb_intersect.cu", ["-fmad=false"]),
     ("gsb_raster.cu", []),
+    ("gsb_raster_rs.cu", []),
     ("gsb_misc.cu", []),
     ("gsb_fused.cu", ["-fmad=false"]),
     ("gsb_loss.cu", []),

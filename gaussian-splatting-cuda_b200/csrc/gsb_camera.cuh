@@ -243,4 +243,35 @@ __device__ inline bool cam_unproject_normalized(const CamModel &m, float px, flo
     return true;
 }
 
+// ---- rolling shutter (Cameras.cuh:268-320) ------------------------------------------------------------------------------
+struct Quat {
+    float w, x, y, z;
+};
+// glm::slerp: shortest arc, linear interpolation when the endpoints (almost) coincide (not renormalised, like GLM)
+__device__ __forceinline__ Quat quat_slerp(Quat a, Quat b, float t) {
+    float c = a.w * b.w + a.x * b.x + a.y * b.y + a.z * b.z;
+    if (c < 0.0f) { b.w = -b.w; b.x = -b.x; b.y = -b.y; b.z = -b.z; c = -c; }
+    Quat r;
+    if (c > 1.0f - 1.1920929e-07f) {
+        r.w = a.w * (1.0f - t) + b.w * t; r.x = a.x * (1.0f - t) + b.x * t;
+        r.y = a.y * (1.0f - t) + b.y * t; r.z = a.z * (1.0f - t) + b.z * t;
+        return r;
+    }
+    const float ang = acosf(c);
+    const float s0 = sinf((1.0f - t) * ang), s1 = sinf(t * ang), sd = sinf(ang);
+    r.w = (s0 * a.w + s1 * b.w) / sd; r.x = (s0 * a.x + s1 * b.x) / sd;
+    r.y = (s0 * a.y + s1 * b.y) / sd; r.z = (s0 * a.z + s1 * b.z) / sd;
+    return r;
+}
+// Relative frame time in [0, 1] of an image point for the four rolling directions (0 for a global shutter)
+__device__ __forceinline__ float shutter_relative_time(int shutter_type, float px, float py, float W, float H) {
+    switch (shutter_type) {
+        case GSB_SHUTTER_ROLLING_TOP_TO_BOTTOM: return floorf(py) / (H - 1.0f);
+        case GSB_SHUTTER_ROLLING_LEFT_TO_RIGHT: return floorf(px) / (W - 1.0f);
+        case GSB_SHUTTER_ROLLING_BOTTOM_TO_TOP: return (H - ceilf(py)) / (H - 1.0f);
+        case GSB_SHUTTER_ROLLING_RIGHT_TO_LEFT: return (W - ceilf(px)) / (W - 1.0f);
+        default: return 0.0f;
+    }
+}
+
 } // namespace gsb

@@ -22,7 +22,8 @@ constexpr int kProjThreads = 256;
 struct ProjParams {
     uint32_t C, N;
     const float *means, *quats, *scales, *opacities;
-    const float *viewmats0, *Ks;
+    const float *viewmats0, *viewmats1, *Ks;
+    int32_t shutter;
     uint32_t W, H;
     float eps2d, near_plane, far_plane, radius_clip;
     GsbUTParams ut;
@@ -87,7 +88,7 @@ __global__ void __launch_bounds__(kProjThreads) projection_ut_kernel(const ProjP
                         p.tangential ? p.tangential + (size_t)cid * p.n_tangential : nullptr, p.n_tangential,
                         p.thin_prism ? p.thin_prism + (size_t)cid * p.n_thin_prism : nullptr, p.n_thin_prism);
     __syncthreads();
-    const ProjPose pp = proj_pose_from_viewmat(p.viewmats0 + cid * 16);
+    const ProjPose pp = proj_pose_from_viewmat(p.viewmats0 + cid * 16, p.viewmats1 ? p.viewmats1 + cid * 16 : nullptr, p.shutter);
     ProjConsts pk;
     pk.W = p.W; pk.H = p.H; pk.eps2d = p.eps2d; pk.near_plane = p.near_plane; pk.far_plane = p.far_plane;
     pk.radius_clip = p.radius_clip; pk.ut = p.ut;
@@ -145,13 +146,15 @@ extern "C" int gsb_projection_ut(
     if (!cam || !cam->viewmats0 || !cam->Ks) return GSB_E_INVALID;
     if (C == 0 || N == 0) return GSB_OK; // ProjectionUT3DGSFused.cu:242-245
     if (!means || !quats || !scales || !radii || !means2d || !depths || !conics) return GSB_E_INVALID;
-    if ((cam->camera_model != GSB_CAMERA_PINHOLE && cam->camera_model != GSB_CAMERA_FISHEYE) || cam->viewmats1 ||
-        cam->shutter_type != GSB_SHUTTER_GLOBAL)
-        return GSB_E_UNSUPPORTED; // orthographic / rolling shutter: no caller of the reference uses them
+    if (cam->camera_model != GSB_CAMERA_PINHOLE && cam->camera_model != GSB_CAMERA_FISHEYE)
+        return GSB_E_UNSUPPORTED; // orthographic: the reference has no such branch either (ProjectionUT3DGSFused.cu:130-134)
+    if (cam->shutter_type < GSB_SHUTTER_ROLLING_TOP_TO_BOTTOM || cam->shutter_type > GSB_SHUTTER_GLOBAL) return GSB_E_INVALID;
     gsb::ProjParams p;
     p.C = C; p.N = N;
     p.means = means; p.quats = quats; p.scales = scales; p.opacities = opacities;
     p.viewmats0 = cam->viewmats0; p.Ks = cam->Ks;
+    // without an end-of-frame pose the start pose is used for both ends (Cameras.cuh:54-56): a global shutter
+    p.viewmats1 = cam->viewmats1; p.shutter = cam->viewmats1 ? cam->shutter_type : GSB_SHUTTER_GLOBAL;
     p.W = image_width; p.H = image_height;
     p.eps2d = eps2d; p.near_plane = near_plane; p.far_plane = far_plane; p.radius_clip = radius_clip;
     p.ut = cam->ut;

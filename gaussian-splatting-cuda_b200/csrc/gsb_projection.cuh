@@ -29,13 +29,25 @@ struct ProjConsts {
 // Camera pose terms: the start pose (global shutter: also the end pose) and the centre-of-shutter pose
 // slerp(q, q, 0.5), 0.5 t + 0.5 t of Cameras.cuh:268-280, evaluated like GLM does.
 struct ProjPose {
-    CamPose pose;
+    CamPose pose;       // start of frame
+    CamPose pose1;      // end of frame (== pose for a global shutter)
+    int shutter;        // GSB_SHUTTER_*
     float mw, mx, my, mz;
     V3<float> t_mid, t0;
 };
-__device__ __forceinline__ ProjPose proj_pose_from_viewmat(const float *viewmat) {
+__device__ __forceinline__ ProjPose proj_pose_from_viewmat(const float *viewmat, const float *viewmat1 = nullptr,
+                                                           int shutter = GSB_SHUTTER_GLOBAL) {
     ProjPose r;
     const CamPose pose = cam_pose_from_viewmat(viewmat);
+    if (viewmat1 != nullptr && shutter != GSB_SHUTTER_GLOBAL) { // centre-of-shutter pose between two different poses
+        const CamPose p1 = cam_pose_from_viewmat(viewmat1);
+        const Quat qm = quat_slerp(Quat{pose.qw, pose.qx, pose.qy, pose.qz}, Quat{p1.qw, p1.qx, p1.qy, p1.qz}, 0.5f);
+        r.pose = pose; r.pose1 = p1; r.shutter = shutter;
+        r.mw = qm.w; r.mx = qm.x; r.my = qm.y; r.mz = qm.z;
+        r.t_mid = {0.5f * pose.tx + 0.5f * p1.tx, 0.5f * pose.ty + 0.5f * p1.ty, 0.5f * pose.tz + 0.5f * p1.tz};
+        r.t0 = {pose.tx, pose.ty, pose.tz};
+        return r;
+    }
     float mw, mx, my, mz;
     {
         const float cosT = pose.qw * pose.qw + pose.qx * pose.qx + pose.qy * pose.qy + pose.qz * pose.qz;
@@ -49,11 +61,38 @@ __device__ __forceinline__ ProjPose proj_pose_from_viewmat(const float *viewmat)
             my = (s0 * pose.qy + s0 * pose.qy) / sd; mz = (s0 * pose.qz + s0 * pose.qz) / sd;
         }
     }
-    r.pose = pose;
+    r.pose = pose; r.pose1 = pose; r.shutter = GSB_SHUTTER_GLOBAL;
     r.mw = mw; r.mx = mx; r.my = my; r.mz = mz;
     r.t_mid = {0.5f * pose.tx + 0.5f * pose.tx, 0.5f * pose.ty + 0.5f * pose.ty, 0.5f * pose.tz + 0.5f * pose.tz};
     r.t0 = {pose.tx, pose.ty, pose.tz};
     return r;
+}
+
+// world_point_to_image_point_shutter_pose for a rolling shutter (Cameras.cuh:371-413): the projection with the
+// start-of-frame pose (or, if that one is invalid, the end-of-frame pose) seeds ten fixed-point iterations
+// "time of the row / column the point falls on -> interpolated pose -> projection".  (px, py, valid) enter with the
+// start-pose projection and leave with the result.
+__device__ __forceinline__ bool project_rolling(const ProjConsts &p, const CamModel &cm, const ProjPose &pp, V3<float> pt,
+                                                bool valid_start, float &px, float &py) {
+    const CamPose &a = pp.pose, &b = pp.pose1;
+    const V3<float> t1 = {b.tx, b.ty, b.tz};
+    float ex, ey;
+    const bool valid_end = cam_project(cm, quat_rotate(b.qw, b.qx, b.qy, b.qz, pt) + t1, p.ut.in_image_margin_factor, ex, ey);
+    if (!valid_start) {
+        px = ex; py = ey;
+        if (!valid_end) return false;
+    }
+    const Quat qa{a.qw, a.qx, a.qy, a.qz}, qb{b.qw, b.qx, b.qy, b.qz};
+    for (int it = 0; it < 10; ++it) {
+        const float tau = shutter_relative_time(pp.shutter, px, py, cm.W, cm.H);
+        const Quat q = quat_slerp(qa, qb, tau);
+        const V3<float> t = {(1.0f - tau) * a.tx + tau * b.tx, (1.0f - tau) * a.ty + tau * b.ty,
+                             (1.0f - tau) * a.tz + tau * b.tz};
+        float nx, ny;
+        cam_project(cm, quat_rotate(q.w, q.x, q.y, q.z, pt) + t, p.ut.in_image_margin_factor, nx, ny);
+        px = nx; py = ny;
+    }
+    return true;
 }
 
 struct ProjResult {
@@ -106,7 +145,8 @@ __device__ __forceinline__ ProjResult project_gaussian(const ProjConsts &p, cons
             }
             const V3<float> cam = quat_rotate(pose.qw, pose.qx, pose.qy, pose.qz, pt) + pp.t0;
             float px, py;
-            const bool pv = cam_project(s_cm, cam, p.ut.in_image_margin_factor, px, py);
+            bool pv = cam_project(s_cm, cam, p.ut.in_image_margin_factor, px, py);
+            if (pp.shutter != GSB_SHUTTER_GLOBAL) pv = project_rolling(p, s_cm, pp, pt, pv, px, py);
             if (p.ut.require_all_sigma_points_valid) {
                 valid = valid && pv;
                 if (!pv) { early = true; break; }

@@ -304,40 +304,6 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
 // backward
 // ------------------------------------------------------------------------------------------
 
-// Sum 16 per-lane values across the warp: after the call lane L holds in v[0] the warp-wide total of
-// slot (L >> 1).  16 shuffles (8+4+2+1+1) instead of 16 x 5.  On entry lanes 16..31 hold slot (i ^ 8) in
-// v[i] (they built their registers pre-swapped), so stage one needs no lane-dependent selects.
-__device__ __forceinline__ void butterfly16_preswapped(float (&v)[16]) {
-    const uint32_t lane = threadIdx.x & 31;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i + 8], 16);
-    {
-        const bool hi = lane & 8;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float send = hi ? v[i] : v[i + 4];
-            const float keep = hi ? v[i + 4] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const bool hi = lane & 4;
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const float send = hi ? v[i] : v[i + 2];
-            const float keep = hi ? v[i + 2] : v[i];
-            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-        }
-    }
-    {
-        const bool hi = lane & 2;
-        const float send = hi ? v[0] : v[1];
-        const float keep = hi ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
-    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-}
-
 // Per-thread state of the backward sweep for the thread's two pixels (lo = pixel 0, hi = pixel 1).
 struct BwdState {
     f2 T;      // running transmittance (restored front-to-back value at the current Gaussian)
@@ -583,11 +549,26 @@ static inline size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 static int check_camera(const GsbCamera *cam) {
     if (!cam || !cam->viewmats0 || !cam->Ks) return GSB_E_INVALID;
-    if ((cam->camera_model != GSB_CAMERA_PINHOLE && cam->camera_model != GSB_CAMERA_FISHEYE) || cam->viewmats1 ||
-        cam->shutter_type != GSB_SHUTTER_GLOBAL)
-        return GSB_E_UNSUPPORTED; // orthographic / rolling shutter
+    if (cam->camera_model != GSB_CAMERA_PINHOLE && cam->camera_model != GSB_CAMERA_FISHEYE)
+        return GSB_E_UNSUPPORTED; // orthographic: no such branch in the reference either
+    if (cam->shutter_type < GSB_SHUTTER_ROLLING_TOP_TO_BOTTOM || cam->shutter_type > GSB_SHUTTER_GLOBAL) return GSB_E_INVALID;
     return GSB_OK;
 }
+// A rolling shutter needs the per-pixel-pose kernels of gsb_raster_rs.cu; without an end-of-frame pose the start pose
+// serves for both ends (Cameras.cuh:54-56), i.e. a global shutter.
+static bool rolling_shutter(const GsbCamera *cam) {
+    return cam->viewmats1 != nullptr && cam->shutter_type != GSB_SHUTTER_GLOBAL;
+}
+int raster_rs_fwd(uint32_t N, uint64_t n_isects, const float *means, const float *quats, const float *scales,
+                  const float *colors, const float *opacities, const float *backgrounds, const uint8_t *masks, uint32_t W,
+                  uint32_t H, const GsbCamera *cam, const int32_t *tile_offsets, const int32_t *flatten_ids, float *renders,
+                  float *alphas, int32_t *last_ids, void *workspace, cudaStream_t s);
+int raster_rs_bwd(uint32_t N, uint64_t n_isects, const float *means, const float *quats, const float *scales,
+                  const float *colors, const float *opacities, const float *backgrounds, const uint8_t *masks, uint32_t W,
+                  uint32_t H, const GsbCamera *cam, const int32_t *tile_offsets, const int32_t *flatten_ids,
+                  const float *render_alphas, const int32_t *last_ids, const float *v_render_colors,
+                  const float *v_render_alphas, float *v_means, float *v_quats, float *v_scales, float *v_colors,
+                  float *v_opacities, void *workspace, size_t rec_bytes, cudaStream_t s);
 
 static bool general_camera(const GsbCamera *cam) {
     return cam->camera_model == GSB_CAMERA_FISHEYE || cam->radial_coeffs || cam->tangential_coeffs ||
@@ -665,6 +646,9 @@ extern "C" int gsb_raster_fwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < gsb_raster_fwd_workspace(N))
         return GSB_E_WORKSPACE;
     cudaStream_t s = as_stream(stream);
+    if (rolling_shutter(cam))
+        return raster_rs_fwd(N, n_isects, means, quats, scales, colors, opacities, backgrounds, masks, image_width,
+                             image_height, cam, tile_offsets, flatten_ids, renders, alphas, last_ids, workspace, s);
     GaussRec *recs = reinterpret_cast<GaussRec *>(workspace);
     if (N > 0 && n_isects > 0) {
         {
@@ -709,6 +693,11 @@ extern "C" int gsb_raster_bwd(uint32_t C, uint32_t N, uint64_t n_isects, const f
     if (n_isects > 0x7fffffffull) return GSB_E_INVALID;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255) || workspace_bytes < gsb_raster_bwd_workspace(N))
         return GSB_E_WORKSPACE;
+    if (rolling_shutter(cam))
+        return raster_rs_bwd(N, n_isects, means, quats, scales, colors, opacities, backgrounds, masks, image_width,
+                             image_height, cam, tile_offsets, flatten_ids, render_alphas, last_ids, v_render_colors,
+                             v_render_alphas, v_means, v_quats, v_scales, v_colors, v_opacities, workspace,
+                             align256((size_t)N * sizeof(GaussRec)), s);
     GaussRec *recs = reinterpret_cast<GaussRec *>(workspace);
     float *moments = reinterpret_cast<float *>(reinterpret_cast<char *>(workspace) + align256((size_t)N * sizeof(GaussRec)));
     {
@@ -742,6 +731,7 @@ extern "C" int gsb_raster_fwd_recs(uint32_t N, uint32_t capacity, const void *wo
                                    gsb_stream_t stream) {
     using namespace gsb;
     if (int rc = check_camera(cam)) return rc;
+    if (rolling_shutter(cam)) return GSB_E_UNSUPPORTED; // the fused path is global-shutter only
     if (image_width == 0 || image_height == 0) return GSB_OK;
     if (!renders || !alphas || !last_ids || !tile_offsets) return GSB_E_INVALID;
     if (capacity > 0 && !flatten_ids) return GSB_E_INVALID;
@@ -761,6 +751,7 @@ extern "C" int gsb_raster_bwd_recs(uint32_t N, uint32_t capacity, void *workspac
                                    const float *v_render_colors, const float *v_render_alphas, gsb_stream_t stream) {
     using namespace gsb;
     if (int rc = check_camera(cam)) return rc;
+    if (rolling_shutter(cam)) return GSB_E_UNSUPPORTED;
     if (N == 0 || image_width == 0 || image_height == 0) return GSB_OK;
     if (!tile_offsets || !render_alphas || !last_ids || !v_render_colors || !v_render_alphas) return GSB_E_INVALID;
     if (capacity > 0 && !flatten_ids) return GSB_E_INVALID;

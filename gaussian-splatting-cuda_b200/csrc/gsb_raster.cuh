@@ -152,6 +152,59 @@ __device__ __forceinline__ void make_record(const CamConst &cam, const float (&m
     }
 }
 
+// dL/dq of R = rotmat(q / |q|) from dL/dR (vR[k][i] = dL/dR[k][i], math indices), normalisation included
+// (Utils.cuh:104-126): qn = q / |q|, inv_qnorm = 1 / |q|.
+__device__ __forceinline__ void quat_vjp_from_rotmat_grad(const float (&qn)[4], float inv_qnorm, const float (&vR)[3][3],
+                                                          float (&oq)[4]) {
+    const float w = qn[0], x = qn[1], y = qn[2], z = qn[3];
+    float vq[4];
+    vq[0] = 2.f * (x * (vR[2][1] - vR[1][2]) + y * (vR[0][2] - vR[2][0]) + z * (vR[1][0] - vR[0][1]));
+    vq[1] = 2.f * (-2.f * x * (vR[1][1] + vR[2][2]) + y * (vR[1][0] + vR[0][1]) + z * (vR[2][0] + vR[0][2]) +
+                   w * (vR[2][1] - vR[1][2]));
+    vq[2] = 2.f * (x * (vR[1][0] + vR[0][1]) - 2.f * y * (vR[0][0] + vR[2][2]) + z * (vR[2][1] + vR[1][2]) +
+                   w * (vR[0][2] - vR[2][0]));
+    vq[3] = 2.f * (x * (vR[2][0] + vR[0][2]) + y * (vR[2][1] + vR[1][2]) - 2.f * z * (vR[0][0] + vR[1][1]) +
+                   w * (vR[1][0] - vR[0][1]));
+    const float dq = vq[0] * w + vq[1] * x + vq[2] * y + vq[3] * z;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) oq[k] = (vq[k] - dq * qn[k]) * inv_qnorm;
+}
+
+// Sum 16 per-lane values across the warp: after the call lane L holds in v[0] the warp-wide total of
+// slot (L >> 1).  16 shuffles (8+4+2+1+1) instead of 16 x 5.  On entry lanes 16..31 hold slot (i ^ 8) in
+// v[i] (they built their registers pre-swapped), so stage one needs no lane-dependent selects.
+__device__ __forceinline__ void butterfly16_preswapped(float (&v)[16]) {
+    const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i + 8], 16);
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float send = hi ? v[i] : v[i + 4];
+            const float keep = hi ? v[i + 4] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const float send = hi ? v[i] : v[i + 2];
+            const float keep = hi ? v[i + 2] : v[i];
+            v[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool hi = lane & 2;
+        const float send = hi ? v[0] : v[1];
+        const float keep = hi ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+
+
 // Moment row of a Gaussian (16 floats, kMomFloats), x / y in pixels relative to (pcx, pcy):
 //   w1 = dL/dNs, w2 = dL/dDs, g = dL/d(power) summed, c = dL/d(colour).
 // Slot s and slot s ^ 8 are partners in the first stage of the warp reduction: they differ only in the
@@ -231,17 +284,7 @@ __device__ __forceinline__ void finalize_gaussian(const CamConst &cam, const flo
                 os[i] = (float)(-vsi * gg.inv_s[i] * gg.inv_s[i]);
             }
             // quaternion VJP including the normalisation (Utils.cuh:104-126)
-            const FT w = gg.qn[0], x = gg.qn[1], y = gg.qn[2], z = gg.qn[3];
-            FT vq[4];
-            vq[0] = FT(2) * (x * (vRg[2][1] - vRg[1][2]) + y * (vRg[0][2] - vRg[2][0]) + z * (vRg[1][0] - vRg[0][1]));
-            vq[1] = FT(2) * (-FT(2) * x * (vRg[1][1] + vRg[2][2]) + y * (vRg[1][0] + vRg[0][1]) + z * (vRg[2][0] + vRg[0][2]) +
-                           w * (vRg[2][1] - vRg[1][2]));
-            vq[2] = FT(2) * (x * (vRg[1][0] + vRg[0][1]) - FT(2) * y * (vRg[0][0] + vRg[2][2]) + z * (vRg[2][1] + vRg[1][2]) +
-                           w * (vRg[0][2] - vRg[2][0]));
-            vq[3] = FT(2) * (x * (vRg[2][0] + vRg[0][2]) + y * (vRg[2][1] + vRg[1][2]) - FT(2) * z * (vRg[0][0] + vRg[1][1]) +
-                           w * (vRg[1][0] - vRg[0][1]));
-            const FT dq = vq[0] * w + vq[1] * x + vq[2] * y + vq[3] * z;
-            for (int k = 0; k < 4; ++k) oq[k] = (float)((vq[k] - dq * gg.qn[k]) * gg.inv_qnorm);
+            quat_vjp_from_rotmat_grad(gg.qn, gg.inv_qnorm, vRg, oq);
             oo = (opac > 0.f) ? m[kS_G] / opac : 0.f; // sum vis * v_alpha
         }
     }

@@ -435,9 +435,6 @@ def test_unsupported_configurations_fail_loudly(native, cuda_device):
     with pytest.raises(RuntimeError, match="not supported"):  # orthographic: rejected by the reference too
         native.projection_ut_3dgs_fused(t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"],
                                         sc["width"], sc["height"], camera_model=native.ORTHO)
-    with pytest.raises(RuntimeError, match="not supported"):  # rolling shutter (second pose given)
-        native.projection_ut_3dgs_fused(t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"],
-                                        sc["width"], sc["height"], viewmats1=t["viewmats"], rs_type=0)
     with pytest.raises(RuntimeError, match="CUDA"):
         native.quats_to_rotmats(torch.randn(4, 4))
 

@@ -238,3 +238,57 @@ def test_distorted_cameras_reference_vs_b200(native, ref, cuda_device, model):
     g_new = native.rasterize_to_pixels_from_world_3dgs_bwd(*fa, ar, lr, vr, va, **kw)
     for nm, a, b in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), g_new, g_ref):
         assert_grad_close(a, b, nm, sc["means"].shape[0], tag=f"{model} b200 vs reference kernels")
+
+
+# ------------------------------------------------------------------------------------------
+# a2: rolling shutter (Cameras.cuh:268-413) -- per-pixel camera poses; pinned by the reference's kernels only
+# (the CPU oracle restates the global shutter: "parity unpinned" on the CPU side for this mode)
+# ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("rs_type", [0, 1, 2, 3], ids=["top_to_bottom", "left_to_right", "bottom_to_top", "right_to_left"])
+def test_rolling_shutter_reference_vs_b200(native, ref, cuda_device, rs_type):
+    sc = scenes.scene_small(N=3000, width=208, height=128, view=2)
+    W, H = sc["width"], sc["height"]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    t = to_dev(sc, cuda_device)
+    # end-of-frame pose: the start pose moved by a few degrees and centimetres
+    ang = np.deg2rad(2.5)
+    dR = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float64)
+    V0 = sc["viewmats"][0].astype(np.float64)
+    V1 = V0.copy()
+    V1[:3, :3] = dR @ V0[:3, :3]
+    V1[:3, 3] = dR @ V0[:3, 3] + np.array([0.04, -0.02, 0.03])
+    vm1 = torch.from_numpy(V1[None].astype(np.float32)).to(cuda_device)
+    kw = dict(viewmats1=vm1, rs_type=rs_type)
+    pa = (t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"], W, H, 0.3, 0.01, 1e4, 0.0)
+    r_ref, m_ref, d_ref, c_ref, _ = ref.projection_ut_3dgs_fused(*pa, **kw)
+    r_new, m_new, d_new, c_new, _ = native.projection_ut_3dgs_fused(*pa, **kw)
+    mism = int((r_ref != r_new).any(-1).sum())
+    both = ((r_ref > 0).all(-1) & (r_new > 0).all(-1)).cpu().numpy()
+    em = rel(m_new.cpu().numpy()[both], m_ref.cpu().numpy()[both])
+    # the rolling projection really differs from the global one (the test would be vacuous otherwise)
+    r_glob, m_glob, _, _, _ = ref.projection_ut_3dgs_fused(*pa)
+    moved = float((m_glob - m_ref)[torch.from_numpy(both).to(cuda_device)].abs().max())
+    print(f"[rs {rs_type}] radii differ {mism}/{r_ref.shape[1]}, means2d rel {em:.2e}, visible {both.sum()}, "
+          f"max shift vs global shutter {moved:.2f} px")
+    assert mism <= 6 and em < 1e-4 and both.sum() > 1000 and moved > 1.0
+    vis = (r_ref > 0).all(-1)
+    m2 = torch.where(vis[..., None], m_ref, torch.zeros_like(m_ref))
+    dp = torch.where(vis, d_ref, torch.zeros_like(d_ref))
+    _, ids, flat = ref.intersect_tile(m2, r_ref, dp, 1, 16, tw, th, True)
+    off = ref.intersect_offset(ids, 1, tw, th)
+    rng = np.random.default_rng(5 + rs_type)
+    colors = torch.from_numpy(rng.random((1, sc["means"].shape[0], 3), dtype=np.float32)).to(cuda_device)
+    fa = (t["means"], t["quats"], t["scales"], colors, t["opacities"][None], t["background"], None, W, H, 16,
+          t["viewmats"], t["Ks"], off, flat)
+    rr, ar, lr = ref.rasterize_to_pixels_from_world_3dgs_fwd(*fa, **kw)
+    rn, an, ln = native.rasterize_to_pixels_from_world_3dgs_fwd(*fa, **kw)
+    e = rel(rn.cpu().numpy(), rr.cpu().numpy())
+    lm = float((ln != lr).float().mean())
+    print(f"[rs {rs_type}] image rel_l2 b200 vs reference {e:.2e}; last_ids differ {lm:.2e}")
+    assert e < 1e-4 and rel(an.cpu().numpy(), ar.cpu().numpy()) < 1e-4 and lm < 3e-3
+    vr = torch.from_numpy(rng.standard_normal((1, H, W, 3)).astype(np.float32)).to(cuda_device)
+    va = torch.from_numpy(rng.standard_normal((1, H, W, 1)).astype(np.float32)).to(cuda_device)
+    g_ref = ref.rasterize_to_pixels_from_world_3dgs_bwd(*fa, ar, lr, vr, va, **kw)
+    g_new = native.rasterize_to_pixels_from_world_3dgs_bwd(*fa, ar, lr, vr, va, **kw)
+    for nm, a, b in zip(("v_means", "v_quats", "v_scales", "v_colors", "v_opacities"), g_new, g_ref):
+        assert_grad_close(a, b, nm, sc["means"].shape[0], tag=f"rolling shutter {rs_type} b200 vs reference kernels")
