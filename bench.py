@@ -320,7 +320,8 @@ def run_b200(args):
     cabi.gsb_profile_read.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)]
     names = ("means", "quats", "scales", "opacities", "sh_coeffs")
     raw_names = ("means", "sh0", "shN", "scaling_raw", "rotation_raw", "opacity_raw")
-    compact = world > 1 and args.exchange == "compact"
+    compact = world > 1 and args.exchange in ("compact", "peer")
+    peer = {"obj": None, "why": None}   # peer-memory exchange, built with the workload (needs N)
 
     def sync_all():
         if world > 1:
@@ -393,7 +394,10 @@ def run_b200(args):
             loss = (out.render_colors - Pd["target"]).abs().mean()
             loss.backward()
             if compact:
-                multiview.exchange_gradients_compact(Pd, deferred, overlap_group=pg2)
+                if peer["obj"] is not None:
+                    multiview.exchange_gradients_peer(Pd, deferred, peer["obj"], overlap_group=pg2)
+                else:
+                    multiview.exchange_gradients_compact(Pd, deferred, overlap_group=pg2)
             elif world > 1:
                 multiview.allreduce_gradients([Pd[k].grad for k in names])
             self.stats["n_isects"], self.stats["vis"] = out.n_isects, out.visibility
@@ -480,6 +484,18 @@ def run_b200(args):
     wl = Workload(cfg, args.gaussians, view=(rank if world > 1 else None))
     N, W, H = wl.N, wl.W, wl.H
     warm = max(args.warmup, 3)
+    if world > 1 and args.exchange == "peer":
+        # collective: every rank tries, and every rank falls back if ANY rank failed (the paths must not be mixed)
+        try:
+            peer["obj"] = multiview.PeerColourExchange(N, dev)
+            ok = 1
+        except Exception as e:
+            peer["why"], ok = repr(e)[:200], 0
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            peer["obj"] = None
+            peer["why"] = peer["why"] or "another rank could not map symmetric memory"
 
     # ---- warm-up + device-resident timing (the contract's K steps) -------------------------------------------
     for _ in range(warm):
@@ -510,6 +526,21 @@ def run_b200(args):
                   "gradients) exceeds the 126 MB L2; no explicit flush"}
     line["config"] = cfgd
     line["intersections_per_sec"] = wl.stats["n_isects"] * world / (ms_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (SURVEY.md 8d algorithmic bytes) ---------------------------------------
+    peak, peak_src = load_peaks()
+    I, Pn = wl.stats["n_isects"], W * H
+    dom = max(prof, key=lambda k: prof[k]["avg_ms"]) if prof else None
+    algo = {"raster_bwd": 60 * I + 24 * Pn + 112 * N, "raster_fwd": 48 * I + 20 * Pn}
+    if dom in algo:
+        achieved = algo[dom] / (prof[dom]["avg_ms"] * 1e-3) / 1e9
+        traffic, traffic_src = ncu_traffic(dom, N, W, H)
+        line["roofline"] = {
+            "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+            "algorithmic_bytes_per_launch": algo[dom], "avg_kernel_ms": prof[dom]["avg_ms"],
+            "note": "the blend is FP32-issue/LSU/atomic bound by construction (SURVEY.md 8d): the HBM fraction is the "
+                    "figure north_star asks for, the pipe utilisations are in profiles/"}
 
     if args.quick:
         if rank == 0:
@@ -549,7 +580,10 @@ def run_b200(args):
             multiview.allreduce_gradients(bufs)
         ms_ar = timed(lambda: multiview.allreduce_gradients(bufs), 20) / 20
         nbytes = sum(b.numel() * 4 for b in bufs)
-        line["exchange"] = {"mode": args.exchange, "overlap": "geometry all-reduce on a second communicator",
+        line["exchange"] = {"mode": ("peer" if peer["obj"] is not None else
+                                     ("compact" if compact else "allreduce")),
+                            "peer_fallback_reason": peer["why"],
+                            "overlap": "geometry all-reduce on a second communicator",
                             "allreduce_236B_ms": ms_ar, "allreduce_bytes": nbytes,
                             "allreduce_bus_GBps": 2.0 * (world - 1) / world * nbytes / (ms_ar * 1e-3) / 1e9,
                             "nvlink5_peak_GBps_per_direction": 900.0,
@@ -586,21 +620,6 @@ def run_b200(args):
                 "ms_per_step": ms_u, "e2e_resident_ms": ms_u_res}}
     except Exception as e:
         line["fused"] = {"unavailable": repr(e)[:300]}
-
-    # ---- roofline of the dominant kernel (SURVEY.md 8d algorithmic bytes) ---------------------------------------
-    peak, peak_src = load_peaks()
-    I, Pn = wl.stats["n_isects"], W * H
-    dom = max(prof, key=lambda k: prof[k]["avg_ms"]) if prof else None
-    algo = {"raster_bwd": 60 * I + 24 * Pn + 112 * N, "raster_fwd": 48 * I + 20 * Pn}
-    if dom in algo:
-        achieved = algo[dom] / (prof[dom]["avg_ms"] * 1e-3) / 1e9
-        traffic, traffic_src = ncu_traffic(dom, N, W, H)
-        line["roofline"] = {
-            "kernel": dom, "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-            "algorithmic_bytes_per_launch": algo[dom], "avg_kernel_ms": prof[dom]["avg_ms"],
-            "note": "the blend is FP32-issue/LSU/atomic bound by construction (SURVEY.md 8d): the HBM fraction is the "
-                    "figure north_star asks for, the pipe utilisations are in profiles/"}
 
     # ---- same-box GPU baseline: the reference's own gsplat CUDA kernels (oracle/_ref), same call sites ------------
     rb = None
@@ -790,7 +809,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--exchange", choices=("compact", "allreduce"), default="compact",
+    ap.add_argument("--exchange", choices=("compact", "allreduce", "peer"), default="compact",
                     help="N>1 gradient exchange: compact (all-gather colour gradients + multi-view SH backward) or "
                          "plain all-reduce of the five gradient tensors")
     ap.add_argument("--steps", type=int, default=30)

@@ -108,6 +108,11 @@ class OpsBackend:
         once from their gathered colour gradients; returns v_coeffs, accumulates into v_means."""
         return self.ns.spherical_harmonics_bwd_views(degrees_to_use, means, campos, coeffs, v_colors, v_means)
 
+    def spherical_harmonics_bwd_views_peer(self, degrees_to_use, means, coeffs, view_addrs, v_means):
+        """The same with the gather inside the kernel (gsb_sh_bwd_views_peer): `view_addrs` are the device addresses
+        of the V ranks' symmetric-memory blocks [M*3 colour gradients | 3 camera position]."""
+        return self.ns.spherical_harmonics_bwd_views_peer(degrees_to_use, means, coeffs, list(view_addrs), v_means)
+
     def intersect_tile(self, means2d, radii, depths, C, tile_size, tile_width, tile_height, sort=True):
         return self.ns.intersect_tile(means2d, radii, depths, C, tile_size, tile_width, tile_height, sort)
 

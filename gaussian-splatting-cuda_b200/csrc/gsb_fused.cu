@@ -25,7 +25,7 @@
 
 namespace gsb {
 
-constexpr int kFusedThreads = 128; // 96-122 registers per thread: 128-thread CTAs keep 4-5 of them on an SM
+constexpr int kFusedThreads = 128; // 110-128 registers per thread: four 128-thread CTAs per SM (five would spill)
 
 struct FusedParams {
     uint32_t N, K; // K = SH coefficients per Gaussian including sh0
@@ -93,7 +93,7 @@ __device__ __forceinline__ void stage_rows_in(float *s_rows, const float *g_rows
 }
 
 template <int DEG>
-__global__ void __launch_bounds__(kFusedThreads, 5) fused_front_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, 4) fused_front_kernel(const FusedParams p) {
     constexpr int NB = (DEG + 1) * (DEG + 1);
     extern __shared__ __align__(128) float s_rows[]; // [kFusedThreads][(K-1)*3]
     __shared__ FusedCam s_cam;

@@ -279,6 +279,7 @@ struct BinArgs {
     uint32_t *chunk_run;  // [P + 1] first run of every chunk (written by hist)
     int32_t *flatten_ids;
     uint32_t cap;         // capacity of flatten_ids (>= n_isects unless the caller under-allocated)
+    const float *depths;  // [C * N] (scatter pass: order repair)
 };
 
 constexpr int kBinThreads = 256;
@@ -308,110 +309,13 @@ __device__ __forceinline__ uint32_t chunk_first_run(const BinArgs &a, uint32_t p
     return first_run_after(a.rt.end, n_runs, s);
 }
 
-template <bool kScatter>
-__global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) {
-    extern __shared__ uint32_t s_cnt[]; // [t_cnt]
-    __shared__ uint32_t s_range[2];
-    const uint32_t tid = threadIdx.x, lane = tid & 31;
-    const uint32_t p = blockIdx.x;
-    uint32_t *row = a.M + (size_t)p * a.T_total + a.t_lo;
-    const unsigned long long I = a.ctl->n_isects;
-    const uint32_t n_runs = a.ctl->n_runs;
-    if (tid < 32) {
-        const uint32_t ra = kScatter ? a.chunk_run[p] : chunk_first_run(a, p, I, n_runs);
-        const uint32_t rb = kScatter ? a.chunk_run[p + 1] : chunk_first_run(a, p + 1, I, n_runs);
-        if (tid == 0) {
-            s_range[0] = ra; s_range[1] = rb;
-            if (!kScatter) {
-                a.chunk_run[p] = ra;
-                if (p == a.P - 1) a.chunk_run[a.P] = n_runs;
-            }
-        }
-    }
-    if (kScatter) {
-        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) s_cnt[t] = row[t];
-    } else {
-        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) s_cnt[t] = 0;
-    }
-    __syncthreads();
-    const uint32_t ra = s_range[0], rb = s_range[1];
-
-    auto place = [&](uint32_t idx, uint32_t cam_base, uint32_t x, uint32_t y) {
-        const uint32_t g = cam_base + y * a.tile_width + x - a.t_lo;
-        if (g < a.t_cnt) {
-            const uint32_t pos = atomicAdd(&s_cnt[g], 1u);
-            if (kScatter && pos < a.cap) a.flatten_ids[pos] = (int32_t)idx;
-        }
-    };
-    for (uint32_t r0 = ra + (tid & ~31u); r0 < rb; r0 += kBinThreads) { // warp-uniform trip count
-        const uint32_t r = r0 + lane;
-        uint32_t idx = 0, bx = 0, by = 0;
-        if (r < rb) {
-            idx = a.rt.idx[r];
-            const uint2 b = a.rt.box[r];
-            bx = b.x; by = b.y;
-        }
-        const uint32_t w = by & 0xffffu, h = by >> 16, n = w * h; // 0 for the lanes past the chunk
-        const uint32_t x0 = bx & 0xffffu, y0 = bx >> 16;
-        const uint32_t cam_base = a.multi_cam ? (idx / a.N) * a.n_tiles : 0u;
-        // runs of up to 32 tiles: one lane each
-        if (n > 0 && n <= 32) {
-            // four tiles per trip: the four shared-memory atomics are in flight together (their return value, the
-            // slot, is what the store waits for)
-            uint32_t x = x0, y = y0;
-            for (uint32_t j = 0; j < n; j += 4) {
-                uint32_t g[4], pos[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    g[u] = (j + u < n) ? cam_base + y * a.tile_width + x - a.t_lo : 0xffffffffu;
-                    if (++x == x0 + w) { x = x0; ++y; }
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) pos[u] = (g[u] < a.t_cnt) ? atomicAdd(&s_cnt[g[u]], 1u) : 0xffffffffu;
-                if (kScatter) {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (pos[u] < a.cap) a.flatten_ids[pos[u]] = (int32_t)idx;
-                }
-            }
-        }
-        // larger runs: the whole warp strides over the box
-        uint32_t big = __ballot_sync(0xffffffffu, n > 32);
-        while (big) {
-            const int src = __ffs(big) - 1;
-            big &= big - 1;
-            const uint32_t bidx = __shfl_sync(0xffffffffu, idx, src), bcam = __shfl_sync(0xffffffffu, cam_base, src);
-            const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-            const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
-            for (uint32_t j = lane; j < bn; j += 32) {
-                const uint32_t dy = j / bw, dx = j - dy * bw;
-                place(bidx, bcam, bx0 + dx, by0 + dy);
-            }
-        }
-    }
-    if (!kScatter) {
-        __syncthreads();
-        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) row[t] = s_cnt[t];
-    }
-}
-
-// Order repair of the (chunk, tile) groups: one lane per group, a warp for the large ones.
+// Order repair of the (chunk, tile) groups: one lane per group, a warp for the large ones.  Called by all 32 lanes
+// of a warp, each with its own group: chunk p, global tile t, slots [start, start + c) of flatten_ids.
 constexpr int kSmallGroup = 16;
 
-__global__ void __launch_bounds__(kBinThreads) group_repair_kernel(const BinArgs a, const uint32_t *__restrict__ toff,
-                                                                   const float *__restrict__ depths) {
+__device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__restrict__ depths, uint32_t p,
+                                              uint32_t t, uint32_t start, uint32_t c) {
     const uint32_t lane = threadIdx.x & 31;
-    const unsigned long long i = (unsigned long long)blockIdx.x * kBinThreads + threadIdx.x;
-    const unsigned long long total = (unsigned long long)a.P * a.T_total;
-    uint32_t start = 0, c = 0, p = 0, t = 0;
-    if (i < total) {
-        p = (uint32_t)(i / a.T_total);
-        t = (uint32_t)(i - (unsigned long long)p * a.T_total);
-        start = a.M[i];
-        uint32_t end = (p + 1 < a.P) ? a.M[i + a.T_total] : toff[t + 1];
-        if (end > a.cap) end = a.cap;
-        c = end > start ? end - start : 0u;
-    }
     if (c >= 2 && c <= 4) {
         // the common case (a group holds 1.35 intersections on average): a 4-element sorting network in registers
         uint32_t id0 = (uint32_t)a.flatten_ids[start], id1 = (uint32_t)a.flatten_ids[start + 1];
@@ -513,6 +417,116 @@ __global__ void __launch_bounds__(kBinThreads) group_repair_kernel(const BinArgs
     }
 }
 
+template <bool kScatter>
+__global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) {
+    extern __shared__ uint32_t s_cnt[]; // [t_cnt]
+    __shared__ uint32_t s_range[2];
+    __shared__ uint32_t s_nwork;
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    const uint32_t p = blockIdx.x;
+    if (tid == 0) s_nwork = 0;
+    uint32_t *row = a.M + (size_t)p * a.T_total + a.t_lo;
+    const unsigned long long I = a.ctl->n_isects;
+    const uint32_t n_runs = a.ctl->n_runs;
+    if (tid < 32) {
+        const uint32_t ra = kScatter ? a.chunk_run[p] : chunk_first_run(a, p, I, n_runs);
+        const uint32_t rb = kScatter ? a.chunk_run[p + 1] : chunk_first_run(a, p + 1, I, n_runs);
+        if (tid == 0) {
+            s_range[0] = ra; s_range[1] = rb;
+            if (!kScatter) {
+                a.chunk_run[p] = ra;
+                if (p == a.P - 1) a.chunk_run[a.P] = n_runs;
+            }
+        }
+    }
+    if (kScatter) {
+        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) s_cnt[t] = row[t];
+    } else {
+        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) s_cnt[t] = 0;
+    }
+    __syncthreads();
+    const uint32_t ra = s_range[0], rb = s_range[1];
+
+    auto place = [&](uint32_t idx, uint32_t cam_base, uint32_t x, uint32_t y) {
+        const uint32_t g = cam_base + y * a.tile_width + x - a.t_lo;
+        if (g < a.t_cnt) {
+            const uint32_t pos = atomicAdd(&s_cnt[g], 1u);
+            if (kScatter && pos < a.cap) a.flatten_ids[pos] = (int32_t)idx;
+        }
+    };
+    for (uint32_t r0 = ra + (tid & ~31u); r0 < rb; r0 += kBinThreads) { // warp-uniform trip count
+        const uint32_t r = r0 + lane;
+        uint32_t idx = 0, bx = 0, by = 0;
+        if (r < rb) {
+            idx = a.rt.idx[r];
+            const uint2 b = a.rt.box[r];
+            bx = b.x; by = b.y;
+        }
+        const uint32_t w = by & 0xffffu, h = by >> 16, n = w * h; // 0 for the lanes past the chunk
+        const uint32_t x0 = bx & 0xffffu, y0 = bx >> 16;
+        const uint32_t cam_base = a.multi_cam ? (idx / a.N) * a.n_tiles : 0u;
+        // runs of up to 32 tiles: one lane each
+        if (n > 0 && n <= 32) {
+            // four tiles per trip: the four shared-memory atomics are in flight together (their return value, the
+            // slot, is what the store waits for)
+            uint32_t x = x0, y = y0;
+            for (uint32_t j = 0; j < n; j += 4) {
+                uint32_t g[4], pos[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    g[u] = (j + u < n) ? cam_base + y * a.tile_width + x - a.t_lo : 0xffffffffu;
+                    if (++x == x0 + w) { x = x0; ++y; }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) pos[u] = (g[u] < a.t_cnt) ? atomicAdd(&s_cnt[g[u]], 1u) : 0xffffffffu;
+                if (kScatter) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (pos[u] < a.cap) a.flatten_ids[pos[u]] = (int32_t)idx;
+                }
+            }
+        }
+        // larger runs: the whole warp strides over the box
+        uint32_t big = __ballot_sync(0xffffffffu, n > 32);
+        while (big) {
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t bidx = __shfl_sync(0xffffffffu, idx, src), bcam = __shfl_sync(0xffffffffu, cam_base, src);
+            const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+            const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
+            for (uint32_t j = lane; j < bn; j += 32) {
+                const uint32_t dy = j / bw, dx = j - dy * bw;
+                place(bidx, bcam, bx0 + dx, by0 + dy);
+            }
+        }
+    }
+    __syncthreads();
+    if (!kScatter) {
+        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) row[t] = s_cnt[t];
+    } else {
+        // the CTA's own groups, while their slots are still in L2: row[] holds the first slot, the counter the end.
+        // Most groups have one member: the tiles whose group needs sorting are first compacted into a work list so
+        // that every lane of the repair loop has a group (the loop is a chain of dependent gathers).
+        uint16_t *work = reinterpret_cast<uint16_t *>(s_cnt + a.t_cnt);
+        for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) {
+            const uint32_t start = row[t], end = min(s_cnt[t], a.cap);
+            if (end > start + 1) work[atomicAdd(&s_nwork, 1u)] = (uint16_t)t;
+        }
+        __syncthreads();
+        const uint32_t n_work = s_nwork;
+        for (uint32_t i0 = tid & ~31u; i0 < n_work; i0 += kBinThreads) { // warp-uniform trip count
+            const uint32_t i = i0 + lane;
+            uint32_t t = 0, start = 0, c = 0;
+            if (i < n_work) {
+                t = work[i];
+                start = row[t];
+                c = min(s_cnt[t], a.cap) - start;
+            }
+            repair_groups(a, a.depths, p, a.t_lo + t, start, c);
+        }
+    }
+}
+
 // isect_ids of the sorted list, written in order (coalesced) instead of scattered with the values:
 //   key[pos] = cam << (32 + tile_bits) | tile << 32 | depth bits of flatten_ids[pos]
 // the tile of a position is found in the closed offsets table tile_off[0 .. T] (tile_off[T] = n_isects).
@@ -558,7 +572,13 @@ __global__ void __launch_bounds__(kIsectThreads) col_segsum_kernel(const uint32_
     const uint32_t s = blockIdx.y;
     const uint32_t p0 = s * seg_len, p1 = min(P, p0 + seg_len);
     uint32_t acc = 0;
-    for (uint32_t p = p0; p < p1; ++p) acc += M[(size_t)p * T + t];
+    uint32_t p = p0;
+    for (; p + 4 <= p1; p += 4) { // four independent loads in flight
+        const uint32_t v0 = M[(size_t)p * T + t], v1 = M[(size_t)(p + 1) * T + t];
+        const uint32_t v2 = M[(size_t)(p + 2) * T + t], v3 = M[(size_t)(p + 3) * T + t];
+        acc += (v0 + v1) + (v2 + v3);
+    }
+    for (; p < p1; ++p) acc += M[(size_t)p * T + t];
     seg[(size_t)s * T + t] = acc;
 }
 // col_tilescan (one CTA): seg[s][t] -> exclusive prefix over s plus the tile's first slot; tile offsets out.
@@ -571,15 +591,28 @@ __global__ void __launch_bounds__(kSortThreads) col_tilescan_kernel(uint32_t *__
     for (uint32_t t0 = 0; t0 < T; t0 += kSortThreads) {
         const uint32_t t = t0 + threadIdx.x;
         uint32_t tot = 0;
-        if (t < T)
+        if (t < T) {
+#pragma unroll 8
             for (uint32_t s = 0; s < S; ++s) tot += seg[(size_t)s * T + t];
+        }
         uint32_t all;
         const uint32_t inc = block_scan_inclusive<uint32_t>(tot, s_warp, all);
         if (t < T) {
             uint32_t run = carry + inc - tot; // first slot of tile t
             toff[t] = run;
             if (tile_offsets) tile_offsets[t] = (int32_t)run;
-            for (uint32_t s = 0; s < S; ++s) {
+            uint32_t s = 0;
+            for (; s + 8 <= S; s += 8) { // eight loads in flight, then the eight stores
+                uint32_t v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = seg[(size_t)(s + k) * T + t];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    seg[(size_t)(s + k) * T + t] = run;
+                    run += v[k];
+                }
+            }
+            for (; s < S; ++s) {
                 const uint32_t v = seg[(size_t)s * T + t];
                 seg[(size_t)s * T + t] = run;
                 run += v;
@@ -600,7 +633,17 @@ __global__ void __launch_bounds__(kIsectThreads) col_apply_kernel(uint32_t *__re
     const uint32_t s = blockIdx.y;
     const uint32_t p0 = s * seg_len, p1 = min(P, p0 + seg_len);
     uint32_t run = seg[(size_t)s * T + t];
-    for (uint32_t p = p0; p < p1; ++p) {
+    uint32_t p = p0;
+    for (; p + 4 <= p1; p += 4) { // loads first: a store to M would otherwise fence the next load
+        const uint32_t v0 = M[(size_t)p * T + t], v1 = M[(size_t)(p + 1) * T + t];
+        const uint32_t v2 = M[(size_t)(p + 2) * T + t], v3 = M[(size_t)(p + 3) * T + t];
+        M[(size_t)p * T + t] = run;
+        M[(size_t)(p + 1) * T + t] = run + v0;
+        M[(size_t)(p + 2) * T + t] = run + v0 + v1;
+        M[(size_t)(p + 3) * T + t] = run + v0 + v1 + v2;
+        run += (v0 + v1) + (v2 + v3);
+    }
+    for (; p < p1; ++p) {
         const uint32_t v = M[(size_t)p * T + t];
         M[(size_t)p * T + t] = run;
         run += v;
@@ -670,11 +713,12 @@ static SegPlan seg_plan(uint64_t n) {
     return s;
 }
 
-constexpr uint32_t kMaxWindowTiles = 48 * 1024; // 192 KB of shared-memory counters per warp at most
+constexpr uint32_t kMaxWindowTiles = 36 * 1024; // 144 KB of counters (+ 72 KB work list in the scatter pass) at most
 
 struct BinPlan {
     uint32_t T_total, t_win, n_win, P, S, seg_len;
-    size_t smem;
+    size_t smem;         // counters of the histogram pass
+    size_t smem_scatter; // counters + 16-bit work list of the scatter pass
 };
 static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t tile_height) {
     const DeviceShape &d = device_shape();
@@ -685,6 +729,7 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
     b.n_win = (b.T_total + b.t_win - 1) / b.t_win;
     if (b.n_win == 0) b.n_win = 1;
     b.smem = (size_t)b.t_win * 4;
+    b.smem_scatter = (size_t)b.t_win * 6;
     uint32_t per_sm = (uint32_t)((size_t)d.smem_sm / (b.smem + 1024));
     if (per_sm < 1) per_sm = 1;
     if (per_sm > 8) per_sm = 8; // 8 x 256 threads fill an SM
@@ -701,7 +746,8 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
     if (P > cap) P = cap;
     if (P < 1) P = 1;
     b.P = (uint32_t)P;
-    uint32_t S = b.T_total ? (65536u + b.T_total - 1) / b.T_total : 1u;
+    // column scan: S segments of chunks per tile column, about a quarter of a million threads
+    uint32_t S = b.T_total ? (262144u + b.T_total - 1) / b.T_total : 1u;
     if (S > 64) S = 64;
     if (S > b.P) S = b.P;
     if (S < 1) S = 1;
@@ -913,7 +959,7 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
         BinArgs a;
         a.rt = rt; a.ctl = ctl; a.N = N; a.n_tiles = tile_width * tile_height; a.tile_width = tile_width;
         a.multi_cam = C > 1 ? 1u : 0u;
-        a.T_total = bp.T_total; a.P = bp.P; a.M = M; a.flatten_ids = nullptr; a.cap = 0;
+        a.T_total = bp.T_total; a.P = bp.P; a.M = M; a.flatten_ids = nullptr; a.cap = 0; a.depths = nullptr;
         a.chunk_run = reinterpret_cast<uint32_t *>(base + w.chunk_run);
         if (bp.smem > 48 * 1024)
             GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -962,25 +1008,18 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depth
     a.multi_cam = C > 1 ? 1u : 0u;
     a.chunk_run = reinterpret_cast<uint32_t *>(base + w.chunk_run);
     a.T_total = bp.T_total; a.P = bp.P; a.M = reinterpret_cast<uint32_t *>(base + w.M);
-    a.flatten_ids = flatten_ids; a.cap = (uint32_t)n_isects;
-    if (bp.smem > 48 * 1024)
-        GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bp.smem));
+    a.flatten_ids = flatten_ids; a.cap = (uint32_t)n_isects; a.depths = depths;
+    if (bp.smem_scatter > 48 * 1024)
+        GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)bp.smem_scatter));
     {
         ProfScope ps("isect_emit", s);
         for (uint32_t wnd = 0; wnd < bp.n_win; ++wnd) {
             a.t_lo = wnd * bp.t_win;
             a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
-            tile_bin_kernel<true><<<bp.P, kBinThreads, bp.smem, s>>>(a);
+            tile_bin_kernel<true><<<bp.P, kBinThreads, bp.smem_scatter, s>>>(a);
             GSB_LAUNCH_CHECK();
         }
-    }
-    {
-        ProfScope ps("isect_repair", s);
-        a.t_lo = 0; a.t_cnt = bp.T_total;
-        const unsigned long long groups = (unsigned long long)bp.P * bp.T_total;
-        group_repair_kernel<<<(unsigned)((groups + kBinThreads - 1) / kBinThreads), kBinThreads, 0, s>>>(
-            a, reinterpret_cast<const uint32_t *>(base + w.toff), depths);
-        GSB_LAUNCH_CHECK();
     }
     if (isect_ids) { // only the operator API wants the 64-bit keys back (intersect_offset consumes them)
         const uint32_t grid = (uint32_t)((n_isects + kIsectThreads * 4 - 1) / (kIsectThreads * 4));

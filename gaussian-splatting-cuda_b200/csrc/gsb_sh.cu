@@ -268,18 +268,33 @@ __global__ void __launch_bounds__(kShThreads) sh_bwd_k16_kernel(uint32_t M, cons
 // exactly zero (Gaussian not blended in that view) cost one 12-byte load.  The gradient w.r.t. the view
 // directions is chained to the Gaussian's position (dir = mean - campos) and ACCUMULATED into v_means.
 // ------------------------------------------------------------------------------------------
-template <int DEG, bool kRow16Path>
+// kTable: view v's colour gradients and camera position are read through a table of per-view pointers instead of
+// from one stacked tensor -- the pointers may be PEER memory (NVLink-mapped buffers of the other ranks,
+// gsb_sh_bwd_views_peer): the all-gather of the exchange step then happens inside this kernel, overlapped with the
+// expansion, and the gathered tensor never exists.
+constexpr int kMaxViewPtrs = 16;
+struct ViewTable {
+    const float *vc[kMaxViewPtrs]; // [M,3] each
+    const float *cp[kMaxViewPtrs]; // [3] each
+};
+
+template <int DEG, bool kRow16Path, bool kTable>
 __global__ void __launch_bounds__(kShThreads) sh_bwd_views_kernel(uint32_t M, uint32_t K, uint32_t V,
                                                                   const float *__restrict__ means,
                                                                   const float *__restrict__ campos,
                                                                   const float *__restrict__ coeffs,
                                                                   const float *__restrict__ v_colors,
                                                                   float *__restrict__ v_coeffs,
-                                                                  float *__restrict__ v_means) {
+                                                                  float *__restrict__ v_means, const ViewTable tbl) {
     constexpr int NB = (DEG + 1) * (DEG + 1);
     extern __shared__ __align__(128) float s_rows[]; // row path: in rows [T][52] then out rows [T][52]
     __shared__ __align__(8) uint64_t s_bar;
+    __shared__ float s_cp[kMaxViewPtrs * 3];
     const uint32_t tid = threadIdx.x;
+    if constexpr (kTable) { // camera positions once per CTA (remote loads), not once per thread and view
+        if (tid < V * 3) s_cp[tid] = tbl.cp[tid / 3][tid % 3];
+        __syncthreads();
+    }
     const uint32_t e = blockIdx.x * kShThreads + tid;
     const bool inside = e < M;
     float *row_in = nullptr, *row_out = nullptr;
@@ -303,11 +318,24 @@ __global__ void __launch_bounds__(kShThreads) sh_bwd_views_kernel(uint32_t M, ui
     if (inside) { mx = means[(size_t)e * 3]; my = means[(size_t)e * 3 + 1]; mz = means[(size_t)e * 3 + 2]; }
     if constexpr (kRow16Path) mbar_wait(&s_bar, 0);
     if (inside) {
+        float n0 = 0.f, n1 = 0.f, n2 = 0.f; // table path: the next view's colours are in flight during this view's math
+        if constexpr (kTable) {
+            if (V > 0) { const float *gc = tbl.vc[0] + (size_t)e * 3; n0 = gc[0]; n1 = gc[1]; n2 = gc[2]; }
+        }
         for (uint32_t v = 0; v < V; ++v) {
-            const float *gc = v_colors + ((size_t)v * M + e) * 3;
-            const float g0 = gc[0], g1 = gc[1], g2 = gc[2];
+            float g0, g1, g2;
+            const float *cpv;
+            if constexpr (kTable) {
+                g0 = n0; g1 = n1; g2 = n2;
+                if (v + 1 < V) { const float *gc = tbl.vc[v + 1] + (size_t)e * 3; n0 = gc[0]; n1 = gc[1]; n2 = gc[2]; }
+                cpv = s_cp + v * 3;
+            } else {
+                const float *gc = v_colors + ((size_t)v * M + e) * 3;
+                g0 = gc[0]; g1 = gc[1]; g2 = gc[2];
+                cpv = campos + v * 3;
+            }
             if (g0 == 0.f && g1 == 0.f && g2 == 0.f) continue;
-            float x = mx - campos[v * 3], y = my - campos[v * 3 + 1], z = mz - campos[v * 3 + 2], inorm = 1.f;
+            float x = mx - cpv[0], y = my - cpv[1], z = mz - cpv[2], inorm = 1.f;
             if constexpr (DEG >= 1) {
                 inorm = rsqrtf(x * x + y * y + z * z);
                 x *= inorm; y *= inorm; z *= inorm;
@@ -434,22 +462,20 @@ extern "C" int gsb_sh_bwd(uint32_t M, uint32_t K, uint32_t degree, const float *
     return GSB_OK;
 }
 
-extern "C" int gsb_sh_bwd_views(uint32_t M, uint32_t K, uint32_t degree, uint32_t V, const float *means,
-                                const float *campos, const float *coeffs, const float *v_colors, float *v_coeffs,
-                                float *v_means, gsb_stream_t stream) {
-    if (M == 0) return GSB_OK;
-    if (!means || !coeffs || !v_coeffs || !v_means || (V > 0 && (!campos || !v_colors))) return GSB_E_INVALID;
-    if (degree > 4 || (degree + 1) * (degree + 1) > K) return GSB_E_INVALID;
-    const dim3 grid((M + gsb::kShThreads - 1) / gsb::kShThreads);
-    cudaStream_t s = gsb::as_stream(stream);
-    gsb::ProfScope ps("sh_bwd_views", s);
-    if (K == 16 && degree <= 3 && gsb::aligned16(coeffs) && gsb::aligned16(v_coeffs)) {
-        const size_t smem = (size_t)2 * gsb::kShThreads * gsb::kRowStride16 * 4;
+namespace gsb {
+template <bool kTable>
+static int sh_bwd_views_launch(uint32_t M, uint32_t K, uint32_t degree, uint32_t V, const float *means,
+                               const float *campos, const float *coeffs, const float *v_colors, float *v_coeffs,
+                               float *v_means, const ViewTable &tbl, cudaStream_t s) {
+    const dim3 grid((M + kShThreads - 1) / kShThreads);
+    ProfScope ps("sh_bwd_views", s);
+    if (K == 16 && degree <= 3 && aligned16(coeffs) && aligned16(v_coeffs)) {
+        const size_t smem = (size_t)2 * kShThreads * kRowStride16 * 4;
         #define GSB_SH_VIEWS16(D)                                                                                      \
-            cudaFuncSetAttribute(gsb::sh_bwd_views_kernel<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+            cudaFuncSetAttribute(sh_bwd_views_kernel<D, true, kTable>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                  (int)smem);                                                                           \
-            gsb::sh_bwd_views_kernel<D, true><<<grid, gsb::kShThreads, smem, s>>>(M, K, V, means, campos, coeffs,      \
-                                                                                  v_colors, v_coeffs, v_means)
+            sh_bwd_views_kernel<D, true, kTable><<<grid, kShThreads, smem, s>>>(M, K, V, means, campos, coeffs,        \
+                                                                                v_colors, v_coeffs, v_means, tbl)
         switch (degree) {
         case 0: GSB_SH_VIEWS16(0); break;
         case 1: GSB_SH_VIEWS16(1); break;
@@ -461,8 +487,8 @@ extern "C" int gsb_sh_bwd_views(uint32_t M, uint32_t K, uint32_t degree, uint32_
         return GSB_OK;
     }
     #define GSB_SH_VIEWS(D)                                                                                            \
-        gsb::sh_bwd_views_kernel<D, false><<<grid, gsb::kShThreads, 0, s>>>(M, K, V, means, campos, coeffs, v_colors,  \
-                                                                            v_coeffs, v_means)
+        sh_bwd_views_kernel<D, false, kTable><<<grid, kShThreads, 0, s>>>(M, K, V, means, campos, coeffs, v_colors,    \
+                                                                          v_coeffs, v_means, tbl)
     switch (degree) {
     case 0: GSB_SH_VIEWS(0); break;
     case 1: GSB_SH_VIEWS(1); break;
@@ -473,4 +499,34 @@ extern "C" int gsb_sh_bwd_views(uint32_t M, uint32_t K, uint32_t degree, uint32_
     #undef GSB_SH_VIEWS
     GSB_LAUNCH_CHECK();
     return GSB_OK;
+}
+} // namespace gsb
+
+extern "C" int gsb_sh_bwd_views(uint32_t M, uint32_t K, uint32_t degree, uint32_t V, const float *means,
+                                const float *campos, const float *coeffs, const float *v_colors, float *v_coeffs,
+                                float *v_means, gsb_stream_t stream) {
+    if (M == 0) return GSB_OK;
+    if (!means || !coeffs || !v_coeffs || !v_means || (V > 0 && (!campos || !v_colors))) return GSB_E_INVALID;
+    if (degree > 4 || (degree + 1) * (degree + 1) > K) return GSB_E_INVALID;
+    gsb::ViewTable tbl = {};
+    return gsb::sh_bwd_views_launch<false>(M, K, degree, V, means, campos, coeffs, v_colors, v_coeffs, v_means, tbl,
+                                           gsb::as_stream(stream));
+}
+
+extern "C" int gsb_sh_bwd_views_peer(uint32_t M, uint32_t K, uint32_t degree, uint32_t V, const float *means,
+                                     const float *const *campos_views, const float *coeffs,
+                                     const float *const *v_colors_views, float *v_coeffs, float *v_means,
+                                     gsb_stream_t stream) {
+    if (M == 0) return GSB_OK;
+    if (!means || !coeffs || !v_coeffs || !v_means || (V > 0 && (!campos_views || !v_colors_views))) return GSB_E_INVALID;
+    if (degree > 4 || (degree + 1) * (degree + 1) > K) return GSB_E_INVALID;
+    if (V > (uint32_t)gsb::kMaxViewPtrs) return GSB_E_UNSUPPORTED;
+    gsb::ViewTable tbl = {};
+    for (uint32_t v = 0; v < V; ++v) {
+        if (!campos_views[v] || !v_colors_views[v]) return GSB_E_INVALID;
+        tbl.vc[v] = v_colors_views[v];
+        tbl.cp[v] = campos_views[v];
+    }
+    return gsb::sh_bwd_views_launch<true>(M, K, degree, V, means, nullptr, coeffs, nullptr, v_coeffs, v_means, tbl,
+                                          gsb::as_stream(stream));
 }

@@ -118,6 +118,79 @@ def exchange_gradients_compact(params: dict, deferred, sh_views_fn=None, average
             params[k].grad.div_(average_over)
 
 
+class PeerColourExchange:
+    """This rank's block [N*3 colour gradients | camera position] in NVLink-mapped symmetric memory
+    (torch.distributed._symmetric_memory: cuMem allocations exchanged between the ranks of one node, every rank holds
+    the device address of every peer's block).  The SH expansion (gsb_sh_bwd_views_peer) reads its V views straight
+    from the peers through NVSwitch: the all-gather of the exchange step runs INSIDE the kernel, overlapped with the
+    expansion, and the gathered [V,N,3] tensor is never written or re-read.  Construction is collective; it raises
+    when symmetric memory is not available (the caller then keeps the NCCL all-gather path)."""
+
+    def __init__(self, n_gauss: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        grp = group if group is not None else dist.group.WORLD
+        self.n = int(n_gauss)
+        try:  # older releases want the group enabled first; newer ones deprecate the call
+            symm.enable_symm_mem_for_group(grp.group_name)
+        except Exception:
+            pass
+        self.buf = symm.empty(self.n * 3 + 4, dtype=torch.float32, device=device)
+        self.hdl = symm.rendezvous(self.buf, grp)
+        self.addrs = [int(a) for a in self.hdl.buffer_ptrs]
+        self.world = int(self.hdl.world_size)
+        if len(self.addrs) != self.world or any(a == 0 for a in self.addrs):
+            raise RuntimeError("symmetric memory rendezvous returned no peer addresses")
+
+    def publish(self, v_colors: torch.Tensor, campos: torch.Tensor) -> None:
+        """Copy this rank's view into its block, then a device-side barrier: every rank's block is complete."""
+        self.buf[: self.n * 3].copy_(v_colors.reshape(-1))
+        self.buf[self.n * 3: self.n * 3 + 3].copy_(campos.reshape(3))
+        self.hdl.barrier(channel=0)
+
+    def release(self) -> None:
+        """Device-side barrier after the expansion: nobody still reads a block when its owner overwrites it."""
+        self.hdl.barrier(channel=1)
+
+
+def exchange_gradients_peer(params: dict, deferred, peer: PeerColourExchange, sh_views_peer_fn=None,
+                            average_over: int | None = None, group=None, overlap_group=None) -> None:
+    """exchange_gradients_compact with the colour all-gather fused into the SH expansion kernel over peer memory
+    (one view per rank).  Same sums in the same order as the compact path: the results are bit-identical."""
+    if sh_views_peer_fn is None:
+        from . import default_backend
+        sh_views_peer_fn = default_backend().spherical_harmonics_bwd_views_peer
+    if isinstance(deferred, (list, tuple)):
+        if len(deferred) != 1:
+            raise ValueError("the peer-memory exchange carries one view per rank")
+        deferred = deferred[0]
+    means, coeffs = params["means"], params["sh_coeffs"]
+    geo = [params[k].grad for k in ("means", "quats", "scales", "opacities")]
+    dev = means.device
+    pending = None
+    if overlap_group is not None:
+        comp, side = torch.cuda.current_stream(dev), _side_stream(dev)
+        side.wait_stream(comp)
+        with torch.cuda.stream(side):
+            allreduce_gradients(geo, group=overlap_group)
+        pending = side
+        for g in geo:
+            g.record_stream(side)
+    peer.publish(deferred.v_colors, deferred.campos)
+    if pending is None:
+        allreduce_gradients(geo, group=group)
+    with torch.no_grad():
+        v_means = torch.zeros_like(means.grad) if pending is not None else means.grad
+        coeffs.grad = sh_views_peer_fn(deferred.sh_degree, means.detach().contiguous(), coeffs.detach().contiguous(),
+                                       peer.addrs, v_means)
+        peer.release()
+        if pending is not None:
+            torch.cuda.current_stream(dev).wait_stream(pending)
+            means.grad.add_(v_means)
+    if average_over and average_over != 1:
+        for k in ("means", "quats", "scales", "opacities", "sh_coeffs"):
+            params[k].grad.div_(average_over)
+
+
 def max_over_ranks(value: float, device, group=None) -> float:
     """Device timing of a multi-GPU step is the maximum over ranks."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:

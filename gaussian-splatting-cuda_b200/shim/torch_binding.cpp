@@ -118,6 +118,34 @@ Tensor sh_bwd_views(int64_t degree, const Tensor &means, const Tensor &campos, c
     return v_coeffs;
 }
 
+// The same step reading every view through its own device address (include/gsb200.h, gsb_sh_bwd_views_peer): the
+// addresses are those of NVLink-mapped symmetric-memory buffers of the V ranks (torch.distributed._symmetric_memory
+// buffer_ptrs), so they arrive as integers; view v's block is [M*3 colour gradients | 3 camera position] floats.
+Tensor sh_bwd_views_peer(int64_t degree, const Tensor &means, const Tensor &coeffs, std::vector<int64_t> view_addrs,
+                         Tensor v_means) {
+    TORCH_CHECK(means.is_cuda() && coeffs.is_cuda() && v_means.is_cuda(), "sh_bwd_views_peer: CUDA tensors expected");
+    TORCH_CHECK(means.is_contiguous() && coeffs.is_contiguous() && v_means.is_contiguous(),
+                "sh_bwd_views_peer: contiguous tensors expected");
+    TORCH_CHECK(means.scalar_type() == at::kFloat && coeffs.scalar_type() == at::kFloat &&
+                    v_means.scalar_type() == at::kFloat,
+                "sh_bwd_views_peer: float32 tensors expected");
+    const int64_t M = means.size(0), K = coeffs.size(-2), V = (int64_t)view_addrs.size();
+    TORCH_CHECK(coeffs.numel() == M * K * 3 && v_means.numel() == M * 3, "sh_bwd_views_peer: shape mismatch");
+    std::vector<const float *> vc((size_t)V), cp((size_t)V);
+    for (int64_t v = 0; v < V; ++v) {
+        TORCH_CHECK(view_addrs[(size_t)v] != 0 && (view_addrs[(size_t)v] & 3) == 0, "sh_bwd_views_peer: bad view address");
+        vc[(size_t)v] = reinterpret_cast<const float *>(static_cast<uintptr_t>(view_addrs[(size_t)v]));
+        cp[(size_t)v] = vc[(size_t)v] + M * 3;
+    }
+    const c10::cuda::CUDAGuard guard(means.device());
+    Tensor v_coeffs = at::empty_like(coeffs);
+    const int rc = gsb_sh_bwd_views_peer((uint32_t)M, (uint32_t)K, (uint32_t)degree, (uint32_t)V, means.data_ptr<float>(),
+                                         cp.data(), coeffs.data_ptr<float>(), vc.data(), v_coeffs.data_ptr<float>(),
+                                         v_means.data_ptr<float>(), c10::cuda::getCurrentCUDAStream().stream());
+    TORCH_CHECK(rc == 0, "gsb_sh_bwd_views_peer failed: ", gsb_error_string(rc));
+    return v_coeffs;
+}
+
 // Extended operators (include/gsplat/FusedOps.h).  Flattened like the rest: the result struct becomes a tuple.
 std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fused_fwd(
     const Tensor &means, const Tensor &sh0, const Tensor &shN, const Tensor &scaling_raw, const Tensor &rotation_raw,
@@ -194,6 +222,9 @@ TORCH_LIBRARY(gsplat_b200, m) {
     m.def("spherical_harmonics_bwd_views(int degree, Tensor means, Tensor campos, Tensor coeffs, Tensor v_colors, "
           "Tensor(a!) v_means) -> Tensor",
           &sh_bwd_views);
+    m.def("spherical_harmonics_bwd_views_peer(int degree, Tensor means, Tensor coeffs, int[] view_addrs, "
+          "Tensor(a!) v_means) -> Tensor",
+          &sh_bwd_views_peer);
     m.def("rasterize_from_world_fused_fwd", &fused_fwd);
     m.def("rasterize_from_world_fused_bwd(Tensor means, Tensor sh0, Tensor shN, Tensor scaling_raw, Tensor rotation_raw, "
           "Tensor opacity_raw, int sh_degree, float scaling_modifier, Tensor viewmat, Tensor K, int width, int height, "

@@ -141,6 +141,16 @@ GSB_API int gsb_sh_bwd_views(uint32_t M, uint32_t K, uint32_t degrees_to_use, ui
                              const float *means, const float *campos /* [V,3] */, const float *coeffs,
                              const float *v_colors /* [V,M,3] */, float *v_coeffs, float *v_means,
                              gsb_stream_t stream);
+/* The same step with the all-gather INSIDE the kernel: view v's colour gradients [M,3] and camera position [3] are
+ * read through per-view device pointers (host arrays of V <= 16 pointers), which may point into PEER memory --
+ * NVLink-mapped buffers of the other ranks (CUDA IPC / symmetric memory).  The remote reads overlap the expansion
+ * and the gathered [V,M,3] tensor is never materialised.  The caller orders the kernel after every rank's write of
+ * its buffer (a device-side barrier) and must not overwrite its buffer before all ranks have finished reading. */
+GSB_API int gsb_sh_bwd_views_peer(uint32_t M, uint32_t K, uint32_t degrees_to_use, uint32_t V, const float *means,
+                                  const float *const *campos_views /* host array [V] of device ptrs to [3] */,
+                                  const float *coeffs,
+                                  const float *const *v_colors_views /* host array [V] of device ptrs to [M,3] */,
+                                  float *v_coeffs, float *v_means, gsb_stream_t stream);
 
 /* ---- a5: gsplat::intersect_tile (Ops.h:28-38, Intersect.cpp:15-122,
  *      IntersectTile.cu:24-114,290-328) ----------------------------------------------

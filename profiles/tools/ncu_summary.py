@@ -44,6 +44,7 @@ def full(kernel):
     if not os.path.exists(p): return
     txt = subprocess.run(['ncu', '-i', p, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
+    if len(rows) < 3: return
     hdr, units, vals = rows[0], rows[1], rows[-1]
     out.append(f"## `{kernel}` (`ncu --set full --clock-control none --import-source on`, 1 launch)\n")
     out.append("| metric | value |\n|---|---:|")
@@ -55,8 +56,9 @@ def full(kernel):
     st.sort(key=lambda t: -t[1])
     out.append("\nTop warp-stall reasons (warps per issue-active cycle): " + ", ".join(f"{n} {v:.2f}" for n, v in st[:7]) + "\n")
 launches()
-for k in ('raster_bwd_kernel', 'raster_fwd_kernel', 'isect_emit_balanced_kernel'):
+for k in ('raster_bwd_kernel', 'raster_fwd_kernel', 'tile_bin_kernel', 'ssim_l1_kernel', 'fused_front_kernel',
+          'fused_back_kernel'):
     full(k)
-open(f'profiles/{tag}_ncu_summary.md', 'w').write(f"# ncu summary {tag}\n\nSource artefacts: `gpurun_out/launches_{tag}.csv`, `gpurun_out/prof_raster_*_{tag}.ncu-rep` "
+open(f'profiles/{tag}_ncu_summary.md', 'w').write(f"# ncu summary {tag}\n\nSource artefacts: `gpurun_out/launches_{tag}.csv`, `gpurun_out/prof_*_{tag}.ncu-rep` "
      f"(scratch, not tracked); this file is the tracked digest.\n\n" + "\n".join(out) + "\n")
 print("\n".join(out))

@@ -118,7 +118,9 @@ def test_fused_distorted_cameras(native, cuda_device, model):
     dev = lambda a: None if a is None else torch.from_numpy(a).to(cuda_device)
     out = run_pair(native, sc, cuda_device, 3, camera_model=cfg["camera_model"], radial_coeffs=dev(cfg["radial"]),
                    tangential_coeffs=dev(cfg["tangential"]), thin_prism_coeffs=dev(cfg["thin_prism"]))
-    compare(out, 2500, model)
+    # distorted cameras: the per-pixel Newton undistortion amplifies last-bit differences of the activations, and the
+    # gradient sums are order-dependent (REDs): the standard gradient tolerance applies, not the tight fused one
+    compare(out, 2500, model, rel_tol=1e-3)
 
 
 def test_fused_vs_cpu_oracle(native, orc, cuda_device):

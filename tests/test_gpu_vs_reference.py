@@ -244,33 +244,60 @@ def test_distorted_cameras_reference_vs_b200(native, ref, cuda_device, model):
 # a2: rolling shutter (Cameras.cuh:268-413) -- per-pixel camera poses; pinned by the reference's kernels only
 # (the CPU oracle restates the global shutter: "parity unpinned" on the CPU side for this mode)
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("rs_type", [0, 1, 2, 3], ids=["top_to_bottom", "left_to_right", "bottom_to_top", "right_to_left"])
-def test_rolling_shutter_reference_vs_b200(native, ref, cuda_device, rs_type):
-    sc = scenes.scene_small(N=3000, width=208, height=128, view=2)
-    W, H = sc["width"], sc["height"]
-    tw, th = (W + 15) // 16, (H + 15) // 16
+RS_IDS = ["top_to_bottom", "left_to_right", "bottom_to_top", "right_to_left"]
+
+
+def _rolling_inputs(sc, cuda_device, rs_type):
+    """End-of-frame pose = the start pose turned by 0.4 degrees and moved by millimetres: the image moves by ~25 px
+    over the frame, i.e. ~0.2 px per row / column.  The reference's projection is a fixed-point iteration
+    row -> pose -> projection -> row through floor(); it only converges when the image moves by less than one
+    pixel per row (with more, the ten iterations wander and the result depends on the last ulp of sin())."""
     t = to_dev(sc, cuda_device)
-    # end-of-frame pose: the start pose moved by a few degrees and centimetres
-    ang = np.deg2rad(2.5)
+    ang = np.deg2rad(0.4)
     dR = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float64)
     V0 = sc["viewmats"][0].astype(np.float64)
     V1 = V0.copy()
     V1[:3, :3] = dR @ V0[:3, :3]
-    V1[:3, 3] = dR @ V0[:3, 3] + np.array([0.04, -0.02, 0.03])
+    V1[:3, 3] = dR @ V0[:3, 3] + np.array([0.006, -0.003, 0.004])
     vm1 = torch.from_numpy(V1[None].astype(np.float32)).to(cuda_device)
-    kw = dict(viewmats1=vm1, rs_type=rs_type)
+    return t, dict(viewmats1=vm1, rs_type=rs_type)
+
+
+@pytest.mark.parametrize("rs_type", [0, 1, 2, 3], ids=RS_IDS)
+def test_rolling_shutter_projection_reference_vs_b200(native, ref, cuda_device, rs_type):
+    sc = scenes.scene_small(N=3000, width=208, height=128, view=2)
+    W, H = sc["width"], sc["height"]
+    t, kw = _rolling_inputs(sc, cuda_device, rs_type)
     pa = (t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"], W, H, 0.3, 0.01, 1e4, 0.0)
     r_ref, m_ref, d_ref, c_ref, _ = ref.projection_ut_3dgs_fused(*pa, **kw)
     r_new, m_new, d_new, c_new, _ = native.projection_ut_3dgs_fused(*pa, **kw)
     mism = int((r_ref != r_new).any(-1).sum())
-    both = ((r_ref > 0).all(-1) & (r_new > 0).all(-1)).cpu().numpy()
-    em = rel(m_new.cpu().numpy()[both], m_ref.cpu().numpy()[both])
+    both = ((r_ref > 0).all(-1) & (r_new > 0).all(-1))
+    dm = (m_new - m_ref)[both].abs().max(-1).values
+    em = rel(m_new[both].cpu().numpy(), m_ref[both].cpu().numpy())
+    ed = rel(d_new[both].cpu().numpy(), d_ref[both].cpu().numpy())
+    ec = rel(c_new[both].cpu().numpy(), c_ref[both].cpu().numpy())
     # the rolling projection really differs from the global one (the test would be vacuous otherwise)
     r_glob, m_glob, _, _, _ = ref.projection_ut_3dgs_fused(*pa)
-    moved = float((m_glob - m_ref)[torch.from_numpy(both).to(cuda_device)].abs().max())
-    print(f"[rs {rs_type}] radii differ {mism}/{r_ref.shape[1]}, means2d rel {em:.2e}, visible {both.sum()}, "
+    moved = float((m_glob - m_ref)[both].abs().max())
+    off = float((dm > 0.02).float().mean())
+    print(f"[rs {rs_type}] radii differ {mism}/{r_ref.shape[1]}, means2d rel {em:.2e}, depths rel {ed:.2e}, conics rel "
+          f"{ec:.2e}, visible {int(both.sum())}, max |d means2d| {float(dm.max()):.3f} px, off by > 0.02 px: {off:.2e}, "
           f"max shift vs global shutter {moved:.2f} px")
-    assert mism <= 6 and em < 1e-4 and both.sum() > 1000 and moved > 1.0
+    # a sigma point whose row estimate sits on a floor() boundary may settle one row apart in the two builds: that
+    # moves it by one row's worth of motion (0.2 px) -- bounded, and rare
+    assert int(both.sum()) > 1000 and moved > 5.0
+    assert mism <= 15 and em < 1e-4 and ed < 1e-6 and float(dm.max()) < 0.3 and off < 0.02
+
+
+@pytest.mark.parametrize("rs_type", [0, 1, 2, 3], ids=RS_IDS)
+def test_rolling_shutter_blend_reference_vs_b200(native, ref, cuda_device, rs_type):
+    sc = scenes.scene_small(N=3000, width=208, height=128, view=2)
+    W, H = sc["width"], sc["height"]
+    tw, th = (W + 15) // 16, (H + 15) // 16
+    t, kw = _rolling_inputs(sc, cuda_device, rs_type)
+    pa = (t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"], W, H, 0.3, 0.01, 1e4, 0.0)
+    r_ref, m_ref, d_ref, c_ref, _ = ref.projection_ut_3dgs_fused(*pa, **kw)
     vis = (r_ref > 0).all(-1)
     m2 = torch.where(vis[..., None], m_ref, torch.zeros_like(m_ref))
     dp = torch.where(vis, d_ref, torch.zeros_like(d_ref))
