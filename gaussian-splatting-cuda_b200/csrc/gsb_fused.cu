@@ -93,7 +93,7 @@ __device__ __forceinline__ void stage_rows_in(float *s_rows, const float *g_rows
 }
 
 template <int DEG>
-__global__ void __launch_bounds__(kFusedThreads, 4) fused_front_kernel(const FusedParams p) {
+__global__ void __launch_bounds__(kFusedThreads, 5) fused_front_kernel(const FusedParams p) {
     constexpr int NB = (DEG + 1) * (DEG + 1);
     extern __shared__ __align__(128) float s_rows[]; // [kFusedThreads][(K-1)*3]
     __shared__ FusedCam s_cam;
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(kFusedThreads, 4) fused_front_kernel(const Fus
         scale[2] = act_scale(p.scaling_raw[(size_t)g * 3 + 2], p.scaling_modifier);
         opac = act_opacity(p.opacity_raw[g]);
         const V3<float> m = {mean[0], mean[1], mean[2]};
-        pr = project_gaussian(p.pk, s_cam.cm, s_cam.pp, m, scale, quat[0], quat[1], quat[2], quat[3], true, opac);
+        pr = project_gaussian<false>(p.pk, s_cam.cm, s_cam.pp, m, scale, quat[0], quat[1], quat[2], quat[3], true, opac);
         keep = pr.keep;
         reinterpret_cast<int2 *>(p.radii)[g] = make_int2(pr.rx, pr.ry);
         reinterpret_cast<float2 *>(p.means2d)[g] = make_float2(pr.mx, pr.my);

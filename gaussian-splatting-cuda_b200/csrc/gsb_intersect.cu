@@ -313,9 +313,9 @@ __device__ __forceinline__ uint32_t chunk_first_run(const BinArgs &a, uint32_t p
 // of a warp, each with its own group: chunk p, global tile t, slots [start, start + c) of flatten_ids.
 constexpr int kSmallGroup = 16;
 
-__device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__restrict__ depths, uint32_t p,
-                                              uint32_t t, uint32_t start, uint32_t c) {
-    const uint32_t lane = threadIdx.x & 31;
+// groups of two to four members: a 4-element sorting network in registers
+__device__ __forceinline__ void repair_small(const BinArgs &a, const float *__restrict__ depths, uint32_t start,
+                                             uint32_t c) {
     if (c >= 2 && c <= 4) {
         // the common case (a group holds 1.35 intersections on average): a 4-element sorting network in registers
         uint32_t id0 = (uint32_t)a.flatten_ids[start], id1 = (uint32_t)a.flatten_ids[start + 1];
@@ -340,6 +340,14 @@ __device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__r
             if (c > 2) a.flatten_ids[start + 2] = (int32_t)id2;
             if (c > 3) a.flatten_ids[start + 3] = (int32_t)id3;
         }
+    }
+}
+
+__device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__restrict__ depths, uint32_t p,
+                                              uint32_t t, uint32_t start, uint32_t c) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (c >= 2 && c <= 4) {
+        repair_small(a, depths, start, c);
     } else if (c > 4 && c <= 8) {
         // up to eight: Batcher's odd-even merge network (19 comparators) in registers, padding with +inf keys
         uint32_t id[8], k[8];
@@ -421,10 +429,10 @@ template <bool kScatter>
 __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) {
     extern __shared__ uint32_t s_cnt[]; // [t_cnt]
     __shared__ uint32_t s_range[2];
-    __shared__ uint32_t s_nwork;
+    __shared__ uint32_t s_nwork[2];
     const uint32_t tid = threadIdx.x, lane = tid & 31;
     const uint32_t p = blockIdx.x;
-    if (tid == 0) s_nwork = 0;
+    if (tid < 2) s_nwork[tid] = 0;
     uint32_t *row = a.M + (size_t)p * a.T_total + a.t_lo;
     const unsigned long long I = a.ctl->n_isects;
     const uint32_t n_runs = a.ctl->n_runs;
@@ -505,20 +513,34 @@ __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) 
         for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) row[t] = s_cnt[t];
     } else {
         // the CTA's own groups, while their slots are still in L2: row[] holds the first slot, the counter the end.
-        // Most groups have one member: the tiles whose group needs sorting are first compacted into a work list so
-        // that every lane of the repair loop has a group (the loop is a chain of dependent gathers).
+        // Most groups have one member.  The tiles whose group needs sorting are compacted into a work list so that
+        // every lane of the repair loops has a group (they are chains of dependent gathers) -- groups of up to four
+        // from the front of the list, larger ones from the back, so that a warp runs ONE of the sorting paths.
         uint16_t *work = reinterpret_cast<uint16_t *>(s_cnt + a.t_cnt);
         for (uint32_t t = tid; t < a.t_cnt; t += kBinThreads) {
             const uint32_t start = row[t], end = min(s_cnt[t], a.cap);
-            if (end > start + 1) work[atomicAdd(&s_nwork, 1u)] = (uint16_t)t;
+            if (end > start + 1) {
+                if (end - start <= 4) work[atomicAdd(&s_nwork[0], 1u)] = (uint16_t)t;
+                else work[a.t_cnt - 1 - atomicAdd(&s_nwork[1], 1u)] = (uint16_t)t;
+            }
         }
         __syncthreads();
-        const uint32_t n_work = s_nwork;
-        for (uint32_t i0 = tid & ~31u; i0 < n_work; i0 += kBinThreads) { // warp-uniform trip count
+        const uint32_t n_small = s_nwork[0], n_large = s_nwork[1];
+        for (uint32_t i0 = tid & ~31u; i0 < n_small; i0 += kBinThreads) { // warp-uniform trip count
             const uint32_t i = i0 + lane;
             uint32_t t = 0, start = 0, c = 0;
-            if (i < n_work) {
+            if (i < n_small) {
                 t = work[i];
+                start = row[t];
+                c = min(s_cnt[t], a.cap) - start;
+            }
+            repair_small(a, a.depths, start, c);
+        }
+        for (uint32_t i0 = tid & ~31u; i0 < n_large; i0 += kBinThreads) {
+            const uint32_t i = i0 + lane;
+            uint32_t t = 0, start = 0, c = 0;
+            if (i < n_large) {
+                t = work[a.t_cnt - 1 - i];
                 start = row[t];
                 c = min(s_cnt[t], a.cap) - start;
             }
@@ -566,7 +588,8 @@ __global__ void __launch_bounds__(kIsectThreads) isect_keys_kernel(uint32_t n, c
 // col_segsum: seg[s][t] = sum of M[p][t] over the chunks p of segment s.
 __global__ void __launch_bounds__(kIsectThreads) col_segsum_kernel(const uint32_t *__restrict__ M, uint32_t T,
                                                                    uint32_t P, uint32_t seg_len,
-                                                                   uint32_t *__restrict__ seg) {
+                                                                   uint32_t *__restrict__ seg,
+                                                                   uint32_t *__restrict__ tot) {
     const uint32_t t = blockIdx.x * kIsectThreads + threadIdx.x;
     if (t >= T) return;
     const uint32_t s = blockIdx.y;
@@ -580,9 +603,10 @@ __global__ void __launch_bounds__(kIsectThreads) col_segsum_kernel(const uint32_
     }
     for (; p < p1; ++p) acc += M[(size_t)p * T + t];
     seg[(size_t)s * T + t] = acc;
+    if (acc) atomicAdd(&tot[t], acc); // the tile's intersection count (zeroed before the launch)
 }
-// col_tilescan (one CTA): seg[s][t] -> exclusive prefix over s plus the tile's first slot; tile offsets out.
-__global__ void __launch_bounds__(kSortThreads) col_tilescan_kernel(uint32_t *__restrict__ seg, uint32_t T, uint32_t S,
+// col_tilescan (one CTA): exclusive scan of the tiles' counts -> first slot of every tile (the tile offsets, a6).
+__global__ void __launch_bounds__(kSortThreads) col_tilescan_kernel(const uint32_t *__restrict__ tot, uint32_t T,
                                                                     uint32_t *__restrict__ toff /* [T + 1] */,
                                                                     int32_t *__restrict__ tile_offsets /*nullable*/,
                                                                     int write_total) {
@@ -590,33 +614,13 @@ __global__ void __launch_bounds__(kSortThreads) col_tilescan_kernel(uint32_t *__
     uint32_t carry = 0;
     for (uint32_t t0 = 0; t0 < T; t0 += kSortThreads) {
         const uint32_t t = t0 + threadIdx.x;
-        uint32_t tot = 0;
-        if (t < T) {
-#pragma unroll 8
-            for (uint32_t s = 0; s < S; ++s) tot += seg[(size_t)s * T + t];
-        }
+        const uint32_t v = t < T ? tot[t] : 0u;
         uint32_t all;
-        const uint32_t inc = block_scan_inclusive<uint32_t>(tot, s_warp, all);
+        const uint32_t inc = block_scan_inclusive<uint32_t>(v, s_warp, all);
         if (t < T) {
-            uint32_t run = carry + inc - tot; // first slot of tile t
-            toff[t] = run;
-            if (tile_offsets) tile_offsets[t] = (int32_t)run;
-            uint32_t s = 0;
-            for (; s + 8 <= S; s += 8) { // eight loads in flight, then the eight stores
-                uint32_t v[8];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) v[k] = seg[(size_t)(s + k) * T + t];
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    seg[(size_t)(s + k) * T + t] = run;
-                    run += v[k];
-                }
-            }
-            for (; s < S; ++s) {
-                const uint32_t v = seg[(size_t)s * T + t];
-                seg[(size_t)s * T + t] = run;
-                run += v;
-            }
+            const uint32_t first = carry + inc - v;
+            toff[t] = first;
+            if (tile_offsets) tile_offsets[t] = (int32_t)first;
         }
         carry += all;
     }
@@ -627,12 +631,15 @@ __global__ void __launch_bounds__(kSortThreads) col_tilescan_kernel(uint32_t *__
 }
 // col_apply: M[p][t] = first output slot of chunk p in tile t.
 __global__ void __launch_bounds__(kIsectThreads) col_apply_kernel(uint32_t *__restrict__ M, uint32_t T, uint32_t P,
-                                                                  uint32_t seg_len, const uint32_t *__restrict__ seg) {
+                                                                  uint32_t seg_len, const uint32_t *__restrict__ seg,
+                                                                  const uint32_t *__restrict__ toff) {
     const uint32_t t = blockIdx.x * kIsectThreads + threadIdx.x;
     if (t >= T) return;
     const uint32_t s = blockIdx.y;
     const uint32_t p0 = s * seg_len, p1 = min(P, p0 + seg_len);
-    uint32_t run = seg[(size_t)s * T + t];
+    uint32_t run = toff[t]; // first slot of the tile + what the earlier segments of this column hold
+#pragma unroll 8
+    for (uint32_t s2 = 0; s2 < s; ++s2) run += seg[(size_t)s2 * T + t];
     uint32_t p = p0;
     for (; p + 4 <= p1; p += 4) { // loads first: a store to M would otherwise fence the next load
         const uint32_t v0 = M[(size_t)p * T + t], v1 = M[(size_t)(p + 1) * T + t];
@@ -758,7 +765,7 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
 
 // Workspace of the plan; everything the emit needs afterwards lives here too.
 struct PlanWs {
-    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, M, seg, toff, chunk_run,
+    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, M, seg, tot, toff, chunk_run,
         total;
 };
 static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp) {
@@ -774,6 +781,7 @@ static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp) {
     w.rt_end = take(n * 4); w.rt_idx = take(n * 4); w.rt_box = take(n * 8); w.rt_key = take(n * 4);
     w.M = take((size_t)b.P * b.T_total * 4);
     w.seg = take((size_t)b.S * b.T_total * 4);
+    w.tot = take((size_t)b.T_total * 4);
     w.toff = take(((size_t)b.T_total + 1) * 4);
     w.chunk_run = take(((size_t)b.P + 1) * 4);
     w.total = off + 256;
@@ -974,12 +982,13 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
     {
         ProfScope ps("isect_colscan", s);
         const dim3 cgrid((bp.T_total + kIsectThreads - 1) / kIsectThreads, bp.S);
-        col_segsum_kernel<<<cgrid, kIsectThreads, 0, s>>>(M, bp.T_total, bp.P, bp.seg_len, seg);
+        uint32_t *tot = reinterpret_cast<uint32_t *>(base + w.tot), *toff = reinterpret_cast<uint32_t *>(base + w.toff);
+        GSB_CUDA_TRY(cudaMemsetAsync(tot, 0, (size_t)bp.T_total * 4, s));
+        col_segsum_kernel<<<cgrid, kIsectThreads, 0, s>>>(M, bp.T_total, bp.P, bp.seg_len, seg, tot);
         GSB_LAUNCH_CHECK();
-        col_tilescan_kernel<<<1, kSortThreads, 0, s>>>(seg, bp.T_total, bp.S, reinterpret_cast<uint32_t *>(base + w.toff),
-                                                    tile_offsets_out, tile_offsets_total);
+        col_tilescan_kernel<<<1, kSortThreads, 0, s>>>(tot, bp.T_total, toff, tile_offsets_out, tile_offsets_total);
         GSB_LAUNCH_CHECK();
-        col_apply_kernel<<<cgrid, kIsectThreads, 0, s>>>(M, bp.T_total, bp.P, bp.seg_len, seg);
+        col_apply_kernel<<<cgrid, kIsectThreads, 0, s>>>(M, bp.T_total, bp.P, bp.seg_len, seg, toff);
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;

@@ -35,6 +35,7 @@ struct ProjParams {
     uint32_t inputs_aligned16; // every input base pointer is 16-byte aligned: full slabs may use bulk copies
 };
 
+template <bool kRolling>
 __global__ void __launch_bounds__(kProjThreads) projection_ut_kernel(const ProjParams p) {
     __shared__ __align__(128) float s_means[kProjThreads * 3];
     __shared__ __align__(128) float s_scales[kProjThreads * 3];
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(kProjThreads) projection_ut_kernel(const ProjP
     if (tid < cnt) {
         const V3<float> mean = {s_means[tid * 3], s_means[tid * 3 + 1], s_means[tid * 3 + 2]};
         const float sc[3] = {s_scales[tid * 3], s_scales[tid * 3 + 1], s_scales[tid * 3 + 2]};
-        const ProjResult r = project_gaussian(pk, s_cm, pp, mean, sc, s_quats[tid * 4], s_quats[tid * 4 + 1],
+        const ProjResult r = project_gaussian<kRolling>(pk, s_cm, pp, mean, sc, s_quats[tid * 4], s_quats[tid * 4 + 1],
                                               s_quats[tid * 4 + 2], s_quats[tid * 4 + 3], p.opacities != nullptr,
                                               p.opacities ? s_opac[tid] : 0.f);
         keep = r.keep;
@@ -168,7 +169,10 @@ extern "C" int gsb_projection_ut(
     dim3 grid((N + gsb::kProjThreads - 1) / gsb::kProjThreads, C);
     {
         gsb::ProfScope ps("projection_ut", gsb::as_stream(stream));
-        gsb::projection_ut_kernel<<<grid, gsb::kProjThreads, 0, gsb::as_stream(stream)>>>(p);
+        if (p.shutter != GSB_SHUTTER_GLOBAL)
+            gsb::projection_ut_kernel<true><<<grid, gsb::kProjThreads, 0, gsb::as_stream(stream)>>>(p);
+        else
+            gsb::projection_ut_kernel<false><<<grid, gsb::kProjThreads, 0, gsb::as_stream(stream)>>>(p);
     }
     GSB_LAUNCH_CHECK();
     return GSB_OK;

@@ -104,6 +104,8 @@ struct ProjResult {
 };
 
 // One Gaussian: activated scale, quaternion as stored (normalised here like the reference, :63), optional opacity.
+// kRolling = false compiles the rolling-shutter iteration out (global-shutter callers keep their register budget).
+template <bool kRolling>
 __device__ __forceinline__ ProjResult project_gaussian(const ProjConsts &p, const CamModel &s_cm, const ProjPose &pp,
                                                        V3<float> mean, const float (&sc)[3], float qw, float qx,
                                                        float qy, float qz, bool has_opacity, float opacity_in) {
@@ -146,7 +148,9 @@ __device__ __forceinline__ ProjResult project_gaussian(const ProjConsts &p, cons
             const V3<float> cam = quat_rotate(pose.qw, pose.qx, pose.qy, pose.qz, pt) + pp.t0;
             float px, py;
             bool pv = cam_project(s_cm, cam, p.ut.in_image_margin_factor, px, py);
-            if (pp.shutter != GSB_SHUTTER_GLOBAL) pv = project_rolling(p, s_cm, pp, pt, pv, px, py);
+            if constexpr (kRolling) {
+                if (pp.shutter != GSB_SHUTTER_GLOBAL) pv = project_rolling(p, s_cm, pp, pt, pv, px, py);
+            }
             if (p.ut.require_all_sigma_points_valid) {
                 valid = valid && pv;
                 if (!pv) { early = true; break; }

@@ -40,6 +40,14 @@ def available() -> bool:
     return os.path.exists(os.path.join(OUT, "libgsplat_ref.so"))
 
 
+# "precise": the same sources WITHOUT --use_fast_math, registered as torch.ops.gsplat_ref_precise.  The rolling-shutter
+# pose interpolation calls sin() on angles of a few milliradians: sin.approx has an ABSOLUTE error of ~2^-21, i.e.
+# 1e-4 relative there, and the unscented transform's -99 / +16.67 weights amplify that a hundredfold -- the fast-math
+# build's rolling-shutter outputs carry ~0.1 px of noise.  The precise build is the noise-free statement of the same
+# algorithm and is what the rolling-shutter parity tests compare against.
+VARIANTS = {"fast": ("libgsplat_ref.so", "gsplat_ref", True), "precise": ("libgsplat_ref_precise.so", "gsplat_ref_precise", False)}
+
+
 def _stamp() -> str:
     h = hashlib.sha256()
     for f in CU + CPP:
@@ -54,27 +62,28 @@ def _stamp() -> str:
     return h.hexdigest()
 
 
-def build(verbose: bool = True, jobs: int = 7) -> str | None:
+def build(verbose: bool = True, jobs: int = 7, variant: str = "fast") -> str | None:
     if not os.path.isdir(REF):
         return None
     from torch.utils import cpp_extension as ce
 
+    so_name, ns, fast = VARIANTS[variant]
     os.makedirs(OUT, exist_ok=True)
-    so = os.path.join(OUT, "libgsplat_ref.so")
+    so = os.path.join(OUT, so_name)
     stamp_file = so + ".stamp"
-    st = _stamp()
+    st = _stamp() + variant
     if os.path.exists(so) and os.path.exists(stamp_file) and open(stamp_file).read() == st:
         return so
     inc = []
     for i in [os.path.join(HERE, "glm_shim"), REF] + TRAIN_INC + ce.include_paths():
         inc += ["-I", i]
     common = ["-O3", "-std=c++20", "-Xcompiler", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=1", "-ccbin", CXX,
-              "-gencode", "arch=compute_100,code=sm_100", "--use_fast_math", "--expt-relaxed-constexpr",
-              "-diag-suppress", "20012,20011,20014,177,550"]
+              "-gencode", "arch=compute_100,code=sm_100", "--expt-relaxed-constexpr", f"-DREF_NS={ns}",
+              "-diag-suppress", "20012,20011,20014,177,550"] + (["--use_fast_math"] if fast else [])
 
     def compile_one(src: str):
         sp = src if os.path.isabs(src) else os.path.join(REF, src)
-        obj = os.path.join(OUT, os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        obj = os.path.join(OUT, variant + "_" + os.path.basename(src).rsplit(".", 1)[0] + ".o")
         cmd = [NVCC, "-c", sp, "-o", obj, "-x", "cu"] + common + inc
         if verbose:
             print("[build_ref]", os.path.basename(src), flush=True)
@@ -84,7 +93,7 @@ def build(verbose: bool = True, jobs: int = 7) -> str | None:
             raise RuntimeError(f"reference source failed to compile: {src}")
         return obj
 
-    srcs = CU + CPP + TRAIN_CU + [os.path.join(HERE, f) for f in EXTRA]
+    srcs = CU + CPP + ((TRAIN_CU + [os.path.join(HERE, f) for f in EXTRA]) if fast else [os.path.join(HERE, EXTRA[0])])
     with ThreadPoolExecutor(max_workers=jobs) as ex:
         objs = list(ex.map(compile_one, srcs))
     tl = ce.library_paths()[0]
@@ -94,7 +103,7 @@ def build(verbose: bool = True, jobs: int = 7) -> str | None:
     p = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode != 0:
         sys.stderr.write(p.stdout[-6000:])
-        raise RuntimeError("linking oracle/_ref/libgsplat_ref.so failed")
+        raise RuntimeError(f"linking oracle/_ref/{so_name} failed")
     for o in objs:
         os.remove(o)
     with open(stamp_file, "w") as f:
@@ -157,4 +166,5 @@ def build_l3_harness(verbose: bool = True) -> str | None:
 
 if __name__ == "__main__":
     print(build())
+    print(build(variant="precise"))
     print(build_l3_harness())

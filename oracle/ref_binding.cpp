@@ -87,7 +87,12 @@ void add_noise(const Tensor &raw_opacities, const Tensor &raw_scales, const Tens
 }
 } // namespace
 
-TORCH_LIBRARY(gsplat_ref, m) {
+#ifndef REF_NS
+#define REF_NS gsplat_ref
+#endif
+#define REF_TORCH_LIBRARY(ns, m) TORCH_LIBRARY(ns, m) // expands REF_NS before TORCH_LIBRARY pastes it
+
+REF_TORCH_LIBRARY(REF_NS, m) {
     m.def("spherical_harmonics_fwd", &sh_fwd);
     m.def("spherical_harmonics_bwd", &sh_bwd);
     m.def("intersect_tile", &intersect_tile);

@@ -33,3 +33,27 @@ def _ns():
 def backend(pkg):
     """An OpsBackend (class from the product package) bound to the reference library."""
     return pkg.OpsBackend(_ns)
+
+
+PRECISE_SO = os.path.join(_HERE, "_ref", "libgsplat_ref_precise.so")
+_loaded_precise = False
+
+
+def precise_available() -> bool:
+    return os.path.exists(PRECISE_SO)
+
+
+def _ns_precise():
+    global _loaded_precise
+    if not _loaded_precise:
+        if not precise_available():
+            raise RuntimeError(f"{PRECISE_SO} not built (python oracle/build_ref.py in the build container)")
+        torch.ops.load_library(PRECISE_SO)
+        _loaded_precise = True
+    return torch.ops.gsplat_ref_precise
+
+
+def backend_precise(pkg):
+    """The same reference sources compiled WITHOUT --use_fast_math (oracle/build_ref.py, VARIANTS): the oracle of the
+    rolling-shutter tests, whose fast-math build is dominated by sin.approx noise."""
+    return pkg.OpsBackend(_ns_precise)

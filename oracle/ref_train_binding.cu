@@ -39,7 +39,12 @@ void adam_step(Tensor param, Tensor exp_avg, Tensor exp_avg_sq, const Tensor &gr
 }
 } // namespace
 
-TORCH_LIBRARY_FRAGMENT(gsplat_ref, m) {
+#ifndef REF_NS
+#define REF_NS gsplat_ref
+#endif
+#define REF_TORCH_LIBRARY_FRAGMENT(ns, m) TORCH_LIBRARY_FRAGMENT(ns, m)
+
+REF_TORCH_LIBRARY_FRAGMENT(REF_NS, m) {
     m.def("fusedssim", &ssim_fwd);
     m.def("fusedssim_backward", &ssim_bwd);
     m.def("adam_step(Tensor(a!) param, Tensor(b!) exp_avg, Tensor(c!) exp_avg_sq, Tensor grad, float lr, float beta1, "

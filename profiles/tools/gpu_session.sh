@@ -1,7 +1,7 @@
 #!/bin/bash
 # One GPU session (runs under gpurun): parity tests, bench lines, per-kernel times of a training iteration, ncu evidence.
-# usage: profiles/tools/gpu_session.sh <tag>
-TAG=${1:-r2}
+# usage: profiles/tools/gpu_session.sh <tag> [full]      (full: also the complete bench line)
+TAG=${1:-r2}; MODE=${2:-quick}
 O=gpurun_out
 mkdir -p $O
 timeout 1500 python -m pytest tests -q -m gpu -rs -s > $O/${TAG}_gputest.log 2>&1; echo "pytest rc=$?" >> $O/${TAG}_gputest.log
@@ -9,7 +9,7 @@ timeout 120 python bench.py --quick > $O/${TAG}_benchB.json 2> $O/${TAG}_benchB.
 timeout 120 python bench.py --quick --config D > $O/${TAG}_benchD.json 2> /dev/null
 timeout 120 python profiles/tools/train_prof.py --config B > $O/${TAG}_trainB.json 2> $O/${TAG}_trainB.err
 timeout 120 python profiles/tools/train_prof.py --config D > $O/${TAG}_trainD.json 2> /dev/null
-timeout 900 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err
+if [ "$MODE" = full ]; then timeout 900 python bench.py > $O/${TAG}_bench.json 2> $O/${TAG}_bench.err; fi
 # launch list of two steps (shares of the step; cold-cache, serialised)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $O/launches_${TAG}.csv \
     python bench.py --steps 2 --warmup 1 --quick > $O/bench_under_ncu_${TAG}.log 2>&1

@@ -1,7 +1,8 @@
 """Worker of tests/test_multigpu_nccl.py (one process per GPU, launched by torchrun): every rank renders its own view
 of the same small scene and the ranks exchange gradients three ways -- plain all-reduce, compact exchange, compact
-exchange with the geometry all-reduce overlapped on a second communicator.  All three must give every rank the SUM of
-the per-view gradients, which rank 0 also computes alone by rendering all views itself."""
+exchange with the geometry all-reduce overlapped on a second communicator, and the compact exchange with the colour
+all-gather fused into the SH expansion kernel over NVLink peer memory (when symmetric memory can be mapped).  All must
+give every rank the SUM of the per-view gradients, which rank 0 also computes alone by rendering all views itself."""
 import os
 import sys
 
@@ -55,16 +56,42 @@ def main():
         torch.cuda.synchronize()
         results[mode] = {k: P[k].grad.clone() for k in names}
 
+    # peer-memory exchange: construction is collective; all ranks agree on whether it is available
+    peer, why = None, ""
+    try:
+        peer = mv.PeerColourExchange(sc["means"].shape[0], dev)
+        okp = 1
+    except Exception as e:  # no symmetric memory on this box: reported, the NCCL paths are still checked
+        why, okp = repr(e)[:300], 0
+    flagp = torch.tensor([okp], device=dev)
+    dist.all_reduce(flagp, op=dist.ReduceOp.MIN)
+    if int(flagp.item()) == 1:
+        for mode in ("peer", "peer_overlap"):
+            t, P = fresh(sc)
+            d = pkg.DeferredSHBackward()
+            render(P, sc, t, d)
+            mv.exchange_gradients_peer(P, d, peer, overlap_group=pg2 if mode == "peer_overlap" else None)
+            torch.cuda.synchronize()
+            results[mode] = {k: P[k].grad.clone() for k in names}
+    else:
+        print(f"rank {rank}: peer-memory exchange unavailable: {why or 'another rank failed'}", flush=True)
+
     def rel(a, b):
         return float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
 
     ok = True
     msgs = []
     for k in names:
-        for mode in ("compact", "compact_overlap"):
+        for mode in [m for m in ("compact", "compact_overlap", "peer", "peer_overlap") if m in results]:
             e = rel(results[mode][k], results["allreduce"][k])
             msgs.append(f"rank {rank} {mode} vs allreduce {k}: {e:.2e}")
             ok = ok and e < 2e-5
+    if "peer" in results:  # same sums in the same order as the NCCL all-gather path (each mode renders again, and the
+        # blend's atomic adds retire in a different order every time: last-bit differences only)
+        for k in names:
+            e = rel(results["peer"][k], results["compact"][k])
+            msgs.append(f"rank {rank} peer vs compact {k}: {e:.2e}")
+            ok = ok and e < 5e-6
     if rank == 0:  # the sum of the views' gradients, computed without any collective
         total = None
         for v in range(world):

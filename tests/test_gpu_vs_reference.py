@@ -24,6 +24,15 @@ def ref(native):
     return ref_ops.backend(native)
 
 
+@pytest.fixture(scope="module")
+def ref_precise(native):
+    """The reference's kernels compiled without --use_fast_math (oracle/build_ref.py VARIANTS)."""
+    from oracle import ref_ops
+    if not ref_ops.precise_available():
+        pytest.skip("oracle/_ref/libgsplat_ref_precise.so not built")
+    return ref_ops.backend_precise(native)
+
+
 def _scene(name):
     return {"a": lambda: scenes.scene_a(background=False),
             "small_rot": lambda: scenes.scene_small(N=3000, width=200, height=120, view=1),
@@ -248,50 +257,58 @@ RS_IDS = ["top_to_bottom", "left_to_right", "bottom_to_top", "right_to_left"]
 
 
 def _rolling_inputs(sc, cuda_device, rs_type):
-    """End-of-frame pose = the start pose turned by 0.4 degrees and moved by millimetres: the image moves by ~25 px
-    over the frame, i.e. ~0.2 px per row / column.  The reference's projection is a fixed-point iteration
-    row -> pose -> projection -> row through floor(); it only converges when the image moves by less than one
-    pixel per row (with more, the ten iterations wander and the result depends on the last ulp of sin())."""
+    """End-of-frame pose = the start pose turned by 2.5 degrees and moved by a few centimetres."""
     t = to_dev(sc, cuda_device)
-    ang = np.deg2rad(0.4)
+    ang = np.deg2rad(2.5)
     dR = np.array([[np.cos(ang), 0, np.sin(ang)], [0, 1, 0], [-np.sin(ang), 0, np.cos(ang)]], np.float64)
     V0 = sc["viewmats"][0].astype(np.float64)
     V1 = V0.copy()
     V1[:3, :3] = dR @ V0[:3, :3]
-    V1[:3, 3] = dR @ V0[:3, 3] + np.array([0.006, -0.003, 0.004])
+    V1[:3, 3] = dR @ V0[:3, 3] + np.array([0.04, -0.02, 0.03])
     vm1 = torch.from_numpy(V1[None].astype(np.float32)).to(cuda_device)
     return t, dict(viewmats1=vm1, rs_type=rs_type)
 
 
 @pytest.mark.parametrize("rs_type", [0, 1, 2, 3], ids=RS_IDS)
-def test_rolling_shutter_projection_reference_vs_b200(native, ref, cuda_device, rs_type):
+def test_rolling_shutter_projection_reference_vs_b200(native, ref, ref_precise, cuda_device, rs_type):
+    """Oracle: the reference's projection kernel built WITHOUT --use_fast_math.  Under fast-math the pose interpolation
+    evaluates sin() of milliradian angles with sin.approx (absolute error 2^-21: 1e-5..1e-4 relative there) separately
+    for each sigma point, and the unscented transform's weights (-99, +16.67) amplify the differences a hundredfold:
+    the fast build's rolling-shutter outputs are noisy at the 0.1 px level (printed below as the floor).  The product
+    kernel uses the accurate sinf and has to agree with the precise build."""
     sc = scenes.scene_small(N=3000, width=208, height=128, view=2)
     W, H = sc["width"], sc["height"]
     t, kw = _rolling_inputs(sc, cuda_device, rs_type)
     pa = (t["means"], t["quats"], t["scales"], t["opacities"], t["viewmats"], t["Ks"], W, H, 0.3, 0.01, 1e4, 0.0)
-    r_ref, m_ref, d_ref, c_ref, _ = ref.projection_ut_3dgs_fused(*pa, **kw)
+    r_ref, m_ref, d_ref, c_ref, _ = ref_precise.projection_ut_3dgs_fused(*pa, **kw)
+    r_fast, m_fast, _, _, _ = ref.projection_ut_3dgs_fused(*pa, **kw)
     r_new, m_new, d_new, c_new, _ = native.projection_ut_3dgs_fused(*pa, **kw)
     mism = int((r_ref != r_new).any(-1).sum())
     both = ((r_ref > 0).all(-1) & (r_new > 0).all(-1))
     dm = (m_new - m_ref)[both].abs().max(-1).values
-    em = rel(m_new[both].cpu().numpy(), m_ref[both].cpu().numpy())
+    ok = dm <= 0.02
+    em = rel(m_new[both][ok].cpu().numpy(), m_ref[both][ok].cpu().numpy())
     ed = rel(d_new[both].cpu().numpy(), d_ref[both].cpu().numpy())
-    ec = rel(c_new[both].cpu().numpy(), c_ref[both].cpu().numpy())
+    ec = rel(c_new[both][ok].cpu().numpy(), c_ref[both][ok].cpu().numpy())
+    off = float((~ok).float().mean())
     # the rolling projection really differs from the global one (the test would be vacuous otherwise)
-    r_glob, m_glob, _, _, _ = ref.projection_ut_3dgs_fused(*pa)
-    moved = float((m_glob - m_ref)[both].abs().max())
-    off = float((dm > 0.02).float().mean())
-    print(f"[rs {rs_type}] radii differ {mism}/{r_ref.shape[1]}, means2d rel {em:.2e}, depths rel {ed:.2e}, conics rel "
-          f"{ec:.2e}, visible {int(both.sum())}, max |d means2d| {float(dm.max()):.3f} px, off by > 0.02 px: {off:.2e}, "
-          f"max shift vs global shutter {moved:.2f} px")
-    # a sigma point whose row estimate sits on a floor() boundary may settle one row apart in the two builds: that
-    # moves it by one row's worth of motion (0.2 px) -- bounded, and rare
-    assert int(both.sum()) > 1000 and moved > 5.0
-    assert mism <= 15 and em < 1e-4 and ed < 1e-6 and float(dm.max()) < 0.3 and off < 0.02
+    _, m_glob, _, _, _ = ref_precise.projection_ut_3dgs_fused(*pa)
+    moved = float((m_glob - m_ref)[both].abs().max(-1).values.median())
+    bf = ((r_ref > 0).all(-1) & (r_fast > 0).all(-1))
+    floor_fast = float(((m_fast - m_ref)[bf].abs().max(-1).values > 0.02).float().mean())
+    print(f"[rs {rs_type}] vs precise reference: radii differ {mism}/{r_ref.shape[1]}, means2d rel {em:.2e}, depths rel "
+          f"{ed:.2e}, conics rel {ec:.2e}, visible {int(both.sum())}, off by > 0.02 px: {off:.2e} (max {float(dm.max()):.3f} "
+          f"px); median shift vs global shutter {moved:.2f} px; the reference's own fast-math build vs its precise build: "
+          f"{floor_fast:.2e} off by > 0.02 px, radii differ {int((r_ref != r_fast).any(-1).sum())}")
+    assert int(both.sum()) > 1000 and moved > 1.0
+    # a sigma point whose row estimate sits exactly on a floor() boundary may settle one row apart (amplified by the UT
+    # weights): a handful of Gaussians at most
+    assert mism <= 10 and off < 5e-3 and em < 1e-5 and ed < 1e-6 and ec < 1e-3
 
 
 @pytest.mark.parametrize("rs_type", [0, 1, 2, 3], ids=RS_IDS)
-def test_rolling_shutter_blend_reference_vs_b200(native, ref, cuda_device, rs_type):
+def test_rolling_shutter_blend_reference_vs_b200(native, ref_precise, cuda_device, rs_type):
+    ref = ref_precise  # see the projection test: per-pixel poses through sin.approx are the fast build's noise
     sc = scenes.scene_small(N=3000, width=208, height=128, view=2)
     W, H = sc["width"], sc["height"]
     tw, th = (W + 15) // 16, (H + 15) // 16
