@@ -740,6 +740,73 @@ def run_b200(args):
     except Exception as e:
         line["train"] = {"unavailable": repr(e)[:300]}
 
+    # ---- the reference's default rasterizer (fastgs, EWA) on the same scene: forward + backward -------
+    def fastgs_block(w, steps):
+        from gsplat_b200 import fastgs as fg
+        R = w.raw()
+        V = w.P["viewmats"][0].detach()
+        K = w.host["Ks"][0]
+        campos = (-V[:3, :3].T @ V[:3, 3]).contiguous()
+        st = fg.FastGSSettings(cam_position=campos, active_sh_bases=(w.deg + 1) ** 2, width=w.W, height=w.H,
+                               focal_x=float(K[0, 0]), focal_y=float(K[1, 1]), center_x=float(K[0, 2]), center_y=float(K[1, 2]))
+        names_f = ("means", "scaling_raw", "rotation_raw", "opacity_raw", "sh0", "shN")
+        tgt = w.P["target"][0].permute(2, 0, 1).contiguous()
+        bgc = w.P["background"][0]
+        info = {}
+
+        def make_step(backend):
+            def step():
+                for k in names_f:
+                    R[k].grad = None
+                img, alpha = fg.fast_rasterize(backend, R["means"], R["scaling_raw"], R["rotation_raw"],
+                                               R["opacity_raw"].reshape(-1, 1), R["sh0"], R["shN"], V, st, bg_color=bgc)
+                loss = (img - tgt).abs().mean()
+                loss.backward()
+                return loss
+            return step
+        out = {"what": "fast_gs::rasterization forward_wrapper + backward_wrapper through the reference caller's sequence "
+                       "(fast_rasterizer.cpp:12-74: raw parameters in, background composite, L1 loss, autograd), "
+                       "device-resident"}
+        mine = make_step(fg.default_backend())
+        for _ in range(3):
+            mine()
+        ms = timed(mine, steps) / steps
+        prof = read_profile(mine, max(steps, 10))
+        with torch.no_grad():
+            _, _, c = fg.default_backend().forward(R["means"], R["scaling_raw"], R["rotation_raw"], R["opacity_raw"].reshape(-1, 1),
+                                                   R["sh0"], R["shN"], V, st)
+        out["b200"] = {"ms_per_step": ms, "value": w.N / (ms * 1e-3), "unit": UNIT, "instances": int(c["ints"][1]),
+                       "distribution": distribution(mine, warm=5, n=50),
+                       "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in prof.items()}}
+        del c
+        if not args.no_ref_cuda:
+            try:
+                from oracle import ref_fastgs
+                if ref_fastgs.available():
+                    rbe = ref_fastgs.backend(fg)
+                    ref = make_step(rbe)
+                    for _ in range(3):
+                        ref()
+                    ms_r = timed(ref, steps) / steps
+                    with torch.no_grad():
+                        _, _, c = rbe.forward(R["means"], R["scaling_raw"], R["rotation_raw"], R["opacity_raw"].reshape(-1, 1),
+                                              R["sh0"], R["shN"], V, st)
+                    out["reference_cuda"] = {"ms_per_step": ms_r, "value": w.N / (ms_r * 1e-3), "unit": UNIT,
+                                             "instances": int(c["ints"][1]), "buckets": int(c["ints"][2]),
+                                             "distribution": distribution(ref, warm=3, n=30),
+                                             "what": "reference fastgs/rasterization/*.cu compiled unmodified (-O3 "
+                                                     "--use_fast_math, sm_100) by oracle/build_ref.py, same call sites"}
+                    out["speedup"] = ms_r / ms
+                    del c
+            except Exception as e:
+                out["reference_cuda"] = {"unavailable": repr(e)[:200]}
+        return out
+
+    try:
+        line["fastgs"] = fastgs_block(wl, args.steps)
+    except Exception as e:
+        line["fastgs"] = {"unavailable": repr(e)[:300]}
+
     # ---- the other configs of BASELINE.json (N=1 line only) ---------------------------------------------------------
     configs = {}
     if cfg == "B" and not args.no_other_configs:
@@ -791,6 +858,10 @@ def run_b200(args):
                 d["train"] = train_block(wd, 10)
             except Exception as e:
                 d["train"] = {"unavailable": repr(e)[:200]}
+            try:
+                d["fastgs"] = fastgs_block(wd, 10)
+            except Exception as e:
+                d["fastgs"] = {"unavailable": repr(e)[:200]}
             configs["D"] = d
             del wd
         except Exception as e:

@@ -3,7 +3,8 @@
 Artifacts (all under gaussian-splatting-cuda_b200/lib/, git-ignored, shipped to the GPU box):
   libgsb200.so           the C-ABI CUDA library (include/gsb200.h); no torch dependency
   libgsplat_b200.so      the libtorch shim exporting the reference's gsplat:: operator API
-                         (include/gsplat/Ops.h) + a TORCH_LIBRARY binding used by tests/bench
+                         (include/gsplat/Ops.h), its fast_gs::rasterization API (include/fastgs/rasterization_api.h)
+                         + a TORCH_LIBRARY binding used by tests/bench
 """
 from __future__ import annotations
 
@@ -40,9 +41,10 @@ CUDA_SOURCES = [
     ("gsb_fused.cu", ["-fmad=false"]),
     ("gsb_loss.cu", []),
     ("gsb_optim.cu", []),
+    ("gsb_fastgs.cu", []),
 ]
-CUDA_HEADERS = ["gsb_common.cuh", "gsb_raster.cuh", "gsb_camera.cuh", "gsb_devsort.cuh", "gsb_sh.cuh", "gsb_projection.cuh"]
-SHIM_SOURCES = ["Ops.cpp", "FusedOps.cpp", "torch_binding.cpp"]
+CUDA_HEADERS = ["gsb_common.cuh", "gsb_raster.cuh", "gsb_camera.cuh", "gsb_devsort.cuh", "gsb_sh.cuh", "gsb_projection.cuh", "gsb_ewa.cuh"]
+SHIM_SOURCES = ["Ops.cpp", "FusedOps.cpp", "FastGs.cpp", "torch_binding.cpp", "fastgs_binding.cpp"]
 
 
 def _run(cmd: list[str], verbose: bool) -> str:
@@ -114,9 +116,10 @@ def build_shim(verbose: bool = False, force: bool = False) -> str:
     flags = ["-O2", "-std=c++17", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=1", "-Wall",
              "-Wno-unused-variable", "-DGSB_NO_GLM"]
     incs = []
-    for i in [os.path.join(INC, "gsplat"), INC] + tinc + [cuda_inc]:
+    for i in [os.path.join(INC, "gsplat"), os.path.join(INC, "fastgs"), INC] + tinc + [cuda_inc]:
         incs += ["-I", i]
-    hdrs = [os.path.join(INC, "gsb200.h")] + [os.path.join(INC, "gsplat", h) for h in ("Ops.h", "FusedOps.h", "Common.h", "Cameras.h")]
+    hdrs = [os.path.join(INC, "gsb200.h")] + [os.path.join(INC, "gsplat", h) for h in ("Ops.h", "FusedOps.h", "Common.h", "Cameras.h")] + \
+        [os.path.join(INC, "fastgs", "rasterization_api.h")]
     objs = []
     for src in SHIM_SOURCES:
         sp = os.path.join(SHIM, src)

@@ -30,6 +30,7 @@
 // Chunks are in depth order and groups are ordered by (depth bits, index) inside: every tile's list is ordered by
 // (depth, index) -- the same permutation as the reference's single 46-bit sort, ties included.
 #include "gsb_devsort.cuh"
+#include "gsb_ewa.cuh"
 
 namespace gsb {
 
@@ -142,6 +143,37 @@ __global__ void __launch_bounds__(kIsectThreads) isect_plan_kernel(uint64_t n, c
     }
 }
 
+// EWA path: the front kernel of gsb_fastgs.cu has already computed every primitive's tile box and its
+// EXACT tile count; this step only derives the sort keys (depth bits, 0xffffffff for primitives without tiles).
+__global__ void __launch_bounds__(kIsectThreads) isect_plan_boxes_kernel(uint64_t n, const int32_t *__restrict__ counts,
+                                                                          const float *__restrict__ depths,
+                                                                          uint32_t *__restrict__ keys,
+                                                                          SortCtl *__restrict__ ctl) {
+    __shared__ uint32_t s_or[kIsectThreads / 32], s_nor[kIsectThreads / 32];
+    const uint64_t idx = (uint64_t)blockIdx.x * kIsectThreads + threadIdx.x;
+    uint32_t k_or = 0u, k_nor = 0u;
+    if (idx < n) {
+        uint32_t key = 0xffffffffu;
+        if (counts[idx] > 0) {
+            key = __float_as_uint(depths[idx]);
+            k_or = key;
+            k_nor = ~key;
+        }
+        keys[idx] = key;
+    }
+    k_or = __reduce_or_sync(0xffffffffu, k_or);
+    k_nor = __reduce_or_sync(0xffffffffu, k_nor);
+    if ((threadIdx.x & 31) == 0) { s_or[threadIdx.x >> 5] = k_or; s_nor[threadIdx.x >> 5] = k_nor; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kIsectThreads / 32; ++w) { k_or |= s_or[w]; k_nor |= s_nor[w]; }
+        if (k_or | k_nor) {
+            atomicOr(&ctl->key_or, k_or);
+            atomicOr(&ctl->key_nor, k_nor);
+        }
+    }
+}
+
 // ---- step 3: run table ---------------------------------------------------------------------------------------
 // One scan over the Gaussians in depth order of the pair (has tiles ? 1 : 0, tile count).
 struct RunAcc {
@@ -182,7 +214,15 @@ struct RunTable {
     uint32_t *idx;  // flattened Gaussian index (camera * N + gaussian)
     uint2 *box;
     uint32_t *key;  // depth bits
+    // EWA path only: the run covers the tiles of its box that pass ewa_tile_contributes
+    float4 *f0;     // (mx, my, ca, cb)
+    float2 *f1;     // (cc, thr)
 };
+__device__ __forceinline__ EwaFilter run_filter(const RunTable &rt, uint32_t r) {
+    const float4 a = rt.f0[r];
+    const float2 b = rt.f1[r];
+    return EwaFilter{a.x, a.y, a.z, a.w, b.x, b.y};
+}
 
 __device__ __forceinline__ const uint32_t *sorted_vals(const SortCtl *ctl, const uint32_t *v0, const uint32_t *v1) {
     return (radix_passes_done(ctl, 4) & 1) ? v1 : v0;
@@ -215,7 +255,9 @@ __global__ void __launch_bounds__(kSortThreads) runs_build_kernel(SortCtl *__res
                                                                   const int32_t *__restrict__ counts,
                                                                   const uint2 *__restrict__ boxes, uint64_t n,
                                                                   uint32_t seg, uint32_t nblocks,
-                                                                  const RunAcc *__restrict__ bsum, RunTable rt) {
+                                                                  const RunAcc *__restrict__ bsum, RunTable rt,
+                                                                  const float4 *__restrict__ filt0,
+                                                                  const float2 *__restrict__ filt1) {
     __shared__ RunAcc s_warp[kSortWarps];
     const bool odd = (radix_passes_done(ctl, 4) & 1) != 0;
     const uint32_t *perm = odd ? v1 : v0;
@@ -245,6 +287,7 @@ __global__ void __launch_bounds__(kSortThreads) runs_build_kernel(SortCtl *__res
             rt.idx[k] = idx;
             rt.box[k] = boxes[idx];
             rt.key[k] = keys[i];
+            if (filt0) { rt.f0[k] = filt0[idx]; rt.f1[k] = filt1[idx]; }
         }
         carry += tot;
     }
@@ -343,6 +386,7 @@ __device__ __forceinline__ void repair_small(const BinArgs &a, const float *__re
     }
 }
 
+template <bool kFilter>
 __device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__restrict__ depths, uint32_t p,
                                               uint32_t t, uint32_t start, uint32_t c) {
     const uint32_t lane = threadIdx.x & 31;
@@ -416,6 +460,7 @@ __device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__r
                 const uint2 b = a.rt.box[r];
                 const uint32_t x0 = b.x & 0xffffu, y0 = b.x >> 16, w = b.y & 0xffffu, h = b.y >> 16;
                 cover = tx >= x0 && tx < x0 + w && ty >= y0 && ty < y0 + h && (!a.multi_cam || idx / a.N == cam);
+                if constexpr (kFilter) cover = cover && ewa_tile_contributes(run_filter(a.rt, r), tx, ty);
             }
             const uint32_t m = __ballot_sync(0xffffffffu, cover);
             const uint32_t pos = gstart + written + __popc(m & ((1u << lane) - 1u));
@@ -425,7 +470,7 @@ __device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__r
     }
 }
 
-template <bool kScatter>
+template <bool kScatter, bool kFilter = false>
 __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) {
     extern __shared__ uint32_t s_cnt[]; // [t_cnt]
     __shared__ uint32_t s_range[2];
@@ -465,10 +510,12 @@ __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) 
     for (uint32_t r0 = ra + (tid & ~31u); r0 < rb; r0 += kBinThreads) { // warp-uniform trip count
         const uint32_t r = r0 + lane;
         uint32_t idx = 0, bx = 0, by = 0;
+        EwaFilter flt = {0.f, 0.f, 1.f, 0.f, 1.f, 0.f};
         if (r < rb) {
             idx = a.rt.idx[r];
             const uint2 b = a.rt.box[r];
             bx = b.x; by = b.y;
+            if constexpr (kFilter) flt = run_filter(a.rt, r);
         }
         const uint32_t w = by & 0xffffu, h = by >> 16, n = w * h; // 0 for the lanes past the chunk
         const uint32_t x0 = bx & 0xffffu, y0 = bx >> 16;
@@ -482,7 +529,9 @@ __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) 
                 uint32_t g[4], pos[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    g[u] = (j + u < n) ? cam_base + y * a.tile_width + x - a.t_lo : 0xffffffffu;
+                    bool take = j + u < n;
+                    if constexpr (kFilter) take = take && ewa_tile_contributes(flt, x, y);
+                    g[u] = take ? cam_base + y * a.tile_width + x - a.t_lo : 0xffffffffu;
                     if (++x == x0 + w) { x = x0; ++y; }
                 }
 #pragma unroll
@@ -502,8 +551,17 @@ __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) 
             const uint32_t bidx = __shfl_sync(0xffffffffu, idx, src), bcam = __shfl_sync(0xffffffffu, cam_base, src);
             const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
             const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
+            EwaFilter bf = flt;
+            if constexpr (kFilter) {
+                bf.mx = __shfl_sync(0xffffffffu, flt.mx, src); bf.my = __shfl_sync(0xffffffffu, flt.my, src);
+                bf.ca = __shfl_sync(0xffffffffu, flt.ca, src); bf.cb = __shfl_sync(0xffffffffu, flt.cb, src);
+                bf.cc = __shfl_sync(0xffffffffu, flt.cc, src); bf.thr = __shfl_sync(0xffffffffu, flt.thr, src);
+            }
             for (uint32_t j = lane; j < bn; j += 32) {
                 const uint32_t dy = j / bw, dx = j - dy * bw;
+                if constexpr (kFilter) {
+                    if (!ewa_tile_contributes(bf, bx0 + dx, by0 + dy)) continue;
+                }
                 place(bidx, bcam, bx0 + dx, by0 + dy);
             }
         }
@@ -544,7 +602,7 @@ __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) 
                 start = row[t];
                 c = min(s_cnt[t], a.cap) - start;
             }
-            repair_groups(a, a.depths, p, a.t_lo + t, start, c);
+            repair_groups<kFilter>(a, a.depths, p, a.t_lo + t, start, c);
         }
     }
 }
@@ -765,10 +823,10 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
 
 // Workspace of the plan; everything the emit needs afterwards lives here too.
 struct PlanWs {
-    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, M, seg, tot, toff, chunk_run,
-        total;
+    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, rt_f0, rt_f1, M, seg, tot, toff,
+        chunk_run, total;
 };
-static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp) {
+static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp, bool filter = false) {
     PlanWs w;
     size_t off = 0;
     auto take = [&](size_t bytes) { const size_t o = off; off += align256(bytes); return o; };
@@ -779,6 +837,7 @@ static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp) {
     w.hist = take((size_t)sp.nblocks * kRadixBins * 4);
     w.bsum = take((size_t)sp.nblocks * sizeof(RunAcc));
     w.rt_end = take(n * 4); w.rt_idx = take(n * 4); w.rt_box = take(n * 8); w.rt_key = take(n * 4);
+    w.rt_f0 = filter ? take(n * 16) : 0; w.rt_f1 = filter ? take(n * 8) : 0;
     w.M = take((size_t)b.P * b.T_total * 4);
     w.seg = take((size_t)b.S * b.T_total * 4);
     w.tot = take((size_t)b.T_total * 4);
@@ -902,31 +961,41 @@ extern "C" size_t gsb_isect_plan_workspace(uint32_t C, uint32_t N, uint32_t tile
     return gsb::plan_ws(n, gsb::bin_plan(C, N, tile_width, tile_height), gsb::seg_plan(n)).total;
 }
 
-extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii, const float *depths,
-                              uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
-                              int32_t *tiles_per_gauss, int64_t *n_isects_out, int32_t *tile_offsets_out,
-                              int tile_offsets_total, void *plan_workspace, size_t plan_workspace_bytes,
-                              gsb_stream_t stream) {
-    using namespace gsb;
+namespace gsb {
+// Source of step 1: either the gsplat operator inputs (means2d / radii -> tile boxes here) or the EWA front kernel's
+// precomputed boxes, exact counts and tile-test parameters.
+struct PlanSource {
+    const float *means2d = nullptr;
+    const int32_t *radii = nullptr;
+    uint32_t tile_size = 16;
+    const uint2 *boxes = nullptr;   // EWA
+    const float4 *filt0 = nullptr;  // EWA
+    const float2 *filt1 = nullptr;  // EWA
+    bool ewa() const { return boxes != nullptr; }
+};
+
+static int plan_impl(uint32_t C, uint32_t N, const PlanSource &src, const float *depths, uint32_t tile_width,
+                     uint32_t tile_height, int32_t *tiles_per_gauss, int64_t *n_isects_out, int32_t *tile_offsets_out,
+                     int tile_offsets_total, void *plan_workspace, size_t plan_workspace_bytes, cudaStream_t s) {
     const uint64_t n = (uint64_t)C * N;
     if (!n_isects_out) return GSB_E_INVALID;
-    cudaStream_t s = as_stream(stream);
     const uint64_t T64 = (uint64_t)C * tile_width * tile_height;
     if (n == 0 || T64 == 0) {
         GSB_CUDA_TRY(cudaMemsetAsync(n_isects_out, 0, sizeof(int64_t), s));
         if (tile_offsets_out && T64)
             GSB_CUDA_TRY(cudaMemsetAsync(tile_offsets_out, 0, (T64 + (tile_offsets_total ? 1 : 0)) * 4, s));
-        if (n && tiles_per_gauss) GSB_CUDA_TRY(cudaMemsetAsync(tiles_per_gauss, 0, n * 4, s));
+        if (n && tiles_per_gauss && !src.ewa()) GSB_CUDA_TRY(cudaMemsetAsync(tiles_per_gauss, 0, n * 4, s));
         return GSB_OK;
     }
-    if (!means2d || !radii || !depths || !tiles_per_gauss || tile_size == 0) return GSB_E_INVALID;
+    if (!depths || !tiles_per_gauss) return GSB_E_INVALID;
+    if (src.ewa() ? (!src.filt0 || !src.filt1) : (!src.means2d || !src.radii || src.tile_size == 0)) return GSB_E_INVALID;
     const uint32_t tile_n_bits = bit_width_u32(tile_width * tile_height);
     const uint32_t cam_n_bits = bit_width_u32(C);
     if (tile_n_bits + cam_n_bits > 32) return GSB_E_INVALID; // Intersect.cpp:50
     if (tile_width > 0xffffu || tile_height > 0xffffu || n > 0x7fffffffull || T64 > 0x7fffffffull) return GSB_E_INVALID;
     const BinPlan bp = bin_plan(C, N, tile_width, tile_height);
     const SegPlan sp = seg_plan(n);
-    const PlanWs w = plan_ws(n, bp, sp);
+    const PlanWs w = plan_ws(n, bp, sp, src.ewa());
     if (!plan_workspace || (reinterpret_cast<uintptr_t>(plan_workspace) & 255) || plan_workspace_bytes < w.total)
         return GSB_E_WORKSPACE;
     char *base = reinterpret_cast<char *>(plan_workspace);
@@ -937,15 +1006,20 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
     uint32_t *H = reinterpret_cast<uint32_t *>(base + w.hist);
     RunAcc *bsum = reinterpret_cast<RunAcc *>(base + w.bsum);
     RunTable rt{reinterpret_cast<uint32_t *>(base + w.rt_end), reinterpret_cast<uint32_t *>(base + w.rt_idx),
-                reinterpret_cast<uint2 *>(base + w.rt_box), reinterpret_cast<uint32_t *>(base + w.rt_key)};
+                reinterpret_cast<uint2 *>(base + w.rt_box), reinterpret_cast<uint32_t *>(base + w.rt_key),
+                src.ewa() ? reinterpret_cast<float4 *>(base + w.rt_f0) : nullptr,
+                src.ewa() ? reinterpret_cast<float2 *>(base + w.rt_f1) : nullptr};
     uint32_t *M = reinterpret_cast<uint32_t *>(base + w.M);
     uint32_t *seg = reinterpret_cast<uint32_t *>(base + w.seg);
     {
         ProfScope ps("isect_count", s);
         GSB_CUDA_TRY(cudaMemsetAsync(ctl, 0, sizeof(SortCtl), s));
         const uint32_t grid = (uint32_t)((n + kIsectThreads - 1) / kIsectThreads);
-        isect_plan_kernel<<<grid, kIsectThreads, 0, s>>>(n, means2d, radii, depths, tile_size, tile_width, tile_height,
-                                                        tiles_per_gauss, k0, boxes, ctl);
+        if (src.ewa())
+            isect_plan_boxes_kernel<<<grid, kIsectThreads, 0, s>>>(n, tiles_per_gauss, depths, k0, ctl);
+        else
+            isect_plan_kernel<<<grid, kIsectThreads, 0, s>>>(n, src.means2d, src.radii, depths, src.tile_size, tile_width,
+                                                            tile_height, tiles_per_gauss, k0, boxes, ctl);
         GSB_LAUNCH_CHECK();
     }
     {
@@ -956,8 +1030,9 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
         ProfScope ps("isect_runs", s);
         runs_blocksum_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(ctl, v0, v1, tiles_per_gauss, n, sp.seg, bsum);
         GSB_LAUNCH_CHECK();
-        runs_build_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(ctl, v0, v1, k0, k1, tiles_per_gauss, boxes, n, sp.seg,
-                                                             sp.nblocks, bsum, rt);
+        runs_build_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(ctl, v0, v1, k0, k1, tiles_per_gauss,
+                                                             src.ewa() ? src.boxes : boxes, n, sp.seg, sp.nblocks, bsum,
+                                                             rt, src.filt0, src.filt1);
         GSB_LAUNCH_CHECK();
     }
     // device or pinned-host destination alike
@@ -969,13 +1044,19 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
         a.multi_cam = C > 1 ? 1u : 0u;
         a.T_total = bp.T_total; a.P = bp.P; a.M = M; a.flatten_ids = nullptr; a.cap = 0; a.depths = nullptr;
         a.chunk_run = reinterpret_cast<uint32_t *>(base + w.chunk_run);
-        if (bp.smem > 48 * 1024)
-            GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        if (bp.smem > 48 * 1024) {
+            GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               (int)bp.smem));
+            GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)bp.smem));
+        }
         for (uint32_t wnd = 0; wnd < bp.n_win; ++wnd) {
             a.t_lo = wnd * bp.t_win;
             a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
-            tile_bin_kernel<false><<<bp.P, kBinThreads, bp.smem, s>>>(a);
+            if (src.ewa())
+                tile_bin_kernel<false, true><<<bp.P, kBinThreads, bp.smem, s>>>(a);
+            else
+                tile_bin_kernel<false, false><<<bp.P, kBinThreads, bp.smem, s>>>(a);
             GSB_LAUNCH_CHECK();
         }
     }
@@ -994,39 +1075,44 @@ extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, cons
     return GSB_OK;
 }
 
-extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depths, uint32_t tile_width,
-                                      uint32_t tile_height, uint64_t n_isects, const void *plan_workspace,
-                                      size_t plan_workspace_bytes, int64_t *isect_ids /*nullable*/, int32_t *flatten_ids,
-                                      gsb_stream_t stream) {
-    using namespace gsb;
+static int emit_impl(uint32_t C, uint32_t N, bool filter, const float *depths, uint32_t tile_width, uint32_t tile_height,
+                     uint64_t n_isects, const void *plan_workspace, size_t plan_workspace_bytes, int64_t *isect_ids,
+                     int32_t *flatten_ids, cudaStream_t s) {
     const uint64_t n = (uint64_t)C * N;
     if (n == 0 || n_isects == 0) return GSB_OK;
     if (!plan_workspace || !flatten_ids || !depths) return GSB_E_INVALID;
     if (n_isects > 0x7fffffffull) return GSB_E_INVALID;
     const BinPlan bp = bin_plan(C, N, tile_width, tile_height);
     const SegPlan sp = seg_plan(n);
-    const PlanWs w = plan_ws(n, bp, sp);
+    const PlanWs w = plan_ws(n, bp, sp, filter);
     if ((reinterpret_cast<uintptr_t>(plan_workspace) & 255) || plan_workspace_bytes < w.total) return GSB_E_WORKSPACE;
-    cudaStream_t s = as_stream(stream);
     char *base = const_cast<char *>(reinterpret_cast<const char *>(plan_workspace));
     BinArgs a;
     a.rt = RunTable{reinterpret_cast<uint32_t *>(base + w.rt_end), reinterpret_cast<uint32_t *>(base + w.rt_idx),
-                    reinterpret_cast<uint2 *>(base + w.rt_box), reinterpret_cast<uint32_t *>(base + w.rt_key)};
+                    reinterpret_cast<uint2 *>(base + w.rt_box), reinterpret_cast<uint32_t *>(base + w.rt_key),
+                    filter ? reinterpret_cast<float4 *>(base + w.rt_f0) : nullptr,
+                    filter ? reinterpret_cast<float2 *>(base + w.rt_f1) : nullptr};
     a.ctl = reinterpret_cast<const SortCtl *>(base + w.ctl);
     a.N = N; a.n_tiles = tile_width * tile_height; a.tile_width = tile_width;
     a.multi_cam = C > 1 ? 1u : 0u;
     a.chunk_run = reinterpret_cast<uint32_t *>(base + w.chunk_run);
     a.T_total = bp.T_total; a.P = bp.P; a.M = reinterpret_cast<uint32_t *>(base + w.M);
     a.flatten_ids = flatten_ids; a.cap = (uint32_t)n_isects; a.depths = depths;
-    if (bp.smem_scatter > 48 * 1024)
-        GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (bp.smem_scatter > 48 * 1024) {
+        GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)bp.smem_scatter));
+        GSB_CUDA_TRY(cudaFuncSetAttribute(tile_bin_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int)bp.smem_scatter));
+    }
     {
         ProfScope ps("isect_emit", s);
         for (uint32_t wnd = 0; wnd < bp.n_win; ++wnd) {
             a.t_lo = wnd * bp.t_win;
             a.t_cnt = min(bp.t_win, bp.T_total - a.t_lo);
-            tile_bin_kernel<true><<<bp.P, kBinThreads, bp.smem_scatter, s>>>(a);
+            if (filter)
+                tile_bin_kernel<true, true><<<bp.P, kBinThreads, bp.smem_scatter, s>>>(a);
+            else
+                tile_bin_kernel<true, false><<<bp.P, kBinThreads, bp.smem_scatter, s>>>(a);
             GSB_LAUNCH_CHECK();
         }
     }
@@ -1039,6 +1125,44 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depth
         GSB_LAUNCH_CHECK();
     }
     return GSB_OK;
+}
+
+// EWA entry points used by gsb_fastgs.cu (not part of the C ABI)
+size_t isect_plan_ewa_workspace(uint32_t N, uint32_t tile_width, uint32_t tile_height) {
+    return plan_ws(N, bin_plan(1, N, tile_width, tile_height), seg_plan(N), true).total;
+}
+int isect_plan_ewa(uint32_t N, int32_t *counts, const uint2 *boxes, const float *depths, const float4 *filt0,
+                   const float2 *filt1, uint32_t tile_width, uint32_t tile_height, int64_t *n_isects_out,
+                   int32_t *tile_offsets_out, void *plan_workspace, size_t plan_workspace_bytes, cudaStream_t s) {
+    PlanSource src;
+    src.boxes = boxes; src.filt0 = filt0; src.filt1 = filt1;
+    return plan_impl(1, N, src, depths, tile_width, tile_height, counts, n_isects_out, tile_offsets_out, 1, plan_workspace,
+                     plan_workspace_bytes, s);
+}
+int isect_emit_ewa(uint32_t N, const float *depths, uint32_t tile_width, uint32_t tile_height, uint64_t capacity,
+                   const void *plan_workspace, size_t plan_workspace_bytes, int32_t *flatten_ids, cudaStream_t s) {
+    return emit_impl(1, N, true, depths, tile_width, tile_height, capacity, plan_workspace, plan_workspace_bytes, nullptr,
+                     flatten_ids, s);
+}
+} // namespace gsb
+
+extern "C" int gsb_isect_plan(uint32_t C, uint32_t N, const float *means2d, const int32_t *radii, const float *depths,
+                              uint32_t tile_size, uint32_t tile_width, uint32_t tile_height,
+                              int32_t *tiles_per_gauss, int64_t *n_isects_out, int32_t *tile_offsets_out,
+                              int tile_offsets_total, void *plan_workspace, size_t plan_workspace_bytes,
+                              gsb_stream_t stream) {
+    gsb::PlanSource src;
+    src.means2d = means2d; src.radii = radii; src.tile_size = tile_size;
+    return gsb::plan_impl(C, N, src, depths, tile_width, tile_height, tiles_per_gauss, n_isects_out, tile_offsets_out,
+                          tile_offsets_total, plan_workspace, plan_workspace_bytes, gsb::as_stream(stream));
+}
+
+extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depths, uint32_t tile_width,
+                                      uint32_t tile_height, uint64_t n_isects, const void *plan_workspace,
+                                      size_t plan_workspace_bytes, int64_t *isect_ids /*nullable*/, int32_t *flatten_ids,
+                                      gsb_stream_t stream) {
+    return gsb::emit_impl(C, N, false, depths, tile_width, tile_height, n_isects, plan_workspace, plan_workspace_bytes,
+                          isect_ids, flatten_ids, gsb::as_stream(stream));
 }
 
 extern "C" int gsb_isect_offsets(uint64_t n_isects, const int64_t *isect_ids_sorted, uint32_t C,

@@ -70,6 +70,7 @@ struct TileParams {
     uint32_t n_isects;  // end of the last tile's range when the offsets have no closing entry
     uint32_t cap;       // capacity of flatten_ids: every range is clipped to it (== n_isects on the operator path)
     uint32_t closed;    // tile_offsets has tile_w*tile_h + 1 entries, the last one = n_isects (fused path)
+    uint32_t chw;       // images are [3,H,W] planes (the fastgs API) instead of [H,W,3]
     uint32_t W, H, tile_w, tile_h;
     const GaussRec *recs;
     const float *backgrounds; // [3] or null
@@ -160,7 +161,7 @@ __device__ __forceinline__ void issue_batch(GaussRec *stage, uint64_t *bar, cons
 // ------------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------------
-template <bool kGeneral>
+template <bool kGeneral, bool kEwa = false>
 __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TileParams p, float *__restrict__ renders,
                                                                    float *__restrict__ alphas,
                                                                    int32_t *__restrict__ last_ids) {
@@ -236,18 +237,18 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
               const int32_t rl = c0 + (int32_t)(tid & 31);
               bool cand = false;
               if (rl < cnt)
-                  cand = block_may_pass(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], pc.bx0, pc.bx1, pc.by0, pc.by1);
+                  cand = block_may_pass<kEwa>(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], pc.bx0, pc.bx1, pc.by0, pc.by1);
               uint32_t cmask = __ballot_sync(0xffffffffu, cand);
               while (cmask) {
                 const int32_t t = c0 + __ffs(cmask) - 1;
                 cmask &= cmask - 1;
                 const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
-                const PairEval2 e = pair_eval2(q0, q1, q2, f2_add(PX, f2_bc(-q0.x)), f2_add(PY, f2_bc(-q0.y)));
+                const PairEval2 e = pair_eval2<kEwa>(q0, q1, q2, f2_add(PX, f2_bc(-q0.x)), f2_add(PY, f2_bc(-q0.y)));
                 const bool p0 = e.pass0 && !done0, p1 = e.pass1 && !done1;
                 if (!__any_sync(0xffffffffu, p0 || p1)) continue;
                 const float4 q3 = rec4[t * 4 + 3];
                 if (p0) {
-                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw(f2_lo(e.Ns), f2_lo(e.Ds), q2.z));
+                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw<kEwa>(f2_lo(e.Ns), f2_lo(e.Ds), q2.z));
                     if (alpha >= kAlphaThreshold) {
                         const float nT = T0 * (1.0f - alpha);
                         if (nT <= kMinTransmittance) {
@@ -261,7 +262,7 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
                     }
                 }
                 if (p1) {
-                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw(f2_hi(e.Ns), f2_hi(e.Ds), q2.z));
+                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw<kEwa>(f2_hi(e.Ns), f2_hi(e.Ds), q2.z));
                     if (alpha >= kAlphaThreshold) {
                         const float nT = T1 * (1.0f - alpha);
                         if (nT <= kMinTransmittance) {
@@ -284,18 +285,20 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
     // never retire the CTA with a bulk copy still landing in its shared memory
     if (saturated && b + 1 < n_batches) mbar_wait(&s_full[(b + 1) & 1], (uint32_t)(((b + 1) >> 1) & 1));
 
+    // [H,W,3] rows (gsplat operators) or [3,H,W] planes (fastgs API)
+    const size_t cs = p.chw ? (size_t)p.W * p.H : 1, ps = p.chw ? 1 : 3;
     if (pm.in0) {
         alphas[pix0] = 1.0f - T0;
-        renders[pix0 * 3] = has_bg ? c0r + T0 * bg0 : c0r;
-        renders[pix0 * 3 + 1] = has_bg ? c0g + T0 * bg1 : c0g;
-        renders[pix0 * 3 + 2] = has_bg ? c0b + T0 * bg2 : c0b;
+        renders[pix0 * ps] = has_bg ? c0r + T0 * bg0 : c0r;
+        renders[pix0 * ps + cs] = has_bg ? c0g + T0 * bg1 : c0g;
+        renders[pix0 * ps + 2 * cs] = has_bg ? c0b + T0 * bg2 : c0b;
         last_ids[pix0] = last0;
     }
     if (pm.in1) {
         alphas[pix1] = 1.0f - T1;
-        renders[pix1 * 3] = has_bg ? c1r + T1 * bg0 : c1r;
-        renders[pix1 * 3 + 1] = has_bg ? c1g + T1 * bg1 : c1g;
-        renders[pix1 * 3 + 2] = has_bg ? c1b + T1 * bg2 : c1b;
+        renders[pix1 * ps] = has_bg ? c1r + T1 * bg0 : c1r;
+        renders[pix1 * ps + cs] = has_bg ? c1g + T1 * bg1 : c1g;
+        renders[pix1 * ps + 2 * cs] = has_bg ? c1b + T1 * bg2 : c1b;
         last_ids[pix1] = last1;
     }
 }
@@ -323,16 +326,25 @@ __device__ __forceinline__ float f2_sum(f2 a) { return f2_lo(a) + f2_hi(a); }
 struct EventWeights {
     f2 w1, w2, g, fac;
 };
+template <bool kEwa = false>
 __device__ __forceinline__ EventWeights bwd_weights(BwdState &s, const PairEval2 &e, bool p0, bool p1, float lop,
                                                     float cr, float cg, float cb) {
-    const f2 rD = f2_make(fast_rcp(f2_lo(e.Ds)), fast_rcp(f2_hi(e.Ds)));
-    const f2 ex = f2_fma(e.Ns, rD, f2_bc(lop)); // same rounding as the forward's pair_alpha_raw
+    f2 rD, ex; // same rounding as the forward's pair_alpha_raw
+    if constexpr (kEwa) {
+        rD = f2_bc(1.0f);
+        ex = f2_add(e.Ns, f2_bc(lop));
+    } else {
+        rD = f2_make(fast_rcp(f2_lo(e.Ds)), fast_rcp(f2_hi(e.Ds)));
+        ex = f2_fma(e.Ns, rD, f2_bc(lop));
+    }
     const float ar0 = fast_ex2(f2_lo(ex)), ar1 = fast_ex2(f2_hi(ex));
     const float al0 = fminf(kMaxAlpha, ar0), al1 = fminf(kMaxAlpha, ar1);
     const bool ok0 = p0 && al0 >= kAlphaThreshold, ok1 = p1 && al1 >= kAlphaThreshold;
     const f2 alpha = f2_make(ok0 ? al0 : 0.0f, ok1 ? al1 : 0.0f);
     // Bwd.cu:318: the gradient reaches the Gaussian through alpha only when alpha was not clamped
-    const f2 araw_g = f2_make((ok0 && ar0 <= kMaxAlpha) ? ar0 : 0.0f, (ok1 && ar1 <= kMaxAlpha) ? ar1 : 0.0f);
+    // (the fastgs blend differentiates through the clamped value: kernels_backward.cuh:421-426 has no such test)
+    const f2 araw_g = kEwa ? alpha
+                           : f2_make((ok0 && ar0 <= kMaxAlpha) ? ar0 : 0.0f, (ok1 && ar1 <= kMaxAlpha) ? ar1 : 0.0f);
     const f2 om = f2_fma(alpha, f2_bc(-1.0f), f2_bc(1.0f));
     // the reference evaluates 1/(1-alpha) with the fast-math reciprocal too (Bwd.cu:291 under --use_fast_math)
     float ra0 = 1.0f, ra1 = 1.0f;
@@ -347,15 +359,36 @@ __device__ __forceinline__ EventWeights bwd_weights(BwdState &s, const PairEval2
     const f2 v_alpha = f2_fma(s.T, cv, f2_mul(ra, f2_fma(s.bdot, f2_bc(-1.0f), s.tfva)));
     s.bdot = f2_fma(w.fac, cv, s.bdot);
     w.g = f2_mul(araw_g, v_alpha);
-    const f2 gr = f2_mul(w.g, rD);
-    w.w1 = f2_mul(gr, f2_bc(kLn2));
-    w.w2 = f2_mul(f2_mul(gr, f2_bc(-kLn2)), f2_mul(e.Ns, rD));
+    if constexpr (kEwa) {
+        w.w1 = w.g; // the moments are sums of g {x, y, x^2, xy, y^2}: the conic's chain rule runs per Gaussian
+        w.w2 = f2_bc(0.0f);
+    } else {
+        const f2 gr = f2_mul(w.g, rD);
+        w.w1 = f2_mul(gr, f2_bc(kLn2));
+        w.w2 = f2_mul(f2_mul(gr, f2_bc(-kLn2)), f2_mul(e.Ns, rD));
+    }
     return w;
 }
 
 // Shuffle reduction: the 16 registers of the event, lanes 16..31 pre-swapped (see MomentSlot).
+template <bool kEwa = false>
 __device__ __forceinline__ void event_registers(const BwdState &s, const EventWeights &w, const PairEval2 &e, f2 x, f2 y,
                                                 bool hi16, float (&R)[16]) {
+    if constexpr (kEwa) {
+        // nine live slots (g, g x, g y, g xx, g xy, g yy, colour): lanes 16..31 hold them in the swapped registers
+        const float gs = f2_sum(w.g);
+        const float m1 = f2_sum(f2_mul(w.g, x)), m2 = f2_sum(f2_mul(w.g, y));
+        const float m3 = f2_sum(f2_mul(w.g, e.xx)), m4 = f2_sum(f2_mul(w.g, e.xy)), m5 = f2_sum(f2_mul(w.g, e.yy));
+        R[0] = hi16 ? 0.0f : gs; R[8] = hi16 ? gs : 0.0f;
+        R[1] = hi16 ? 0.0f : m1; R[9] = hi16 ? m1 : 0.0f;
+        R[2] = hi16 ? 0.0f : m2; R[10] = hi16 ? m2 : 0.0f;
+        R[3] = hi16 ? 0.0f : m3; R[11] = hi16 ? m3 : 0.0f;
+        R[4] = hi16 ? 0.0f : m4; R[12] = hi16 ? m4 : 0.0f;
+        R[5] = hi16 ? 0.0f : m5; R[13] = hi16 ? m5 : 0.0f;
+        R[6] = f2_sum(f2_mul(w.fac, s.vA)); R[14] = f2_sum(f2_mul(w.fac, s.vB));
+        R[7] = f2_sum(f2_mul(w.fac, s.vC)); R[15] = f2_sum(f2_mul(w.fac, s.vD));
+        return;
+    }
     const f2 wA = hi16 ? w.w2 : w.w1, wB = hi16 ? w.w1 : w.w2;
     const float gs = f2_sum(w.g), w2s = f2_sum(w.w2);
     R[0] = hi16 ? w2s : gs;
@@ -368,7 +401,7 @@ __device__ __forceinline__ void event_registers(const BwdState &s, const EventWe
     R[7] = f2_sum(f2_mul(w.fac, s.vC)); R[15] = f2_sum(f2_mul(w.fac, s.vD));
 }
 
-template <bool kGeneral>
+template <bool kGeneral, bool kEwa = false>
 __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TileParams p,
                                                                    const float *__restrict__ render_alphas,
                                                                    const int32_t *__restrict__ last_ids,
@@ -402,7 +435,8 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
             const float Tf = 1.0f - render_alphas[pix];
             r.T = Tf;
             r.last = last_ids[pix];
-            r.vr = v_render_colors[pix * 3]; r.vg = v_render_colors[pix * 3 + 1]; r.vb = v_render_colors[pix * 3 + 2];
+            const size_t cs = p.chw ? (size_t)p.W * p.H : 1, ps = p.chw ? 1 : 3;
+            r.vr = v_render_colors[pix * ps]; r.vg = v_render_colors[pix * ps + cs]; r.vb = v_render_colors[pix * ps + 2 * cs];
             const float va = v_render_alphas[pix];
             const float bgd = bg[0] * r.vr + bg[1] * r.vg + bg[2] * r.vb;
             r.tfva = Tf * va - Tf * bgd; // Bwd.cu:307-316
@@ -477,7 +511,7 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
           const int32_t rl = c0 + (int32_t)(tid & 31);
           bool cand = false;
           if (rl >= t_first && rl < cnt)
-              cand = block_may_pass(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], pc.bx0, pc.bx1, pc.by0, pc.by1);
+              cand = block_may_pass<kEwa>(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], pc.bx0, pc.bx1, pc.by0, pc.by1);
           uint32_t cmask = __ballot_sync(0xffffffffu, cand);
           while (cmask) {
             const int32_t t = c0 + __ffs(cmask) - 1;
@@ -485,18 +519,19 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
             const int32_t idx = top - t;
             const float4 q0 = rec4[t * 4], q1 = rec4[t * 4 + 1], q2 = rec4[t * 4 + 2];
             const f2 x = f2_add(PX, f2_bc(-q0.x)), y = f2_add(PY, f2_bc(-q0.y));
-            const PairEval2 e = pair_eval2(q0, q1, q2, x, y);
+            const PairEval2 e = pair_eval2<kEwa>(q0, q1, q2, x, y);
             const bool p0 = e.pass0 && s.in0 && idx <= s.last0;
             const bool p1 = e.pass1 && s.in1 && idx <= s.last1;
             if (!__any_sync(0xffffffffu, p0 || p1)) continue;
             const float4 q3 = rec4[t * 4 + 3];
-            const EventWeights w = bwd_weights(s, e, p0, p1, q2.z, q3.x, q3.y, q3.z);
+            const EventWeights w = bwd_weights<kEwa>(s, e, p0, p1, q2.z, q3.x, q3.y, q3.z);
             float R[16];
-            event_registers(s, w, e, x, y, hi16, R);
+            event_registers<kEwa>(s, w, e, x, y, hi16, R);
             butterfly16_preswapped(R);
             if ((tid & 1) == 0) {
                 const uint32_t slot = (tid & 31) >> 1;
-                if (slot != (uint32_t)kS_PAD)
+                // EWA records: slots 8..13 (the denominator moments) do not exist
+                if (slot != (uint32_t)kS_PAD && !(kEwa && slot >= 8u && slot != (uint32_t)kS_CG))
                     red_add_f32(moments + (size_t)__float_as_int(q3.w) * kMomFloats + slot, R[0]);
             }
           }
@@ -594,7 +629,7 @@ namespace gsb {
 static void fill_tiles(TileParams &p, uint64_t n_isects, uint32_t cap, int closed, uint32_t image_width,
                        uint32_t image_height, const GaussRec *recs, const float *backgrounds, const uint8_t *masks,
                        const int32_t *tile_offsets, const int32_t *flatten_ids, const GsbCamera *cam) {
-    p.n_isects = (uint32_t)n_isects; p.cap = cap; p.closed = closed ? 1u : 0u;
+    p.n_isects = (uint32_t)n_isects; p.cap = cap; p.closed = closed ? 1u : 0u; p.chw = 0u;
     p.W = image_width; p.H = image_height;
     p.tile_w = (image_width + 15) / 16; p.tile_h = (image_height + 15) / 16;
     p.recs = recs; p.backgrounds = backgrounds; p.masks = masks;
@@ -627,6 +662,43 @@ static int launch_bwd(const TileParams &p, const GsbCamera *cam, const float *re
     GSB_LAUNCH_CHECK();
     return GSB_OK;
 }
+
+// ---- EWA records (gsb_fastgs.cu): the same two kernels on pure 2-D conics, [3,H,W] images, no
+// background, closed tile offsets, flatten_ids of `cap` entries --------------------------------------------------------
+static void fill_ewa(TileParams &p, uint32_t cap, uint32_t W, uint32_t H, const GaussRec *recs, const int32_t *tile_offsets,
+                     const int32_t *flatten_ids) {
+    p.n_isects = 0; p.cap = cap; p.closed = 1u; p.chw = 1u;
+    p.W = W; p.H = H; p.tile_w = (W + 15) / 16; p.tile_h = (H + 15) / 16;
+    p.recs = recs; p.backgrounds = nullptr; p.masks = nullptr;
+    p.tile_offsets = tile_offsets; p.flatten_ids = flatten_ids;
+    p.camera_model = GSB_CAMERA_PINHOLE; p.Ks = nullptr; p.radial = p.tangential = p.thin_prism = nullptr;
+    p.n_radial = p.n_tangential = p.n_thin_prism = 0;
+}
+int raster_ewa_fwd(uint32_t cap, const GaussRec *recs, uint32_t W, uint32_t H, const int32_t *tile_offsets,
+                   const int32_t *flatten_ids, float *image, float *alpha, int32_t *last_ids, cudaStream_t s) {
+    TileParams p;
+    fill_ewa(p, cap, W, H, recs, tile_offsets, flatten_ids);
+    {
+        ProfScope ps("ewa_blend_fwd", s);
+        raster_fwd_kernel<false, true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, image, alpha, last_ids);
+    }
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+int raster_ewa_bwd(uint32_t cap, const GaussRec *recs, uint32_t W, uint32_t H, const int32_t *tile_offsets,
+                   const int32_t *flatten_ids, const float *alpha, const int32_t *last_ids, const float *grad_image,
+                   const float *grad_alpha, float *moments, cudaStream_t s) {
+    TileParams p;
+    fill_ewa(p, cap, W, H, recs, tile_offsets, flatten_ids);
+    {
+        ProfScope ps("ewa_blend_bwd", s);
+        raster_bwd_kernel<false, true><<<p.tile_w * p.tile_h, kTileThreads, 0, s>>>(p, alpha, last_ids, grad_image,
+                                                                                   grad_alpha, moments);
+    }
+    GSB_LAUNCH_CHECK();
+    return GSB_OK;
+}
+
 } // namespace gsb
 
 extern "C" int gsb_raster_fwd(uint32_t C, uint32_t N, uint64_t n_isects, const float *means, const float *quats,

@@ -301,16 +301,24 @@ struct PairEval2 {
     f2 xx, xy, yy;
     bool pass0, pass1;
 };
+// kEwa: the record is a pure 2-D conic (gsb_fastgs.cu): Ds == 1, no denominator arithmetic.
+template <bool kEwa = false>
 __device__ __forceinline__ PairEval2 pair_eval2(const float4 q0, const float4 q1, const float4 q2, f2 x, f2 y) {
     PairEval2 r;
     r.xx = f2_mul(x, x); r.xy = f2_mul(x, y); r.yy = f2_mul(y, y);
     r.Ns = f2_fma(f2_bc(q1.x), r.yy, f2_fma(f2_bc(q0.w), r.xy, f2_mul(f2_bc(q0.z), r.xx)));
-    f2 D = f2_fma(f2_bc(q1.y), x, f2_bc(1.0f));
-    D = f2_fma(f2_bc(q1.z), y, D);
-    D = f2_fma(f2_bc(q1.w), r.xx, D);
-    D = f2_fma(f2_bc(q2.x), r.xy, D);
-    r.Ds = f2_fma(f2_bc(q2.y), r.yy, D);
-    const f2 t = f2_fma(f2_bc(-q2.w), r.Ds, r.Ns); // Ns >= tau * Ds
+    f2 t;
+    if constexpr (kEwa) {
+        r.Ds = f2_bc(1.0f);
+        t = f2_add(r.Ns, f2_bc(-q2.w)); // Ns >= tau
+    } else {
+        f2 D = f2_fma(f2_bc(q1.y), x, f2_bc(1.0f));
+        D = f2_fma(f2_bc(q1.z), y, D);
+        D = f2_fma(f2_bc(q1.w), r.xx, D);
+        D = f2_fma(f2_bc(q2.x), r.xy, D);
+        r.Ds = f2_fma(f2_bc(q2.y), r.yy, D);
+        t = f2_fma(f2_bc(-q2.w), r.Ds, r.Ns); // Ns >= tau * Ds
+    }
     r.pass0 = f2_lo(t) >= 0.0f;
     r.pass1 = f2_hi(t) >= 0.0f;
     return r;
@@ -322,10 +330,33 @@ __device__ __forceinline__ PairEval2 pair_eval2(const float4 q0, const float4 q1
 // box, else the best point on the (at most two) box edges facing it.  One lane tests one record,
 // so a warp classifies 32 records per pass; `slack` absorbs the float rounding of both this test
 // and pair_eval's, keeping the cull strictly conservative.  Non-concave forms are never culled.
+template <bool kEwa = false>
 __device__ __forceinline__ bool block_may_pass(const float4 q0, const float4 q1, const float4 q2, float bx0,
                                                float bx1, float by0, float by1) {
     const float tau = q2.w;
     if (!(tau < 3.0e38f)) return false; // dead record (tau = +inf)
+    if constexpr (kEwa) {
+        // pure conic (the d-slots of the record carry other data): F = Ns - tau, maximal at the box point nearest to
+        // the centre in the conic's metric -- the centre itself if it lies inside the box
+        const float A = q0.z, B = q0.w, C = q1.x;
+        const float x0 = bx0 - q0.x, x1 = bx1 - q0.x, y0 = by0 - q0.y, y1 = by1 - q0.y;
+        if (!(A < 0.0f && C < 0.0f && 4.0f * A * C - B * B > 0.0f)) return true;
+        const bool xin = x0 <= 0.0f && x1 >= 0.0f, yin = y0 <= 0.0f && y1 >= 0.0f;
+        if (xin && yin) return true; // F(0, 0) = -tau >= 0 for every visible primitive
+        auto Fv = [&](float x, float y) { return (A * x + B * y) * x + C * y * y - tau; };
+        float fmax = -3.0e38f;
+        if (!xin) {
+            const float xc = fminf(fmaxf(0.0f, x0), x1);
+            const float yc = fminf(fmaxf(-(B * xc) / (2.0f * C), y0), y1);
+            fmax = fmaxf(fmax, Fv(xc, yc));
+        }
+        if (!yin) {
+            const float yc = fminf(fmaxf(0.0f, y0), y1);
+            const float xc = fminf(fmaxf(-(B * yc) / (2.0f * A), x0), x1);
+            fmax = fmaxf(fmax, Fv(xc, yc));
+        }
+        return fmax >= -0.02f;
+    }
     const float A = __fmaf_rn(-tau, q1.w, q0.z), B = __fmaf_rn(-tau, q2.x, q0.w), C = __fmaf_rn(-tau, q2.y, q1.x);
     const float D = -tau * q1.y, E = -tau * q1.z, F0 = -tau;
     const float x0 = bx0 - q0.x, x1 = bx1 - q0.x, y0 = by0 - q0.y, y1 = by1 - q0.y;
@@ -355,7 +386,9 @@ __device__ __forceinline__ bool block_may_pass(const float4 q0, const float4 q1,
 }
 
 // alpha_raw = opac * exp(power) = 2^(Ns/Ds + lop)
+template <bool kEwa = false>
 __device__ __forceinline__ float pair_alpha_raw(float Ns, float Ds, float lop) {
+    if constexpr (kEwa) return fast_ex2(__fadd_rn(Ns, lop));
     return fast_ex2(__fmaf_rn(Ns, fast_rcp(Ds), lop));
 }
 

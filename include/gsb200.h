@@ -334,6 +334,48 @@ GSB_API int gsb_adam_step(const GsbAdamGroup *groups, uint32_t n_groups, gsb_str
 GSB_API int gsb_adam_step_dynamic(const GsbAdamGroup *groups, uint32_t n_groups, const float *dynamic_scalars,
                                   gsb_stream_t stream);
 
+/* ---- the reference's default rasterizer ("fastgs", EWA splatting of 2-D conics) ----------------------
+ * fast_gs::rasterization::forward / backward (fastgs/rasterization/src/forward.cu:15-199, src/backward.cu:14-116;
+ * API fastgs/rasterization/include/rasterization_api.h:25-75 -> include/fastgs/rasterization_api.h + shim/FastGs.cpp).
+ * RAW parameters in (log-scales, un-normalised (w,x,y,z) quaternions, logit opacities, sh0 [N,1,3], shN [N,rest,3]),
+ * image [3,H,W] and alpha [1,H,W] out (no background: the caller composites it, fast_rasterizer.cpp:71).
+ * The three opaque buffers play the role of the reference's per_primitive / per_tile / per_instance blobs: the caller
+ * allocates them (sizes below; the instance buffer holds n_instances int32), keeps them from forward to backward and
+ * never looks inside.  Forward is two calls because the instance count sizes the third buffer:
+ *   gsb_fastgs_forward_plan   per-primitive set-up, depth order, tile histogram; *n_instances_out (DEVICE or PINNED HOST
+ *                             int64, written asynchronously on `stream`) = number of (primitive, tile) instances
+ *   gsb_fastgs_forward_blend  instances placed in (tile, depth) order, blended; `capacity` = entries of `instances`
+ *                             (>= n_instances for an exact result; smaller capacities drop the farthest-sorted slots)
+ *   gsb_fastgs_backward       blend gradient + the set-up's chain rule; writes EVERY element of the six gradients
+ *                             (the reference zero-fills them first), grad_w2c [4,4] if non-NULL, and adds to
+ *                             densification_info [2,N] if non-NULL (kernels_backward.cuh:252-255). */
+typedef struct GsbFastgsView {
+    const float *w2c;          /* [4,4] world->camera, row-major, DEVICE */
+    const float *cam_position; /* [3] DEVICE */
+    uint32_t width, height;
+    float focal_x, focal_y, center_x, center_y, near_plane, far_plane;
+    uint32_t active_sh_bases;     /* 1, 4, 9 or 16 */
+    uint32_t total_bases_sh_rest; /* rows of shN per primitive */
+} GsbFastgsView;
+GSB_API size_t gsb_fastgs_primitive_bytes(uint32_t N, uint32_t width, uint32_t height);
+GSB_API size_t gsb_fastgs_tile_bytes(uint32_t width, uint32_t height);
+GSB_API int gsb_fastgs_forward_plan(uint32_t N, const float *means, const float *scales_raw,
+                                    const float *rotations_raw /*16-byte aligned*/, const float *opacities_raw,
+                                    const float *sh0, const float *shN, const GsbFastgsView *view, void *per_primitive,
+                                    size_t per_primitive_bytes, void *per_tile, size_t per_tile_bytes,
+                                    int64_t *n_instances_out, gsb_stream_t stream);
+GSB_API int gsb_fastgs_forward_blend(uint32_t N, const GsbFastgsView *view, void *per_primitive,
+                                     size_t per_primitive_bytes, void *per_tile, size_t per_tile_bytes, int32_t *instances,
+                                     uint64_t capacity, float *image, float *alpha, gsb_stream_t stream);
+GSB_API int gsb_fastgs_backward(uint32_t N, const float *means, const float *scales_raw, const float *rotations_raw,
+                                const float *shN, const GsbFastgsView *view,
+                                void *per_primitive, size_t per_primitive_bytes, const void *per_tile,
+                                size_t per_tile_bytes, const int32_t *instances, uint64_t capacity, const float *alpha,
+                                const float *grad_image, const float *grad_alpha, float *grad_means,
+                                float *grad_scales_raw, float *grad_rotations_raw /*16-byte aligned*/,
+                                float *grad_opacities_raw, float *grad_sh0, float *grad_shN, float *grad_w2c /*nullable*/,
+                                float *densification_info /*nullable*/, gsb_stream_t stream);
+
 /* ---- link-surface ops used by the densification strategies -------------------------
  * gsplat::quats_to_rotmats (Ops.h:46-48, QuatToRotmatCUDA.cu:14-39): [N,4] -> [N,3,3] */
 GSB_API int gsb_quat_to_rotmat(uint32_t N, const float *quats, float *rotmats, gsb_stream_t stream);

@@ -89,3 +89,23 @@ def scene_small(N=2000, width=200, height=120, sh_degree=3, seed=7, view=None):
         eye = np.array([3.0 * np.sin(ang), 0.2, 3.0 - 3.0 * np.cos(ang)])
         viewmat = look_at(eye, (0.0, 0.0, 3.0))
     return _finish(rng, N, sh_degree, means, scales, width, height, 160.0, 170.0, viewmat=viewmat)
+
+
+def fastgs_inputs(scene: dict, seed: int = 3) -> dict:
+    """The RAW parameters the reference's fastgs rasterizer takes (fast_rasterizer.cpp:24-54) for a scene dict:
+    log-scales, un-normalised quaternions, logit opacities, sh0 / shN split, w2c and the camera position."""
+    rng = np.random.default_rng(seed)
+    n = scene["means"].shape[0]
+    sh = scene["sh_coeffs"]
+    V = scene["viewmats"][0].astype(np.float64)
+    Ks = scene["Ks"][0]
+    qscale = (rng.random((n, 1), dtype=np.float32) * 1.5 + 0.5).astype(np.float32)
+    o = scene["opacities"].astype(np.float64)
+    return dict(
+        means=scene["means"], scales_raw=np.log(scene["scales"]).astype(np.float32),
+        rotations_raw=(scene["quats"] * qscale).astype(np.float32),
+        opacities_raw=np.log(o / (1.0 - o)).astype(np.float32).reshape(n, 1),
+        sh0=np.ascontiguousarray(sh[:, :1, :]), shN=np.ascontiguousarray(sh[:, 1:, :]),
+        w2c=scene["viewmats"][0].copy(), cam_position=(-V[:3, :3].T @ V[:3, 3]).astype(np.float32),
+        active_sh_bases=(scene["sh_degree"] + 1) ** 2, width=scene["width"], height=scene["height"],
+        fx=float(Ks[0, 0]), fy=float(Ks[1, 1]), cx=float(Ks[0, 2]), cy=float(Ks[1, 2]), near_plane=0.01, far_plane=1e10)

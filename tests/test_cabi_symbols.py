@@ -20,7 +20,8 @@ def test_header_declares_expected_entry_points():
     names = _declared()
     for n in ("gsb_projection_ut", "gsb_sh_fwd", "gsb_sh_bwd", "gsb_isect_count", "gsb_isect_emit", "gsb_isect_sort", "gsb_isect_plan", "gsb_isect_emit_planned",
               "gsb_isect_offsets", "gsb_raster_fwd", "gsb_raster_bwd", "gsb_quat_to_rotmat", "gsb_relocation",
-              "gsb_add_noise"):
+              "gsb_add_noise", "gsb_fastgs_primitive_bytes", "gsb_fastgs_tile_bytes", "gsb_fastgs_forward_plan",
+              "gsb_fastgs_forward_blend", "gsb_fastgs_backward"):
         assert n in names
 
 
@@ -61,6 +62,9 @@ def test_shim_exports_reference_operator_symbols(pkg):
                "quats_to_rotmats", "relocation", "add_noise", "projection_ut_3dgs_fused",
                "rasterize_to_pixels_from_world_3dgs_fwd", "rasterize_to_pixels_from_world_3dgs_bwd"):
         assert f"gsplat::{fn}(" in out, fn
+    # the reference's fastgs API (fastgs/rasterization/include/rasterization_api.h:25-75)
+    for fn in ("forward_wrapper", "backward_wrapper"):
+        assert f"fast_gs::rasterization::{fn}(" in out, fn
 
 
 def test_native_library_loads_and_fails_loudly_without_gpu(native):

@@ -184,3 +184,70 @@ def test_shim_rejects_cpu_tensors_like_the_reference(pkg):
     with pytest.raises(RuntimeError, match="CUDA"):
         pkg.default_backend().spherical_harmonics_bwd_views(3, means, torch.zeros(1, 3), torch.randn(N, 16, 3),
                                                            torch.randn(1, N, 3), torch.zeros(N, 3))
+
+
+class GsbFastgsView(C.Structure):
+    _fields_ = [("w2c", C.c_void_p), ("cam_position", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32),
+                ("focal_x", C.c_float), ("focal_y", C.c_float), ("center_x", C.c_float), ("center_y", C.c_float),
+                ("near_plane", C.c_float), ("far_plane", C.c_float), ("active_sh_bases", C.c_uint32),
+                ("total_bases_sh_rest", C.c_uint32)]
+
+
+def fastgs_view(active=16, rest=15, w=64, h=48):
+    v = GsbFastgsView()
+    v.w2c, v.cam_position = PTR.value, PTR.value
+    v.width, v.height = w, h
+    v.focal_x = v.focal_y = 50.0
+    v.center_x, v.center_y = w / 2, h / 2
+    v.near_plane, v.far_plane = 0.01, 1e10
+    v.active_sh_bases, v.total_bases_sh_rest = active, rest
+    return v
+
+
+def test_fastgs_argument_validation(lib):
+    """SURVEY.md 8 f4 entry points (gsb_fastgs_*): view / buffer checks run before anything touches the device."""
+    lib.gsb_fastgs_primitive_bytes.restype = C.c_size_t
+    lib.gsb_fastgs_tile_bytes.restype = C.c_size_t
+    pb = lib.gsb_fastgs_primitive_bytes(u32(100), u32(64), u32(48))
+    tb = lib.gsb_fastgs_tile_bytes(u32(64), u32(48))
+    assert pb >= 100 * (64 + 64 + 4 + 8 + 4 + 16 + 8) and pb % 256 == 0
+    assert tb >= (4 * 3 + 1) * 4 + 64 * 48 * 4
+    assert lib.gsb_fastgs_primitive_bytes(u32(200), u32(64), u32(48)) > pb
+    n_out = np.zeros(1, np.int64)
+    NOUT = C.c_void_p(n_out.ctypes.data)
+    v = fastgs_view()
+
+    def plan(view, prim=PTR, prim_bytes=pb, tile=PTR, tile_bytes=tb, nout=NOUT):
+        return lib.gsb_fastgs_forward_plan(u32(100), PTR, PTR, PTR, PTR, PTR, PTR, view, prim, sz(prim_bytes), tile,
+                                           sz(tile_bytes), nout, NULL)
+
+    assert plan(None) == E_INVALID
+    assert plan(C.byref(fastgs_view(active=5))) == E_INVALID            # not a full SH degree
+    assert plan(C.byref(fastgs_view(active=16, rest=3))) == E_INVALID   # more active bases than stored
+    assert plan(C.byref(fastgs_view(w=0))) == E_INVALID
+    assert plan(C.byref(v), nout=NULL) == E_INVALID
+    assert plan(C.byref(v), prim_bytes=1024) == E_WORKSPACE
+    assert plan(C.byref(v), tile_bytes=16) == E_WORKSPACE
+    assert plan(C.byref(v), prim=NULL) == E_WORKSPACE
+    big = np.zeros(pb + 512, np.uint8)
+    aligned = (big.ctypes.data + 255) & ~255
+    assert plan(C.byref(v), prim=C.c_void_p(aligned + 4)) == E_WORKSPACE  # misaligned
+    assert lib.gsb_fastgs_forward_blend(u32(100), C.byref(v), PTR, sz(pb), PTR, sz(tb), NULL, u64(10), PTR, PTR,
+                                        NULL) == E_INVALID              # capacity without an instance buffer
+    assert lib.gsb_fastgs_forward_blend(u32(100), C.byref(v), PTR, sz(pb), PTR, sz(tb), PTR, u64(10), NULL, PTR,
+                                        NULL) == E_INVALID
+    # backward with N == 0 is a no-op; missing gradients are rejected
+    assert lib.gsb_fastgs_backward(u32(0), NULL, NULL, NULL, NULL, C.byref(v), NULL, sz(0), NULL, sz(0), NULL, u64(0), NULL,
+                                   NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL, NULL) == OK
+    assert lib.gsb_fastgs_backward(u32(100), PTR, PTR, PTR, PTR, C.byref(v), PTR, sz(pb), PTR, sz(tb), PTR, u64(10), PTR, PTR,
+                                   PTR, NULL, PTR, PTR, PTR, PTR, PTR, NULL, NULL, NULL) == E_INVALID
+
+
+def test_fastgs_shim_rejects_cpu_tensors(pkg):
+    import torch
+    pkg.load()
+    N = 8
+    with pytest.raises(RuntimeError, match="CUDA"):
+        torch.ops.gsplat_b200.fastgs_forward(torch.randn(N, 3), torch.randn(N, 3), torch.randn(N, 4), torch.randn(N, 1),
+                                             torch.randn(N, 1, 3), torch.randn(N, 15, 3), torch.eye(4), torch.zeros(3), 16,
+                                             64, 48, 50.0, 50.0, 32.0, 24.0, 0.01, 1e10)

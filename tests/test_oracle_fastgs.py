@@ -1,0 +1,107 @@
+"""CPU tests of the fastgs (EWA) oracle, SURVEY.md 8 f4 (oracle/fastgs_oracle.c).
+
+The reference holds no test vectors for this path; the oracle is pinned to the reference's own kernels on the GPU box
+(tests/test_gpu_fastgs.py).  Here: self-consistency -- the analytic backward against central differences of the smooth
+float64 build, float32 against float64, and the structural properties of the forward."""
+import numpy as np
+import pytest
+
+import scenes
+from oracle import fastgs_oracle as fgo
+
+
+def _scene(n=60, w=72, h=56, deg=3, view=1, seed=5):
+    sc = scenes.scene_small(N=n, width=w, height=h, sh_degree=deg, seed=seed, view=view)
+    return scenes.fastgs_inputs(sc)
+
+
+def _loss_weights(inp, seed=0):
+    rng = np.random.default_rng(seed)
+    return (rng.standard_normal((3, inp["height"], inp["width"])).astype(np.float32),
+            rng.standard_normal((1, inp["height"], inp["width"])).astype(np.float32))
+
+
+def _render(inp, precision, **kw):
+    args = {k: inp[k] for k in ("means", "scales_raw", "rotations_raw", "opacities_raw", "sh0", "shN", "w2c",
+                                 "cam_position", "active_sh_bases", "width", "height", "fx", "fy", "cx", "cy",
+                                 "near_plane", "far_plane")}
+    return fgo.render(**args, precision=precision, **kw)
+
+
+@pytest.mark.parametrize("deg", [0, 1, 2, 3])
+def test_backward_matches_central_differences(deg):
+    inp = _scene(n=40, deg=deg)
+    gi, ga = _loss_weights(inp)
+    out = _render(inp, "f64s", grad_image=gi, grad_alpha=ga, want_w2c_grad=True)
+
+    def loss(x):
+        o = _render(x, "f64s")
+        return float((o["image"].astype(np.float64) * gi).sum() + (o["alpha"].astype(np.float64) * ga).sum())
+
+    rng = np.random.default_rng(1)
+    eps = 2.0 ** -9  # exactly representable steps: the interface arrays are float32, outputs float32
+    for key, gkey in (("means", "grad_means"), ("scales_raw", "grad_scales_raw"), ("rotations_raw", "grad_rotations_raw"),
+                      ("opacities_raw", "grad_opacities_raw"), ("sh0", "grad_sh0"), ("shN", "grad_shN"), ("w2c", "grad_w2c")):
+        if inp[key].size == 0:
+            continue
+        d = rng.standard_normal(inp[key].shape).astype(np.float32)
+        if key == "w2c":
+            d[3] = 0  # the last row is not a parameter
+            d[:3, :3] *= 0.05
+        d = (np.round(d * 64) / 64).astype(np.float32)
+        step = np.float32(eps * (0.05 if key in ("means", "w2c") else 1.0))
+        plus, minus = dict(inp), dict(inp)
+        plus[key] = (inp[key] + step * d).astype(np.float32)
+        minus[key] = (inp[key] - step * d).astype(np.float32)
+        if key == "w2c":  # the camera position is not tied to w2c in this API: keep it fixed
+            pass
+        actual = (plus[key].astype(np.float64) - minus[key].astype(np.float64))
+        fd = (loss(plus) - loss(minus))
+        an = float((out[gkey].reshape(actual.shape) * actual).sum())
+        # the rendered outputs are float32: the difference of two losses carries ~1e-7 * |loss| of rounding
+        scale = max(abs(an), 1e-3)
+        assert abs(fd - an) <= 2e-2 * scale + 2e-4, (key, fd, an)
+
+
+def test_float32_agrees_with_float64():
+    inp = _scene(n=300, w=120, h=88)
+    gi, ga = _loss_weights(inp)
+    a = _render(inp, "f32", grad_image=gi, grad_alpha=ga)
+    b = _render(inp, "f64", grad_image=gi, grad_alpha=ga)
+    assert np.abs(a["image"] - b["image"]).max() < 5e-3  # a threshold may flip a single contribution (<= 1/255 * colour)
+    assert np.mean(np.abs(a["image"] - b["image"]) > 1e-4) < 5e-3
+    for k in ("grad_means", "grad_scales_raw", "grad_rotations_raw", "grad_opacities_raw", "grad_sh0", "grad_shN"):
+        den = np.linalg.norm(b[k]) + 1e-12
+        assert np.linalg.norm(a[k] - b[k]) / den < 2e-2, k
+
+
+def test_forward_properties():
+    inp = _scene(n=200, w=100, h=70)
+    out = _render(inp, "f32")
+    img, al = out["image"], out["alpha"][0]
+    assert img.shape == (3, 70, 100) and al.shape == (70, 100)
+    assert (al >= 0).all() and (al <= 1 - 1e-4 + 1e-6).all()  # transmittance never drops below 1e-4
+    assert (img >= 0).all()  # colours are clamped at zero before blending
+    assert out["n_instances"] == int(out["n_touched"].sum())
+    # a primitive behind the near plane or with negligible opacity is culled
+    far = dict(inp)
+    far["opacities_raw"] = np.full_like(inp["opacities_raw"], -12.0)
+    o2 = _render(far, "f32")
+    assert o2["n_instances"] == 0 and not o2["image"].any() and not o2["alpha"].any()
+    # permuting the primitives does not change the picture (order is by depth)
+    perm = np.random.default_rng(0).permutation(inp["means"].shape[0])
+    p = dict(inp)
+    for k in ("means", "scales_raw", "rotations_raw", "opacities_raw", "sh0", "shN"):
+        p[k] = np.ascontiguousarray(inp[k][perm])
+    o3 = _render(p, "f32")
+    assert np.abs(o3["image"] - img).max() < 1e-5
+
+
+def test_densification_info_accumulates():
+    inp = _scene(n=50)
+    gi, ga = _loss_weights(inp)
+    dens = np.zeros((2, inp["means"].shape[0]), np.float32)
+    out = _render(inp, "f32", grad_image=gi, grad_alpha=ga, densification_info=dens)
+    d = out["densification_info"]
+    vis = out["n_touched"] > 0
+    assert (d[0][vis] == 1).all() and (d[0][~vis] == 0).all() and (d[1] >= 0).all()
