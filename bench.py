@@ -49,7 +49,8 @@ UNIT = "Gaussians/s"
 CSRC = os.path.join(ROOT, "gaussian-splatting-cuda_b200", "csrc")
 KERNEL_NAMES = ("projection_ut", "sh_fwd", "isect_count", "isect_depth_sort", "isect_runs", "isect_tile_hist",
                 "isect_colscan", "isect_emit", "isect_repair", "isect_keys", "isect_sort", "isect_offsets", "raster_prep", "raster_fwd", "raster_bwd", "raster_finalize", "sh_bwd",
-                "sh_bwd_views", "fused_front", "fused_back", "ssim_l1_fwd", "ssim_l1_bwd", "adam_step")
+                "sh_bwd_views", "fused_front", "fused_back", "ssim_l1_fwd", "ssim_l1_bwd", "adam_step",
+                "fgs_front", "ewa_blend_fwd", "ewa_blend_bwd", "fgs_back")
 WORKLOADS = {
     "A": "10k synthetic Gaussians, 256x256, SH deg 0, 1 camera (BASELINE.json configs[0])",
     "B": "1M synthetic Gaussians, 1920x1080, SH deg 3, 16x16 tiles, fwd+bwd on 1xB200 (BASELINE.json configs[1])",

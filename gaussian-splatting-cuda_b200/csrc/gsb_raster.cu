@@ -14,7 +14,8 @@
 //             batch b+1 overlaps the blending of batch b.  Per pair: MUFU-free rejection test,
 //             then warp-vote: only warps with a surviving lane pay for rcp/ex2 and the colour row.
 //             A warp whose 64 pixels are saturated stops blending; the CTA leaves when all are.
-//   bwd       same tiling, back-to-front from the CTA-wide max(last_ids); 15 moments per pair are
+//   bwd       same tiling, back-to-front from the CTA-wide max(last_ids), three-stage ring released by per-warp
+//             mbarrier arrivals (no CTA barrier per batch); 15 moments per pair are
 //             summed over the thread's two pixels, reduced across the warp with a 16-value
 //             butterfly (16 shuffles instead of 15 x 5) and added to a per-Gaussian 64-byte row
 //             with one 16-lane red.global.add.f32.
@@ -408,8 +409,14 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
                                                                    const float *__restrict__ v_render_colors,
                                                                    const float *__restrict__ v_render_alphas,
                                                                    float *__restrict__ moments) {
-    __shared__ __align__(128) GaussRec s_rec[kStages][kBatch];
-    __shared__ __align__(8) uint64_t s_full[kStages];
+    // Three stages; a stage is filled through its "full" mbarrier (TMA byte count) and released through its "empty"
+    // mbarrier (one arrival per warp): no CTA-wide barrier in the loop, a warp with nothing to do in a batch runs ahead
+    // of its neighbours (measured against the two-stage / __syncthreads ring: 0.785 vs 0.799 ms at config B, 1.035 vs
+    // 1.061 ms at 6 M; 64-register / 8-CTA builds of either were slower: profiles/r2_experiments.md).
+    constexpr int kRing = 3;
+    __shared__ __align__(128) GaussRec s_rec[kRing][kBatch];
+    __shared__ __align__(8) uint64_t s_full[kRing];
+    __shared__ __align__(8) uint64_t s_empty[kRing];
     __shared__ int32_t s_warp_max[kTileThreads / 32];
     __shared__ CamModel s_cm;
     const uint32_t tile_id = blockIdx.x;
@@ -470,7 +477,7 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
     int32_t wmax = __reduce_max_sync(0xffffffffu, max(s.last0, s.last1));
     if ((tid & 31) == 0) s_warp_max[tid >> 5] = wmax;
     if (tid == 0) {
-        for (int st = 0; st < kStages; ++st) mbar_init(&s_full[st], 1);
+        for (int st = 0; st < kRing; ++st) { mbar_init(&s_full[st], 1); mbar_init(&s_empty[st], kTileThreads / 32); }
         mbar_fence_init();
     }
     __syncthreads();
@@ -486,22 +493,28 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
 
     int32_t gid_next = 0;
     {
-        const int32_t idx = hi - (int32_t)tid;
-        const int32_t gid = (idx >= range_start) ? p.flatten_ids[idx] : 0;
-        issue_batch(s_rec[0], &s_full[0], p.recs, gid, (uint32_t)min(total, kBatch));
-        const int32_t idx1 = idx - kBatch;
+#pragma unroll
+        for (int j = 0; j < kRing - 1; ++j) { // batches 0 .. kRing-2 in flight
+            const int32_t idx = hi - j * kBatch - (int32_t)tid;
+            const int32_t gid = (idx >= range_start) ? p.flatten_ids[idx] : 0;
+            if (j < n_batches) issue_batch(s_rec[j], &s_full[j], p.recs, gid, (uint32_t)min(total - j * kBatch, kBatch));
+        }
+        const int32_t idx1 = hi - (kRing - 1) * kBatch - (int32_t)tid;
         gid_next = (idx1 >= range_start) ? p.flatten_ids[idx1] : 0;
     }
 
     for (int32_t b = 0; b < n_batches; ++b) {
-        const int st = b & 1;
-        if (b + 1 < n_batches) {
-            const int32_t cnt1 = min(total - (b + 1) * kBatch, kBatch);
-            issue_batch(s_rec[st ^ 1], &s_full[st ^ 1], p.recs, gid_next, (uint32_t)cnt1);
-            const int32_t idx2 = hi - (b + 2) * kBatch - (int32_t)tid;
+        const int st = b % kRing;
+        const int32_t nb = b + kRing - 1;
+        if (nb < n_batches) {
+            const int sn = nb % kRing; // the stage batch b-1 used
+            if (b >= 1) mbar_wait(&s_empty[sn], (uint32_t)(((b - 1) / kRing) & 1));
+            const int32_t cnt1 = min(total - nb * kBatch, kBatch);
+            issue_batch(s_rec[sn], &s_full[sn], p.recs, gid_next, (uint32_t)cnt1);
+            const int32_t idx2 = hi - (nb + 1) * kBatch - (int32_t)tid;
             gid_next = (idx2 >= range_start) ? p.flatten_ids[idx2] : 0;
         }
-        mbar_wait(&s_full[st], (uint32_t)((b >> 1) & 1));
+        mbar_wait(&s_full[st], (uint32_t)((b / kRing) & 1));
 
         const int32_t cnt = min(total - b * kBatch, kBatch);
         const int32_t top = hi - b * kBatch; // sorted index of slot 0
@@ -536,7 +549,8 @@ __global__ void __launch_bounds__(kTileThreads) raster_bwd_kernel(const TilePara
             }
           }
         }
-        __syncthreads(); // stage `st` may be refilled by batch b+2
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(&s_empty[st]); // this warp is done with stage `st`
     }
 }
 

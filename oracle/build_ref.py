@@ -168,23 +168,33 @@ FASTGS = "/root/reference/fastgs"
 FASTGS_CU = ["rasterization/src/forward.cu", "rasterization/src/backward.cu", "rasterization/src/rasterization_api.cu"]
 
 
-def build_fastgs(verbose: bool = True) -> str | None:
+def build_fastgs(verbose: bool = True, gencode: str = "arch=compute_90,code=compute_90", so_name: str = "libfastgs_ref.so") -> str | None:
     """The reference's fastgs rasterizer, compiled unmodified from where it lies with its own flags
-    (fastgs/CMakeLists.txt:58: -O3 --use_fast_math --expt-relaxed-constexpr) for sm_100, plus the product's
+    (fastgs/CMakeLists.txt:58: -O3 --use_fast_math --expt-relaxed-constexpr), plus the product's
     shim/fastgs_binding.cpp compiled against the REFERENCE's rasterization_api.h: oracle/_ref/libfastgs_ref.so,
-    torch.ops.fastgs_ref.*  (the pin of oracle/fastgs_oracle.c and of the B200 path; the same-box GPU baseline)."""
+    torch.ops.fastgs_ref.*  (the pin of oracle/fastgs_oracle.c and of the B200 path; the same-box GPU baseline).
+
+    Target: compute_90 PTX, JIT-compiled for the B200 by the driver at load time -- NOT sm_100 SASS.  Built for sm_100
+    with this image's CUDA 12.9 CUB, the reference's tile sort (cub::DeviceRadixSort::SortPairs on 16-bit keys,
+    forward.cu:139-145) fails for more than a few hundred thousand instances: a cudaMemsetAsync inside CUB returns
+    "invalid argument", the keys stay unsorted, the bucket count is garbage and forward() asks for terabytes
+    (measured on the B200: 640x368 / 257 k instances fine, 1280x720 / 487 k instances not; compute-sanitizer log in
+    profiles/r2_experiments.md).  The same unmodified sources as compute_90 PTX make CUB select its sm_90 tuning and
+    run correctly at every size tested (1 M and 6 M Gaussians at 1080p); the reference's own kernels use no sm_100
+    feature, so nothing is lost on their side."""
     if not os.path.isdir(FASTGS):
         return None
     from torch.utils import cpp_extension as ce
 
     os.makedirs(OUT, exist_ok=True)
-    so = os.path.join(OUT, "libfastgs_ref.so")
+    so = os.path.join(OUT, so_name)
     binding = os.path.join(os.path.dirname(HERE), "gaussian-splatting-cuda_b200", "shim", "fastgs_binding.cpp")
     h = hashlib.sha256()
     for root, _, files in os.walk(os.path.join(FASTGS, "rasterization")):
         for f in sorted(files):
             h.update(open(os.path.join(root, f), "rb").read())
     h.update(open(binding, "rb").read())
+    h.update(gencode.encode())
     st = h.hexdigest()
     if os.path.exists(so) and os.path.exists(so + ".stamp") and open(so + ".stamp").read() == st:
         return so
@@ -192,11 +202,11 @@ def build_fastgs(verbose: bool = True) -> str | None:
     for i in [os.path.join(FASTGS, "rasterization", "include"), os.path.join(FASTGS, "utils")] + ce.include_paths():
         inc += ["-I", i]
     common = ["-O3", "-std=c++20", "-Xcompiler", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=1", "-ccbin", CXX, "-gencode",
-              "arch=compute_100,code=sm_100", "--expt-relaxed-constexpr", "--use_fast_math", "-DFGS_REFERENCE_LIBRARY",
+              gencode, "--expt-relaxed-constexpr", "--use_fast_math", "-DFGS_REFERENCE_LIBRARY",
               "-diag-suppress", "20012,186,221,177,550"]
 
     def compile_one(src: str):
-        obj = os.path.join(OUT, "fgs_" + os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        obj = os.path.join(OUT, "fgs_" + so_name + "_" + os.path.basename(src).rsplit(".", 1)[0] + ".o")
         if verbose:
             print("[build_ref] fastgs", os.path.basename(src), flush=True)
         p = subprocess.run([NVCC, "-c", src, "-o", obj, "-x", "cu"] + common + inc, stdout=subprocess.PIPE,
@@ -209,12 +219,12 @@ def build_fastgs(verbose: bool = True) -> str | None:
     with ThreadPoolExecutor(max_workers=4) as ex:
         objs = list(ex.map(compile_one, [os.path.join(FASTGS, f) for f in FASTGS_CU] + [binding]))
     tl = ce.library_paths()[0]
-    p = subprocess.run([NVCC, "-shared", "-o", so] + objs + ["-gencode", "arch=compute_100,code=sm_100", "-ccbin", CXX, "-L", tl,
+    p = subprocess.run([NVCC, "-shared", "-o", so] + objs + ["-gencode", gencode, "-ccbin", CXX, "-L", tl,
                         "-ltorch", "-ltorch_cpu", "-lc10", "-ltorch_cuda", "-lc10_cuda", "-Xlinker", "-rpath," + tl,
                         "-Xlinker", "-Bsymbolic"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if p.returncode != 0:
         sys.stderr.write(p.stdout[-6000:])
-        raise RuntimeError("linking oracle/_ref/libfastgs_ref.so failed")
+        raise RuntimeError(f"linking oracle/_ref/{so_name} failed")
     for o in objs:
         os.remove(o)
     with open(so + ".stamp", "w") as f:
