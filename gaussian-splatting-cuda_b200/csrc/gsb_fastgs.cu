@@ -32,11 +32,13 @@ namespace gsb {
 
 // gsb_intersect.cu
 size_t isect_plan_ewa_workspace(uint32_t N, uint32_t tile_width, uint32_t tile_height);
-int isect_plan_ewa(uint32_t N, int32_t *counts, const uint2 *boxes, const float *depths, const float4 *filt0,
-                   const float2 *filt1, uint32_t tile_width, uint32_t tile_height, int64_t *n_isects_out,
-                   int32_t *tile_offsets_out, void *plan_workspace, size_t plan_workspace_bytes, cudaStream_t s);
-int isect_emit_ewa(uint32_t N, const float *depths, uint32_t tile_width, uint32_t tile_height, uint64_t capacity,
-                   const void *plan_workspace, size_t plan_workspace_bytes, int32_t *flatten_ids, cudaStream_t s);
+int isect_plan_ewa(uint32_t N, int32_t *counts, const uint2 *boxes, const uint32_t *masks, const float *depths,
+                   const float4 *filt0, const float2 *filt1, uint32_t tile_width, uint32_t tile_height,
+                   int64_t *n_isects_out, int32_t *tile_offsets_out, void *plan_workspace, size_t plan_workspace_bytes,
+                   cudaStream_t s);
+int isect_emit_ewa(uint32_t N, const float4 *filt0, const float2 *filt1, const float *depths, uint32_t tile_width,
+                   uint32_t tile_height, uint64_t capacity, const void *plan_workspace, size_t plan_workspace_bytes,
+                   int32_t *flatten_ids, cudaStream_t s);
 // gsb_raster.cu
 int raster_ewa_fwd(uint32_t cap, const GaussRec *recs, uint32_t W, uint32_t H, const int32_t *tile_offsets,
                    const int32_t *flatten_ids, float *image, float *alpha, int32_t *last_ids, cudaStream_t s);
@@ -46,7 +48,7 @@ int raster_ewa_bwd(uint32_t cap, const GaussRec *recs, uint32_t W, uint32_t H, c
 
 constexpr int kFgsThreads = 128;
 constexpr float kDilation = 0.3f;        // rasterization_config.h:16
-constexpr uint32_t kSeqTiles = 16;       // boxes up to this many tiles are counted by their own lane
+constexpr uint32_t kSeqTiles = 32;       // boxes up to this many tiles are tested by their own lane: one mask bit per tile
 
 struct FgsParams {
     uint32_t N, rest, active; // rest = SH bases in shN per primitive, active = active bases including sh0
@@ -58,6 +60,7 @@ struct FgsParams {
     float *moments;
     int32_t *counts;
     uint2 *boxes;
+    uint32_t *masks; // tile-test results of boxes of up to 32 tiles (bit j = tile j of the box, row-major)
     float *depths;
     float4 *filt0;
     float2 *filt1;
@@ -220,13 +223,14 @@ __global__ void __launch_bounds__(kFgsThreads) fgs_front_kernel(const FgsParams 
     // exact number of tiles (kernels_forward.cuh:180-187, kernel_utils.cuh:141-209): small boxes by their own lane,
     // large ones by the whole warp
     const uint32_t area = active ? bw * bh : 0u;
-    uint32_t n_tiles = 0;
+    uint32_t n_tiles = 0, tmask = 0;
     if (area > 0 && area <= kSeqTiles) {
         uint32_t x = x0, y = y0;
         for (uint32_t j = 0; j < area; ++j) {
-            n_tiles += ewa_tile_contributes(flt, x, y) ? 1u : 0u;
+            tmask |= (ewa_tile_contributes(flt, x, y) ? 1u : 0u) << j;
             if (++x == x0 + bw) { x = x0; ++y; }
         }
+        n_tiles = __popc(tmask);
     }
     uint32_t big = __ballot_sync(0xffffffffu, area > kSeqTiles);
     while (big) {
@@ -250,6 +254,7 @@ __global__ void __launch_bounds__(kFgsThreads) fgs_front_kernel(const FgsParams 
     if (tid < cnt) {
         p.counts[g] = visible ? (int32_t)n_tiles : 0;
         p.boxes[g] = make_uint2(x0 | (y0 << 16), bw | (bh << 16));
+        p.masks[g] = tmask;
         p.depths[g] = depth;
         p.filt0[g] = make_float4(flt.mx, flt.my, flt.ca, flt.cb);
         p.filt1[g] = make_float2(flt.cc, flt.thr);
@@ -487,7 +492,7 @@ static inline size_t a256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 // layout of the per-primitive buffer (opaque to the caller, carried from forward to backward)
 struct PrimLayout {
-    size_t recs, moments, counts, boxes, depths, filt0, filt1, plan, plan_bytes, total;
+    size_t recs, moments, counts, boxes, masks, depths, filt0, filt1, plan, plan_bytes, total;
 };
 static PrimLayout prim_layout(uint32_t N, uint32_t gw, uint32_t gh) {
     PrimLayout l;
@@ -497,6 +502,7 @@ static PrimLayout prim_layout(uint32_t N, uint32_t gw, uint32_t gh) {
     l.moments = take((size_t)N * kMomFloats * 4);
     l.counts = take((size_t)N * 4);
     l.boxes = take((size_t)N * 8);
+    l.masks = take((size_t)N * 4);
     l.depths = take((size_t)N * 4);
     l.filt0 = take((size_t)N * 16);
     l.filt1 = take((size_t)N * 8);
@@ -541,6 +547,7 @@ static void fill_params(FgsParams &p, uint32_t N, const GsbFastgsView *v, const 
     p.moments = reinterpret_cast<float *>(prim + l.moments);
     p.counts = reinterpret_cast<int32_t *>(prim + l.counts);
     p.boxes = reinterpret_cast<uint2 *>(prim + l.boxes);
+    p.masks = reinterpret_cast<uint32_t *>(prim + l.masks);
     p.depths = reinterpret_cast<float *>(prim + l.depths);
     p.filt0 = reinterpret_cast<float4 *>(prim + l.filt0);
     p.filt1 = reinterpret_cast<float2 *>(prim + l.filt1);
@@ -602,7 +609,7 @@ extern "C" int gsb_fastgs_forward_plan(uint32_t N, const float *means, const flo
     }
     FgsParams q;
     fill_params(q, N, v, means, scales_raw, rotations_raw, opacities_raw, sh0, shN, prim, l);
-    return isect_plan_ewa(N, q.counts, q.boxes, q.depths, q.filt0, q.filt1, gw, gh, n_instances_out, tile_offsets,
+    return isect_plan_ewa(N, q.counts, q.boxes, q.masks, q.depths, q.filt0, q.filt1, gw, gh, n_instances_out, tile_offsets,
                           prim + l.plan, l.plan_bytes, s);
 }
 
@@ -624,7 +631,9 @@ extern "C" int gsb_fastgs_forward_blend(uint32_t N, const GsbFastgsView *view, v
     cudaStream_t s = as_stream(stream);
     char *prim = reinterpret_cast<char *>(per_primitive);
     char *tile = reinterpret_cast<char *>(per_tile);
-    if (int rc = isect_emit_ewa(N, reinterpret_cast<const float *>(prim + l.depths), gw, gh, capacity, prim + l.plan,
+    if (int rc = isect_emit_ewa(N, reinterpret_cast<const float4 *>(prim + l.filt0),
+                                reinterpret_cast<const float2 *>(prim + l.filt1),
+                                reinterpret_cast<const float *>(prim + l.depths), gw, gh, capacity, prim + l.plan,
                                 l.plan_bytes, instances, s))
         return rc;
     return raster_ewa_fwd((uint32_t)capacity, reinterpret_cast<const GaussRec *>(prim + l.recs), v->width, v->height,

@@ -214,13 +214,16 @@ struct RunTable {
     uint32_t *idx;  // flattened Gaussian index (camera * N + gaussian)
     uint2 *box;
     uint32_t *key;  // depth bits
-    // EWA path only: the run covers the tiles of its box that pass ewa_tile_contributes
-    float4 *f0;     // (mx, my, ca, cb)
-    float2 *f1;     // (cc, thr)
+    // EWA path only: the run covers the tiles of its box that pass ewa_tile_contributes.  For boxes of
+    // up to 32 tiles the front kernel has already evaluated the test: bit j of `mask` = tile j of the box (row-major)
+    // passes.  Larger boxes (rare) evaluate the test again from the per-primitive parameters.
+    uint32_t *mask;
+    const float4 *f0;     // per primitive: (mx, my, ca, cb)
+    const float2 *f1;     // per primitive: (cc, thr)
 };
-__device__ __forceinline__ EwaFilter run_filter(const RunTable &rt, uint32_t r) {
-    const float4 a = rt.f0[r];
-    const float2 b = rt.f1[r];
+__device__ __forceinline__ EwaFilter prim_filter(const RunTable &rt, uint32_t idx) {
+    const float4 a = rt.f0[idx];
+    const float2 b = rt.f1[idx];
     return EwaFilter{a.x, a.y, a.z, a.w, b.x, b.y};
 }
 
@@ -256,8 +259,7 @@ __global__ void __launch_bounds__(kSortThreads) runs_build_kernel(SortCtl *__res
                                                                   const uint2 *__restrict__ boxes, uint64_t n,
                                                                   uint32_t seg, uint32_t nblocks,
                                                                   const RunAcc *__restrict__ bsum, RunTable rt,
-                                                                  const float4 *__restrict__ filt0,
-                                                                  const float2 *__restrict__ filt1) {
+                                                                  const uint32_t *__restrict__ masks) {
     __shared__ RunAcc s_warp[kSortWarps];
     const bool odd = (radix_passes_done(ctl, 4) & 1) != 0;
     const uint32_t *perm = odd ? v1 : v0;
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(kSortThreads) runs_build_kernel(SortCtl *__res
             rt.idx[k] = idx;
             rt.box[k] = boxes[idx];
             rt.key[k] = keys[i];
-            if (filt0) { rt.f0[k] = filt0[idx]; rt.f1[k] = filt1[idx]; }
+            if (masks) rt.mask[k] = masks[idx];
         }
         carry += tot;
     }
@@ -460,7 +462,11 @@ __device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__r
                 const uint2 b = a.rt.box[r];
                 const uint32_t x0 = b.x & 0xffffu, y0 = b.x >> 16, w = b.y & 0xffffu, h = b.y >> 16;
                 cover = tx >= x0 && tx < x0 + w && ty >= y0 && ty < y0 + h && (!a.multi_cam || idx / a.N == cam);
-                if constexpr (kFilter) cover = cover && ewa_tile_contributes(run_filter(a.rt, r), tx, ty);
+                if constexpr (kFilter) {
+                    if (cover)
+                        cover = (w * h <= 32u) ? ((a.rt.mask[r] >> ((ty - y0) * w + (tx - x0))) & 1u) != 0u
+                                               : ewa_tile_contributes(prim_filter(a.rt, idx), tx, ty);
+                }
             }
             const uint32_t m = __ballot_sync(0xffffffffu, cover);
             const uint32_t pos = gstart + written + __popc(m & ((1u << lane) - 1u));
@@ -509,13 +515,12 @@ __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) 
     };
     for (uint32_t r0 = ra + (tid & ~31u); r0 < rb; r0 += kBinThreads) { // warp-uniform trip count
         const uint32_t r = r0 + lane;
-        uint32_t idx = 0, bx = 0, by = 0;
-        EwaFilter flt = {0.f, 0.f, 1.f, 0.f, 1.f, 0.f};
+        uint32_t idx = 0, bx = 0, by = 0, tmask = 0xffffffffu;
         if (r < rb) {
             idx = a.rt.idx[r];
             const uint2 b = a.rt.box[r];
             bx = b.x; by = b.y;
-            if constexpr (kFilter) flt = run_filter(a.rt, r);
+            if constexpr (kFilter) tmask = a.rt.mask[r];
         }
         const uint32_t w = by & 0xffffu, h = by >> 16, n = w * h; // 0 for the lanes past the chunk
         const uint32_t x0 = bx & 0xffffu, y0 = bx >> 16;
@@ -530,7 +535,7 @@ __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) 
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     bool take = j + u < n;
-                    if constexpr (kFilter) take = take && ewa_tile_contributes(flt, x, y);
+                    if constexpr (kFilter) take = take && ((tmask >> (j + u)) & 1u);
                     g[u] = take ? cam_base + y * a.tile_width + x - a.t_lo : 0xffffffffu;
                     if (++x == x0 + w) { x = x0; ++y; }
                 }
@@ -551,12 +556,8 @@ __global__ void __launch_bounds__(kBinThreads) tile_bin_kernel(const BinArgs a) 
             const uint32_t bidx = __shfl_sync(0xffffffffu, idx, src), bcam = __shfl_sync(0xffffffffu, cam_base, src);
             const uint32_t bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
             const uint32_t bw = __shfl_sync(0xffffffffu, w, src), bn = __shfl_sync(0xffffffffu, n, src);
-            EwaFilter bf = flt;
-            if constexpr (kFilter) {
-                bf.mx = __shfl_sync(0xffffffffu, flt.mx, src); bf.my = __shfl_sync(0xffffffffu, flt.my, src);
-                bf.ca = __shfl_sync(0xffffffffu, flt.ca, src); bf.cb = __shfl_sync(0xffffffffu, flt.cb, src);
-                bf.cc = __shfl_sync(0xffffffffu, flt.cc, src); bf.thr = __shfl_sync(0xffffffffu, flt.thr, src);
-            }
+            EwaFilter bf = {0.f, 0.f, 1.f, 0.f, 1.f, 0.f};
+            if constexpr (kFilter) bf = prim_filter(a.rt, bidx); // one broadcast load per warp
             for (uint32_t j = lane; j < bn; j += 32) {
                 const uint32_t dy = j / bw, dx = j - dy * bw;
                 if constexpr (kFilter) {
@@ -823,7 +824,7 @@ static BinPlan bin_plan(uint32_t C, uint32_t N, uint32_t tile_width, uint32_t ti
 
 // Workspace of the plan; everything the emit needs afterwards lives here too.
 struct PlanWs {
-    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, rt_f0, rt_f1, M, seg, tot, toff,
+    size_t ctl, keys0, keys1, vals0, vals1, boxes, hist, bsum, rt_end, rt_idx, rt_box, rt_key, rt_mask, M, seg, tot, toff,
         chunk_run, total;
 };
 static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp, bool filter = false) {
@@ -837,7 +838,7 @@ static PlanWs plan_ws(uint64_t n, const BinPlan &b, const SegPlan &sp, bool filt
     w.hist = take((size_t)sp.nblocks * kRadixBins * 4);
     w.bsum = take((size_t)sp.nblocks * sizeof(RunAcc));
     w.rt_end = take(n * 4); w.rt_idx = take(n * 4); w.rt_box = take(n * 8); w.rt_key = take(n * 4);
-    w.rt_f0 = filter ? take(n * 16) : 0; w.rt_f1 = filter ? take(n * 8) : 0;
+    w.rt_mask = filter ? take(n * 4) : 0;
     w.M = take((size_t)b.P * b.T_total * 4);
     w.seg = take((size_t)b.S * b.T_total * 4);
     w.tot = take((size_t)b.T_total * 4);
@@ -969,8 +970,9 @@ struct PlanSource {
     const int32_t *radii = nullptr;
     uint32_t tile_size = 16;
     const uint2 *boxes = nullptr;   // EWA
-    const float4 *filt0 = nullptr;  // EWA
-    const float2 *filt1 = nullptr;  // EWA
+    const uint32_t *masks = nullptr; // EWA: tile-test results of boxes of up to 32 tiles
+    const float4 *filt0 = nullptr;   // EWA: test parameters (for the larger boxes)
+    const float2 *filt1 = nullptr;   // EWA
     bool ewa() const { return boxes != nullptr; }
 };
 
@@ -988,7 +990,8 @@ static int plan_impl(uint32_t C, uint32_t N, const PlanSource &src, const float 
         return GSB_OK;
     }
     if (!depths || !tiles_per_gauss) return GSB_E_INVALID;
-    if (src.ewa() ? (!src.filt0 || !src.filt1) : (!src.means2d || !src.radii || src.tile_size == 0)) return GSB_E_INVALID;
+    if (src.ewa() ? (!src.filt0 || !src.filt1 || !src.masks) : (!src.means2d || !src.radii || src.tile_size == 0))
+        return GSB_E_INVALID;
     const uint32_t tile_n_bits = bit_width_u32(tile_width * tile_height);
     const uint32_t cam_n_bits = bit_width_u32(C);
     if (tile_n_bits + cam_n_bits > 32) return GSB_E_INVALID; // Intersect.cpp:50
@@ -1007,8 +1010,7 @@ static int plan_impl(uint32_t C, uint32_t N, const PlanSource &src, const float 
     RunAcc *bsum = reinterpret_cast<RunAcc *>(base + w.bsum);
     RunTable rt{reinterpret_cast<uint32_t *>(base + w.rt_end), reinterpret_cast<uint32_t *>(base + w.rt_idx),
                 reinterpret_cast<uint2 *>(base + w.rt_box), reinterpret_cast<uint32_t *>(base + w.rt_key),
-                src.ewa() ? reinterpret_cast<float4 *>(base + w.rt_f0) : nullptr,
-                src.ewa() ? reinterpret_cast<float2 *>(base + w.rt_f1) : nullptr};
+                src.ewa() ? reinterpret_cast<uint32_t *>(base + w.rt_mask) : nullptr, src.filt0, src.filt1};
     uint32_t *M = reinterpret_cast<uint32_t *>(base + w.M);
     uint32_t *seg = reinterpret_cast<uint32_t *>(base + w.seg);
     {
@@ -1032,7 +1034,7 @@ static int plan_impl(uint32_t C, uint32_t N, const PlanSource &src, const float 
         GSB_LAUNCH_CHECK();
         runs_build_kernel<<<sp.nblocks, kSortThreads, 0, s>>>(ctl, v0, v1, k0, k1, tiles_per_gauss,
                                                              src.ewa() ? src.boxes : boxes, n, sp.seg, sp.nblocks, bsum,
-                                                             rt, src.filt0, src.filt1);
+                                                             rt, src.masks);
         GSB_LAUNCH_CHECK();
     }
     // device or pinned-host destination alike
@@ -1075,7 +1077,8 @@ static int plan_impl(uint32_t C, uint32_t N, const PlanSource &src, const float 
     return GSB_OK;
 }
 
-static int emit_impl(uint32_t C, uint32_t N, bool filter, const float *depths, uint32_t tile_width, uint32_t tile_height,
+static int emit_impl(uint32_t C, uint32_t N, bool filter, const float4 *filt0, const float2 *filt1, const float *depths,
+                     uint32_t tile_width, uint32_t tile_height,
                      uint64_t n_isects, const void *plan_workspace, size_t plan_workspace_bytes, int64_t *isect_ids,
                      int32_t *flatten_ids, cudaStream_t s) {
     const uint64_t n = (uint64_t)C * N;
@@ -1090,8 +1093,7 @@ static int emit_impl(uint32_t C, uint32_t N, bool filter, const float *depths, u
     BinArgs a;
     a.rt = RunTable{reinterpret_cast<uint32_t *>(base + w.rt_end), reinterpret_cast<uint32_t *>(base + w.rt_idx),
                     reinterpret_cast<uint2 *>(base + w.rt_box), reinterpret_cast<uint32_t *>(base + w.rt_key),
-                    filter ? reinterpret_cast<float4 *>(base + w.rt_f0) : nullptr,
-                    filter ? reinterpret_cast<float2 *>(base + w.rt_f1) : nullptr};
+                    filter ? reinterpret_cast<uint32_t *>(base + w.rt_mask) : nullptr, filt0, filt1};
     a.ctl = reinterpret_cast<const SortCtl *>(base + w.ctl);
     a.N = N; a.n_tiles = tile_width * tile_height; a.tile_width = tile_width;
     a.multi_cam = C > 1 ? 1u : 0u;
@@ -1131,17 +1133,18 @@ static int emit_impl(uint32_t C, uint32_t N, bool filter, const float *depths, u
 size_t isect_plan_ewa_workspace(uint32_t N, uint32_t tile_width, uint32_t tile_height) {
     return plan_ws(N, bin_plan(1, N, tile_width, tile_height), seg_plan(N), true).total;
 }
-int isect_plan_ewa(uint32_t N, int32_t *counts, const uint2 *boxes, const float *depths, const float4 *filt0,
-                   const float2 *filt1, uint32_t tile_width, uint32_t tile_height, int64_t *n_isects_out,
+int isect_plan_ewa(uint32_t N, int32_t *counts, const uint2 *boxes, const uint32_t *masks, const float *depths,
+                   const float4 *filt0, const float2 *filt1, uint32_t tile_width, uint32_t tile_height, int64_t *n_isects_out,
                    int32_t *tile_offsets_out, void *plan_workspace, size_t plan_workspace_bytes, cudaStream_t s) {
     PlanSource src;
-    src.boxes = boxes; src.filt0 = filt0; src.filt1 = filt1;
+    src.boxes = boxes; src.masks = masks; src.filt0 = filt0; src.filt1 = filt1;
     return plan_impl(1, N, src, depths, tile_width, tile_height, counts, n_isects_out, tile_offsets_out, 1, plan_workspace,
                      plan_workspace_bytes, s);
 }
-int isect_emit_ewa(uint32_t N, const float *depths, uint32_t tile_width, uint32_t tile_height, uint64_t capacity,
-                   const void *plan_workspace, size_t plan_workspace_bytes, int32_t *flatten_ids, cudaStream_t s) {
-    return emit_impl(1, N, true, depths, tile_width, tile_height, capacity, plan_workspace, plan_workspace_bytes, nullptr,
+int isect_emit_ewa(uint32_t N, const float4 *filt0, const float2 *filt1, const float *depths, uint32_t tile_width,
+                   uint32_t tile_height, uint64_t capacity, const void *plan_workspace, size_t plan_workspace_bytes,
+                   int32_t *flatten_ids, cudaStream_t s) {
+    return emit_impl(1, N, true, filt0, filt1, depths, tile_width, tile_height, capacity, plan_workspace, plan_workspace_bytes, nullptr,
                      flatten_ids, s);
 }
 } // namespace gsb
@@ -1161,7 +1164,7 @@ extern "C" int gsb_isect_emit_planned(uint32_t C, uint32_t N, const float *depth
                                       uint32_t tile_height, uint64_t n_isects, const void *plan_workspace,
                                       size_t plan_workspace_bytes, int64_t *isect_ids /*nullable*/, int32_t *flatten_ids,
                                       gsb_stream_t stream) {
-    return gsb::emit_impl(C, N, false, depths, tile_width, tile_height, n_isects, plan_workspace, plan_workspace_bytes,
+    return gsb::emit_impl(C, N, false, nullptr, nullptr, depths, tile_width, tile_height, n_isects, plan_workspace, plan_workspace_bytes,
                           isect_ids, flatten_ids, gsb::as_stream(stream));
 }
 

@@ -17,15 +17,17 @@ for K in raster_bwd_kernel raster_fwd_kernel tile_bin_kernel; do
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:${K} -s 4 -c 2 -f -o $O/prof_${K}_${TAG} \
     python bench.py --steps 1 --warmup 1 --quick > $O/ncu_${K}_${TAG}.log 2>&1
 done
-for K in fgs_front_kernel fgs_back_kernel; do
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:${K} -s 2 -c 1 -f -o $O/prof_${K}_${TAG} \
-    python bench.py --steps 1 --warmup 1 --quick > $O/ncu_${K}_${TAG}.log 2>&1
+# fastgs path: front / back kernels, the EWA instantiations of the blend kernels, the filtered walks
+timeout 120 python profiles/tools/fastgs_prof.py --config B > $O/${TAG}_fastgsB.json 2> $O/${TAG}_fastgsB.err
+timeout 120 python profiles/tools/fastgs_prof.py --config D > $O/${TAG}_fastgsD.json 2> /dev/null
+for K in fgs_front_kernel fgs_back_kernel raster_bwd_kernel raster_fwd_kernel tile_bin_kernel; do
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:${K} -s 2 -c 1 -f -o $O/prof_fastgs_${K}_${TAG} \
+    python profiles/tools/fastgs_prof.py --iters 1 > $O/ncu_fastgs_${K}_${TAG}.log 2>&1
 done
-# the EWA instantiations of the blend kernels (template arguments <false, true>): the 2nd..3rd launches of the fastgs block
-for K in raster_bwd_kernel raster_fwd_kernel; do
-timeout 300 ncu --set full --clock-control none --import-source on -k "regex:${K}<.*1>|${K}<false, true>" -s 2 -c 1 -f -o $O/prof_ewa_${K}_${TAG} \
-    python bench.py --steps 1 --warmup 1 --quick > $O/ncu_ewa_${K}_${TAG}.log 2>&1
-done
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_fastgs_${TAG}.csv \
+    python profiles/tools/fastgs_prof.py --iters 2 > $O/fastgs_under_ncu_${TAG}.log 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches_fastgs_ref_${TAG}.csv \
+    python profiles/tools/fastgs_prof.py --iters 2 --reference > $O/fastgs_ref_under_ncu_${TAG}.log 2>&1
 for K in ssim_l1_kernel fused_front_kernel fused_back_kernel; do
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:${K} -s 2 -c 1 -f -o $O/prof_${K}_${TAG} \
     python profiles/tools/train_prof.py --iters 1 > $O/ncu_${K}_${TAG}.log 2>&1

@@ -210,7 +210,7 @@ def test_fastgs_argument_validation(lib):
     lib.gsb_fastgs_tile_bytes.restype = C.c_size_t
     pb = lib.gsb_fastgs_primitive_bytes(u32(100), u32(64), u32(48))
     tb = lib.gsb_fastgs_tile_bytes(u32(64), u32(48))
-    assert pb >= 100 * (64 + 64 + 4 + 8 + 4 + 16 + 8) and pb % 256 == 0
+    assert pb >= 100 * (64 + 64 + 4 + 8 + 4 + 4 + 16 + 8) and pb % 256 == 0
     assert tb >= (4 * 3 + 1) * 4 + 64 * 48 * 4
     assert lib.gsb_fastgs_primitive_bytes(u32(200), u32(64), u32(48)) > pb
     n_out = np.zeros(1, np.int64)
