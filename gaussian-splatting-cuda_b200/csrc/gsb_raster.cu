@@ -240,6 +240,25 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
               if (rl < cnt)
                   cand = block_may_pass<kEwa>(rec4[rl * 4], rec4[rl * 4 + 1], rec4[rl * 4 + 2], pc.bx0, pc.bx1, pc.by0, pc.by1);
               uint32_t cmask = __ballot_sync(0xffffffffu, cand);
+              // (evaluating two surviving records per trip to interleave their FFMA2 -> MUFU chains was measured slower:
+              // 0.436 vs 0.420 ms at config B, profiles/r2_experiments.md)
+              auto blend = [&](bool pass, float alpha_raw, const float4 q3, int32_t idx, float &T, float &cr, float &cg,
+                               float &cb, int32_t &last, bool &done) {
+                  if (pass && !done) {
+                      const float alpha = fminf(kMaxAlpha, alpha_raw);
+                      if (alpha >= kAlphaThreshold) {
+                          const float nT = T * (1.0f - alpha);
+                          if (nT <= kMinTransmittance) {
+                              done = true; // this Gaussian is NOT composited (Fwd.cu:244-248)
+                          } else {
+                              const float vis = alpha * T;
+                              cr += q3.x * vis; cg += q3.y * vis; cb += q3.z * vis;
+                              last = idx;
+                              T = nT;
+                          }
+                      }
+                  }
+              };
               while (cmask) {
                 const int32_t t = c0 + __ffs(cmask) - 1;
                 cmask &= cmask - 1;
@@ -248,34 +267,8 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
                 const bool p0 = e.pass0 && !done0, p1 = e.pass1 && !done1;
                 if (!__any_sync(0xffffffffu, p0 || p1)) continue;
                 const float4 q3 = rec4[t * 4 + 3];
-                if (p0) {
-                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw<kEwa>(f2_lo(e.Ns), f2_lo(e.Ds), q2.z));
-                    if (alpha >= kAlphaThreshold) {
-                        const float nT = T0 * (1.0f - alpha);
-                        if (nT <= kMinTransmittance) {
-                            done0 = true; // this Gaussian is NOT composited (Fwd.cu:244-248)
-                        } else {
-                            const float vis = alpha * T0;
-                            c0r += q3.x * vis; c0g += q3.y * vis; c0b += q3.z * vis;
-                            last0 = batch_start + t;
-                            T0 = nT;
-                        }
-                    }
-                }
-                if (p1) {
-                    const float alpha = fminf(kMaxAlpha, pair_alpha_raw<kEwa>(f2_hi(e.Ns), f2_hi(e.Ds), q2.z));
-                    if (alpha >= kAlphaThreshold) {
-                        const float nT = T1 * (1.0f - alpha);
-                        if (nT <= kMinTransmittance) {
-                            done1 = true;
-                        } else {
-                            const float vis = alpha * T1;
-                            c1r += q3.x * vis; c1g += q3.y * vis; c1b += q3.z * vis;
-                            last1 = batch_start + t;
-                            T1 = nT;
-                        }
-                    }
-                }
+                if (p0) blend(true, pair_alpha_raw<kEwa>(f2_lo(e.Ns), f2_lo(e.Ds), q2.z), q3, batch_start + t, T0, c0r, c0g, c0b, last0, done0);
+                if (p1) blend(true, pair_alpha_raw<kEwa>(f2_hi(e.Ns), f2_hi(e.Ds), q2.z), q3, batch_start + t, T1, c1r, c1g, c1b, last1, done1);
               }
               if (__all_sync(0xffffffffu, done0 && done1)) break;
             }

@@ -164,6 +164,58 @@ def build_l3_harness(verbose: bool = True) -> str | None:
     return so
 
 
+FAST_L3_SRC = "/root/reference/src/training/rasterization/fast_rasterizer_autograd.cpp"
+
+
+def build_fastgs_l3_harness(verbose: bool = True) -> str | None:
+    """The reference's fast_rasterizer_autograd.cpp (unmodified) + oracle/ref_fastgs_l3_harness.cpp linked against THIS
+    repository's drop-in library: oracle/_ref/libref_fastgs_l3_b200.so (tests/test_gpu_fastgs.py executes it)."""
+    if not os.path.exists(FAST_L3_SRC):
+        return None
+    from torch.utils import cpp_extension as ce
+
+    root = os.path.dirname(HERE)
+    lib_dir = os.path.join(root, "gaussian-splatting-cuda_b200", "lib")
+    if not os.path.exists(os.path.join(lib_dir, "libgsplat_b200.so")):
+        return None
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, "libref_fastgs_l3_b200.so")
+    harness = os.path.join(HERE, "ref_fastgs_l3_harness.cpp")
+    h = hashlib.sha256()
+    for f in (FAST_L3_SRC, harness, os.path.join(root, "include", "fastgs", "rasterization_api.h")):
+        h.update(open(f, "rb").read())
+    st = h.hexdigest()
+    if os.path.exists(so) and os.path.exists(so + ".stamp") and open(so + ".stamp").read() == st:
+        return so
+    inc = []
+    for i in [os.path.join(root, "include", "fastgs"), "/root/reference/src/training"] + ce.include_paths() + ["/usr/local/cuda/include"]:
+        inc += ["-I", i]
+    objs = []
+    for src in (FAST_L3_SRC, harness):
+        obj = os.path.join(OUT, "fl3_" + os.path.basename(src).rsplit(".", 1)[0] + ".o")
+        if verbose:
+            print("[build_ref] fastgs L3", os.path.basename(src), flush=True)
+        p = subprocess.run([CXX, "-std=c++20", "-O2", "-fPIC", "-D_GLIBCXX_USE_CXX11_ABI=1", "-c", src, "-o", obj] + inc,
+                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout[-6000:])
+            raise RuntimeError(f"fastgs L3 harness source failed to compile: {src}")
+        objs.append(obj)
+    tl = ce.library_paths()[0]
+    p = subprocess.run([CXX, "-shared", "-o", so] + objs + ["-L", lib_dir, "-lgsplat_b200", "-lgsb200", "-L", tl, "-ltorch",
+                        "-ltorch_cpu", "-lc10", "-ltorch_cuda", "-lc10_cuda", "-Wl,--no-undefined",
+                        "-Wl,-rpath,$ORIGIN/../../gaussian-splatting-cuda_b200/lib", "-Wl,-rpath," + tl],
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if p.returncode != 0:
+        sys.stderr.write(p.stdout[-6000:])
+        raise RuntimeError("linking oracle/_ref/libref_fastgs_l3_b200.so failed")
+    for o in objs:
+        os.remove(o)
+    with open(so + ".stamp", "w") as f:
+        f.write(st)
+    return so
+
+
 FASTGS = "/root/reference/fastgs"
 FASTGS_CU = ["rasterization/src/forward.cu", "rasterization/src/backward.cu", "rasterization/src/rasterization_api.cu"]
 
@@ -237,3 +289,4 @@ if __name__ == "__main__":
     print(build(variant="precise"))
     print(build_l3_harness())
     print(build_fastgs())
+    print(build_fastgs_l3_harness())

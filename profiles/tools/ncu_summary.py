@@ -2,8 +2,10 @@
 import csv, collections, re, subprocess, sys, io, os
 tag = sys.argv[1]
 out = []
-def launches():
-    rows = list(csv.reader(open(f'gpurun_out/launches_{tag}.csv')))
+def launches(path=None, title=None):
+    path = path or f'gpurun_out/launches_{tag}.csv'
+    if not os.path.exists(path): return
+    rows = list(csv.reader(open(path)))
     hi = [i for i, r in enumerate(rows) if 'Kernel Name' in r][0]
     hdr = rows[hi]; ik = hdr.index('Kernel Name'); iv = hdr.index('Metric Value')
     agg = collections.OrderedDict()
@@ -11,12 +13,16 @@ def launches():
         if len(r) <= iv: continue
         full = r[ik]
         if 'gsb::' in full:
-            name = re.search(r'gsb::\w+(<\d+>)?', full).group(0)
+            name = re.search(r'gsb::\w+(<[\w, ]+>)?', full).group(0)
+        elif 'fast_gs::' in full:
+            name = 'fast_gs::' + re.search(r'(\w+)\(', full).group(1)
+        elif 'cub::' in full:
+            name = 'cub::' + re.search(r'cub::(?:\w+::)*(\w+)', full).group(1)
         else:
             name = re.sub(r'<.*', '', re.sub(r'^void ', '', full))[:70]
         agg.setdefault(name, [0, 0.0]); agg[name][0] += 1; agg[name][1] += float(r[iv].replace(',', ''))
     tot = sum(v for _, v in agg.values())
-    out.append(f"## Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, `bench.py --steps 2 --warmup 1`)\n")
+    out.append(f"## {title or 'Launch list (`ncu --metrics gpu__time_duration.sum --clock-control none`, `bench.py --steps 2 --warmup 1`)'}\n")
     out.append(f"{sum(c for c, _ in agg.values())} launches captured, {tot/1e6:.2f} ms of device time (cold-cache, serialised: compare SHARES).\n")
     out.append("| kernel | launches | total µs | share |\n|---|---:|---:|---:|")
     mine = 0.0
@@ -39,14 +45,16 @@ WANT = [('gpu__time_duration.sum', 'duration'), ('dram__bytes_read.sum', 'DRAM r
         ('smsp__thread_inst_executed_per_inst_executed.ratio', 'active threads / instruction'),
         ('sm__warps_active.avg.pct_of_peak_sustained_active', 'achieved occupancy %'),
         ('launch__registers_per_thread', 'registers / thread'), ('launch__grid_size', 'grid'), ('launch__block_size', 'block')]
-def full(kernel):
-    p = f'gpurun_out/prof_{kernel}_{tag}.ncu-rep'
+def full(kernel, prefix='', note=''):
+    p = f'gpurun_out/prof_{prefix}{kernel}_{tag}.ncu-rep'
     if not os.path.exists(p): return
     txt = subprocess.run(['ncu', '-i', p, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     if len(rows) < 3: return
     hdr, units, vals = rows[0], rows[1], rows[-1]
-    out.append(f"## `{kernel}` (`ncu --set full --clock-control none --import-source on`, 1 launch)\n")
+    name = hdr.index('Kernel Name') if 'Kernel Name' in hdr else None
+    out.append(f"## `{kernel}`{note} (`ncu --set full --clock-control none --import-source on`, 1 launch)\n")
+    if name is not None: out.append(f"Captured instance: `{vals[name][:110]}`\n")
     out.append("| metric | value |\n|---|---:|")
     for m, label in WANT:
         if m in hdr:
@@ -59,6 +67,11 @@ launches()
 for k in ('raster_bwd_kernel', 'raster_fwd_kernel', 'tile_bin_kernel', 'ssim_l1_kernel', 'fused_front_kernel',
           'fused_back_kernel'):
     full(k)
+# fastgs path: profiles/tools/fastgs_prof.py
+launches(f'gpurun_out/launches_fastgs_{tag}.csv', 'fastgs path, this backend: launch list of `profiles/tools/fastgs_prof.py --iters 2`')
+launches(f'gpurun_out/launches_fastgs_ref_{tag}.csv', "fastgs path, the reference's own kernels: launch list of `fastgs_prof.py --iters 2 --reference`")
+for k in ('fgs_front_kernel', 'raster_fwd_kernel', 'raster_bwd_kernel', 'fgs_back_kernel', 'tile_bin_kernel'):
+    full(k, 'fastgs_', ' in the fastgs path')
 open(f'profiles/{tag}_ncu_summary.md', 'w').write(f"# ncu summary {tag}\n\nSource artefacts: `gpurun_out/launches_{tag}.csv`, `gpurun_out/prof_*_{tag}.ncu-rep` "
      f"(scratch, not tracked); this file is the tracked digest.\n\n" + "\n".join(out) + "\n")
 print("\n".join(out))

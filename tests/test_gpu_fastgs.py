@@ -155,8 +155,8 @@ def test_fastgs_edge_cases(native, cuda_device):
         run(fg, be, bad, cuda_device, gi, ga)
 
 
-def test_fastgs_reference_l3_caller_matches_python_mirror(native, cuda_device):
-    """Structural: forward's context carries what the backward needs and nothing depends on Python-side state."""
+def test_fastgs_forward_context_is_self_contained(native, cuda_device):
+    """Forward's opaque buffers carry what the backward needs; nothing depends on Python-side or library state."""
     fg = _fg(native)
     be = fg.default_backend()
     inp = scenes.fastgs_inputs(scenes.scene_small(N=800, width=96, height=64, sh_degree=3, seed=9))
@@ -172,6 +172,47 @@ def test_fastgs_reference_l3_caller_matches_python_mirror(native, cuda_device):
     g2 = be.backward(c2, gi, ga, img2, al2, P["means"], P["scales_raw"], P["rotations_raw"], P["shN"], w2c, s)
     for a, b in zip(g1[:6], g2[:6]):
         assert rel(a, b) < 1e-5  # float atomics: order-dependent in the last bits only
+
+
+@pytest.mark.parametrize("deg", [0, 3])
+def test_reference_fastgs_caller_runs_on_the_b200_backend(native, cuda_device, deg):
+    """The reference's OWN caller of its default rasterizer -- FastGSRasterize of fast_rasterizer_autograd.cpp, compiled
+    unmodified against include/fastgs/rasterization_api.h and linked against libgsplat_b200.so
+    (oracle/_ref/libref_fastgs_l3_b200.so, oracle/ref_fastgs_l3_harness.cpp) -- executes forward and backward on the B200
+    through this backend and agrees with the package's Python mirror of the same sequence."""
+    import os
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libref_fastgs_l3_b200.so")
+    if not os.path.exists(so):
+        pytest.fail("oracle/_ref/libref_fastgs_l3_b200.so is missing: build() in the container that holds /root/reference")
+    torch.ops.load_library(so)
+    fg = _fg(native)
+    inp = scenes.fastgs_inputs(scenes.scene_small(N=3000, width=200, height=120, sh_degree=deg, seed=21, view=3))
+    gi, ga = _weights(inp, cuda_device, 5)
+    bg = torch.tensor([0.2, 0.5, 0.7], device=cuda_device)
+    n = inp["means"].shape[0]
+    res = {}
+    for tag in ("reference_cpp", "python_mirror"):
+        P = _leaves(inp, cuda_device)
+        w2c = torch.from_numpy(inp["w2c"]).to(cuda_device)
+        dens = torch.zeros((2, n), device=cuda_device)
+        s = _settings(fg, inp, cuda_device)
+        if tag == "reference_cpp":
+            img, alpha = torch.ops.ref_fastgs_l3_b200.fast_render(
+                P["means"], P["scales_raw"], P["rotations_raw"], P["opacities_raw"], P["sh0"], P["shN"], w2c, s.cam_position,
+                deg, inp["width"], inp["height"], inp["fx"], inp["fy"], inp["cx"], inp["cy"], bg, dens)
+        else:
+            img, alpha = fg.fast_rasterize(fg.default_backend(), P["means"], P["scales_raw"], P["rotations_raw"],
+                                           P["opacities_raw"], P["sh0"], P["shN"], w2c, s, bg_color=bg, densification_info=dens)
+        ((img * gi).sum() + (alpha * ga).sum()).backward()
+        torch.cuda.synchronize()
+        res[tag] = (img.detach(), alpha.detach(), {k: (P[k].grad if P[k].grad is not None else torch.zeros_like(P[k])) for k in PARAMS}, dens)
+    assert torch.equal(res["reference_cpp"][0], res["python_mirror"][0])  # same kernels, same inputs, same order
+    assert torch.equal(res["reference_cpp"][1], res["python_mirror"][1])
+    assert float(res["python_mirror"][1].mean()) > 0.05
+    for k in PARAMS:
+        assert_grad_close(res["reference_cpp"][2][k], res["python_mirror"][2][k], k, n, rel_tol=2e-5,
+                          tag=f"reference C++ fastgs caller vs Python mirror (deg {deg})")
+    assert torch.equal(res["reference_cpp"][3][0], res["python_mirror"][3][0]) and float(res["python_mirror"][3][0].sum()) > 100
 
 
 @pytest.mark.parametrize("cfg,n_gauss", [("B", 1_000_000), ("D", 6_000_000)], ids=["configB_1M", "configD_6M"])
