@@ -808,6 +808,70 @@ def run_b200(args):
     except Exception as e:
         line["fastgs"] = {"unavailable": repr(e)[:300]}
 
+    # ---- a training iteration on the reference's DEFAULT path: fastgs render -> SSIM/L1 loss -> backward -> Adam ---------
+    def fastgs_train_block(w, steps):
+        from gsplat_b200 import fastgs as fg, training
+        V = w.P["viewmats"][0].detach()
+        K = w.host["Ks"][0]
+        campos = (-V[:3, :3].T @ V[:3, 3]).contiguous()
+        st = fg.FastGSSettings(cam_position=campos, active_sh_bases=(w.deg + 1) ** 2, width=w.W, height=w.H,
+                               focal_x=float(K[0, 0]), focal_y=float(K[1, 1]), center_x=float(K[0, 2]), center_y=float(K[1, 2]))
+        tgt_chw = w.P["target"][0].permute(2, 0, 1).contiguous()
+        host_tgt = tgt_chw.cpu().pin_memory()
+        host_w2c = V.cpu().pin_memory()
+        bgc = w.P["background"][0].detach()
+        out = {"what": "fastgs forward -> background composite -> SSIM/L1 loss and gradient -> fastgs backward -> Adam; camera + "
+                       "target H2D and loss D2H every iteration"}
+        P1 = {k: v.detach().clone().requires_grad_(True) for k, v in w.raw().items()}
+        ts = training.FastGsTrainStep(P1, w.deg, w.W, w.H, optimizer=training.FusedAdam(P1))
+
+        def it_b200():
+            w2c = host_w2c.to(dev, non_blocking=True)
+            tg = host_tgt.to(dev, non_blocking=True)
+            return float(ts(w2c, st, tg, bgc).item())
+        for _ in range(3):
+            it_b200()
+        ms = timed(it_b200, steps) / steps
+        prof_t = read_profile(it_b200, max(steps, 10))
+        out["b200"] = {"ms_per_iter": ms, "iters_per_sec": 1e3 / ms, "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in prof_t.items()},
+                       "what": "gsb_fastgs_* + gsb_ssim_l1 on [3,H,W] planes + one-launch Adam; no autograd graph"}
+        del ts, P1
+        if not args.no_ref_cuda:
+            try:
+                from oracle import ref_fastgs, ref_train
+                if ref_fastgs.available():
+                    rbe = ref_fastgs.backend(fg)
+                    P2 = {k: v.detach().clone().requires_grad_(True) for k, v in w.raw().items()}
+                    ropt = ref_train.RefFusedAdam(P2, training.AdamConfig().lrs())
+                    state = {"it": 0}
+
+                    def it_ref():
+                        w2c = host_w2c.to(dev, non_blocking=True)
+                        tg = host_tgt.to(dev, non_blocking=True)
+                        img, _ = fg.fast_rasterize(rbe, P2["means"], P2["scaling_raw"], P2["rotation_raw"],
+                                                   P2["opacity_raw"].reshape(-1, 1), P2["sh0"], P2["shN"], w2c, st, bg_color=bgc)
+                        loss = ref_train.ref_photometric_loss(torch.clamp(img, 0.0, 1.0), tg, 0.2)  # trainer.cpp:103-126
+                        loss.backward()
+                        state["it"] += 1
+                        ropt.step(state["it"], training.PARAM_GROUPS)
+                        ropt.zero_grad()
+                        return float(loss.item())
+                    for _ in range(2):
+                        it_ref()
+                    ms_r = timed(it_ref, steps) / steps
+                    out["reference_cuda"] = {"ms_per_iter": ms_r, "iters_per_sec": 1e3 / ms_r,
+                                             "what": "the reference's own kernels for every stage (fastgs rasterizer, ssim.cu, "
+                                                     "adam_kernels.cuh) glued by torch autograd exactly as its trainer does"}
+                    out["speedup"] = ms_r / ms
+            except Exception as e:
+                out["reference_cuda"] = {"unavailable": repr(e)[:200]}
+        return out
+
+    try:
+        line["train_fastgs"] = fastgs_train_block(wl, args.steps)
+    except Exception as e:
+        line["train_fastgs"] = {"unavailable": repr(e)[:300]}
+
     # ---- the other configs of BASELINE.json (N=1 line only) ---------------------------------------------------------
     configs = {}
     if cfg == "B" and not args.no_other_configs:
@@ -863,6 +927,10 @@ def run_b200(args):
                 d["fastgs"] = fastgs_block(wd, 10)
             except Exception as e:
                 d["fastgs"] = {"unavailable": repr(e)[:200]}
+            try:
+                d["train_fastgs"] = fastgs_train_block(wd, 10)
+            except Exception as e:
+                d["train_fastgs"] = {"unavailable": repr(e)[:200]}
             configs["D"] = d
             del wd
         except Exception as e:

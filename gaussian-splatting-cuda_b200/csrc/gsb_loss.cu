@@ -39,12 +39,12 @@ __constant__ float c_win[11] = {0.001028380084f, 0.007598758135f, 0.03600077213f
 
 struct LossParams {
     uint32_t H, W;
-    const float *renders;   // [H,W,3], unclamped
+    const float *renders;   // [H,W,3] or [3,H,W] (renders_chw), unclamped
     const float *target;    // [3,H,W] (target_chw) or [H,W,3]
-    int target_chw;
+    int target_chw, renders_chw;
     float lambda;           // weight of the SSIM term (lambda_dssim)
     float grad_scale;       // upstream gradient of the scalar loss
-    float *v_renders;       // [H,W,3] or null (evaluation)
+    float *v_renders;       // laid out like renders, or null (evaluation)
     double *acc;            // [2] running sums (|x - y|, ssim), zeroed before the launch
     unsigned int *done;     // [1] CTA counter, zeroed before the launch
     float *loss_out;        // [3] loss, l1 mean, ssim mean
@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(kLossThreads, 3) ssim_l1_kernel(const LossPara
             const int gy = ty0 + r - 2 * kHalo;
             const bool row_ok = gy >= 0 && gy < H;
             const size_t gyc = row_ok ? (size_t)gy : 0;
-            const float *rrow = p.renders + gyc * W * 3 + c;
+            const float *rrow = p.renders_chw ? p.renders + ((size_t)c * H + gyc) * W : p.renders + gyc * W * 3 + c;
+            const int rstep = p.renders_chw ? 1 : 3;
             const float *trow = p.target_chw ? p.target + ((size_t)c * H + gyc) * W : p.target + gyc * W * 3 + c;
             const int tstep = p.target_chw ? 1 : 3;
 #pragma unroll
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(kLossThreads, 3) ssim_l1_kernel(const LossPara
                     const int gx = tx0 + q - 2 * kHalo;
                     float X = 0.f, Y = 0.f;
                     if (row_ok && gx >= 0 && gx < W) {
-                        const float raw = rrow[gx * 3];
+                        const float raw = rrow[gx * rstep];
                         X = fminf(fmaxf(raw, 0.f), 1.f);
                         Y = trow[gx * tstep];
                         // the tile's own pixels remember whether the clamp was active (dLoss/d(render) = 0 there)
@@ -259,7 +260,8 @@ __global__ void __launch_bounds__(kLossThreads, 3) ssim_l1_kernel(const LossPara
                     if (p.v_renders) {
                         float g = f2_lo(a01[o]) + (2.f * px.x) * f2_hi(a01[o]) + px.y * a2[o]; // ssim.cu:411
                         g += l1_w * (d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f));
-                        p.v_renders[((size_t)gy * W + gx) * 3 + c] = s_pass[r0 + o][q] ? g : 0.f;
+                        const size_t oi = p.renders_chw ? ((size_t)c * H + gy) * W + gx : ((size_t)gy * W + gx) * 3 + c;
+                        p.v_renders[oi] = s_pass[r0 + o][q] ? g : 0.f;
                     }
                 }
             }
@@ -309,7 +311,8 @@ extern "C" int gsb_ssim_l1(uint32_t image_width, uint32_t image_height, const fl
     GSB_CUDA_TRY(cudaMemsetAsync(workspace, 0, 64, s));
     LossParams p;
     p.H = image_height; p.W = image_width;
-    p.renders = renders; p.target = target; p.target_chw = target_chw;
+    p.renders = renders; p.target = target;
+    p.target_chw = (target_chw & 1) != 0; p.renders_chw = (target_chw & 2) != 0; // GSB_LOSS_TARGET_CHW | GSB_LOSS_RENDERS_CHW
     p.lambda = lambda_dssim; p.grad_scale = grad_scale; p.v_renders = v_renders;
     p.acc = reinterpret_cast<double *>(workspace);
     p.done = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(workspace) + 32);

@@ -216,8 +216,11 @@ GSB_EXPORT std::tuple<at::Tensor, at::Tensor> photometric_loss_fused(const at::T
     const c10::cuda::CUDAGuard guard(renders.device());
     CHECK_F32(renders);
     CHECK_F32(target);
-    TORCH_CHECK(renders.dim() == 4 && renders.size(0) == 1 && renders.size(3) == 3, "renders must be [1,H,W,3]");
-    const int64_t H = renders.size(1), W = renders.size(2);
+    // [1,H,W,3] (the from-world blend's output) or [3,H,W] planes (the fastgs path's image)
+    const bool r_chw = renders.dim() == 3 && renders.size(0) == 3;
+    TORCH_CHECK(r_chw || (renders.dim() == 4 && renders.size(0) == 1 && renders.size(3) == 3),
+                "renders must be [1,H,W,3] or [3,H,W]");
+    const int64_t H = renders.size(1), W = renders.size(2); // the same two dimensions in both layouts
     TORCH_CHECK(target.numel() == 3 * H * W, "target must hold 3*H*W elements");
     const bool hwc = target.dim() == 4 && target.size(-1) == 3 && target.size(1) == H;
     const bool chw = (target.dim() == 3 && target.size(0) == 3) || (target.dim() == 4 && target.size(1) == 3 && !hwc);
@@ -226,7 +229,8 @@ GSB_EXPORT std::tuple<at::Tensor, at::Tensor> photometric_loss_fused(const at::T
     at::Tensor v_renders;
     if (compute_grad) v_renders = at::empty_like(renders);
     at::Tensor ws = at::empty({(int64_t)gsb_ssim_l1_workspace()}, renders.options().dtype(at::kByte));
-    gsb_check(gsb_ssim_l1((uint32_t)W, (uint32_t)H, renders.data_ptr<float>(), target.data_ptr<float>(), chw ? 1 : 0,
+    gsb_check(gsb_ssim_l1((uint32_t)W, (uint32_t)H, renders.data_ptr<float>(), target.data_ptr<float>(),
+                          (chw ? GSB_LOSS_TARGET_CHW : 0) | (r_chw ? GSB_LOSS_RENDERS_CHW : 0),
                           lambda_dssim, 1.0f, compute_grad ? v_renders.data_ptr<float>() : nullptr, stats.data_ptr<float>(),
                           ws.data_ptr(), (size_t)ws.numel(), cur_stream()),
               "photometric_loss_fused");

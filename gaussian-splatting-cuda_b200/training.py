@@ -251,3 +251,44 @@ class GraphedTrainStep:
     def overflowed(self) -> bool:
         """True when the last iteration had more intersections than the captured buffers hold (re-capture then)."""
         return int(self.n_isects.item()) > self.capacity
+
+
+@dataclass
+class FastGsTrainStep:
+    """One training iteration on the reference's DEFAULT rasterizer path (SURVEY.md 8 f4 + f2 + f3), ordered like
+    the reference's trainer (trainer.cpp: fast_rasterize -> photometric loss -> backward -> optimizer step):
+    fastgs forward (raw parameters in) -> background composite (fast_rasterizer.cpp:71) -> fused SSIM + L1 loss and
+    gradient on the [3,H,W] image -> fastgs backward -> one-launch Adam.  No autograd graph is built: the loss kernel
+    returns dLoss/d(image) and the backward takes it directly."""
+    params: dict                          # PARAM_GROUPS -> leaf tensors (opacity_raw [N,1] or [N])
+    sh_degree: int
+    width: int
+    height: int
+    lambda_dssim: float = 0.2
+    optimizer: FusedAdam | None = None
+    backend: object = None                # fastgs.FastGsBackend; default: this library
+    iteration: int = 0
+    last: dict = field(default_factory=dict)
+
+    def __call__(self, w2c, settings, target, background=None, densification_info=None):
+        from . import fastgs as fg
+        be = self.backend or fg.default_backend()
+        P = self.params
+        self.iteration += 1
+        with torch.no_grad():
+            opac = P["opacity_raw"].reshape(-1, 1)
+            image, alpha, ctx = be.forward(P["means"], P["scaling_raw"], P["rotation_raw"], opac, P["sh0"], P["shN"], w2c, settings)
+            final = image + (1.0 - alpha) * background.reshape(3, 1, 1) if background is not None else image
+            stats, v_final = _product_ns().photometric_loss_fused(final.contiguous(), target.contiguous(),
+                                                                  float(self.lambda_dssim), True)
+            v_alpha = (-(v_final * background.reshape(3, 1, 1)).sum(0, keepdim=True) if background is not None
+                       else torch.zeros_like(alpha))
+            g = be.backward(ctx, v_final, v_alpha.contiguous(), image, alpha, P["means"], P["scaling_raw"], P["rotation_raw"],
+                            P["shN"], w2c, settings, densification_info)
+            for k, gk in zip(("means", "scaling_raw", "rotation_raw", "opacity_raw", "sh0", "shN"), g[:6]):
+                P[k].grad = gk.reshape(P[k].shape)
+        if self.optimizer is not None:
+            self.optimizer.step(self.iteration)
+            self.optimizer.zero_grad()
+        self.last = {"n_instances": int(ctx["ints"][1]), "stats": stats}
+        return stats[0]

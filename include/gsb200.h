@@ -305,9 +305,12 @@ GSB_API int gsb_fused_back(const GsbSplatRaw *splats, const GsbCamera *cam, uint
  * loss = (1 - lambda) * mean|clamp(render,0,1) - target| + lambda * (1 - mean SSIM_valid)
  * (src/training/trainer.cpp:103-126; fused_ssim(..., "valid"): 11x11 Gaussian window, zero padding, map cropped by 5
  * per side: src/training/kernels/ssim.cu:64-420, include/kernels/fused_ssim.cuh:27-117).
- * renders [H,W,3] is the blend's output (unclamped); target is [3,H,W] (target_chw != 0, the reference's layout) or
- * [H,W,3].  v_renders [H,W,3] = grad_scale * dLoss/d(renders) including the clamp mask, or NULL to evaluate only.
+ * renders [H,W,3] is the blend's output (unclamped); target is [3,H,W] (the reference's layout) or [H,W,3].
+ * target_chw is a bit set: GSB_LOSS_TARGET_CHW (1) = target is [3,H,W]; GSB_LOSS_RENDERS_CHW (2) = renders AND v_renders
+ * are [3,H,W] planes (the fastgs path's image).
+ * v_renders (laid out like renders) = grad_scale * dLoss/d(renders) including the clamp mask, or NULL to evaluate only.
  * loss_out: DEVICE float[3] = (loss, l1 mean, ssim mean).  workspace: gsb_ssim_l1_workspace() bytes, 256-aligned. */
+enum { GSB_LOSS_TARGET_CHW = 1, GSB_LOSS_RENDERS_CHW = 2 };
 GSB_API size_t gsb_ssim_l1_workspace(void);
 GSB_API int gsb_ssim_l1(uint32_t image_width, uint32_t image_height, const float *renders, const float *target,
                         int target_chw, float lambda_dssim, float grad_scale, float *v_renders /*nullable*/,

@@ -71,8 +71,9 @@ std::tuple<at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tensor, at::Tenso
 
 // loss = (1 - lambda) * l1(clamp(render, 0, 1), target) + lambda * (1 - fused_ssim(.., "valid")) of
 // src/training/trainer.cpp:103-126 and, when `compute_grad`, dLoss/d(renders) in the same kernel.
-// renders [1,H,W,3] (the blend's output), target [3,H,W] / [1,3,H,W] (the reference's layout) or [1,H,W,3].
-// Returns (stats = device float[3]: loss, l1 mean, ssim mean;  v_renders [1,H,W,3] or an undefined tensor).
+// renders [1,H,W,3] (the from-world blend's output) or [3,H,W] (the fastgs image), target [3,H,W] / [1,3,H,W] (the
+// reference's layout) or [1,H,W,3].
+// Returns (stats = device float[3]: loss, l1 mean, ssim mean;  v_renders shaped like renders, or an undefined tensor).
 std::tuple<at::Tensor, at::Tensor> photometric_loss_fused(const at::Tensor renders, const at::Tensor target,
                                                           const float lambda_dssim, const bool compute_grad);
 

@@ -93,6 +93,74 @@ if cs:
         w("\n| kernel scope (D) | ms |\n|---|---:|")
         for n, v in D.get("kernels_ms", {}).items():
             w(f"| `{n}` | {f(v, 4)} |")
+fgs = d.get("fastgs", {})
+if "b200" in fgs:
+    w("\n## fastgs (EWA) path, SURVEY.md 8 f4: forward + backward through the reference caller's sequence, device-resident\n")
+    w("| config | this repo ms/step | reference fastgs kernels ms/step | ratio | instances |\n|---|---:|---:|---:|---:|")
+    w(f"| B | {f(fgs['b200']['ms_per_step'])} | {f(fgs.get('reference_cuda', {}).get('ms_per_step'))} | {f(fgs.get('speedup'), 2)}× | {fgs['b200'].get('instances')} |")
+    fd = cs.get("D", {}).get("fastgs", {}) if cs else {}
+    if "b200" in fd:
+        w(f"| D | {f(fd['b200']['ms_per_step'])} | {f(fd.get('reference_cuda', {}).get('ms_per_step'))} | {f(fd.get('speedup'), 2)}× | {fd['b200'].get('instances')} |")
+    w("\n| kernel scope (fastgs) | B ms | D ms |\n|---|---:|---:|")
+    kd = fd.get("b200", {}).get("kernels_ms", {})
+    for n, v in fgs["b200"].get("kernels_ms", {}).items():
+        w(f"| `{n}` | {f(v, 4)} | {f(kd.get(n), 4)} |")
+    w("\nThe reference's kernels are its own sources compiled unmodified as compute_90 PTX (oracle/build_ref.py explains why).")
+    tf, tfd = d.get("train_fastgs", {}), (cs.get("D", {}).get("train_fastgs", {}) if cs else {})
+    if "b200" in tf:
+        w("\n### Training iteration on the fastgs path (render + background + SSIM/L1 loss + backward + Adam; camera + target H2D, loss D2H)\n")
+        w("| config | this repo ms/iteration (it/s) | reference kernels ms/iteration (it/s) | ratio |\n|---|---:|---:|---:|")
+        for nm, t in (("B", tf), ("D", tfd)):
+            if "b200" in t:
+                rc2 = t.get("reference_cuda", {})
+                w(f"| {nm} | {f(t['b200']['ms_per_iter'])} ({f(t['b200']['iters_per_sec'], 1)}) | {f(rc2.get('ms_per_iter'))} "
+                  f"({f(rc2.get('iters_per_sec'), 1)}) | {f(t.get('speedup'), 2)}× |")
+
+# ---- the results table, re-derived from the same line -------------------------------------------------
+import os
+import re
+bl = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "BASELINE.md")
+if os.path.exists(bl) and "ops_ms" in d and cs:
+    ob, orf = ops.get("b200", {}), ops.get("reference_cuda", {})
+    fwd_names = ("projection_ut_3dgs_fused", "spherical_harmonics_fwd", "intersect_tile", "intersect_offset",
+                 "rasterize_to_pixels_from_world_3dgs_fwd")
+    bwd_names = ("rasterize_to_pixels_from_world_3dgs_bwd", "spherical_harmonics_bwd")
+    sm = lambda o, ns: sum(o.get(n, 0.0) for n in ns) if o else None
+    a, D = cs.get("A", {}), cs.get("D", {})
+    rows = ["| Config | Impl | GPUs | N | I | fwd ms | bwd ms | Gaussians/s (fwd+bwd) | iters/s | HBM GB/s (algorithmic) | % HBM roofline | binding pipe & % |",
+            "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+    if a:
+        rows.append(f"| A | CPU oracle ({a['cpu_oracle']['cores']} cores; 1 core: {a['cpu_oracle']['one_thread']['ms_per_step']:.0f} ms) | 0 | 10 k | "
+                    f"{a['b200'].get('intersections')} | — | — ({a['cpu_oracle']['ms_per_step']:.1f} ms fwd+bwd) | {a['cpu_oracle']['value']:.3g} | — | — | — | — |")
+        rows.append(f"| A | reference gsplat sm_100 / new sm_100a | 1 | 10 k | {a['b200'].get('intersections')} | — | — "
+                    f"({f(a.get('reference_cuda', {}).get('ms_per_step'))} / {f(a['b200']['ms_per_step'])} ms fwd+bwd, launch-bound) | "
+                    f"{a.get('reference_cuda', {}).get('value', 0):.3g} / {a['b200']['value']:.3g} | — | — | — | — |")
+    rows.append(f"| B | reference gsplat sm_100 | 1 | 1 M | {cfg['intersections']} | {f(sm(orf, fwd_names))} | {f(sm(orf, bwd_names))} | "
+                f"{r.get('value', 0):.3g} ({f(r.get('ms_per_step'))} ms) | {f(tr.get('reference_cuda', {}).get('iters_per_sec'), 1)} | — | — | (its blend backward: 5.7 ms of atomics + per-pair VJP) |")
+    rows.append(f"| B | new sm_100a | 1 | 1 M | {cfg['intersections']} | {f(sm(ob, fwd_names))} | {f(sm(ob, bwd_names))} | "
+                f"{d['value']:.3g} ({f(d['ms_per_step'])} ms) | {f(tr.get('b200', {}).get('iters_per_sec'), 1)} (graph: "
+                f"{f(tr.get('b200_cuda_graph', {}).get('iters_per_sec'), 1)}) | {ro['achieved']:.0f} (`{ro['kernel']}`) | {100 * ro['frac']:.1f} % | "
+                f"instruction issue 79 % (blend backward), 74 % + XU 38 % (blend forward): profiles/ |")
+    if "b200" in fgs:
+        rows.append(f"| B (fastgs / EWA path) | reference fastgs / new sm_100a | 1 | 1 M | {fgs['b200'].get('instances')} instances | — | — | "
+                    f"{fgs.get('reference_cuda', {}).get('value', 0):.3g} / {fgs['b200']['value']:.3g} "
+                    f"({f(fgs.get('reference_cuda', {}).get('ms_per_step'))} / {f(fgs['b200']['ms_per_step'])} ms) | — | — | — | instruction issue 84 % (EWA blend backward) |")
+    rows.append("| C | reference / new | 1 | — | — | — | — | — | not run: needs the reference's trainer, dataset loader and densification strategies (out of scope, SURVEY.md §8); the training-iteration rows of B and D are the per-iteration figures | — | — | — |")
+    if D:
+        dt = D.get("train", {})
+        rows.append(f"| D | reference / new | 1 | 6 M | {D['intersections']} | — | — | {D.get('reference_cuda', {}).get('value', 0):.3g} / {D['value']:.3g} "
+                    f"({f(D.get('reference_cuda', {}).get('ms_per_step'))} / {f(D['ms_per_step'])} ms) | "
+                    f"{f(dt.get('reference_cuda', {}).get('iters_per_sec'), 1)} / {f(dt.get('b200', {}).get('iters_per_sec'), 1)} (render + loss + Adam; MCMC noise / relocation kernels exist, not in the loop) | — | — | — |")
+    rows.append("| E | new | 2/4/8 | 1 M | — | — | — | see `profiles/r2_bench.md` \"Multi-GPU\" / the driver's SCALE record | — | — | — | — |")
+    txt = open(bl).read()
+    head = "### 2.4 Results table"
+    i = txt.index(head)
+    j = txt.index("\n", i)
+    note = (f"\n\nFilled by `profiles/tools/bench_report.py` from `{main_path}` (B200, SM {d['clocks']['sm_mhz']:.0f} MHz, no throttle "
+            f"reasons); fwd / bwd = sums of the per-operator CUDA-event times of the L3 sequence, the Gaussians/s column is the "
+            f"whole step including the torch glue.\n\n")
+    open(bl, "w").write(txt[:j] + note + "\n".join(rows) + "\n")
+
 if rest:
     w("\n## Multi-GPU (one view per rank, replicated parameters, gradient exchange)\n")
     w("| GPUs | ms/step | Gaussians/s (all ranks) | efficiency vs N x (1 GPU) | e2e_resident ms | exchange | all-reduce of 236 B/Gaussian |\n|---:|---:|---:|---:|---:|---|---|")

@@ -52,6 +52,12 @@ def test_photometric_loss_and_gradient_vs_torch(native, cuda_device, H, W):
     # the same target in the blend's own layout
     loss2, _ = training.photometric_loss(renders.detach(), target.permute(1, 2, 0)[None].contiguous(), 0.2)
     assert abs(float(loss2) - float(loss)) < 1e-7
+    # renders (and their gradient) as [3,H,W] planes: the fastgs path's image layout
+    planes = renders.detach()[0].permute(2, 0, 1).contiguous().requires_grad_(True)
+    loss3, _ = training.photometric_loss(planes, target, 0.2)
+    (loss3 * 1.7).backward()
+    assert abs(float(loss3) - float(loss)) < 1e-7
+    assert torch.equal(planes.grad, renders.grad[0].permute(2, 0, 1))
 
 
 def test_fused_adam_matches_reference_formula(native, cuda_device):
