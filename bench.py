@@ -836,6 +836,38 @@ def run_b200(args):
         out["b200"] = {"ms_per_iter": ms, "iters_per_sec": 1e3 / ms, "kernels_ms": {k: round(v["avg_ms"], 4) for k, v in prof_t.items()},
                        "what": "gsb_fastgs_* + gsb_ssim_l1 on [3,H,W] planes + one-launch Adam; no autograd graph"}
         del ts, P1
+        try:  # no read-back (capacity-sized instance buffer), then the same iteration replayed from one CUDA graph
+            P3 = {k: v.detach().clone().requires_grad_(True) for k, v in w.raw().items()}
+            ts3 = training.FastGsTrainStep(P3, w.deg, w.W, w.H, optimizer=training.FusedAdam(P3))
+            ts3.size_capacity(V, st)
+
+            def it_cap():
+                w2c = host_w2c.to(dev, non_blocking=True)
+                tg = host_tgt.to(dev, non_blocking=True)
+                return float(ts3(w2c, st, tg, bgc).item())
+            for _ in range(3):
+                it_cap()
+            ms_c = timed(it_cap, steps) / steps
+            assert int(ts3.last["n_instances"].item()) <= ts3.capacity
+            out["b200_capacity"] = {"ms_per_iter": ms_c, "iters_per_sec": 1e3 / ms_c,
+                                    "what": "forward_capacity (include/fastgs/rasterization_ext.h): no host read-back inside"}
+            del ts3, P3
+            P4 = {k: v.detach().clone().requires_grad_(True) for k, v in w.raw().items()}
+            gts = training.GraphedFastGsTrainStep(P4, w.deg, st)
+            host_campos, host_bg = campos.cpu().pin_memory(), bgc.cpu().pin_memory()
+            gts.capture(V, campos, tgt_chw, bgc)
+
+            def it_graph():
+                return float(gts(host_w2c, host_campos, host_tgt, host_bg).item())
+            for _ in range(3):
+                it_graph()
+            ms_g = timed(it_graph, steps) / steps
+            assert not gts.overflowed()
+            out["b200_cuda_graph"] = {"ms_per_iter": ms_g, "iters_per_sec": 1e3 / ms_g,
+                                      "what": "the same iteration replayed from one captured CUDA graph"}
+            del gts, P4
+        except Exception as e:
+            out["b200_cuda_graph"] = {"unavailable": repr(e)[:300]}
         if not args.no_ref_cuda:
             try:
                 from oracle import ref_fastgs, ref_train
@@ -863,6 +895,8 @@ def run_b200(args):
                                              "what": "the reference's own kernels for every stage (fastgs rasterizer, ssim.cu, "
                                                      "adam_kernels.cuh) glued by torch autograd exactly as its trainer does"}
                     out["speedup"] = ms_r / ms
+                    if "ms_per_iter" in out.get("b200_cuda_graph", {}):
+                        out["speedup_cuda_graph"] = ms_r / out["b200_cuda_graph"]["ms_per_iter"]
             except Exception as e:
                 out["reference_cuda"] = {"unavailable": repr(e)[:200]}
         return out

@@ -119,7 +119,7 @@ def build_shim(verbose: bool = False, force: bool = False) -> str:
     for i in [os.path.join(INC, "gsplat"), os.path.join(INC, "fastgs"), INC] + tinc + [cuda_inc]:
         incs += ["-I", i]
     hdrs = [os.path.join(INC, "gsb200.h")] + [os.path.join(INC, "gsplat", h) for h in ("Ops.h", "FusedOps.h", "Common.h", "Cameras.h")] + \
-        [os.path.join(INC, "fastgs", "rasterization_api.h")]
+        [os.path.join(INC, "fastgs", "rasterization_api.h"), os.path.join(INC, "fastgs", "rasterization_ext.h")]
     objs = []
     for src in SHIM_SOURCES:
         sp = os.path.join(SHIM, src)

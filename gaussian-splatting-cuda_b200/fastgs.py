@@ -37,8 +37,17 @@ class FastGsBackend:
     def ns(self):
         return self._get()
 
-    def forward(self, means, scales_raw, rotations_raw, opacities_raw, sh0, shN, w2c, s: FastGSSettings):
-        """-> image [3,H,W], alpha [1,H,W], ctx (what the reference's autograd context saves)."""
+    def forward(self, means, scales_raw, rotations_raw, opacities_raw, sh0, shN, w2c, s: FastGSSettings, capacity: int = 0):
+        """-> image [3,H,W], alpha [1,H,W], ctx (what the reference's autograd context saves).
+        capacity > 0 (this backend only, include/fastgs/rasterization_ext.h): the instance buffer holds `capacity` entries
+        and the count stays on the device (ctx["n_instances_dev"]): no host read-back, capturable in a CUDA graph."""
+        if capacity > 0:
+            r = self.ns.fastgs_forward_capacity(means, scales_raw, rotations_raw, opacities_raw, sh0, shN, w2c, s.cam_position,
+                                                s.active_sh_bases, s.width, s.height, s.focal_x, s.focal_y, s.center_x,
+                                                s.center_y, s.near_plane, s.far_plane, int(capacity))
+            ints = torch.tensor([-1, int(capacity), 0, 0, 0], dtype=torch.int64)
+            return r[0], r[1], dict(buffers=(r[2], r[3], r[4], torch.empty(0, dtype=torch.uint8, device=means.device)),
+                                    ints=ints, n_instances_dev=r[5])
         r = self.ns.fastgs_forward(means, scales_raw, rotations_raw, opacities_raw, sh0, shN, w2c, s.cam_position,
                                    s.active_sh_bases, s.width, s.height, s.focal_x, s.focal_y, s.center_x, s.center_y,
                                    s.near_plane, s.far_plane)

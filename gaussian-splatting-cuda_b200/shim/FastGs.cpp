@@ -10,6 +10,7 @@
 #include <cuda_runtime_api.h>
 
 #include "fastgs/rasterization_api.h"
+#include "fastgs/rasterization_ext.h"
 #include "gsb200.h"
 
 #define GSB_EXPORT __attribute__((visibility("default")))
@@ -53,12 +54,20 @@ View make_view(const at::Tensor &w2c, const at::Tensor &cam_position, int active
 
 namespace fast_gs::rasterization {
 
-GSB_EXPORT std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, int, int, int, int, int>
-forward_wrapper(const torch::Tensor &means, const torch::Tensor &scales_raw, const torch::Tensor &rotations_raw,
-                const torch::Tensor &opacities_raw, const torch::Tensor &sh_coefficients_0,
-                const torch::Tensor &sh_coefficients_rest, const torch::Tensor &w2c, const torch::Tensor &cam_position,
-                const int active_sh_bases, const int width, const int height, const float focal_x, const float focal_y,
-                const float center_x, const float center_y, const float near_plane, const float far_plane) {
+namespace {
+struct ForwardOut {
+    at::Tensor image, alpha, per_primitive, per_tile, per_instance, n_instances_dev;
+    int64_t n_instances;
+};
+// capacity < 0: exact -- the instance count is read back (one stream synchronisation) and sizes per_instance_buffers.
+// capacity >= 0: the instance buffer holds `capacity` entries, the count stays on the device (n_instances_dev), nothing
+// in the call reads a device value on the host: the call can be captured in a CUDA graph.
+ForwardOut forward_impl(const torch::Tensor &means, const torch::Tensor &scales_raw, const torch::Tensor &rotations_raw,
+                        const torch::Tensor &opacities_raw, const torch::Tensor &sh_coefficients_0,
+                        const torch::Tensor &sh_coefficients_rest, const torch::Tensor &w2c, const torch::Tensor &cam_position,
+                        const int active_sh_bases, const int width, const int height, const float focal_x, const float focal_y,
+                        const float center_x, const float center_y, const float near_plane, const float far_plane,
+                        const int64_t capacity) {
     FGS_F32(means); FGS_F32(scales_raw); FGS_F32(rotations_raw); FGS_F32(opacities_raw); FGS_F32(sh_coefficients_0);
     FGS_F32(sh_coefficients_rest);
     const c10::cuda::CUDAGuard guard(means.device());
@@ -71,36 +80,77 @@ forward_wrapper(const torch::Tensor &means, const torch::Tensor &scales_raw, con
     TORCH_CHECK(active_sh_bases == 1 || active_sh_bases == 4 || active_sh_bases == 9 || active_sh_bases == 16,
                 "active_sh_bases must be 1, 4, 9 or 16");
     TORCH_CHECK(active_sh_bases <= rest + 1, "active_sh_bases exceeds the stored SH coefficients");
+    TORCH_CHECK(capacity <= 0x7fffffffLL, "fastgs forward: capacity beyond 2^31 instances");
     View view = make_view(w2c, cam_position, active_sh_bases, rest, width, height, focal_x, focal_y, center_x, center_y,
                           near_plane, far_plane);
     const auto f32 = means.options().dtype(at::kFloat);
     const auto u8 = means.options().dtype(at::kByte);
-    at::Tensor image = at::empty({3, height, width}, f32);
-    at::Tensor alpha = at::empty({1, height, width}, f32);
+    ForwardOut o;
+    o.image = at::empty({3, height, width}, f32);
+    o.alpha = at::empty({1, height, width}, f32);
     const size_t prim_core = gsb_fastgs_primitive_bytes((uint32_t)N, (uint32_t)width, (uint32_t)height);
-    at::Tensor per_primitive = at::empty({(int64_t)(prim_core + 256)}, u8);
+    o.per_primitive = at::empty({(int64_t)(prim_core + 256)}, u8);
     const size_t tile_bytes = gsb_fastgs_tile_bytes((uint32_t)width, (uint32_t)height);
-    at::Tensor per_tile = at::empty({(int64_t)(tile_bytes + 256)}, u8);
-    char *prim = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(per_primitive.data_ptr()) + 255) & ~(uintptr_t)255);
-    char *tile = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(per_tile.data_ptr()) + 255) & ~(uintptr_t)255);
-    at::Tensor n_host = at::empty({1}, at::TensorOptions().dtype(at::kLong).pinned_memory(true));
-    n_host.data_ptr<int64_t>()[0] = 0;
+    o.per_tile = at::empty({(int64_t)(tile_bytes + 256)}, u8);
+    char *prim = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(o.per_primitive.data_ptr()) + 255) & ~(uintptr_t)255);
+    char *tile = reinterpret_cast<char *>((reinterpret_cast<uintptr_t>(o.per_tile.data_ptr()) + 255) & ~(uintptr_t)255);
+    const bool exact = capacity < 0;
+    at::Tensor n_host;
+    int64_t *n_out;
+    if (exact) {
+        n_host = at::empty({1}, at::TensorOptions().dtype(at::kLong).pinned_memory(true));
+        n_host.data_ptr<int64_t>()[0] = 0;
+        n_out = n_host.data_ptr<int64_t>();
+    } else {
+        o.n_instances_dev = at::empty({1}, means.options().dtype(at::kLong));
+        n_out = o.n_instances_dev.data_ptr<int64_t>();
+    }
     fgs_check(gsb_fastgs_forward_plan((uint32_t)N, means.data_ptr<float>(), scales_raw.data_ptr<float>(),
                                       rotations_raw.data_ptr<float>(), opacities_raw.data_ptr<float>(),
                                       sh_coefficients_0.data_ptr<float>(), rest ? sh_coefficients_rest.data_ptr<float>() : nullptr,
-                                      &view.v, prim, prim_core, tile, tile_bytes, n_host.data_ptr<int64_t>(), cur_stream()),
+                                      &view.v, prim, prim_core, tile, tile_bytes, n_out, cur_stream()),
               "forward (plan)");
-    auto stream = at::cuda::getCurrentCUDAStream();
-    stream.synchronize(); // the one read-back: sizes per_instance_buffers
-    const int64_t n_instances = n_host.data_ptr<int64_t>()[0];
-    TORCH_CHECK(n_instances <= 0x7fffffffLL, "fastgs forward: more than 2^31 instances");
-    at::Tensor per_instance = at::empty({n_instances * 4}, u8);
+    o.n_instances = capacity;
+    if (exact) {
+        at::cuda::getCurrentCUDAStream().synchronize(); // the one read-back: sizes per_instance_buffers
+        o.n_instances = n_host.data_ptr<int64_t>()[0];
+        TORCH_CHECK(o.n_instances <= 0x7fffffffLL, "fastgs forward: more than 2^31 instances");
+    }
+    o.per_instance = at::empty({o.n_instances * 4}, u8);
     fgs_check(gsb_fastgs_forward_blend((uint32_t)N, &view.v, prim, prim_core, tile, tile_bytes,
-                                       n_instances ? reinterpret_cast<int32_t *>(per_instance.data_ptr()) : nullptr,
-                                       (uint64_t)n_instances, image.data_ptr<float>(), alpha.data_ptr<float>(), cur_stream()),
+                                       o.n_instances ? reinterpret_cast<int32_t *>(o.per_instance.data_ptr()) : nullptr,
+                                       (uint64_t)o.n_instances, o.image.data_ptr<float>(), o.alpha.data_ptr<float>(),
+                                       cur_stream()),
               "forward (blend)");
-    at::Tensor per_bucket = at::empty({0}, u8);
-    return {image, alpha, per_primitive, per_tile, per_instance, per_bucket, -1, (int)n_instances, 0, 0, 0};
+    return o;
+}
+} // namespace
+
+GSB_EXPORT std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, int, int, int, int, int>
+forward_wrapper(const torch::Tensor &means, const torch::Tensor &scales_raw, const torch::Tensor &rotations_raw,
+                const torch::Tensor &opacities_raw, const torch::Tensor &sh_coefficients_0,
+                const torch::Tensor &sh_coefficients_rest, const torch::Tensor &w2c, const torch::Tensor &cam_position,
+                const int active_sh_bases, const int width, const int height, const float focal_x, const float focal_y,
+                const float center_x, const float center_y, const float near_plane, const float far_plane) {
+    ForwardOut o = forward_impl(means, scales_raw, rotations_raw, opacities_raw, sh_coefficients_0, sh_coefficients_rest, w2c,
+                                cam_position, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane,
+                                far_plane, -1);
+    at::Tensor per_bucket = at::empty({0}, means.options().dtype(at::kByte));
+    return {o.image, o.alpha, o.per_primitive, o.per_tile, o.per_instance, per_bucket, -1, (int)o.n_instances, 0, 0, 0};
+}
+
+GSB_EXPORT std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>
+forward_capacity(const torch::Tensor &means, const torch::Tensor &scales_raw, const torch::Tensor &rotations_raw,
+                 const torch::Tensor &opacities_raw, const torch::Tensor &sh_coefficients_0,
+                 const torch::Tensor &sh_coefficients_rest, const torch::Tensor &w2c, const torch::Tensor &cam_position,
+                 const int active_sh_bases, const int width, const int height, const float focal_x, const float focal_y,
+                 const float center_x, const float center_y, const float near_plane, const float far_plane,
+                 const int64_t instance_capacity) {
+    TORCH_CHECK(instance_capacity >= 0, "forward_capacity: instance_capacity must be >= 0");
+    ForwardOut o = forward_impl(means, scales_raw, rotations_raw, opacities_raw, sh_coefficients_0, sh_coefficients_rest, w2c,
+                                cam_position, active_sh_bases, width, height, focal_x, focal_y, center_x, center_y, near_plane,
+                                far_plane, instance_capacity);
+    return {o.image, o.alpha, o.per_primitive, o.per_tile, o.per_instance, o.n_instances_dev};
 }
 
 GSB_EXPORT std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor>

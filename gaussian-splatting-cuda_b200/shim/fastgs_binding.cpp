@@ -6,6 +6,9 @@
 #include <torch/library.h>
 
 #include "rasterization_api.h"
+#ifndef FGS_REFERENCE_LIBRARY
+#include "rasterization_ext.h"
+#endif
 
 namespace {
 using at::Tensor;
@@ -40,6 +43,17 @@ std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fastgs_backwa
     if (!gw.defined()) gw = at::empty({0}, means.options());
     return std::make_tuple(std::get<0>(r), std::get<1>(r), std::get<2>(r), std::get<3>(r), std::get<4>(r), std::get<5>(r), gw);
 }
+#ifndef FGS_REFERENCE_LIBRARY
+std::tuple<Tensor, Tensor, Tensor, Tensor, Tensor, Tensor> fastgs_forward_capacity(
+    const Tensor &means, const Tensor &scales_raw, const Tensor &rotations_raw, const Tensor &opacities_raw,
+    const Tensor &sh0, const Tensor &shN, const Tensor &w2c, const Tensor &cam_position, int64_t active_sh_bases,
+    int64_t width, int64_t height, double fx, double fy, double cx, double cy, double near_plane, double far_plane,
+    int64_t instance_capacity) {
+    return fast_gs::rasterization::forward_capacity(means, scales_raw, rotations_raw, opacities_raw, sh0, shN, w2c, cam_position,
+                                                    (int)active_sh_bases, (int)width, (int)height, (float)fx, (float)fy,
+                                                    (float)cx, (float)cy, (float)near_plane, (float)far_plane, instance_capacity);
+}
+#endif
 } // namespace
 
 #ifdef FGS_REFERENCE_LIBRARY
@@ -48,6 +62,9 @@ TORCH_LIBRARY(fastgs_ref, m) {
 TORCH_LIBRARY_FRAGMENT(gsplat_b200, m) {
 #endif
     m.def("fastgs_forward", &fastgs_forward);
+#ifndef FGS_REFERENCE_LIBRARY
+    m.def("fastgs_forward_capacity", &fastgs_forward_capacity);
+#endif
     m.def("fastgs_backward(Tensor(a!) densification_info, Tensor grad_image, Tensor grad_alpha, Tensor image, Tensor alpha, "
           "Tensor means, Tensor scales_raw, Tensor rotations_raw, Tensor shN, Tensor per_primitive, Tensor per_tile, "
           "Tensor per_instance, Tensor per_bucket, Tensor w2c, Tensor cam_position, int active_sh_bases, int width, "

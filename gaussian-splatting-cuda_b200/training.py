@@ -267,8 +267,21 @@ class FastGsTrainStep:
     lambda_dssim: float = 0.2
     optimizer: FusedAdam | None = None
     backend: object = None                # fastgs.FastGsBackend; default: this library
+    capacity: int = 0                     # > 0: instance buffer sized from it, no host read-back (rasterization_ext.h)
     iteration: int = 0
     last: dict = field(default_factory=dict)
+
+    def size_capacity(self, w2c, settings, slack: float = 1.25):
+        """One exact (synchronising) forward sizes the instance capacity for the following iterations."""
+        from . import fastgs as fg
+        be = self.backend or fg.default_backend()
+        P = self.params
+        with torch.no_grad():
+            _, _, ctx = be.forward(P["means"], P["scaling_raw"], P["rotation_raw"], P["opacity_raw"].reshape(-1, 1), P["sh0"],
+                                   P["shN"], w2c, settings)
+        n = int(ctx["ints"][1])
+        self.capacity = int(n * slack) + 1024
+        return n
 
     def __call__(self, w2c, settings, target, background=None, densification_info=None):
         from . import fastgs as fg
@@ -277,7 +290,8 @@ class FastGsTrainStep:
         self.iteration += 1
         with torch.no_grad():
             opac = P["opacity_raw"].reshape(-1, 1)
-            image, alpha, ctx = be.forward(P["means"], P["scaling_raw"], P["rotation_raw"], opac, P["sh0"], P["shN"], w2c, settings)
+            image, alpha, ctx = be.forward(P["means"], P["scaling_raw"], P["rotation_raw"], opac, P["sh0"], P["shN"], w2c, settings,
+                                           capacity=self.capacity)
             final = image + (1.0 - alpha) * background.reshape(3, 1, 1) if background is not None else image
             stats, v_final = _product_ns().photometric_loss_fused(final.contiguous(), target.contiguous(),
                                                                   float(self.lambda_dssim), True)
@@ -290,5 +304,76 @@ class FastGsTrainStep:
         if self.optimizer is not None:
             self.optimizer.step(self.iteration)
             self.optimizer.zero_grad()
-        self.last = {"n_instances": int(ctx["ints"][1]), "stats": stats}
+        # capacity mode: the count is a device tensor (compare it with the capacity when convenient)
+        self.last = {"n_instances": ctx.get("n_instances_dev", int(ctx["ints"][1])), "stats": stats}
         return stats[0]
+
+
+class GraphedFastGsTrainStep(GraphedTrainStep):
+    """GraphedTrainStep on the fastgs path: fastgs forward (capacity mode) -> background composite -> loss-and-gradient
+    kernel -> fastgs backward -> Adam with device-side scalars, captured once and replayed.  The camera pose, camera
+    position, background and target are static device buffers refreshed before each replay; the intrinsics and the image
+    size are launch arguments and therefore fixed per captured graph (one graph per camera resolution)."""
+
+    def __init__(self, params: dict, sh_degree: int, settings, cfg: AdamConfig | None = None, lambda_dssim: float = 0.2,
+                 capacity_slack: float = 1.25):
+        super().__init__(params, sh_degree, settings.width, settings.height, cfg, lambda_dssim, capacity_slack)
+        from . import fastgs as fg
+        dev = self.dev
+        self.static = {"w2c": torch.zeros((4, 4), device=dev), "campos": torch.zeros((3,), device=dev),
+                       "background": torch.zeros((3,), device=dev), "target": torch.zeros((3, self.H, self.W), device=dev)}
+        self.settings = fg.FastGSSettings(cam_position=self.static["campos"], active_sh_bases=settings.active_sh_bases,
+                                          width=settings.width, height=settings.height, focal_x=settings.focal_x,
+                                          focal_y=settings.focal_y, center_x=settings.center_x, center_y=settings.center_y,
+                                          near_plane=settings.near_plane, far_plane=settings.far_plane)
+        self.be = fg.default_backend()
+        self.step = FastGsTrainStep(params, sh_degree, settings.width, settings.height, lambda_dssim, optimizer=None,
+                                    backend=self.be)
+
+    def _body(self):
+        P, S = self.params, self.static
+        self.step.capacity = self.capacity
+        loss = self.step(S["w2c"], self.settings, S["target"], S["background"])
+        names = [k for k in PARAM_GROUPS if P[k].numel() > 0]
+        with torch.no_grad():
+            _product_ns().fused_adam_step_dynamic([P[k] for k in names], [P[k].grad for k in names],
+                                                  [self.opt.exp_avg[k] for k in names],
+                                                  [self.opt.exp_avg_sq[k] for k in names],
+                                                  self.dyn[[PARAM_GROUPS.index(k) for k in names]].contiguous()
+                                                  if len(names) != len(PARAM_GROUPS) else self.dyn,
+                                                  self.opt.cfg.beta1, self.opt.cfg.beta2, self.opt.cfg.eps)
+        return loss, self.step.last["stats"], self.step.last["n_instances"]
+
+    def _set_inputs(self, w2c, cam_position, target, background):
+        S = self.static
+        S["w2c"].copy_(w2c.reshape(4, 4), non_blocking=True)
+        S["campos"].copy_(cam_position.reshape(3), non_blocking=True)
+        S["target"].copy_(target.reshape(3, self.H, self.W), non_blocking=True)
+        if background is not None:
+            S["background"].copy_(background.reshape(3), non_blocking=True)
+
+    def capture(self, w2c, cam_position, target, background=None):
+        self._set_inputs(w2c, cam_position, target, background)
+        self.step.capacity = 0
+        n = self.step.size_capacity(self.static["w2c"], self.settings, self.slack)
+        self.capacity = self.step.capacity
+        self.dyn.zero_()  # warm-up iterations must not move the parameters: every group disabled
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                self._body()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss, self.stats, self.n_isects = self._body()
+        return n
+
+    def __call__(self, w2c, cam_position, target, background=None):
+        if self.graph is None:
+            self.capture(w2c, cam_position, target, background)
+        self.iteration += 1
+        self._set_inputs(w2c, cam_position, target, background)
+        self._set_scalars()
+        self.graph.replay()
+        return self.loss

@@ -109,12 +109,14 @@ if "b200" in fgs:
     tf, tfd = d.get("train_fastgs", {}), (cs.get("D", {}).get("train_fastgs", {}) if cs else {})
     if "b200" in tf:
         w("\n### Training iteration on the fastgs path (render + background + SSIM/L1 loss + backward + Adam; camera + target H2D, loss D2H)\n")
-        w("| config | this repo ms/iteration (it/s) | reference kernels ms/iteration (it/s) | ratio |\n|---|---:|---:|---:|")
+        w("| config | this repo, API-exact forward (one read-back) | no read-back (capacity) | one CUDA graph | reference kernels | ratio eager / graph |\n|---|---:|---:|---:|---:|---:|")
         for nm, t in (("B", tf), ("D", tfd)):
             if "b200" in t:
                 rc2 = t.get("reference_cuda", {})
-                w(f"| {nm} | {f(t['b200']['ms_per_iter'])} ({f(t['b200']['iters_per_sec'], 1)}) | {f(rc2.get('ms_per_iter'))} "
-                  f"({f(rc2.get('iters_per_sec'), 1)}) | {f(t.get('speedup'), 2)}× |")
+                w(f"| {nm} | {f(t['b200']['ms_per_iter'])} ms ({f(t['b200']['iters_per_sec'], 1)} it/s) | "
+                  f"{f(t.get('b200_capacity', {}).get('ms_per_iter'))} ms | {f(t.get('b200_cuda_graph', {}).get('ms_per_iter'))} ms "
+                  f"({f(t.get('b200_cuda_graph', {}).get('iters_per_sec'), 1)} it/s) | {f(rc2.get('ms_per_iter'))} ms "
+                  f"({f(rc2.get('iters_per_sec'), 1)} it/s) | {f(t.get('speedup'), 2)}× / {f(t.get('speedup_cuda_graph'), 2)}× |")
 
 # ---- the results table, re-derived from the same line -------------------------------------------------
 import os

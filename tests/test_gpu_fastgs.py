@@ -283,3 +283,53 @@ def test_fastgs_training_iteration(native, cuda_device):
     print("fastgs training losses (iterations 1, 501, 1001):", losses)
     assert losses[-1] < losses[0]
     assert all(not torch.equal(P3[k].detach(), before[k]) for k in P3)
+
+
+def test_fastgs_capacity_mode_and_graphed_iteration(native, cuda_device):
+    """include/fastgs/rasterization_ext.h: forward_capacity (no host read-back) renders what forward_wrapper renders when
+    the capacity suffices, clips when it does not, and lets the whole training iteration replay from one CUDA graph with the
+    same parameter updates as the eager iteration."""
+    import importlib
+    fg = _fg(native)
+    training = importlib.import_module(native.__name__ + ".training")
+    be = fg.default_backend()
+    inp = scenes.fastgs_inputs(scenes.scene_small(N=2500, width=160, height=112, sh_degree=3, seed=6, view=2))
+    dev = cuda_device
+    P = _leaves(inp, dev, requires_grad=False)
+    w2c = torch.from_numpy(inp["w2c"]).to(dev)
+    s = _settings(fg, inp, dev)
+    img, al, c = be.forward(P["means"], P["scales_raw"], P["rotations_raw"], P["opacities_raw"], P["sh0"], P["shN"], w2c, s)
+    n = int(c["ints"][1])
+    img2, al2, c2 = be.forward(P["means"], P["scales_raw"], P["rotations_raw"], P["opacities_raw"], P["sh0"], P["shN"], w2c, s,
+                               capacity=n + 100)
+    assert torch.equal(img, img2) and torch.equal(al, al2) and int(c2["n_instances_dev"].item()) == n
+    gi, ga = _weights(inp, dev, 8)
+    g1 = be.backward(c, gi, ga, img, al, P["means"], P["scales_raw"], P["rotations_raw"], P["shN"], w2c, s)
+    g2 = be.backward(c2, gi, ga, img2, al2, P["means"], P["scales_raw"], P["rotations_raw"], P["shN"], w2c, s)
+    for a, b in zip(g1[:6], g2[:6]):
+        assert rel(a, b) < 1e-5
+    # too small a capacity: reported through the device-side count, no out-of-bounds access, still a finite image
+    img3, _, c3 = be.forward(P["means"], P["scales_raw"], P["rotations_raw"], P["opacities_raw"], P["sh0"], P["shN"], w2c, s,
+                             capacity=n // 2)
+    assert int(c3["n_instances_dev"].item()) == n > n // 2 and bool(torch.isfinite(img3).all())
+    be.backward(c3, gi, ga, img3, al, P["means"], P["scales_raw"], P["rotations_raw"], P["shN"], w2c, s)
+    torch.cuda.synchronize()
+    # graph == eager over a few iterations (Adam included; the shN group is frozen for the first 1000 iterations in both)
+    names = {"means": "means", "scaling_raw": "scales_raw", "rotation_raw": "rotations_raw", "opacity_raw": "opacities_raw",
+             "sh0": "sh0", "shN": "shN"}
+    g = torch.Generator(device=dev).manual_seed(1)
+    target = torch.rand((3, inp["height"], inp["width"]), device=dev, generator=g)
+    bg = torch.tensor([0.3, 0.2, 0.1], device=dev)
+    PA = {k: torch.from_numpy(inp[v]).to(dev).requires_grad_(True) for k, v in names.items()}
+    PB = {k: torch.from_numpy(inp[v]).to(dev).requires_grad_(True) for k, v in names.items()}
+    eager = training.FastGsTrainStep(PA, 3, inp["width"], inp["height"], optimizer=training.FusedAdam(PA))
+    graphed = training.GraphedFastGsTrainStep(PB, 3, s)
+    la, lb = [], []
+    for _ in range(5):
+        la.append(float(eager(w2c, s, target, bg)))
+        lb.append(float(graphed(w2c, s.cam_position, target, bg)))
+    assert not graphed.overflowed()
+    print("eager losses", la, "graph losses", lb)
+    assert max(abs(a - b) for a, b in zip(la, lb)) < 1e-5
+    for k in PA:
+        assert rel(PB[k].detach(), PA[k].detach()) < 1e-5, k
