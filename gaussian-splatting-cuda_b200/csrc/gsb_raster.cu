@@ -201,8 +201,8 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
     __syncthreads();
 
     const PixelCoords pc = pixel_coords<kGeneral>(p, pm, tile_x, tile_y, &s_cm);
-    float T0 = 1.f, T1 = 1.f;
-    float c0r = 0.f, c0g = 0.f, c0b = 0.f, c1r = 0.f, c1g = 0.f, c1b = 0.f;
+    // blend state of the thread's two pixels as packed pairs (lo = pixel 0, hi = pixel 1)
+    f2 T = f2_bc(1.0f), CR = f2_bc(0.0f), CG = f2_bc(0.0f), CB = f2_bc(0.0f);
     int32_t last0 = 0, last1 = 0;
     bool done0 = !pm.in0 || !pc.ok0, done1 = !pm.in1 || !pc.ok1;
     const f2 PX = f2_make(pc.px0, pc.px1), PY = f2_make(pc.py0, pc.py1);
@@ -242,23 +242,6 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
               uint32_t cmask = __ballot_sync(0xffffffffu, cand);
               // (evaluating two surviving records per trip to interleave their FFMA2 -> MUFU chains was measured slower:
               // 0.436 vs 0.420 ms at config B, profiles/r2_experiments.md)
-              auto blend = [&](bool pass, float alpha_raw, const float4 q3, int32_t idx, float &T, float &cr, float &cg,
-                               float &cb, int32_t &last, bool &done) {
-                  if (pass && !done) {
-                      const float alpha = fminf(kMaxAlpha, alpha_raw);
-                      if (alpha >= kAlphaThreshold) {
-                          const float nT = T * (1.0f - alpha);
-                          if (nT <= kMinTransmittance) {
-                              done = true; // this Gaussian is NOT composited (Fwd.cu:244-248)
-                          } else {
-                              const float vis = alpha * T;
-                              cr += q3.x * vis; cg += q3.y * vis; cb += q3.z * vis;
-                              last = idx;
-                              T = nT;
-                          }
-                      }
-                  }
-              };
               while (cmask) {
                 const int32_t t = c0 + __ffs(cmask) - 1;
                 cmask &= cmask - 1;
@@ -267,8 +250,24 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
                 const bool p0 = e.pass0 && !done0, p1 = e.pass1 && !done1;
                 if (!__any_sync(0xffffffffu, p0 || p1)) continue;
                 const float4 q3 = rec4[t * 4 + 3];
-                if (p0) blend(true, pair_alpha_raw<kEwa>(f2_lo(e.Ns), f2_lo(e.Ds), q2.z), q3, batch_start + t, T0, c0r, c0g, c0b, last0, done0);
-                if (p1) blend(true, pair_alpha_raw<kEwa>(f2_hi(e.Ns), f2_hi(e.Ds), q2.z), q3, batch_start + t, T1, c1r, c1g, c1b, last1, done1);
+                // Both pixels branch-free on packed pairs (the warp executes both sides of a per-pixel branch anyway:
+                // 40 of 64 pixels pass per event).  A pixel that does not contribute gets alpha = 0: T and colour stay.
+                f2 ex;
+                if constexpr (kEwa) ex = f2_add(e.Ns, f2_bc(q2.z));
+                else ex = f2_fma(e.Ns, f2_make(fast_rcp(f2_lo(e.Ds)), fast_rcp(f2_hi(e.Ds))), f2_bc(q2.z));
+                const float al0 = fminf(kMaxAlpha, fast_ex2(f2_lo(ex))), al1 = fminf(kMaxAlpha, fast_ex2(f2_hi(ex)));
+                const bool ok0 = p0 && al0 >= kAlphaThreshold, ok1 = p1 && al1 >= kAlphaThreshold;
+                f2 alpha = f2_make(ok0 ? al0 : 0.0f, ok1 ? al1 : 0.0f);
+                const f2 nT = f2_mul(T, f2_fma(alpha, f2_bc(-1.0f), f2_bc(1.0f)));
+                // a Gaussian that would push the transmittance to 1e-4 is NOT composited and ends the pixel (Fwd.cu:244-248)
+                const bool sat0 = ok0 && f2_lo(nT) <= kMinTransmittance, sat1 = ok1 && f2_hi(nT) <= kMinTransmittance;
+                alpha = f2_make(sat0 ? 0.0f : f2_lo(alpha), sat1 ? 0.0f : f2_hi(alpha));
+                const f2 vis = f2_mul(alpha, T);
+                CR = f2_fma(f2_bc(q3.x), vis, CR); CG = f2_fma(f2_bc(q3.y), vis, CG); CB = f2_fma(f2_bc(q3.z), vis, CB);
+                T = f2_make(sat0 ? f2_lo(T) : f2_lo(nT), sat1 ? f2_hi(T) : f2_hi(nT));
+                if (ok0 && !sat0) last0 = batch_start + t;
+                if (ok1 && !sat1) last1 = batch_start + t;
+                done0 = done0 || sat0; done1 = done1 || sat1;
               }
               if (__all_sync(0xffffffffu, done0 && done1)) break;
             }
@@ -281,18 +280,19 @@ __global__ void __launch_bounds__(kTileThreads) raster_fwd_kernel(const TilePara
 
     // [H,W,3] rows (gsplat operators) or [3,H,W] planes (fastgs API)
     const size_t cs = p.chw ? (size_t)p.W * p.H : 1, ps = p.chw ? 1 : 3;
+    const float T0 = f2_lo(T), T1 = f2_hi(T);
     if (pm.in0) {
         alphas[pix0] = 1.0f - T0;
-        renders[pix0 * ps] = has_bg ? c0r + T0 * bg0 : c0r;
-        renders[pix0 * ps + cs] = has_bg ? c0g + T0 * bg1 : c0g;
-        renders[pix0 * ps + 2 * cs] = has_bg ? c0b + T0 * bg2 : c0b;
+        renders[pix0 * ps] = has_bg ? f2_lo(CR) + T0 * bg0 : f2_lo(CR);
+        renders[pix0 * ps + cs] = has_bg ? f2_lo(CG) + T0 * bg1 : f2_lo(CG);
+        renders[pix0 * ps + 2 * cs] = has_bg ? f2_lo(CB) + T0 * bg2 : f2_lo(CB);
         last_ids[pix0] = last0;
     }
     if (pm.in1) {
         alphas[pix1] = 1.0f - T1;
-        renders[pix1 * ps] = has_bg ? c1r + T1 * bg0 : c1r;
-        renders[pix1 * ps + cs] = has_bg ? c1g + T1 * bg1 : c1g;
-        renders[pix1 * ps + 2 * cs] = has_bg ? c1b + T1 * bg2 : c1b;
+        renders[pix1 * ps] = has_bg ? f2_hi(CR) + T1 * bg0 : f2_hi(CR);
+        renders[pix1 * ps + cs] = has_bg ? f2_hi(CG) + T1 * bg1 : f2_hi(CG);
+        renders[pix1 * ps + 2 * cs] = has_bg ? f2_hi(CB) + T1 * bg2 : f2_hi(CB);
         last_ids[pix1] = last1;
     }
 }
