@@ -15,12 +15,17 @@ What the N=1 line carries:
                            gsplat CUDA kernels built unmodified in oracle/_ref) through one harness, same call sites
   e2e / e2e_resident       the same metric with host<->device copies in the timed region, for both libraries
   fused                    the extended operator over the raw SplatData tensors
+  train                    a training iteration (render + SSIM/L1 loss + backward + Adam), eager and from one CUDA graph
+  fastgs, train_fastgs     the reference's DEFAULT rasterizer path and a training iteration on it, beside
+                           the reference's own fastgs kernels
   configs                  config A (CPU oracle at full size, all cores + 1 thread; GPU beside it) and config D (6 M)
   roofline, cpu_baseline   as the task contract asks
 
 N>1 (launched by torchrun, one rank per GPU): every rank renders its own view of the same 1 M
-Gaussians (config E) and the per-Gaussian gradients are exchanged over NCCL; weak scaling,
-value = N_gaussians x n_gpus / max-over-ranks time.
+Gaussians (config E: eight cameras on a ring, taken in the order 0, 180, 90, 270 degrees and then the diagonals, so
+that 2 and 4 ranks hold equally expensive views) and the per-Gaussian gradients are exchanged over NCCL; weak scaling,
+value = N_gaussians x n_gpus / max-over-ranks time; `exchange.step_without_collectives_ms` is the same step with the
+collectives left out.
 
 --impl reference times the reference's CPU path of the same hot path: the oracle port
 (oracle/gut_oracle.c, OpenMP over all host cores) on a bounded sample (a sub-frustum crop of the
@@ -312,7 +317,8 @@ def run_b200(args):
     pg2 = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        pg2 = dist.new_group()  # second communicator: the geometry all-reduce overlaps the colour all-gather
+        if not args.no_overlap:
+            pg2 = dist.new_group()  # second communicator: the geometry all-reduce overlaps the colour all-gather
     pkg = ge.load_package()
     pkg.load()
     from gsplat_b200 import hoststream, multiview
@@ -384,7 +390,7 @@ def run_b200(args):
             self.capacity = 0
 
         # -- operator path: activated parameters in, as gs::training::rasterize hands them to the ops --
-        def step(self, Pd=None, backend=None):
+        def step(self, Pd=None, backend=None, exchange=True):
             Pd = Pd or self.P
             for k in names:
                 Pd[k].grad = None
@@ -398,7 +404,7 @@ def run_b200(args):
                 if peer["obj"] is not None:
                     multiview.exchange_gradients_peer(Pd, deferred, peer["obj"], overlap_group=pg2)
                 else:
-                    multiview.exchange_gradients_compact(Pd, deferred, overlap_group=pg2)
+                    multiview.exchange_gradients_compact(Pd, deferred, overlap_group=pg2, local_only=not exchange)
             elif world > 1:
                 multiview.allreduce_gradients([Pd[k].grad for k in names])
             self.stats["n_isects"], self.stats["vis"] = out.n_isects, out.visibility
@@ -482,7 +488,12 @@ def run_b200(args):
                 return int((ends - off).max().item())
 
     cfg = args.config if world == 1 else "B"
-    wl = Workload(cfg, args.gaussians, view=(rank if world > 1 else None))
+    # Config E: eight cameras on a ring around the slab, one per rank.  The ring positions are not equally expensive (the
+    # four diagonal ones see part of the slab at a third of the distance: 2.45 vs 2.2 ms on one GPU); ranks
+    # take them in the order 0, 180, 90, 270 degrees, then the diagonals, so that 2 and 4 ranks render equally heavy views
+    # and the scaling figure measures the exchange, not the scene.  At 8 ranks every position is in use.
+    VIEW_ORDER = (0, 4, 2, 6, 1, 5, 3, 7)
+    wl = Workload(cfg, args.gaussians, view=(VIEW_ORDER[rank % 8] if world > 1 else None))
     N, W, H = wl.N, wl.W, wl.H
     warm = max(args.warmup, 3)
     if world > 1 and args.exchange == "peer":
@@ -581,10 +592,16 @@ def run_b200(args):
             multiview.allreduce_gradients(bufs)
         ms_ar = timed(lambda: multiview.allreduce_gradients(bufs), 20) / 20
         nbytes = sum(b.numel() * 4 for b in bufs)
+        ms_local = None
+        if compact and peer["obj"] is None:  # the same step without any collective: what the exchange adds
+            for _ in range(3):
+                wl.step(exchange=False)
+            ms_local = timed(lambda: wl.step(exchange=False), args.steps) / args.steps
         line["exchange"] = {"mode": ("peer" if peer["obj"] is not None else
                                      ("compact" if compact else "allreduce")),
                             "peer_fallback_reason": peer["why"],
-                            "overlap": "geometry all-reduce on a second communicator",
+                            "overlap": ("geometry all-reduce on a second communicator" if pg2 is not None else "none"),
+                            "step_without_collectives_ms": ms_local,
                             "allreduce_236B_ms": ms_ar, "allreduce_bytes": nbytes,
                             "allreduce_bus_GBps": 2.0 * (world - 1) / world * nbytes / (ms_ar * 1e-3) / 1e9,
                             "nvlink5_peak_GBps_per_direction": 900.0,
@@ -991,6 +1008,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="B", choices=["A", "B", "D"], help="N=1 workload (BASELINE.json configs)")
     ap.add_argument("--gaussians", type=int, default=None, help="override the config's Gaussian count")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: geometry all-reduce on the compute stream (no second communicator)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-cuda", action="store_true")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the config A / D block of the N=1 line")

@@ -356,7 +356,8 @@ __device__ __forceinline__ uint32_t chunk_first_run(const BinArgs &a, uint32_t p
 
 // Order repair of the (chunk, tile) groups: one lane per group, a warp for the large ones.  Called by all 32 lanes
 // of a warp, each with its own group: chunk p, global tile t, slots [start, start + c) of flatten_ids.
-constexpr int kSmallGroup = 16;
+constexpr int kLaneSortMax = 16;  // groups of up to this many members are sorted by their own lane
+constexpr int kWarpSortMax = 128; // larger groups of up to this many members are rank-sorted by a warp
 
 // groups of two to four members: a 4-element sorting network in registers
 __device__ __forceinline__ void repair_small(const BinArgs &a, const float *__restrict__ depths, uint32_t start,
@@ -421,9 +422,10 @@ __device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__r
             for (int e = 0; e < 8; ++e)
                 if ((uint32_t)e < c) a.flatten_ids[start + e] = (int32_t)id[e];
         }
-    } else if (c > 8 && c <= (uint32_t)kSmallGroup) {
-        // insertion sort on (depth bits, index) in local memory: rare
-        uint32_t ids[kSmallGroup], keys[kSmallGroup];
+    } else if (c > 8 && c <= (uint32_t)kLaneSortMax) {
+        // nine to sixteen: insertion sort on (depth bits, index) in local memory, one group per lane (32 groups of a warp
+        // keep their gathers in flight together; handing these to the warp-wide sort below serialises them: measured)
+        uint32_t ids[kLaneSortMax], keys[kLaneSortMax];
         for (uint32_t k = 0; k < c; ++k) {
             ids[k] = (uint32_t)a.flatten_ids[start + k];
             keys[k] = __float_as_uint(depths[ids[k]]);
@@ -442,8 +444,55 @@ __device__ __forceinline__ void repair_groups(const BinArgs &a, const float *__r
         if (moved)
             for (uint32_t k = 0; k < c; ++k) a.flatten_ids[start + k] = (int32_t)ids[k];
     }
-    // groups beyond the register sort: re-emit the chunk's runs that cover the tile, in run (= depth) order
-    uint32_t big = __ballot_sync(0xffffffffu, c > (uint32_t)kSmallGroup);
+    // kLaneSortMax + 1 to kWarpSortMax members: the whole warp sorts one group at a time by RANK -- every lane holds up to four
+    // (depth bits, index) pairs, counts for each how many of the group's pairs are smaller (pairs are distinct: a Gaussian
+    // appears once per group) and stores it at that position.  O(c^2 / 32) shuffles per group, no dependent re-walk of the
+    // chunk: what keeps the pass flat when depth and screen position correlate and (chunk, tile) groups grow (a camera
+    // looking along the slab's diagonal: groups of 20..60; the per-group re-walk below took 0.83 ms there).
+    uint32_t mid = __ballot_sync(0xffffffffu, c > (uint32_t)kLaneSortMax && c <= (uint32_t)kWarpSortMax);
+    while (mid) {
+        const int src = __ffs(mid) - 1;
+        mid &= mid - 1;
+        const uint32_t gstart = __shfl_sync(0xffffffffu, start, src), gc = __shfl_sync(0xffffffffu, c, src);
+        const uint32_t slots = (gc + 31u) >> 5; // elements per lane, <= kWarpSortMax / 32
+        if (slots == 1u) { // up to 32 members (the common case of this path): one pair per lane, gc shuffle rounds
+            const uint32_t id1 = lane < gc ? (uint32_t)a.flatten_ids[gstart + lane] : 0xffffffffu;
+            const uint32_t k1 = lane < gc ? __float_as_uint(depths[id1]) : 0xffffffffu;
+            uint32_t r1 = 0;
+            for (uint32_t l = 0; l < gc; ++l) {
+                const uint32_t ko = __shfl_sync(0xffffffffu, k1, l), io = __shfl_sync(0xffffffffu, id1, l);
+                r1 += (ko < k1 || (ko == k1 && io < id1)) ? 1u : 0u;
+            }
+            if (lane < gc && r1 != lane) a.flatten_ids[gstart + r1] = (int32_t)id1;
+            continue;
+        }
+        uint32_t id[kWarpSortMax / 32], k[kWarpSortMax / 32];
+#pragma unroll
+        for (int e = 0; e < kWarpSortMax / 32; ++e) {
+            const uint32_t j = (uint32_t)e * 32u + lane;
+            id[e] = j < gc ? (uint32_t)a.flatten_ids[gstart + j] : 0xffffffffu;
+        }
+#pragma unroll
+        for (int e = 0; e < kWarpSortMax / 32; ++e) k[e] = id[e] != 0xffffffffu ? __float_as_uint(depths[id[e]]) : 0xffffffffu;
+        uint32_t rank[kWarpSortMax / 32];
+#pragma unroll
+        for (int e = 0; e < kWarpSortMax / 32; ++e) rank[e] = 0;
+#pragma unroll
+        for (int f = 0; f < kWarpSortMax / 32; ++f) {
+            if ((uint32_t)f < slots) { // warp-uniform
+                for (int l = 0; l < 32; ++l) {
+                    const uint32_t ko = __shfl_sync(0xffffffffu, k[f], l), io = __shfl_sync(0xffffffffu, id[f], l);
+#pragma unroll
+                    for (int e = 0; e < kWarpSortMax / 32; ++e) rank[e] += (ko < k[e] || (ko == k[e] && io < id[e])) ? 1u : 0u;
+                }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < kWarpSortMax / 32; ++e)
+            if (id[e] != 0xffffffffu) a.flatten_ids[gstart + rank[e]] = (int32_t)id[e];
+    }
+    // still larger groups (rare): re-emit the chunk's runs that cover the tile, in run (= depth) order
+    uint32_t big = __ballot_sync(0xffffffffu, c > (uint32_t)kWarpSortMax);
     while (big) {
         const int src = __ffs(big) - 1;
         big &= big - 1;

@@ -54,7 +54,7 @@ def _side_stream(device):
 
 
 def exchange_gradients_compact(params: dict, deferred, sh_views_fn=None, average_over: int | None = None,
-                               group=None, overlap_group=None) -> None:
+                               group=None, overlap_group=None, local_only: bool = False) -> None:
     """The exchange step with 1/2 to 1/3 of the all-reduce's traffic.
 
     `params` maps 'means', 'quats', 'scales', 'opacities', 'sh_coeffs' to the leaf tensors; after
@@ -80,10 +80,16 @@ def exchange_gradients_compact(params: dict, deferred, sh_views_fn=None, average
     means, coeffs = params["means"], params["sh_coeffs"]
     sinks = list(deferred) if isinstance(deferred, (list, tuple)) else [deferred]
     sh_degree = sinks[0].sh_degree
-    vc = torch.stack([d.v_colors for d in sinks]).contiguous()                      # [v_local, N, 3]
-    cp = torch.stack([d.campos.reshape(3) for d in sinks]).contiguous()             # [v_local, 3]
+    if len(sinks) == 1:  # one view per rank (config E): views, no copy kernels
+        vc = sinks[0].v_colors.reshape((1,) + tuple(sinks[0].v_colors.shape[-2:])).contiguous()  # [1, N, 3]
+        cp = sinks[0].campos.reshape(1, 3).contiguous()
+    else:
+        vc = torch.stack([d.v_colors.reshape(d.v_colors.shape[-2:]) for d in sinks]).contiguous()  # [v_local, N, 3]
+        cp = torch.stack([d.campos.reshape(3) for d in sinks]).contiguous()                        # [v_local, 3]
     geo = [params[k].grad for k in ("means", "quats", "scales", "opacities")]
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if local_only:  # measurement aid: this rank's own views only, no collective (what the step costs without the exchange)
+        world = 1
     pending, scratch = None, None
     if world > 1:
         overlap = overlap_group is not None and vc.device.type == "cuda"
