@@ -390,7 +390,7 @@ def run_b200(args):
             self.capacity = 0
 
         # -- operator path: activated parameters in, as gs::training::rasterize hands them to the ops --
-        def step(self, Pd=None, backend=None, exchange=True):
+        def step(self, Pd=None, backend=None, exchange=True, prof=None):
             Pd = Pd or self.P
             for k in names:
                 Pd[k].grad = None
@@ -404,7 +404,7 @@ def run_b200(args):
                 if peer["obj"] is not None:
                     multiview.exchange_gradients_peer(Pd, deferred, peer["obj"], overlap_group=pg2)
                 else:
-                    multiview.exchange_gradients_compact(Pd, deferred, overlap_group=pg2, local_only=not exchange)
+                    multiview.exchange_gradients_compact(Pd, deferred, overlap_group=pg2, local_only=not exchange, prof=prof)
             elif world > 1:
                 multiview.allreduce_gradients([Pd[k].grad for k in names])
             self.stats["n_isects"], self.stats["vis"] = out.n_isects, out.visibility
@@ -597,11 +597,17 @@ def run_b200(args):
             for _ in range(3):
                 wl.step(exchange=False)
             ms_local = timed(lambda: wl.step(exchange=False), args.steps) / args.steps
+            pr = {}
+            for _ in range(10):
+                wl.step(prof=pr)
+            sync_all()
+            phases = {k: (round(v, 4) if v is not None else None) for k, v in multiview.phase_times(pr).items()}
         line["exchange"] = {"mode": ("peer" if peer["obj"] is not None else
                                      ("compact" if compact else "allreduce")),
                             "peer_fallback_reason": peer["why"],
                             "overlap": ("geometry all-reduce on a second communicator" if pg2 is not None else "none"),
                             "step_without_collectives_ms": ms_local,
+                            "phases_ms": (phases if ms_local is not None else None),
                             "allreduce_236B_ms": ms_ar, "allreduce_bytes": nbytes,
                             "allreduce_bus_GBps": 2.0 * (world - 1) / world * nbytes / (ms_ar * 1e-3) / 1e9,
                             "nvlink5_peak_GBps_per_direction": 900.0,

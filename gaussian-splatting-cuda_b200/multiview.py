@@ -46,6 +46,31 @@ def allreduce_gradients(grads: Sequence[torch.Tensor], average_over: int | None 
 _side_streams: dict = {}
 
 
+class _Marker:
+    """Records named CUDA events into prof[name] (a list per name) -- only when a dict is passed; otherwise a no-op."""
+
+    def __init__(self, prof, device):
+        self.prof = prof if (prof is not None and device.type == "cuda") else None
+
+    def __call__(self, name, stream=None):
+        if self.prof is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record(stream) if stream is not None else ev.record()
+        self.prof.setdefault(name, []).append(ev)
+
+
+def phase_times(prof: dict) -> dict:
+    """Average milliseconds between the markers of exchange_gradients_compact (call after a device synchronise)."""
+    def avg(a, b):
+        if a not in prof or b not in prof:
+            return None
+        return sum(x.elapsed_time(y) for x, y in zip(prof[a], prof[b])) / max(len(prof[a]), 1)
+    return {"gather_ms": avg("start", "gathered"), "allreduce_after_gather_ms": avg("gathered", "reduced"),
+            "expand_ms": avg("reduced" if "reduced" in prof else "gathered", "expanded"), "wait_and_add_ms": avg("expanded", "end"),
+            "side_stream_allreduce_ms": avg("ar0", "ar1"), "total_ms": avg("start", "end")}
+
+
 def _side_stream(device):
     key = (device.type, device.index)
     if key not in _side_streams:
@@ -54,7 +79,7 @@ def _side_stream(device):
 
 
 def exchange_gradients_compact(params: dict, deferred, sh_views_fn=None, average_over: int | None = None,
-                               group=None, overlap_group=None, local_only: bool = False) -> None:
+                               group=None, overlap_group=None, local_only: bool = False, prof: dict | None = None) -> None:
     """The exchange step with 1/2 to 1/3 of the all-reduce's traffic.
 
     `params` maps 'means', 'quats', 'scales', 'opacities', 'sh_coeffs' to the leaf tensors; after
@@ -91,13 +116,17 @@ def exchange_gradients_compact(params: dict, deferred, sh_views_fn=None, average
     if local_only:  # measurement aid: this rank's own views only, no collective (what the step costs without the exchange)
         world = 1
     pending, scratch = None, None
+    mark = _Marker(prof, vc.device)  # measurement aid: CUDA events between the phases when `prof` is a dict
+    mark("start")
     if world > 1:
         overlap = overlap_group is not None and vc.device.type == "cuda"
         if overlap:
             comp, side = torch.cuda.current_stream(vc.device), _side_stream(vc.device)
             side.wait_stream(comp)  # the blend gradients are complete
             with torch.cuda.stream(side):
+                mark("ar0", side)
                 allreduce_gradients(geo, group=overlap_group)
+                mark("ar1", side)
             pending = side
             for g in geo:
                 g.record_stream(side)
@@ -105,8 +134,10 @@ def exchange_gradients_compact(params: dict, deferred, sh_views_fn=None, average
         cp_all = torch.empty((world * cp.shape[0], 3), dtype=cp.dtype, device=cp.device)
         dist.all_gather_into_tensor(vc_all.view(-1, vc.shape[-1]), vc.view(-1, vc.shape[-1]), group=group)
         dist.all_gather_into_tensor(cp_all, cp, group=group)
+        mark("gathered")
         if not overlap:
             allreduce_gradients(geo, group=group)
+            mark("reduced")
     else:
         vc_all, cp_all = vc, cp
     with torch.no_grad():
@@ -116,9 +147,11 @@ def exchange_gradients_compact(params: dict, deferred, sh_views_fn=None, average
             v_means = scratch
         coeffs.grad = sh_views_fn(sh_degree, means.detach().contiguous(), cp_all.contiguous(),
                                   coeffs.detach().contiguous(), vc_all.contiguous(), v_means)
+        mark("expanded")
         if pending is not None:
             torch.cuda.current_stream(vc.device).wait_stream(pending)
             means.grad.add_(scratch)
+        mark("end")
     if average_over and average_over != 1:
         for k in ("means", "quats", "scales", "opacities", "sh_coeffs"):
             params[k].grad.div_(average_over)
