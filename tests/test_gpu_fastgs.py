@@ -333,3 +333,20 @@ def test_fastgs_capacity_mode_and_graphed_iteration(native, cuda_device):
     assert max(abs(a - b) for a, b in zip(la, lb)) < 1e-5
     for k in PA:
         assert rel(PB[k].detach(), PA[k].detach()) < 1e-5, k
+
+
+@pytest.mark.parametrize("active", [1, 4, 9])
+def test_fastgs_partially_active_sh(native, cuda_device, active):
+    """Training raises the active SH degree every 1000 iterations while shN always holds 15 bases
+    (fast_rasterizer.cpp:33-34): fewer active bases than stored ones -- the inactive rows get zero gradient."""
+    fg = _fg(native)
+    inp = scenes.fastgs_inputs(scenes.scene_small(N=2000, width=150, height=90, sh_degree=3, seed=31, view=1))
+    inp["active_sh_bases"] = active
+    gi, ga = _weights(inp, cuda_device, 9)
+    mine = run(fg, fg.default_backend(), inp, cuda_device, gi, ga)
+    ref = run(fg, _ref_backend(native), inp, cuda_device, gi, ga)
+    image_close(mine, ref, f"active {active} of 16 bases, b200 vs reference kernels")
+    grads_close(mine, ref, inp["means"].shape[0], f"active {active} of 16 bases")
+    assert not mine["grads"]["shN"][:, active - 1:].any()
+    if active > 1:
+        assert mine["grads"]["shN"][:, :active - 1].any()
