@@ -350,3 +350,24 @@ def test_fastgs_partially_active_sh(native, cuda_device, active):
     assert not mine["grads"]["shN"][:, active - 1:].any()
     if active > 1:
         assert mine["grads"]["shN"][:, :active - 1].any()
+
+
+def test_dump_reference_fastgs_golden(native, cuda_device):
+    """Writes gpurun_out/ref_fastgs_small.npz: outputs of the reference's own fastgs kernels (oracle/_ref/libfastgs_ref.so) on
+    a small scene.  The file is committed as tests/golden/ref_fastgs_small.npz and pins oracle/fastgs_oracle.c in the no-GPU
+    suite (tests/test_oracle_fastgs.py::test_oracle_vs_reference_fastgs_golden)."""
+    import os
+    fg = _fg(native)
+    inp = scenes.fastgs_inputs(scenes.scene_small(N=1500, width=176, height=112, sh_degree=3, seed=13, view=2))
+    rng = np.random.default_rng(17)
+    gi = torch.from_numpy(rng.standard_normal((3, inp["height"], inp["width"])).astype(np.float32)).to(cuda_device)
+    ga = torch.from_numpy(rng.standard_normal((1, inp["height"], inp["width"])).astype(np.float32)).to(cuda_device)
+    n = inp["means"].shape[0]
+    dens = torch.zeros((2, n), device=cuda_device)
+    ref = run(fg, _ref_backend(native), inp, cuda_device, gi, ga, w2c_grad=True, dens=dens)
+    os.makedirs("gpurun_out", exist_ok=True)
+    np.savez_compressed("gpurun_out/ref_fastgs_small.npz", image=ref["image"].cpu().numpy(), alpha=ref["alpha"].cpu().numpy(),
+                        grad_image=gi.cpu().numpy(), grad_alpha=ga.cpu().numpy(), grad_w2c=ref["w2c_grad"].cpu().numpy(),
+                        densification_info=dens.cpu().numpy(),
+                        **{"grad_" + k: v.cpu().numpy() for k, v in ref["grads"].items()})
+    assert float(ref["alpha"].mean()) > 0.05

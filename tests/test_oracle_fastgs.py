@@ -105,3 +105,32 @@ def test_densification_info_accumulates():
     d = out["densification_info"]
     vis = out["n_touched"] > 0
     assert (d[0][vis] == 1).all() and (d[0][~vis] == 0).all() and (d[1] >= 0).all()
+
+
+def test_oracle_vs_reference_fastgs_golden():
+    """Pins the oracle to the REFERENCE'S OWN fastgs kernels without a GPU: tests/golden/ref_fastgs_small.npz was produced on
+    a B200 by tests/test_gpu_fastgs.py::test_dump_reference_fastgs_golden from oracle/_ref/libfastgs_ref.so, i.e.
+    /root/reference/fastgs/rasterization/src/*.cu compiled unmodified (oracle/build_ref.py).  Scene:
+    scenes.scene_small(N=1500, 176x112, SH degree 3, seed 13, view 2) -> scenes.fastgs_inputs; cotangents from numpy
+    default_rng(17)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_fastgs_small.npz"))
+    inp = scenes.fastgs_inputs(scenes.scene_small(N=1500, width=176, height=112, sh_degree=3, seed=13, view=2))
+    n = inp["means"].shape[0]
+    dens = np.zeros((2, n), np.float32)
+    for precision, tol_img, tol_grad in (("f32", 1e-4, 1e-3), ("f64", 1e-4, 1e-3)):
+        o = fgo.render(**inp, grad_image=g["grad_image"], grad_alpha=g["grad_alpha"], want_w2c_grad=True,
+                       densification_info=dens.copy(), precision=precision)
+
+        def rel(a, b):
+            a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+            return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+        assert rel(o["image"], g["image"]) < tol_img and rel(o["alpha"], g["alpha"]) < tol_img
+        assert np.abs(o["image"] - g["image"]).max() < 2e-2  # a pixel at a threshold may gain / lose one contribution
+        for k, gk in (("grad_means", "grad_means"), ("grad_scales_raw", "grad_scales_raw"), ("grad_rotations_raw", "grad_rotations_raw"),
+                      ("grad_opacities_raw", "grad_opacities_raw"), ("grad_sh0", "grad_sh0"), ("grad_shN", "grad_shN")):
+            e = rel(o[k].reshape(g[gk].shape), g[gk])
+            assert e < tol_grad, (precision, k, e)
+        assert rel(o["grad_w2c"][:3], g["grad_w2c"][:3]) < tol_grad
+        assert np.array_equal(o["densification_info"][0], g["densification_info"][0])  # the same primitives are visible
+        assert rel(o["densification_info"][1], g["densification_info"][1]) < tol_grad
