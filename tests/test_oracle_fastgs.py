@@ -134,3 +134,59 @@ def test_oracle_vs_reference_fastgs_golden():
         assert rel(o["grad_w2c"][:3], g["grad_w2c"][:3]) < tol_grad
         assert np.array_equal(o["densification_info"][0], g["densification_info"][0])  # the same primitives are visible
         assert rel(o["densification_info"][1], g["densification_info"][1]) < tol_grad
+
+
+def test_python_mirror_of_the_fastgs_caller_routes_gradients(pkg):
+    """Host logic, no GPU: the package's mirror of FastGSRasterize / fast_rasterize (fastgs.py; reference:
+    fast_rasterizer_autograd.cpp:10-160, fast_rasterizer.cpp:12-74) driven by a stand-in backend that calls the CPU oracle --
+    gradient order, densification_info pass-through, w2c gradient on request, background composite."""
+    import importlib
+
+    import torch
+    fg = importlib.import_module(pkg.__name__ + ".fastgs")
+    inp = _scene(n=80, w=64, h=48, deg=2)
+    keys = ("means", "scales_raw", "rotations_raw", "opacities_raw", "sh0", "shN")
+
+    class OracleBackend:
+        def forward(self, means, scales_raw, rotations_raw, opacities_raw, sh0, shN, w2c, s, capacity=0):
+            self.args = dict(means=means.detach().numpy(), scales_raw=scales_raw.detach().numpy(),
+                             rotations_raw=rotations_raw.detach().numpy(), opacities_raw=opacities_raw.detach().numpy(),
+                             sh0=sh0.detach().numpy(), shN=shN.detach().numpy(), w2c=w2c.detach().numpy(),
+                             cam_position=s.cam_position.numpy(), active_sh_bases=s.active_sh_bases, width=s.width,
+                             height=s.height, fx=s.focal_x, fy=s.focal_y, cx=s.center_x, cy=s.center_y,
+                             near_plane=s.near_plane, far_plane=s.far_plane)
+            o = fgo.render(**self.args, precision="f64")
+            return torch.from_numpy(o["image"]), torch.from_numpy(o["alpha"]), {"n": o["n_instances"]}
+
+        def backward(self, ctx, grad_image, grad_alpha, image, alpha, means, scales_raw, rotations_raw, shN, w2c, s,
+                     densification_info=None, want_w2c_grad=False):
+            o = fgo.render(**self.args, grad_image=grad_image.numpy(), grad_alpha=grad_alpha.numpy(), precision="f64",
+                           want_w2c_grad=want_w2c_grad,
+                           densification_info=None if densification_info is None else densification_info.numpy())
+            if densification_info is not None:
+                densification_info.copy_(torch.from_numpy(o["densification_info"]))
+            g = [torch.from_numpy(o[k]).float() for k in ("grad_means", "grad_scales_raw", "grad_rotations_raw",
+                                                           "grad_opacities_raw", "grad_sh0", "grad_shN")]
+            return (*g, torch.from_numpy(o["grad_w2c"]).float() if want_w2c_grad else None)
+
+    P = {k: torch.from_numpy(inp[k]).requires_grad_(True) for k in keys}
+    w2c = torch.from_numpy(inp["w2c"]).requires_grad_(True)
+    s = fg.FastGSSettings(cam_position=torch.from_numpy(inp["cam_position"]), active_sh_bases=inp["active_sh_bases"],
+                          width=inp["width"], height=inp["height"], focal_x=inp["fx"], focal_y=inp["fy"], center_x=inp["cx"],
+                          center_y=inp["cy"])
+    bg = torch.tensor([0.2, 0.4, 0.6])
+    dens = torch.zeros((2, inp["means"].shape[0]))
+    gi, ga = _loss_weights(inp, 3)
+    image, alpha = fg.fast_rasterize(OracleBackend(), P["means"], P["scales_raw"], P["rotations_raw"], P["opacities_raw"], P["sh0"],
+                                     P["shN"], w2c, s, bg_color=bg, densification_info=dens)
+    ((image * torch.from_numpy(gi)).sum() + (alpha * torch.from_numpy(ga)).sum()).backward()
+    # what the caller's sequence must amount to: image = raw + (1 - alpha) bg, so the rasterizer sees grad_alpha - bg . grad_image
+    raw = _render(inp, "f64")
+    assert np.allclose(image.detach().numpy(), raw["image"] + (1 - raw["alpha"]) * bg.numpy()[:, None, None], atol=1e-6)
+    ga_eff = ga - (gi * bg.numpy()[:, None, None]).sum(0, keepdims=True)
+    want = _render(inp, "f64", grad_image=gi, grad_alpha=ga_eff, want_w2c_grad=True)
+    for k, wk in zip(keys, ("grad_means", "grad_scales_raw", "grad_rotations_raw", "grad_opacities_raw", "grad_sh0", "grad_shN")):
+        assert P[k].grad.shape == P[k].shape
+        assert np.allclose(P[k].grad.numpy().reshape(want[wk].shape), want[wk], rtol=1e-4, atol=1e-7), k
+    assert np.allclose(w2c.grad.numpy()[:3], want["grad_w2c"][:3], rtol=1e-4, atol=1e-6)
+    assert float(dens[0].sum()) == float((raw["n_touched"] > 0).sum())
